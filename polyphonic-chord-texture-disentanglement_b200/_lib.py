@@ -1,0 +1,73 @@
+"""ctypes binding of ``libpolydis_b200.so`` (the C-ABI declared in ``include/polydis_b200.h``).
+
+The library is the product's only compute path.  If it is missing (not built) this module raises
+at import -- there is deliberately no PyTorch / CPU fallback.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_P, _L, _I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
+
+# name -> argument ctypes (every function returns int: 0 ok, cudaError_t > 0, -22 bad argument)
+SIGNATURES = {
+    "pd_gemm_f32": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _P],
+    "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
+    "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
+    "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I,
+                         _I, _P],
+    "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
+    "pd_note_embed_fwd": [_P, _L, _P, _P, _P, _L, _P],
+    "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
+    "pd_greedy_pick": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P],
+    "pd_dur_token": [_P, _L, _L, _P, _P],
+    "pd_transpose_f32": [_P, _I, _I, _P, _P],
+    "pd_chord_feedback": [_P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P],
+    "pd_chord_targets": [_P, _I, _P, _P, _P, _P],
+    "pd_texture_frontend_fwd": [_P, _P, _P, _I, _I, _P, _P],
+    "pd_texture_frontend_bwd": [_P, _P, _P, _I, _I, _P, _P, _P, _P],
+    "pd_ce_fwd": [_P, _L, _P, _L, _I, _I, _P, _P, _P],
+    "pd_ce_bwd": [_P, _L, _P, _L, _I, _I, _P, _P, _P, _L, _P],
+    "pd_exp_fwd": [_P, _L, _P, _P],
+    "pd_mul_f32": [_P, _P, _L, _P, _P],
+    "pd_reparam_fwd": [_P, _P, _P, _I, _I, _P, _L, _P],
+    "pd_reparam_bwd": [_P, _L, _P, _I, _I, _P, _P, _P],
+    "pd_kl_fwd": [_P, _P, _L, _P, _P],
+    "pd_kl_bwd": [_P, _P, _L, _P, _P, _P, _P],
+}
+
+LIB_PATH = _build.LIB_PATH
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is not built; run `python -m polydis_b200.build` (needs nvcc). "
+            "polydis_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is missing
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    return lib
+
+
+lib = _load()
+
+#: incremented on every kernel-launching library call (bench.py reports it as ``gpu_launches``)
+call_count = 0
+
+
+def check(name, code):
+    if code != 0:
+        raise RuntimeError(f"libpolydis_b200: {name} failed with code {code}"
+                           + (" (bad argument)" if code == -22 else " (cudaError_t)"))
+
+
+def call(name, *args):
+    global call_count
+    call_count += 1
+    code = getattr(lib, name)(*args)
+    if code != 0:
+        check(name, code)

@@ -1,0 +1,32 @@
+// Shared helpers for libpolydis_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PD_API extern "C" __attribute__((visibility("default")))
+
+// Every entry point returns 0 on success or a cudaError_t / negative argument-error code.
+#define PD_BAD_ARG (-22)
+
+static inline int pd_launch_status() {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return 0;
+}
+
+static inline unsigned pd_blocks(long n, int per) { return (unsigned)((n + per - 1) / per); }
+
+#define PD_NUM_SMS 148
+
+__device__ __forceinline__ float pd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}

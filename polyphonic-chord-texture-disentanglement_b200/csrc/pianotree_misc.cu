@@ -1,0 +1,258 @@
+// PianoTree grid handling: token preparation, note embedding as a gather (fwd) / column-owned
+// reduction (bwd), greedy token picking and duration feedback tokens.  All HBM-bound integer/byte
+// work: coalesced 512-byte rows, one warp per note, no dense multi-hot tensors.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NOTE_SLOTS = 16, TOK_W = 6, EMB = 128, P_RANGE = 130, NOTE_SIZE = 135;
+constexpr int P_EOS = 129, P_PAD = 130;
+
+// x (B,32,16,6) int64 -> tok int32 (same layout), lengths (B*32), pitch targets (B*32,15),
+// dur targets (B*32,15,5).  One thread per (b,t) step.            ptvae.py:292-297, :498-511
+__global__ void grid_prepare_kernel(const long long* __restrict__ x, long steps, int* tok, int* lengths,
+                                    int* pitch_tgt, int* dur_tgt) {
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= steps) return;
+    const long long* xs = x + s * NOTE_SLOTS * TOK_W;
+    int* ts = tok + s * NOTE_SLOTS * TOK_W;
+    int pads = 0;
+#pragma unroll 4
+    for (int n = 0; n < NOTE_SLOTS; ++n) {
+        int p = (int)xs[n * TOK_W];
+        pads += (p == P_PAD);
+        ts[n * TOK_W] = p;
+#pragma unroll
+        for (int k = 1; k < TOK_W; ++k) {
+            int d = (int)xs[n * TOK_W + k];
+            ts[n * TOK_W + k] = d;
+            if (n >= 1 && dur_tgt) dur_tgt[(s * 15 + (n - 1)) * 5 + (k - 1)] = d;
+        }
+        if (n >= 1 && pitch_tgt) pitch_tgt[s * 15 + (n - 1)] = p;
+    }
+    if (lengths) lengths[s] = NOTE_SLOTS - pads;
+}
+
+// emb[r, :] = bias + (p < 130 ? WT[p] : 0) + sum_k d_k * WT[130+k]   (== Linear(135->128) on the multi-hot,
+// ptvae.py:299-313,:333,:531-535).  One warp per note, lane owns 4 consecutive outputs.
+__global__ void __launch_bounds__(256) note_embed_fwd_kernel(const int* __restrict__ tok, long R,
+                                                             const float* __restrict__ WT,
+                                                             const float* __restrict__ bias, float* out, long ldo) {
+    long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    const int lane = threadIdx.x & 31;
+    const int* t = tok + r * TOK_W;
+    float4 acc = *reinterpret_cast<const float4*>(bias + lane * 4);
+    int p = t[0];
+    if (p >= 0 && p < P_RANGE) {
+        float4 w = *reinterpret_cast<const float4*>(WT + (long)p * EMB + lane * 4);
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        float d = (float)t[1 + k];
+        if (d != 0.0f) {
+            float4 w = *reinterpret_cast<const float4*>(WT + (long)(P_RANGE + k) * EMB + lane * 4);
+            acc.x = fmaf(d, w.x, acc.x); acc.y = fmaf(d, w.y, acc.y);
+            acc.z = fmaf(d, w.z, acc.z); acc.w = fmaf(d, w.w, acc.w);
+        }
+    }
+    *reinterpret_cast<float4*>(out + r * ldo + lane * 4) = acc;
+}
+
+// dWT[p, j] += sum_r [tok_r.pitch == p] g[r, j] ; dWT[130+k, j] += sum_r d_k g[r, j] ; db[j] += sum_r g[r, j].
+// Thread j owns column j of a CTA-private (135+1) x 128 accumulator in shared memory (no intra-CTA
+// atomics), rows are streamed coalesced, one global atomicAdd per accumulator cell per CTA.
+__global__ void __launch_bounds__(EMB) note_embed_bwd_kernel(const int* __restrict__ tok, long R,
+                                                             const float* __restrict__ g, long ldg, float* dWT,
+                                                             float* dbias, long rows_per_cta) {
+    extern __shared__ float acc[];   // (NOTE_SIZE + 1) * EMB
+    const int j = threadIdx.x;
+    for (int i = 0; i <= NOTE_SIZE; ++i) acc[i * EMB + j] = 0.0f;
+    long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
+    for (long r = r0; r < r1; ++r) {
+        const int* t = tok + r * TOK_W;
+        float v = g[r * ldg + j];
+        int p = t[0];
+        if (p >= 0 && p < P_RANGE) acc[p * EMB + j] += v;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float d = (float)t[1 + k];
+            if (d != 0.0f) acc[(P_RANGE + k) * EMB + j] += d * v;
+        }
+        acc[NOTE_SIZE * EMB + j] += v;
+    }
+    for (int i = 0; i < NOTE_SIZE; ++i) {
+        float v = acc[i * EMB + j];
+        if (v != 0.0f) atomicAdd(dWT + i * EMB + j, v);
+    }
+    atomicAdd(dbias + j, acc[NOTE_SIZE * EMB + j]);
+}
+
+// Greedy pick for one note slot n (1..15): argmax pitch (first maximum, like torch.max on CPU),
+// argmax of each duration bit, token row for the embedding gather, EOS length bookkeeping
+// (first n whose pitch is EOS; 15 if none).                           ptvae.py:408-416,:425
+__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ pitch, long ldp,
+                                                          const float* __restrict__ dur, long ldd, long R, int n,
+                                                          int* tok, long ldtok, int* lens) {
+    long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = pitch + r * ldp;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < P_RANGE; i += 32) {
+        float v = p[i];
+        if (v > best || (v != v && best == best)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+        int* t = tok + r * ldtok;
+        t[0] = bi;
+        if (lens) {
+            int L = lens[r];
+            if (L == 0 && bi == P_EOS) L = n;
+            if (n == NOTE_SLOTS - 1 && L == 0) L = NOTE_SLOTS - 1;
+            lens[r] = L;
+        }
+    }
+    if (lane < 5) {
+        const float* d = dur + r * ldd + lane * 2;
+        tok[r * ldtok + 1 + lane] = (d[1] > d[0]) ? 1 : 0;
+    }
+}
+
+// Duration feedback token: 5-wide vector with a single 1 at index == argmax bit (ptvae.py:322-326).
+__global__ void dur_token_kernel(const float* __restrict__ logit, long ldl, long R, float* tok) {
+    long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* l = logit + r * ldl;
+    int one = (l[1] > l[0]) ? 1 : 0;
+    float* t = tok + r * 5;
+    t[0] = one ? 0.f : 1.f; t[1] = one ? 1.f : 0.f; t[2] = 0.f; t[3] = 0.f; t[4] = 0.f;
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int rows, int cols, float* out) {
+    __shared__ float tile[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (x < cols && y0 + i < rows) tile[i][threadIdx.x] = in[(long)(y0 + i) * cols + x];
+    __syncthreads();
+    int ox = blockIdx.y * 32 + threadIdx.x, oy0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (ox < rows && oy0 + i < cols) out[(long)(oy0 + i) * rows + ox] = tile[threadIdx.x][i];
+}
+
+// Chord decoder feedback (ptvae.py:73-78): the reference's advanced-index assignment makes every
+// sample's root/bass one-hot the UNION over the batch of all samples' argmaxes.  Pass 1 marks the
+// union flags, pass 2 writes the (B,36) tokens [union root | per-sample chroma argmax | union bass].
+__global__ void chord_union_kernel(const float* __restrict__ root, long ldr, const float* __restrict__ bass,
+                                   long ldb, int B, float* flags) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float* r = root + (long)b * ldr;
+    const float* s = bass + (long)b * ldb;
+    int ri = 0, si = 0;
+    for (int i = 1; i < 12; ++i) { if (r[i] > r[ri]) ri = i; if (s[i] > s[si]) si = i; }
+    flags[ri] = 1.0f;
+    flags[12 + si] = 1.0f;
+}
+__global__ void chord_token_kernel(const float* __restrict__ chroma, long ldc, const float* __restrict__ flags,
+                                   int B, float* tok, long ldt) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 36) return;
+    int b = i / 36, k = i % 36;
+    float v;
+    if (k < 12) v = flags[k];
+    else if (k < 24) { const float* c = chroma + (long)b * ldc + (k - 12) * 2; v = (c[1] > c[0]) ? 1.f : 0.f; }
+    else v = flags[12 + (k - 24)];
+    tok[(long)b * ldt + k] = v;
+}
+
+// c (B,8,36) -> CE targets: argmax root / chroma bit as class / argmax bass.   model.py:72-74
+__global__ void chord_targets_kernel(const float* __restrict__ c, int rows, int* root, int* chroma, int* bass) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const float* p = c + (long)r * 36;
+    int ri = 0, bi = 0;
+    for (int i = 1; i < 12; ++i) { if (p[i] > p[ri]) ri = i; if (p[24 + i] > p[24 + bi]) bi = i; }
+    root[r] = ri; bass[r] = bi;
+    for (int i = 0; i < 12; ++i) chroma[r * 12 + i] = (int)p[12 + i];
+}
+
+}  // namespace
+
+PD_API int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, int* pitch_tgt,
+                           int* dur_tgt, void* stream) {
+    if (n_steps <= 0) return 0;
+    grid_prepare_kernel<<<pd_blocks(n_steps, 128), 128, 0, (cudaStream_t)stream>>>(x, n_steps, tok, lengths,
+                                                                                   pitch_tgt, dur_tgt);
+    return pd_launch_status();
+}
+
+PD_API int pd_note_embed_fwd(const int* tok, long R, const float* WT, const float* bias, float* out, long ldo,
+                             void* stream) {
+    if (R <= 0) return 0;
+    if ((ldo & 3) || ((uintptr_t)out & 15) || ((uintptr_t)WT & 15) || ((uintptr_t)bias & 15)) return PD_BAD_ARG;
+    note_embed_fwd_kernel<<<pd_blocks(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(tok, R, WT, bias, out, ldo);
+    return pd_launch_status();
+}
+
+PD_API int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias,
+                             void* stream) {
+    if (R <= 0) return 0;
+    static bool attr_set = false;
+    const int smem = (NOTE_SIZE + 1) * EMB * (int)sizeof(float);
+    if (!attr_set) {
+        cudaFuncSetAttribute(note_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_set = true;
+    }
+    long ctas = 3 * PD_NUM_SMS;
+    long rows_per = (R + ctas - 1) / ctas;
+    if (rows_per < 64) rows_per = 64;
+    ctas = (R + rows_per - 1) / rows_per;
+    note_embed_bwd_kernel<<<(unsigned)ctas, EMB, smem, (cudaStream_t)stream>>>(tok, R, g, ldg, dWT, dbias, rows_per);
+    return pd_launch_status();
+}
+
+PD_API int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok,
+                          long ldtok, int* lens, void* stream) {
+    if (R <= 0) return 0;
+    greedy_pick_kernel<<<pd_blocks(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(pitch, ldp, dur, ldd, R, n, tok,
+                                                                                 ldtok, lens);
+    return pd_launch_status();
+}
+
+PD_API int pd_dur_token(const float* logit, long ldl, long R, float* tok, void* stream) {
+    if (R <= 0) return 0;
+    dur_token_kernel<<<pd_blocks(R, 256), 256, 0, (cudaStream_t)stream>>>(logit, ldl, R, tok);
+    return pd_launch_status();
+}
+
+PD_API int pd_transpose_f32(const float* in, int rows, int cols, float* out, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), blk(32, 8);
+    transpose_kernel<<<grid, blk, 0, (cudaStream_t)stream>>>(in, rows, cols, out);
+    return pd_launch_status();
+}
+
+PD_API int pd_chord_feedback(const float* root, long ldr, const float* chroma, long ldc, const float* bass,
+                             long ldb, int B, float* flags24, float* tok, long ldt, void* stream) {
+    if (B <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(flags24, 0, 24 * sizeof(float), st);
+    chord_union_kernel<<<pd_blocks(B, 128), 128, 0, st>>>(root, ldr, bass, ldb, B, flags24);
+    chord_token_kernel<<<pd_blocks((long)B * 36, 128), 128, 0, st>>>(chroma, ldc, flags24, B, tok, ldt);
+    return pd_launch_status();
+}
+
+PD_API int pd_chord_targets(const float* c, int rows, int* root, int* chroma, int* bass, void* stream) {
+    if (rows <= 0) return 0;
+    chord_targets_kernel<<<pd_blocks(rows, 128), 128, 0, (cudaStream_t)stream>>>(c, rows, root, chroma, bass);
+    return pd_launch_status();
+}

@@ -1,0 +1,230 @@
+"""Drop-in for the reference's ``model.py``: ``DisentangleVAE`` with the same constructor, method
+signatures, return conventions and state-dict keys (model.py:11-265 and the ``PytorchModel`` base,
+amc_dl/torch_plus/module.py:8-57), running on libpolydis_b200.
+
+Differences a caller can observe:
+  * CUDA only.  Tensors must live on a B200; there is no CPU path (ops raise otherwise).
+  * ``inference`` / ``swap`` / ``inference_decode`` never materialise or copy the logit tensors the
+    reference moves to the host (ptvae.py:537-544); they return the same ``est_x`` int64 ndarray.
+  * ``run`` draws its reparameterisation noise from torch's CUDA generator (the reference would use
+    the CPU generator on a CPU model); tests inject the noise through ``eps=(eps_chd, eps_rhy)``.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.distributions import Normal
+
+from . import ops
+from .ptvae import RnnEncoder, RnnDecoder, PtvaeDecoder, TextureEncoder
+
+
+class PytorchModel(nn.Module):
+    """Mode-dispatching base (amc_dl/torch_plus/module.py:8-57)."""
+
+    def __init__(self, name, device):
+        self.name = name
+        super().__init__()
+        if device is None:
+            device = torch.device('cuda')
+        self.device = device
+
+    def run(self, *input):
+        raise NotImplementedError
+
+    def loss(self, *input, **kwargs):
+        raise NotImplementedError
+
+    def inference(self, *input):
+        raise NotImplementedError
+
+    def loss_function(self, *input):
+        raise NotImplementedError
+
+    def forward(self, mode, *input, **kwargs):
+        if mode in ["run", 0]:
+            return self.run(*input, **kwargs)
+        elif mode in ['loss', 'train', 1]:
+            return self.loss(*input, **kwargs)
+        elif mode in ['inference', 'eval', 'val', 2]:
+            return self.inference(*input, **kwargs)
+        raise NotImplementedError
+
+    def load_model(self, model_path, map_location=None):
+        if map_location is None:
+            map_location = self.device
+        dic = torch.load(model_path, map_location=map_location)
+        for name in list(dic.keys()):
+            dic[name.replace('module.', '')] = dic.pop(name)
+        self.load_state_dict(dic)
+        self.to(self.device)
+
+    @staticmethod
+    def init_model(*inputs):
+        raise NotImplementedError
+
+
+def _sample(dist, sample, eps=None):
+    """rsample (mu + std*eps) or mean, on the library's reparam kernel (train_utils.py:33-34)."""
+    if not sample:
+        return dist.mean
+    if eps is None:
+        eps = torch.empty(dist.mean.shape, device=dist.mean.device, dtype=torch.float32).normal_()
+    return ops.reparam(dist.mean, dist.scale, eps)
+
+
+class DisentangleVAE(PytorchModel):
+
+    def __init__(self, name, device, chd_encoder, rhy_encoder, decoder, chd_decoder):
+        super().__init__(name, device)
+        self.chd_encoder = chd_encoder
+        self.rhy_encoder = rhy_encoder
+        self.decoder = decoder
+        self.num_step = self.decoder.num_step
+        self.chd_decoder = chd_decoder
+
+    # -- training ----------------------------------------------------------------------------------
+    def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None):
+        """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
+        recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
+        embedded_x, lengths = self.decoder.emb_x(x)
+        dist_chd = self.chd_encoder(c)
+        dist_rhy = self.rhy_encoder(pr_mat)
+        z_chd = _sample(dist_chd, True, None if eps is None else eps[0])
+        z_rhy = _sample(dist_rhy, True, None if eps is None else eps[1])
+        dec_z = torch.cat([z_chd, z_rhy], dim=-1)
+        pitch_outs, dur_outs = self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2)
+        recon_root, recon_chroma, recon_bass = self.chd_decoder(z_chd, False, tfr3, c)
+        return pitch_outs, dur_outs, dist_chd, dist_rhy, recon_root, recon_chroma, recon_bass
+
+    def loss_function(self, x, c, recon_pitch, recon_dur, dist_chd, dist_rhy, recon_root, recon_chroma,
+                      recon_bass, beta, weights, weighted_dur=False):
+        """-> (loss, recon, pitch, dur, kl, kl_chd, kl_rhy, chord, root, chroma, bass).  model.py:57-68"""
+        recon_loss, pl, dl = self.decoder.recon_loss(x, recon_pitch, recon_dur, weights, weighted_dur)
+        kl_loss, kl_chd, kl_rhy = self.kl_loss(dist_chd, dist_rhy)
+        chord_loss, root, chroma, bass = self.chord_loss(c, recon_root, recon_chroma, recon_bass)
+        loss = recon_loss + beta * kl_loss + chord_loss
+        return loss, recon_loss, pl, dl, kl_loss, kl_chd, kl_rhy, chord_loss, root, chroma, bass
+
+    def chord_loss(self, c, recon_root, recon_chroma, recon_bass):
+        root, chroma, bass = ops.chord_targets(c)
+        root_loss = ops.masked_ce(recon_root.reshape(-1, 12), root)
+        chroma_loss = ops.masked_ce(recon_chroma.reshape(-1, 2), chroma)
+        bass_loss = ops.masked_ce(recon_bass.reshape(-1, 12), bass)
+        return root_loss + chroma_loss + bass_loss, root_loss, chroma_loss, bass_loss
+
+    def kl_loss(self, *dists):
+        kl_chd = ops.kl_std_normal(dists[0].mean, dists[0].scale)
+        kl_rhy = ops.kl_std_normal(dists[1].mean, dists[1].scale)
+        return kl_chd + kl_rhy, kl_chd, kl_rhy
+
+    def loss(self, x, c, pr_mat, tfr1=0., tfr2=0., tfr3=0., beta=0.1, weights=(1, 0.5), eps=None):
+        outputs = self.run(x, c, pr_mat, tfr1, tfr2, tfr3, eps=eps)
+        return self.loss_function(x, c, *outputs, beta, weights)
+
+    # -- inference ---------------------------------------------------------------------------------
+    def inference_encode(self, pr_mat, c):
+        self.eval()
+        with torch.no_grad():
+            dist_chd = self.chd_encoder(c)
+            dist_rhy = self.rhy_encoder(pr_mat)
+        return dist_chd, dist_rhy
+
+    def decode_tokens(self, z_chd, z_rhy):
+        """Greedy PianoTree decode -> (B,32,15,6) int32 tokens ON DEVICE (no host copy)."""
+        self.eval()
+        with torch.no_grad():
+            return self.decoder.greedy_tokens(torch.cat([z_chd, z_rhy], dim=-1))
+
+    def inference_decode(self, z_chd, z_rhy):
+        return self.decode_tokens(z_chd, z_rhy).cpu().numpy().astype(np.int64)
+
+    def inference(self, pr_mat, c, sample, eps=None):
+        self.eval()
+        with torch.no_grad():
+            dist_chd = self.chd_encoder(c)
+            dist_rhy = self.rhy_encoder(pr_mat)
+            z_chd = _sample(dist_chd, sample, None if eps is None else eps[0])
+            z_rhy = _sample(dist_rhy, sample, None if eps is None else eps[1])
+        return self.inference_decode(z_chd, z_rhy)
+
+    def swap(self, pr_mat1, pr_mat2, c1, c2, fix_rhy, fix_chd):
+        pr_mat = pr_mat1 if fix_rhy else pr_mat2
+        c = c1 if fix_chd else c2
+        return self.inference(pr_mat, c, sample=False)
+
+    def posterior_sample(self, pr_mat, c, scale=None, sample_chd=True, sample_txt=True):
+        if scale is None and sample_chd and sample_txt:
+            return self.inference(pr_mat, c, sample=True)
+        dist_chd, dist_rhy = self.inference_encode(pr_mat, c)
+        if scale is not None:
+            dist_rhy = Normal(dist_rhy.mean, dist_rhy.scale * scale, validate_args=False)
+            dist_chd = Normal(dist_chd.mean, dist_chd.scale * scale, validate_args=False)
+        with torch.no_grad():
+            z_chd, z_rhy = _sample(dist_chd, True), _sample(dist_rhy, True)
+        if not sample_chd:
+            z_chd = dist_chd.mean
+        if not sample_txt:
+            z_rhy = dist_rhy.mean
+        return self.inference_decode(z_chd, z_rhy)
+
+    def prior_sample(self, x, c, sample_chd=False, sample_rhy=False, scale=1.):
+        dist_chd, dist_rhy = self.inference_encode(x, c)
+        mean = torch.zeros_like(dist_rhy.mean)
+        loc = torch.ones_like(dist_rhy.mean) * scale
+        if sample_chd:
+            dist_chd = Normal(mean, loc, validate_args=False)
+        if sample_rhy:
+            dist_rhy = Normal(mean, loc, validate_args=False)
+        with torch.no_grad():
+            z_chd, z_rhy = _sample(dist_chd, True), _sample(dist_rhy, True)
+        return self.inference_decode(z_chd, z_rhy)
+
+    def gt_sample(self, x):
+        return x[:, :, 1:].cpu().numpy()
+
+    def interp(self, pr_mat1, c1, pr_mat2, c2, interp_chd=False, interp_rhy=False, int_count=10):
+        dist_chd1, dist_rhy1 = self.inference_encode(pr_mat1, c1)
+        dist_chd2, dist_rhy2 = self.inference_encode(pr_mat2, c2)
+        z_chd1, z_rhy1, z_chd2, z_rhy2 = dist_chd1.mean, dist_rhy1.mean, dist_chd2.mean, dist_rhy2.mean
+        if interp_chd:
+            z_chds = self.interp_z(z_chd1, z_chd2, int_count)
+        else:
+            z_chds = z_chd1.unsqueeze(1).repeat(1, int_count, 1)
+        if interp_rhy:
+            z_rhys = self.interp_z(z_rhy1, z_rhy2, int_count)
+        else:
+            z_rhys = z_rhy1.unsqueeze(1).repeat(1, int_count, 1)
+        bs = z_chds.size(0)
+        z_chds = z_chds.view(bs * int_count, -1).contiguous()
+        z_rhys = z_rhys.view(bs * int_count, -1).contiguous()
+        estxs = self.inference_decode(z_chds, z_rhys)
+        return estxs.reshape((bs, int_count, 32, 15, -1))
+
+    def interp_z(self, z1, z2, int_count=10):
+        z1, z2 = z1.cpu().numpy(), z2.cpu().numpy()
+        return torch.stack([self.interp_path(a, b, int_count) for a, b in zip(z1, z2)], dim=0)
+
+    def interp_path(self, z1, z2, interpolation_count=10):
+        """Spherical interpolation of direction, log-linear interpolation of norm (model.py:218-242)."""
+        shape = z1.shape
+        z1, z2 = z1.reshape(-1), z2.reshape(-1)
+        n1, n2 = np.linalg.norm(z1), np.linalg.norm(z2)
+        u1, u2 = z1 / n1, z2 / n2
+        ts = np.linspace(0.0, 1.0, interpolation_count)
+        omega = np.arccos(np.dot(u1 / np.linalg.norm(u1), u2 / np.linalg.norm(u2)))
+        so = np.sin(omega)
+        dirs = np.sin((1.0 - ts) * omega)[:, None] / so * u1[None] + np.sin(ts * omega)[:, None] / so * u2[None]
+        length = np.linspace(np.log(n1), np.log(n2), interpolation_count)
+        out = (dirs * np.exp(length[:, None])).reshape([interpolation_count] + list(shape))
+        return torch.from_numpy(out).to(self.device).float()
+
+    @staticmethod
+    def init_model(device=None, chd_size=256, txt_size=256, num_channel=10):
+        name = 'disvae'
+        if device is None:
+            device = torch.device('cuda')
+        chd_encoder = RnnEncoder(36, 1024, chd_size)
+        rhy_encoder = TextureEncoder(256, 1024, txt_size, num_channel)
+        chd_decoder = RnnDecoder(z_dim=chd_size)
+        pt_decoder = PtvaeDecoder(note_embedding=None, dec_dur_hid_size=64, z_size=chd_size + txt_size)
+        return DisentangleVAE(name, device, chd_encoder, rhy_encoder, pt_decoder, chd_decoder)

@@ -1,0 +1,465 @@
+"""Host-side operators: thin wrappers that hand device pointers to libpolydis_b200 and the autograd
+``Function``s built on them.  PyTorch here is plumbing (allocation, streams, autograd bookkeeping);
+every FLOP below runs in the library's kernels.
+
+Conventions: fp32, batch-first; 2-D operands may have an arbitrary row stride but unit inner stride.
+"""
+import torch
+
+from . import _lib
+
+_call = _lib.call
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"polydis_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    return t
+
+
+def _rows(t):
+    """View ``t`` as (rows, cols) with unit inner stride; returns (tensor2d, row_stride)."""
+    if t.dim() != 2:
+        t = t.reshape(-1, t.shape[-1])
+    if t.stride(1) != 1 and t.shape[1] != 1:
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# raw kernels
+def gemm_nt(x, w, out, bias=None, accumulate=False):
+    """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias)."""
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and out.shape == (M, N) and x.stride(1) == 1 and out.stride(1) == 1
+    assert w.stride(1) == 1 or K == 1
+    _call("pd_gemm_f32", _ptr(x), x.stride(0), 1, _ptr(w), 1, w.stride(0), _ptr(out), out.stride(0),
+          _ptr(bias), M, N, K, int(accumulate), _stream())
+    return out
+
+
+def gemm_nn(x, w, out, accumulate=False):
+    """out (M,N) (+)= x (M,K) @ w (K,N)."""
+    M, K = x.shape
+    N = w.shape[1]
+    assert w.shape[0] == K and out.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1
+    _call("pd_gemm_f32", _ptr(x), x.stride(0), 1, _ptr(w), w.stride(0), 1, _ptr(out), out.stride(0),
+          None, M, N, K, int(accumulate), _stream())
+    return out
+
+
+def gemm_tn(a, b, out, accumulate=False):
+    """out (M,N) (+)= a (R,M)^T @ b (R,N)."""
+    R, M = a.shape
+    N = b.shape[1]
+    assert b.shape[0] == R and out.shape == (M, N) and a.stride(1) == 1 and b.stride(1) == 1
+    _call("pd_gemm_f32", _ptr(a), 1, a.stride(0), _ptr(b), b.stride(0), 1, _ptr(out), out.stride(0),
+          None, M, N, R, int(accumulate), _stream())
+    return out
+
+
+def colsum(x, out, accumulate=False):
+    M, N = x.shape
+    _call("pd_colsum_f32", _ptr(x), x.stride(0), M, N, _ptr(out), int(accumulate), _stream())
+    return out
+
+
+def transpose(x):
+    x = x.contiguous()
+    out = torch.empty(x.shape[1], x.shape[0], device=x.device, dtype=x.dtype)
+    _call("pd_transpose_f32", _ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b on 2-D x with strided rows (nn.Linear; K7 of SURVEY.md 2.2)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x2, _ = _rows(_chk(x, "x"))
+        y = torch.empty(x2.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+        gemm_nt(x2, w, y, b)
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = b is not None
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2, _ = _rows(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
+            gemm_nn(dy2, w, dx)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
+            gemm_tn(dy2, x2, dw)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
+            colsum(dy2, db)
+        return dx, dw, db
+
+
+def linear(x, w, b=None):
+    return _Linear.apply(x, w, b)
+
+
+class _Linear2(torch.autograd.Function):
+    """y = [x1 | x2] W^T + b without materialising the concatenation (dur_hid_linear, ptvae.py:349-352)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, w, b):
+        a, _ = _rows(_chk(x1))
+        c, _ = _rows(_chk(x2))
+        k1 = a.shape[1]
+        y = torch.empty(a.shape[0], w.shape[0], device=a.device, dtype=torch.float32)
+        gemm_nt(a, w[:, :k1], y, b)
+        gemm_nt(c, w[:, k1:], y, None, accumulate=True)
+        ctx.save_for_backward(a, c, w)
+        ctx.shapes = (x1.shape, x2.shape)
+        return y.view(*x1.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, c, w = ctx.saved_tensors
+        k1 = a.shape[1]
+        dy2, _ = _rows(dy)
+        d1 = torch.empty(a.shape, device=dy.device, dtype=torch.float32)
+        d2 = torch.empty(c.shape, device=dy.device, dtype=torch.float32)
+        gemm_nn(dy2, w[:, :k1], d1)
+        gemm_nn(dy2, w[:, k1:], d2)
+        dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
+        gemm_tn(dy2, a, dw[:, :k1])
+        gemm_tn(dy2, c, dw[:, k1:])
+        db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
+        colsum(dy2, db)
+        return d1.view(ctx.shapes[0]), d2.view(ctx.shapes[1]), dw, db
+
+
+def linear_cat2(x1, x2, w, b):
+    return _Linear2.apply(x1, x2, w, b)
+
+
+# ------------------------------------------------------------------------------------------------
+def _gates_fwd(gi, gi2, gh, hprev, hout, rzn, hn, lengths, t):
+    B, H = hout.shape
+    _call("pd_gru_gates_fwd", _ptr(gi), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
+          _ptr(gh), gh.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
+          _ptr(hout), hout.stride(0), _ptr(rzn), 0 if rzn is None else rzn.stride(0),
+          _ptr(hn), 0 if hn is None else hn.stride(0), _ptr(lengths), t, B, H, _stream())
+
+
+def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None):
+    """Run a GRU over precomputed input projections.  gi (B,T,3H) strided view, gi2 (B,3H) or None.
+
+    Returns h_all (B,T,H).  ``save`` (dict) receives rzn / hn for the backward pass.
+    """
+    B, T, H3 = gi.shape
+    H = H3 // 3
+    dev = gi.device
+    h_all = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    gh = torch.empty(B, H3, device=dev, dtype=torch.float32)
+    rzn = hn = None
+    if save is not None:
+        rzn = torch.empty(B, T, H3, device=dev, dtype=torch.float32)
+        hn = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+        save["rzn"], save["hn"] = rzn, hn
+    order = range(T - 1, -1, -1) if reverse else range(T)
+    hprev = h0
+    for t in order:
+        if hprev is None:
+            gemm_nt(gh[:, :0], w_hh[:, :0], gh, b_hh)          # K = 0: gh = b_hh
+        else:
+            gemm_nt(hprev, w_hh, gh, b_hh)
+        _gates_fwd(gi[:, t], gi2, gh, hprev, h_all[:, t],
+                   None if rzn is None else rzn[:, t], None if hn is None else hn[:, t], lengths, t)
+        hprev = h_all[:, t]
+    return h_all
+
+
+class _GruSeq(torch.autograd.Function):
+    """GRU recurrence over precomputed x-projections; BPTT in the backward.  Serves the time / note /
+    duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
+
+    @staticmethod
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse):
+        _chk(gi, "gi")
+        save = {}
+        h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save)
+        ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
+        ctx.reverse = reverse
+        ctx.has_gi2 = gi2 is not None
+        return h_all
+
+    @staticmethod
+    def backward(ctx, dout):
+        rzn, hn, h_all, h0, w_hh, lengths = ctx.saved_tensors
+        B, T, H = h_all.shape
+        dev = dout.device
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        dgi = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
+        dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
+        dgi2 = torch.zeros(B, 3 * H, device=dev, dtype=torch.float32) if ctx.has_gi2 else None
+        dw = torch.zeros(w_hh.shape, device=dev, dtype=torch.float32)
+        dh_a = torch.empty(B, H, device=dev, dtype=torch.float32)
+        dh_b = torch.empty(B, H, device=dev, dtype=torch.float32)
+        order = list(range(T - 1, -1, -1) if ctx.reverse else range(T))
+        dh = None
+        st = _stream()
+        for i in range(T - 1, -1, -1):
+            t = order[i]
+            hprev = h_all[:, order[i - 1]] if i > 0 else h0
+            nxt = dh_b if dh is dh_a else dh_a
+            _call("pd_gru_gates_bwd", _ptr(dh), 0 if dh is None else dh.stride(0), _ptr(dout[:, t]),
+                  dout.stride(0), _ptr(rzn[:, t]), rzn.stride(0), _ptr(hn[:, t]), hn.stride(0), _ptr(hprev),
+                  0 if hprev is None else hprev.stride(0), _ptr(dgi[:, t]), dgi.stride(0),
+                  _ptr(dgh[:, t]), dgh.stride(0), _ptr(nxt), nxt.stride(0), _ptr(dgi2),
+                  0 if dgi2 is None else dgi2.stride(0), _ptr(lengths), t, B, H, st)
+            if hprev is not None:
+                gemm_nn(dgh[:, t], w_hh, nxt, accumulate=True)        # dh_prev += dgh W_hh
+                gemm_tn(dgh[:, t], hprev, dw, accumulate=True)        # dW_hh += dgh^T h_prev
+            dh = nxt
+        db = torch.empty(3 * H, device=dev, dtype=torch.float32)
+        colsum(dgh.view(B * T, 3 * H), db)
+        dh0 = dh if (h0 is not None and ctx.needs_input_grad[2]) else None
+        return dgi, dgi2, dh0, dw, db, None, None
+
+
+def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False):
+    """Autograd-aware GRU over (B,T,3H) input projections; falls to the no-grad loop when nothing
+    requires grad (inference)."""
+    if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
+                                    (h0 is not None and h0.requires_grad)):
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse)
+    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse)
+
+
+# ------------------------------------------------------------------------------------------------
+def grid_prepare(x):
+    """x (B,32,16,6) int64 -> tok int32 (B*512,6), lengths int32 (B*32), pitch_tgt (B*480), dur_tgt (B*2400)."""
+    _chk(x, "x")
+    x = x.contiguous()
+    B = x.shape[0]
+    dev = x.device
+    tok = torch.empty(B * 512, 6, device=dev, dtype=torch.int32)
+    lengths = torch.empty(B * 32, device=dev, dtype=torch.int32)
+    pt = torch.empty(B * 480, device=dev, dtype=torch.int32)
+    dt = torch.empty(B * 2400, device=dev, dtype=torch.int32)
+    _call("pd_grid_prepare", _ptr(x), B * 32, _ptr(tok), _ptr(lengths), _ptr(pt), _ptr(dt), _stream())
+    return tok, lengths, pt, dt
+
+
+class _NoteEmbed(torch.autograd.Function):
+    """note_embedding(multi-hot) as a 6-row gather-add (ptvae.py:299-313,:333); tok int32 (R,6)."""
+
+    @staticmethod
+    def forward(ctx, tok, w, b, out=None):
+        R = tok.shape[0]
+        wt = transpose(w)                                  # (135,128): rows contiguous per pitch
+        if out is None:
+            out = torch.empty(R, 128, device=w.device, dtype=torch.float32)
+        _call("pd_note_embed_fwd", _ptr(tok), R, _ptr(wt), _ptr(b), _ptr(out), out.stride(0), _stream())
+        ctx.save_for_backward(tok)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (tok,) = ctx.saved_tensors
+        g2, _ = _rows(g)
+        dwt = torch.zeros(135, 128, device=g.device, dtype=torch.float32)
+        db = torch.zeros(128, device=g.device, dtype=torch.float32)
+        _call("pd_note_embed_bwd", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db),
+              _stream())
+        return None, transpose(dwt), db, None
+
+
+def note_embed(tok, w, b):
+    return _NoteEmbed.apply(tok, w, b)
+
+
+class _TextureFrontend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pr_mat, w, b):
+        _chk(pr_mat, "pr_mat")
+        pr = pr_mat.contiguous()
+        B, C = pr.shape[0], w.shape[0]
+        out = torch.empty(B, C, 8, 29, device=pr.device, dtype=torch.float32)
+        wc = w.contiguous()
+        _call("pd_texture_frontend_fwd", _ptr(pr), _ptr(wc), _ptr(b), B, C, _ptr(out), _stream())
+        ctx.save_for_backward(pr, wc, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pr, w, b = ctx.saved_tensors
+        g = g.contiguous()
+        dw = torch.zeros_like(w)
+        db = torch.zeros_like(b)
+        _call("pd_texture_frontend_bwd", _ptr(pr), _ptr(w), _ptr(b), pr.shape[0], w.shape[0], _ptr(g),
+              _ptr(dw), _ptr(db), _stream())
+        return None, dw, db
+
+
+def texture_frontend(pr_mat, w, b):
+    return _TextureFrontend.apply(pr_mat, w, b)
+
+
+class _MaskedCE(torch.autograd.Function):
+    """mean CE over rows whose int32 target != ignore (nn.CrossEntropyLoss(ignore_index))."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, ignore):
+        l2, _ = _rows(_chk(logits, "logits"))
+        acc = torch.empty(2, device=l2.device, dtype=torch.float32)
+        loss = torch.empty((), device=l2.device, dtype=torch.float32)
+        _call("pd_ce_fwd", _ptr(l2), l2.stride(0), _ptr(targets), l2.shape[0], l2.shape[1], ignore,
+              _ptr(acc), _ptr(loss), _stream())
+        ctx.save_for_backward(l2, targets, acc)
+        ctx.ignore = ignore
+        ctx.shape = logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        l2, targets, acc = ctx.saved_tensors
+        d = torch.empty(l2.shape, device=l2.device, dtype=torch.float32)
+        g = g.contiguous()
+        _call("pd_ce_bwd", _ptr(l2), l2.stride(0), _ptr(targets), l2.shape[0], l2.shape[1], ctx.ignore,
+              _ptr(acc), _ptr(g), _ptr(d), d.stride(0), _stream())
+        return d.view(ctx.shape), None, None
+
+
+def masked_ce(logits, targets, ignore=-100):
+    return _MaskedCE.apply(logits, targets, ignore)
+
+
+class _Exp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _chk(x).contiguous()
+        y = torch.empty_like(x)
+        _call("pd_exp_fwd", _ptr(x), x.numel(), _ptr(y), _stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (y,) = ctx.saved_tensors
+        g = g.contiguous()
+        d = torch.empty_like(y)
+        _call("pd_mul_f32", _ptr(g), _ptr(y), y.numel(), _ptr(d), _stream())
+        return d
+
+
+def exp(x):
+    return _Exp.apply(x)
+
+
+class _Reparam(torch.autograd.Function):
+    """z = mu + std * eps (Normal.rsample, train_utils.py:33-34); eps None -> z = mu."""
+
+    @staticmethod
+    def forward(ctx, mu, sd, eps):
+        mu, sd = _chk(mu).contiguous(), sd.contiguous()
+        B, D = mu.shape
+        z = torch.empty(B, D, device=mu.device, dtype=torch.float32)
+        _call("pd_reparam_fwd", _ptr(mu), _ptr(sd), _ptr(eps), B, D, _ptr(z), z.stride(0), _stream())
+        ctx.save_for_backward(eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        (eps,) = ctx.saved_tensors
+        dz2, _ = _rows(dz)
+        B, D = dz2.shape
+        dmu = torch.empty(B, D, device=dz.device, dtype=torch.float32)
+        dsd = torch.empty(B, D, device=dz.device, dtype=torch.float32)
+        _call("pd_reparam_bwd", _ptr(dz2), dz2.stride(0), _ptr(eps), B, D, _ptr(dmu), _ptr(dsd), _stream())
+        return dmu, dsd, None
+
+
+def reparam(mu, sd, eps):
+    return _Reparam.apply(mu, sd, eps)
+
+
+class _KL(torch.autograd.Function):
+    """mean over all elements of KL(N(mu, sd) || N(0,1))  (train_utils.py:45-49)."""
+
+    @staticmethod
+    def forward(ctx, mu, sd):
+        mu, sd = _chk(mu).contiguous(), sd.contiguous()
+        out = torch.empty((), device=mu.device, dtype=torch.float32)
+        _call("pd_kl_fwd", _ptr(mu), _ptr(sd), mu.numel(), _ptr(out), _stream())
+        ctx.save_for_backward(mu, sd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, sd = ctx.saved_tensors
+        g = g.contiguous()
+        dmu, dsd = torch.empty_like(mu), torch.empty_like(sd)
+        _call("pd_kl_bwd", _ptr(mu), _ptr(sd), mu.numel(), _ptr(g), _ptr(dmu), _ptr(dsd), _stream())
+        return dmu, dsd
+
+
+def kl_std_normal(mu, sd):
+    return _KL.apply(mu, sd)
+
+
+# ------------------------------------------------------------------------------------------------
+def greedy_pick(pitch, dur, n, tok_out, lens):
+    """pitch (R,130), dur (R,5,2) logits -> tok_out int32 (R,6) view; updates lens (R,) int32."""
+    p2, _ = _rows(pitch)
+    d2 = dur.reshape(dur.shape[0], 10)
+    if d2.stride(1) != 1:
+        d2 = d2.contiguous()
+    R = p2.shape[0]
+    _call("pd_greedy_pick", _ptr(p2), p2.stride(0), _ptr(d2), d2.stride(0), R, n, _ptr(tok_out),
+          tok_out.stride(0), _ptr(lens), _stream())
+
+
+def dur_token(logit):
+    """(R,2) logits -> (R,5) feedback token with the 1 at index == argmax bit (ptvae.py:322-326)."""
+    l2, _ = _rows(logit)
+    tok = torch.empty(l2.shape[0], 5, device=l2.device, dtype=torch.float32)
+    _call("pd_dur_token", _ptr(l2), l2.stride(0), l2.shape[0], _ptr(tok), _stream())
+    return tok
+
+
+def chord_feedback(root, chroma, bass):
+    """(B,12), (B,12,2), (B,12) logits -> (B,36) feedback token (batch-union one-hots, ptvae.py:73-78)."""
+    B = root.shape[0]
+    r2, _ = _rows(root)
+    b2, _ = _rows(bass)
+    c2 = chroma.reshape(B, 24)
+    if c2.stride(1) != 1:
+        c2 = c2.contiguous()
+    flags = torch.empty(24, device=root.device, dtype=torch.float32)
+    tok = torch.empty(B, 36, device=root.device, dtype=torch.float32)
+    _call("pd_chord_feedback", _ptr(r2), r2.stride(0), _ptr(c2), c2.stride(0), _ptr(b2), b2.stride(0), B,
+          _ptr(flags), _ptr(tok), tok.stride(0), _stream())
+    return tok
+
+
+def chord_targets(c):
+    c = _chk(c, "c").contiguous()
+    rows = c.shape[0] * c.shape[1]
+    dev = c.device
+    root = torch.empty(rows, device=dev, dtype=torch.int32)
+    chroma = torch.empty(rows * 12, device=dev, dtype=torch.int32)
+    bass = torch.empty(rows, device=dev, dtype=torch.int32)
+    _call("pd_chord_targets", _ptr(c), rows, _ptr(root), _ptr(chroma), _ptr(bass), _stream())
+    return root, chroma, bass

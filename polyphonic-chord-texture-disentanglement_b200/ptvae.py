@@ -1,0 +1,404 @@
+"""Network modules of the PolyDis hot path with the reference's constructor / forward surface and
+state-dict keys (ptvae.py:11-122,218-575 of the reference), computing on libpolydis_b200 kernels.
+
+The modules only *hold* parameters (same names and shapes as the reference's nn.GRU / nn.Linear /
+nn.Conv2d members, so reference checkpoints load); every forward is restructured for the GPU:
+
+* all step-independent input projections are hoisted out of the recurrences and batched
+  (SURVEY.md 7.3): the constant halves of the reference's ``torch.cat([token, z_in])`` inputs are
+  projected once per sequence and enter the gate kernel as a broadcast term;
+* with full teacher forcing the 32 x 15 x 5 loop nest collapses to 32 + 15 + 5 serial steps over
+  batches of B, 32B and 480B rows;
+* the note embedding is a gather, never a dense multi-hot GEMM;
+* greedy decoding keeps tokens / lengths on the device (no host round trips inside the loops).
+
+Python's ``random`` is consumed in exactly the reference's order (14 draws per time step against
+tfr2, one per time step but the last against tfr1, 8 against tfr3) so seeded runs take the same
+teacher-forcing decisions.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+from torch import nn
+from torch.distributions import Normal
+
+from . import ops
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter holders (names match torch's nn.GRU / nn.Linear / nn.Conv2d state-dict keys)
+class GRUParams(nn.Module):
+    def __init__(self, input_size, hidden_size, bidirectional=False):
+        super().__init__()
+        self.input_size, self.hidden_size, self.bidirectional = input_size, hidden_size, bidirectional
+        k = 1.0 / math.sqrt(hidden_size)
+        for suf in [""] + (["_reverse"] if bidirectional else []):
+            for name, shape in (("weight_ih_l0", (3 * hidden_size, input_size)),
+                                ("weight_hh_l0", (3 * hidden_size, hidden_size)),
+                                ("bias_ih_l0", (3 * hidden_size,)), ("bias_hh_l0", (3 * hidden_size,))):
+                self.register_parameter(name + suf, nn.Parameter(torch.empty(shape).uniform_(-k, k)))
+
+    def dir(self, reverse=False):
+        s = "_reverse" if reverse else ""
+        return (getattr(self, "weight_ih_l0" + s), getattr(self, "weight_hh_l0" + s),
+                getattr(self, "bias_ih_l0" + s), getattr(self, "bias_hh_l0" + s))
+
+
+class LinearParams(nn.Module):
+    def __init__(self, in_features, out_features):
+        super().__init__()
+        k = 1.0 / math.sqrt(in_features)
+        self.weight = nn.Parameter(torch.empty(out_features, in_features).uniform_(-k, k))
+        self.bias = nn.Parameter(torch.empty(out_features).uniform_(-k, k))
+
+    def forward(self, x):
+        return ops.linear(x, self.weight, self.bias)
+
+
+class ConvParams(nn.Module):
+    def __init__(self, out_channels, kh, kw):
+        super().__init__()
+        k = 1.0 / math.sqrt(kh * kw)
+        self.weight = nn.Parameter(torch.empty(out_channels, 1, kh, kw).uniform_(-k, k))
+        self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-k, k))
+
+
+def _bigru_final(gru, x, lengths=None):
+    """Final hidden states [fwd | bwd] of a bi-GRU over x (R,T,I); ``lengths`` int32 (R,) = packed."""
+    outs = []
+    for rev in (False, True):
+        w_ih, w_hh, b_ih, b_hh = gru.dir(rev)
+        gi = ops.linear(x, w_ih, b_ih)
+        h = ops.gru_sequence(gi, None, None, w_hh, b_hh, lengths, rev)
+        outs.append(h[:, 0] if rev else h[:, -1])
+    return torch.cat(outs, -1)
+
+
+def _posterior(h, linear_mu, linear_var):
+    mu = linear_mu(h)
+    std = ops.exp(linear_var(h))           # the reference feeds exp(.) to Normal as its std
+    return Normal(mu, std, validate_args=False)
+
+
+# ------------------------------------------------------------------------------------------------
+class RnnEncoder(nn.Module):
+    """Chord encoder: bi-GRU(36 -> 1024) over 8 chord steps -> Normal(mu, std).  ptvae.py:11-29"""
+
+    def __init__(self, input_dim, hidden_dim, z_dim):
+        super().__init__()
+        self.gru = GRUParams(input_dim, hidden_dim, bidirectional=True)
+        self.linear_mu = LinearParams(hidden_dim * 2, z_dim)
+        self.linear_var = LinearParams(hidden_dim * 2, z_dim)
+        self.input_dim, self.hidden_dim, self.z_dim = input_dim, hidden_dim, z_dim
+
+    def forward(self, x):
+        return _posterior(_bigru_final(self.gru, x), self.linear_mu, self.linear_var)
+
+
+class TextureEncoder(nn.Module):
+    """Texture encoder over the (B,32,128) piano-roll.  ptvae.py:90-122"""
+
+    def __init__(self, emb_size, hidden_dim, z_dim, num_channel=10):
+        super().__init__()
+        self.cnn = nn.Sequential(ConvParams(num_channel, 4, 12))      # key: cnn.0.weight / cnn.0.bias
+        self.fc1 = LinearParams(num_channel * 29, 1000)
+        self.fc2 = LinearParams(1000, emb_size)
+        self.gru = GRUParams(emb_size, hidden_dim, bidirectional=True)
+        self.linear_mu = LinearParams(hidden_dim * 2, z_dim)
+        self.linear_var = LinearParams(hidden_dim * 2, z_dim)
+        self.emb_size, self.hidden_dim, self.z_dim = emb_size, hidden_dim, z_dim
+
+    def forward(self, pr):
+        bs = pr.size(0)
+        y = ops.texture_frontend(pr, self.cnn[0].weight, self.cnn[0].bias)     # (B,C,8,29)
+        y = y.view(bs, 8, -1)                                   # reinterpretation, like the reference
+        y = self.fc2(self.fc1(y))
+        return _posterior(_bigru_final(self.gru, y), self.linear_mu, self.linear_var)
+
+
+class RnnDecoder(nn.Module):
+    """Chord decoder: 8 GRU steps with root / chroma / bass heads.  ptvae.py:32-87"""
+
+    def __init__(self, input_dim=36, z_input_dim=256, hidden_dim=512, z_dim=256, num_step=32):
+        super().__init__()
+        self.z2dec_hid = LinearParams(z_dim, hidden_dim)
+        self.z2dec_in = LinearParams(z_dim, z_input_dim)
+        self.gru = GRUParams(input_dim + z_input_dim, hidden_dim)
+        self.init_input = nn.Parameter(torch.rand(36))
+        self.input_dim, self.hidden_dim, self.z_dim = input_dim, hidden_dim, z_dim
+        self.root_out = LinearParams(hidden_dim, 12)
+        self.chroma_out = LinearParams(hidden_dim, 24)
+        self.bass_out = LinearParams(hidden_dim, 12)
+        self.num_step = num_step
+
+    def forward(self, z_chd, inference, tfr, c=None):
+        bs = z_chd.size(0)
+        if inference:
+            tfr = 0.
+        w_ih, w_hh, b_ih, b_hh = self.gru.dir()
+        h = self.z2dec_hid(z_chd)
+        gi_z = ops.linear(self.z2dec_in(z_chd), w_ih[:, self.input_dim:], b_ih)   # constant over steps
+        tok = self.init_input.expand(bs, self.input_dim)
+        roots, chromas, basses = [], [], []
+        for t in range(int(self.num_step / 4)):
+            gi = ops.linear(tok, w_ih[:, :self.input_dim], None)
+            h = ops.gru_sequence(gi.view(bs, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
+            r, ch, b = self.root_out(h), self.chroma_out(h).view(bs, 12, 2), self.bass_out(h)
+            roots.append(r.unsqueeze(1))
+            chromas.append(ch.unsqueeze(1))
+            basses.append(b.unsqueeze(1))
+            teacher_force = random.random() < tfr
+            if teacher_force and not inference:
+                tok = c[:, t]
+            else:
+                tok = ops.chord_feedback(r.detach(), ch.detach(), b.detach())
+        return torch.cat(roots, 1), torch.cat(chromas, 1), torch.cat(basses, 1)
+
+
+# ------------------------------------------------------------------------------------------------
+class PtvaeDecoder(nn.Module):
+    """PianoTree decoder (time GRU -> note GRU -> duration GRU).  ptvae.py:218-575"""
+
+    def __init__(self, device=None, note_embedding=None, max_simu_note=16, max_pitch=127, min_pitch=0,
+                 pitch_sos=128, pitch_eos=129, pitch_pad=130, dur_pad=2, dur_width=5, num_step=32,
+                 note_emb_size=128, z_size=512, dec_emb_hid_size=128, dec_time_hid_size=1024,
+                 dec_notes_hid_size=512, dec_z_in_size=256, dec_dur_hid_size=16):
+        super().__init__()
+        if (max_simu_note, max_pitch, min_pitch, pitch_sos, pitch_eos, pitch_pad, dur_pad, dur_width,
+                num_step, note_emb_size) != (16, 127, 0, 128, 129, 130, 2, 5, 32, 128):
+            raise NotImplementedError("libpolydis_b200 kernels are specialised to the PolyDis grid "
+                                      "(16 slots, 130 pitch tokens, 5 duration bits, 32 steps, 128-d notes)")
+        self.max_pitch, self.min_pitch = max_pitch, min_pitch
+        self.pitch_sos, self.pitch_eos, self.pitch_pad = pitch_sos, pitch_eos, pitch_pad
+        self.pitch_range = max_pitch - min_pitch + 3
+        self.dur_pad, self.dur_width = dur_pad, dur_width
+        self.note_size = self.pitch_range + dur_width
+        self.max_simu_note, self.num_step = max_simu_note, num_step
+        self.device = device if device is not None else 'cuda'
+        self.note_emb_size, self.z_size = note_emb_size, z_size
+        self.dec_z_in_size, self.dec_emb_hid_size = dec_z_in_size, dec_emb_hid_size
+        self.dec_time_hid_size, self.dec_notes_hid_size = dec_time_hid_size, dec_notes_hid_size
+        self.dec_dur_hid_size = dec_dur_hid_size
+        self.dec_init_input = nn.Parameter(torch.rand(2 * dec_emb_hid_size))
+        self.dur_sos_token = nn.Parameter(torch.rand(dur_width))
+        self.note_embedding = note_embedding if note_embedding is not None else \
+            LinearParams(self.note_size, note_emb_size)
+        self.z2dec_hid_linear = LinearParams(z_size, dec_time_hid_size)
+        self.z2dec_in_linear = LinearParams(z_size, dec_z_in_size)
+        self.dec_notes_emb_gru = GRUParams(note_emb_size, dec_emb_hid_size, bidirectional=True)
+        self.dec_time_gru = GRUParams(dec_z_in_size + 2 * dec_emb_hid_size, dec_time_hid_size)
+        self.dec_time_to_notes_hid = LinearParams(dec_time_hid_size, dec_notes_hid_size)
+        self.dec_notes_gru = GRUParams(dec_time_hid_size + note_emb_size, dec_notes_hid_size)
+        self.pitch_out_linear = LinearParams(dec_notes_hid_size, self.pitch_range)
+        self.dec_dur_gru = GRUParams(dur_width, dec_dur_hid_size)
+        self.dur_hid_linear = LinearParams(self.pitch_range + dec_notes_hid_size, dec_dur_hid_size)
+        self.dur_out_linear = LinearParams(dec_dur_hid_size, 2)
+
+    # -- grid handling ---------------------------------------------------------------------------
+    def get_len_index_tensor(self, ind_x):
+        return ops.grid_prepare(ind_x)[1].view(ind_x.size(0), self.num_step).long()
+
+    def emb_x(self, x):
+        """x (B,32,16,6) int64 -> embedded (B,32,16,128), lengths (B,32) int64.   ptvae.py:531-535"""
+        tok, lengths, _, _ = ops.grid_prepare(x)
+        emb = ops.note_embed(tok, self.note_embedding.weight, self.note_embedding.bias)
+        return emb.view(x.size(0), self.num_step, self.max_simu_note, self.note_emb_size), \
+            lengths.view(x.size(0), self.num_step).long()
+
+    def _summarize(self, notes, lengths32):
+        """(R,16,128) note embeddings with lengths -> (R,256) bi-GRU summary.  ptvae.py:446-453,:480-486"""
+        return _bigru_final(self.dec_notes_emb_gru, notes, lengths32)
+
+    # -- duration level --------------------------------------------------------------------------
+    def _decode_durs(self, h_note, pitch):
+        """h_note (Q,512), pitch logits (Q,130) -> dur logits (Q,5,2).             ptvae.py:345-367"""
+        Q = h_note.size(0)
+        w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
+        dh = ops.linear_cat2(h_note, pitch, self.dur_hid_linear.weight, self.dur_hid_linear.bias)
+        tok = self.dur_sos_token.expand(Q, self.dur_width)
+        outs = []
+        for k in range(self.dur_width):
+            gi = ops.linear(tok, w_ih, b_ih)
+            dh = ops.gru_sequence(gi.view(Q, 1, -1), None, dh, w_hh, b_hh)[:, 0]
+            d = self.dur_out_linear(dh)
+            outs.append(d)
+            if k < self.dur_width - 1:
+                tok = ops.dur_token(d.detach())
+        return torch.stack(outs, 1)
+
+    # -- teacher-forced (tfr1 = tfr2 = 1 decisions): batched phases -------------------------------
+    def _time_inputs(self, z):
+        w_ih, w_hh, b_ih, b_hh = self.dec_time_gru.dir()
+        z_hid = self.z2dec_hid_linear(z)
+        gi_z = ops.linear(self.z2dec_in_linear(z), w_ih[:, 2 * self.dec_emb_hid_size:], b_ih)
+        return z_hid, gi_z, w_ih[:, :2 * self.dec_emb_hid_size], w_hh, b_hh
+
+    def _decode_teacher_forced(self, z, x, lengths32):
+        B = z.size(0)
+        R = B * self.num_step
+        z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
+        notes = x.reshape(R, self.max_simu_note, self.note_emb_size)
+        summ = self._summarize(notes, lengths32).view(B, self.num_step, -1)
+        tok = torch.cat([self.dec_init_input.expand(B, 1, -1), summ[:, :-1]], 1)
+        summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
+        S = summary.reshape(R, self.dec_time_hid_size)
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        h0 = self.dec_time_to_notes_hid(S)
+        gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
+        gi_tok = ops.linear(notes, wn_ih[:, self.dec_time_hid_size:], None)               # (R,16,1536)
+        h = ops.gru_sequence(gi_tok[:, :self.max_simu_note - 1], gi_s, h0, wn_hh, bn_hh)  # (R,15,512)
+        pitch = self.pitch_out_linear(h)                                                  # (R,15,130)
+        Q = R * (self.max_simu_note - 1)
+        dur = self._decode_durs(h.reshape(Q, -1), pitch.reshape(Q, -1))
+        return pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), \
+            dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
+
+    # -- general step-wise path (scheduled sampling / inference) ----------------------------------
+    def _sos_embedding(self, dev):
+        tok = torch.tensor([[self.pitch_sos, 2, 2, 2, 2, 2]], device=dev, dtype=torch.int32)
+        return ops.note_embed(tok, self.note_embedding.weight, self.note_embedding.bias)
+
+    def _decode_step_notes(self, S, notes, inference, tf_row, sos_emb, tok_store, keep_logits):
+        """One time step's 15 note slots.  S (B,1024); notes (B,16,128) ground truth or None.
+        ptvae.py:370-428"""
+        B = S.size(0)
+        w_ih, w_hh, b_ih, b_hh = self.dec_notes_gru.dir()
+        h = self.dec_time_to_notes_hid(S)
+        gi_s = ops.linear(S, w_ih[:, :self.dec_time_hid_size], b_ih)
+        w_tok = w_ih[:, self.dec_time_hid_size:]
+        tok = sos_emb.expand(B, -1) if inference else notes[:, 0]
+        pred = [tok]
+        lens = torch.zeros(B, device=S.device, dtype=torch.int32)
+        pitches, durs = [], []
+        for n in range(1, self.max_simu_note):
+            gi = ops.linear(tok, w_tok, None)
+            h = ops.gru_sequence(gi.view(B, 1, -1), gi_s, h, w_hh, b_hh)[:, 0]
+            p = self.pitch_out_linear(h)
+            d = self._decode_durs(h, p)
+            if keep_logits:
+                pitches.append(p)
+                durs.append(d)
+            ops.greedy_pick(p.detach(), d.detach(), n, tok_store[n - 1], lens)
+            emb = ops.note_embed(tok_store[n - 1], self.note_embedding.weight, self.note_embedding.bias)
+            pred.append(emb)
+            if n == self.max_simu_note - 1:
+                break
+            tok = emb if (inference or not tf_row[n - 1]) else notes[:, n]
+        pitch = torch.stack(pitches, 1) if keep_logits else None
+        dur = torch.stack(durs, 1) if keep_logits else None
+        return pitch, dur, torch.stack(pred, 1), lens
+
+    def _decode_stepwise(self, z, inference, x, lengths32, plan_note, plan_time, keep_logits=True):
+        B = z.size(0)
+        dev = z.device
+        z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
+        summ = None
+        if not inference:
+            summ = self._summarize(x.reshape(B * self.num_step, self.max_simu_note, -1),
+                                   lengths32).view(B, self.num_step, -1)
+        sos_emb = self._sos_embedding(dev) if inference else None
+        # greedy tokens [t][n-1] -> (B,6) int32 rows (pitch, 5 duration bits)
+        tokens = torch.empty(self.num_step, self.max_simu_note - 1, B, 6, device=dev, dtype=torch.int32)
+        tok, h = self.dec_init_input.expand(B, -1), z_hid
+        pitches, durs = [], []
+        for t in range(self.num_step):
+            gi = ops.linear(tok, w_tok, None)
+            h = ops.gru_sequence(gi.view(B, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
+            p, d, pred, plen = self._decode_step_notes(h, None if inference else x[:, t], inference,
+                                                       plan_note[t], sos_emb, tokens[t], keep_logits)
+            if keep_logits:
+                pitches.append(p)
+                durs.append(d)
+            if t == self.num_step - 1:
+                break
+            if plan_time[t] and not inference:
+                tok = summ[:, t]
+            else:
+                tok = self._summarize(pred, plen)
+        self._last_tokens = tokens
+        if not keep_logits:
+            return None, None
+        return torch.stack(pitches, 1), torch.stack(durs, 1)
+
+    def _draw_plan(self, tfr1, tfr2):
+        """Consume python ``random`` in the reference's order (ptvae.py:420,:476)."""
+        plan_note, plan_time = [], []
+        for t in range(self.num_step):
+            plan_note.append([random.random() < tfr2 for _ in range(self.max_simu_note - 2)])
+            if t < self.num_step - 1:
+                plan_time.append(random.random() < tfr1)
+        return plan_note, plan_time
+
+    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2):
+        """z (B,512); x embedded grid (B,32,16,128) + lengths (B,32), or None/None at inference.
+        -> pitch logits (B,32,15,130), dur logits (B,32,15,5,2).               ptvae.py:430-491"""
+        if inference:
+            assert x is None
+            assert lengths is None
+            assert teacher_forcing_ratio1 == 0
+            assert teacher_forcing_ratio2 == 0
+        plan_note, plan_time = self._draw_plan(teacher_forcing_ratio1, teacher_forcing_ratio2)
+        lengths32 = None if lengths is None else lengths.reshape(-1).to(torch.int32)
+        if not inference and all(plan_time) and all(all(r) for r in plan_note):
+            return self._decode_teacher_forced(z, x, lengths32)
+        return self._decode_stepwise(z, inference, x, lengths32, plan_note, plan_time)
+
+    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2):
+        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2)
+
+    def greedy_tokens(self, z):
+        """Greedy decode returning only the int tokens (B,32,15,6) int32 on device -- the logits the
+        reference copies to the host (ptvae.py:537-544) are never materialised."""
+        plan_note, plan_time = self._draw_plan(0., 0.)
+        with torch.no_grad():
+            self._decode_stepwise(z, True, None, None, plan_note, plan_time, keep_logits=False)
+        return self._last_tokens.permute(2, 0, 1, 3).contiguous()
+
+    # -- losses / output formatting ---------------------------------------------------------------
+    def recon_loss(self, x, recon_pitch, recon_dur, weights=(1, 0.5), weighted_dur=False):
+        """Pitch CE (ignore PAD 130) + duration CE (ignore 2).                    ptvae.py:498-529"""
+        _, _, pitch_tgt, dur_tgt = ops.grid_prepare(x)
+        pitch_loss = ops.masked_ce(recon_pitch.reshape(-1, recon_pitch.size(-1)), pitch_tgt, self.pitch_pad)
+        if not weighted_dur:
+            dur_loss = ops.masked_ce(recon_dur.reshape(-1, 2), dur_tgt, self.dur_pad)
+        else:
+            rd = recon_dur.reshape(-1, self.dur_width, 2)
+            gt = dur_tgt.view(-1, self.dur_width)
+            w = [1, 0.6, 0.4, 0.3, 0.3]
+            dur_loss = sum(w[k] * ops.masked_ce(rd[:, k, :], gt[:, k].contiguous(), self.dur_pad)
+                           for k in range(self.dur_width))
+        loss = weights[0] * pitch_loss + weights[1] * dur_loss
+        return loss, pitch_loss, dur_loss
+
+    def output_to_numpy(self, recon_pitch, recon_dur):
+        est_pitch = recon_pitch.max(-1)[1].unsqueeze(-1)
+        est_dur = recon_dur.max(-1)[1]
+        est_x = torch.cat([est_pitch, est_dur], dim=-1).cpu().numpy()
+        return est_x, recon_pitch.cpu().numpy(), recon_dur.cpu().numpy()
+
+    def grid_to_pr_and_notes(self, grid, bpm=60., start=0.):
+        """Token grid (32,15|16,6) -> piano-roll (32,128) + note tuples (pitch, start_s, end_s).
+        Host-side formatting (ptvae.py:558-575); ``pretty_midi`` is not required -- if it is
+        importable, Note objects are returned like the reference, else plain tuples."""
+        try:
+            import pretty_midi
+            mk = lambda p, s, e: pretty_midi.Note(100, int(p), s, e)
+        except ImportError:
+            mk = lambda p, s, e: (100, int(p), s, e)
+        if grid.shape[1] == self.max_simu_note:
+            grid = grid[:, 1:]
+        pr = np.zeros((32, 128), dtype=int)
+        alpha = 0.25 * 60 / bpm
+        notes = []
+        for t in range(32):
+            for n in range(10):
+                note = grid[t, n]
+                if note[0] == self.pitch_eos:
+                    break
+                pitch = note[0] + self.min_pitch
+                dur = int(''.join(str(int(v)) for v in note[1:]), 2) + 1
+                pr[t, pitch] = min(dur, 32 - t)
+                notes.append(mk(pitch, start + t * alpha, start + (t + dur) * alpha))
+        return pr, notes

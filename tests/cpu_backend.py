@@ -1,0 +1,269 @@
+"""numpy emulation of the libpolydis_b200 C-ABI on HOST pointers -- test infrastructure only.
+
+The product has no CPU path.  To test the host-side logic (autograd orchestration, teacher-forcing
+plans, layouts, strides) in the GPU-less build container, the ``-m "not gpu"`` tests swap
+``polydis_b200._lib.call`` for ``CpuBackend.call``: each entry point is re-stated here in numpy on the
+raw pointers + strides the host code passes, exactly per the contract in include/polydis_b200.h.
+The ``-m gpu`` tests then check each CUDA kernel against these same emulations and the whole model
+against the oracle.
+"""
+import ctypes
+
+import numpy as np
+
+
+def _arr(ptr, shape, strides, dtype=np.float32):
+    if ptr is None:
+        return None
+    shape = tuple(int(s) for s in shape)
+    strides = tuple(int(s) for s in strides)
+    item = np.dtype(dtype).itemsize
+    if any(s == 0 for s in shape):
+        return np.zeros(shape, dtype=dtype)
+    span = sum((s - 1) * st for s, st in zip(shape, strides)) + 1
+    buf = (ctypes.c_char * (span * item)).from_address(int(ptr))
+    flat = np.frombuffer(buf, dtype=dtype)
+    return np.lib.stride_tricks.as_strided(flat, shape, tuple(st * item for st in strides))
+
+
+def _sig(x):
+    return 1.0 / (1.0 + np.exp(-x, dtype=np.float32))
+
+
+class CpuBackend:
+    def __init__(self):
+        self.calls = []
+
+    def call(self, name, *a):
+        self.calls.append(name)
+        getattr(self, name)(*a)
+
+    # ---- gemm ----
+    def pd_gemm_f32(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, st):
+        if M <= 0 or N <= 0:
+            return
+        a = _arr(A, (M, K), (sam, sak))
+        b = _arr(B, (K, N), (sbk, sbn))
+        c = _arr(C, (M, N), (ldc, 1))
+        r = (a @ b).astype(np.float32) if K > 0 else np.zeros((M, N), np.float32)
+        if bias is not None:
+            r = r + _arr(bias, (N,), (1,))
+        c[...] = c + r if acc else r
+
+    def pd_colsum_f32(self, X, ldx, M, N, out, acc, st):
+        o = _arr(out, (N,), (1,))
+        s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0
+        o[...] = o + s if acc else s
+
+    def pd_transpose_f32(self, inp, rows, cols, out, st):
+        _arr(out, (cols, rows), (rows, 1))[...] = _arr(inp, (rows, cols), (cols, 1)).T
+
+    # ---- gru gates ----
+    def pd_gru_gates_fwd(self, gi, ldgi, gi2, ldgi2, gh, ldgh, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn,
+                         lengths, t, B, H, st):
+        GI = _arr(gi, (B, 3 * H), (ldgi, 1)).copy()
+        if gi2 is not None:
+            GI = GI + _arr(gi2, (B, 3 * H), (ldgi2, 1))
+        GH = _arr(gh, (B, 3 * H), (ldgh, 1))
+        HP = _arr(hp, (B, H), (ldhp, 1)) if hp is not None else np.zeros((B, H), np.float32)
+        r = _sig(GI[:, :H] + GH[:, :H])
+        z = _sig(GI[:, H:2 * H] + GH[:, H:2 * H])
+        n = np.tanh(GI[:, 2 * H:] + r * GH[:, 2 * H:])
+        h = (1 - z) * n + z * HP
+        act = np.ones(B, bool) if lengths is None else (t < _arr(lengths, (B,), (1,), np.int32))
+        HO = _arr(ho, (B, H), (ldho, 1))
+        HO[...] = np.where(act[:, None], h, HP)
+        if rzn is not None:
+            S = _arr(rzn, (B, 3 * H), (ldrzn, 1))
+            S[act] = np.concatenate([r, z, n], 1)[act]
+        if hn is not None:
+            Q = _arr(hn, (B, H), (ldhn, 1))
+            Q[act] = GH[:, 2 * H:][act]
+
+    def pd_gru_gates_bwd(self, dh, lddh, dh2, lddh2, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                         dhp, lddhp, dgi2, lddgi2, lengths, t, B, H, st):
+        d = np.zeros((B, H), np.float32)
+        if dh is not None:
+            d = d + _arr(dh, (B, H), (lddh, 1))
+        if dh2 is not None:
+            d = d + _arr(dh2, (B, H), (lddh2, 1))
+        act = np.ones(B, bool) if lengths is None else (t < _arr(lengths, (B,), (1,), np.int32))
+        S = _arr(rzn, (B, 3 * H), (ldrzn, 1))
+        r, z, n = S[:, :H], S[:, H:2 * H], S[:, 2 * H:]
+        HN = _arr(hn, (B, H), (ldhn, 1))
+        HP = _arr(hp, (B, H), (ldhp, 1)) if hp is not None else np.zeros((B, H), np.float32)
+        with np.errstate(all="ignore"):
+            dn = d * (1 - z) * (1 - n * n)
+            dz = d * (HP - n) * z * (1 - z)
+            dr = dn * HN * r * (1 - r)
+            dnr = dn * r
+        a = act[:, None]
+        G = _arr(dgi, (B, 3 * H), (lddgi, 1))
+        G[...] = np.where(a, np.concatenate([dr, dz, dn], 1), 0)
+        Gh = _arr(dgh, (B, 3 * H), (lddgh, 1))
+        Gh[...] = np.where(a, np.concatenate([dr, dz, dnr], 1), 0)
+        _arr(dhp, (B, H), (lddhp, 1))[...] = np.where(a, d * z, d)
+        if dgi2 is not None:
+            G2 = _arr(dgi2, (B, 3 * H), (lddgi2, 1))
+            G2[...] = G2 + G
+
+    # ---- pianotree misc ----
+    def pd_grid_prepare(self, x, steps, tok, lengths, pt, dt, st):
+        X = _arr(x, (steps, 16, 6), (96, 6, 1), np.int64)
+        _arr(tok, (steps, 16, 6), (96, 6, 1), np.int32)[...] = X
+        if lengths is not None:
+            _arr(lengths, (steps,), (1,), np.int32)[...] = 16 - (X[:, :, 0] == 130).sum(-1)
+        if pt is not None:
+            _arr(pt, (steps, 15), (15, 1), np.int32)[...] = X[:, 1:, 0]
+        if dt is not None:
+            _arr(dt, (steps, 15, 5), (75, 5, 1), np.int32)[...] = X[:, 1:, 1:]
+
+    def pd_note_embed_fwd(self, tok, R, WT, bias, out, ldo, st):
+        T = _arr(tok, (R, 6), (6, 1), np.int32)
+        W = _arr(WT, (135, 128), (128, 1))
+        o = np.tile(_arr(bias, (128,), (1,)), (R, 1))
+        p = T[:, 0]
+        ok = (p >= 0) & (p < 130)
+        o[ok] += W[p[ok]]
+        o += T[:, 1:].astype(np.float32) @ W[130:]
+        _arr(out, (R, 128), (ldo, 1))[...] = o
+
+    def pd_note_embed_bwd(self, tok, R, g, ldg, dWT, db, st):
+        T = _arr(tok, (R, 6), (6, 1), np.int32)
+        G = _arr(g, (R, 128), (ldg, 1))
+        W = _arr(dWT, (135, 128), (128, 1))
+        p = T[:, 0]
+        ok = (p >= 0) & (p < 130)
+        np.add.at(W, p[ok], G[ok])
+        W[130:] += T[:, 1:].astype(np.float32).T @ G
+        _arr(db, (128,), (1,))[...] += G.sum(0)
+
+    def pd_greedy_pick(self, pitch, ldp, dur, ldd, R, n, tok, ldtok, lens, st):
+        P = _arr(pitch, (R, 130), (ldp, 1))
+        D = _arr(dur, (R, 5, 2), (ldd, 2, 1))
+        T = _arr(tok, (R, 6), (ldtok, 1), np.int32)
+        pi = P.argmax(1)
+        T[:, 0] = pi
+        T[:, 1:] = (D[:, :, 1] > D[:, :, 0]).astype(np.int32)
+        if lens is not None:
+            L = _arr(lens, (R,), (1,), np.int32)
+            L[(L == 0) & (pi == 129)] = n
+            if n == 15:
+                L[L == 0] = 15
+
+    def pd_dur_token(self, logit, ldl, R, tok, st):
+        Lg = _arr(logit, (R, 2), (ldl, 1))
+        T = _arr(tok, (R, 5), (5, 1))
+        one = Lg[:, 1] > Lg[:, 0]
+        T[...] = 0
+        T[:, 0] = ~one
+        T[:, 1] = one
+
+    def pd_chord_feedback(self, root, ldr, chroma, ldc, bass, ldb, B, flags, tok, ldt, st):
+        Rt = _arr(root, (B, 12), (ldr, 1))
+        Ch = _arr(chroma, (B, 12, 2), (ldc, 2, 1))
+        Bs = _arr(bass, (B, 12), (ldb, 1))
+        T = _arr(tok, (B, 36), (ldt, 1))
+        fr = np.zeros(12, np.float32)
+        fb = np.zeros(12, np.float32)
+        fr[Rt.argmax(1)] = 1
+        fb[Bs.argmax(1)] = 1
+        T[:, :12] = fr
+        T[:, 12:24] = (Ch[:, :, 1] > Ch[:, :, 0])
+        T[:, 24:] = fb
+
+    def pd_chord_targets(self, c, rows, root, chroma, bass, st):
+        C = _arr(c, (rows, 36), (36, 1))
+        _arr(root, (rows,), (1,), np.int32)[...] = C[:, :12].argmax(1)
+        _arr(chroma, (rows, 12), (12, 1), np.int32)[...] = C[:, 12:24].astype(np.int32)
+        _arr(bass, (rows,), (1,), np.int32)[...] = C[:, 24:].argmax(1)
+
+    # ---- texture ----
+    @staticmethod
+    def _conv(pr, w, b):
+        B = pr.shape[0]
+        C = w.shape[0]
+        bands = pr.reshape(B, 8, 4, 128)
+        win = np.lib.stride_tricks.sliding_window_view(bands, 12, axis=3)        # (B,8,4,117,12)
+        return np.einsum("bidwk,cdk->bciw", win, w.reshape(C, 4, 12)).astype(np.float32) + b[None, :, None, None]
+
+    def pd_texture_frontend_fwd(self, pr, w, b, B, C, out, st):
+        P = _arr(pr, (B, 32, 128), (4096, 128, 1))
+        y = np.maximum(self._conv(P, _arr(w, (C, 48), (48, 1)), _arr(b, (C,), (1,))), 0)[..., :116]
+        _arr(out, (B, C, 8, 29), (C * 232, 232, 29, 1))[...] = y.reshape(B, C, 8, 29, 4).max(-1)
+
+    def pd_texture_frontend_bwd(self, pr, w, b, B, C, g, dw, db, st):
+        P = _arr(pr, (B, 32, 128), (4096, 128, 1))
+        y = self._conv(P, _arr(w, (C, 48), (48, 1)), _arr(b, (C,), (1,)))[..., :116].reshape(B, C, 8, 29, 4)
+        G = _arr(g, (B, C, 8, 29), (C * 232, 232, 29, 1))
+        q = y.argmax(-1)
+        active = np.take_along_axis(y, q[..., None], -1)[..., 0] > 0
+        gy = np.zeros_like(y)
+        np.put_along_axis(gy, q[..., None], np.where(active, G, 0)[..., None], -1)
+        gy = gy.reshape(B, C, 8, 116)
+        bands = P.reshape(B, 8, 4, 128)
+        win = np.lib.stride_tricks.sliding_window_view(bands, 12, axis=3)[:, :, :, :116]   # (B,8,4,116,12)
+        _arr(dw, (C, 4, 12), (48, 12, 1))[...] += np.einsum("bciw,bidwk->cdk", gy, win)
+        _arr(db, (C,), (1,))[...] += gy.sum((0, 2, 3))
+
+    # ---- losses ----
+    @staticmethod
+    def _lse(L):
+        m = L.max(1, keepdims=True)
+        return m[:, 0] + np.log(np.exp(L - m).sum(1))
+
+    def pd_ce_fwd(self, logits, ldl, tgt, R, C, ignore, acc, loss, st):
+        L = _arr(logits, (R, C), (ldl, 1))
+        T = _arr(tgt, (R,), (1,), np.int32)
+        ok = T != ignore
+        A = _arr(acc, (2,), (1,))
+        A[0] = (self._lse(L[ok]) - L[ok, T[ok]]).sum() if ok.any() else 0.0
+        A[1] = ok.sum()
+        _arr(loss, (1,), (1,))[0] = A[0] / A[1]
+
+    def pd_ce_bwd(self, logits, ldl, tgt, R, C, ignore, acc, gout, dl, lddl, st):
+        L = _arr(logits, (R, C), (ldl, 1))
+        T = _arr(tgt, (R,), (1,), np.int32)
+        ok = T != ignore
+        scale = _arr(gout, (1,), (1,))[0] / _arr(acc, (2,), (1,))[1]
+        m = L.max(1, keepdims=True)
+        p = np.exp(L - m)
+        p /= p.sum(1, keepdims=True)
+        p[np.arange(R)[ok], T[ok]] -= 1
+        _arr(dl, (R, C), (lddl, 1))[...] = np.where(ok[:, None], p * scale, 0)
+
+    def pd_exp_fwd(self, x, n, y, st):
+        _arr(y, (n,), (1,))[...] = np.exp(_arr(x, (n,), (1,)))
+
+    def pd_mul_f32(self, a, b, n, out, st):
+        _arr(out, (n,), (1,))[...] = _arr(a, (n,), (1,)) * _arr(b, (n,), (1,))
+
+    def pd_reparam_fwd(self, mu, sd, eps, B, D, z, ldz, st):
+        m = _arr(mu, (B, D), (D, 1))
+        _arr(z, (B, D), (ldz, 1))[...] = m if eps is None else m + _arr(sd, (B, D), (D, 1)) * _arr(eps, (B, D), (D, 1))
+
+    def pd_reparam_bwd(self, dz, lddz, eps, B, D, dmu, dsd, st):
+        g = _arr(dz, (B, D), (lddz, 1))
+        _arr(dmu, (B, D), (D, 1))[...] = g
+        _arr(dsd, (B, D), (D, 1))[...] = 0 if eps is None else g * _arr(eps, (B, D), (D, 1))
+
+    def pd_kl_fwd(self, mu, sd, n, out, st):
+        m, s = _arr(mu, (n,), (1,)), _arr(sd, (n,), (1,))
+        _arr(out, (1,), (1,))[0] = (-np.log(s) + 0.5 * (s * s + m * m) - 0.5).mean()
+
+    def pd_kl_bwd(self, mu, sd, n, gout, dmu, dsd, st):
+        m, s = _arr(mu, (n,), (1,)), _arr(sd, (n,), (1,))
+        g = _arr(gout, (1,), (1,))[0] / n
+        _arr(dmu, (n,), (1,))[...] = g * m
+        _arr(dsd, (n,), (1,))[...] = g * (s - 1 / s)
+
+
+def install(monkeypatch):
+    """Route polydis_b200's library calls to the numpy emulation for the duration of a test."""
+    from polydis_b200 import _lib, ops
+    be = CpuBackend()
+    monkeypatch.setattr(_lib, "call", be.call)
+    monkeypatch.setattr(ops, "_call", be.call)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    monkeypatch.setattr(ops, "_chk", lambda t, name="tensor": t)
+    return be

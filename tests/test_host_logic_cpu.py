@@ -1,0 +1,91 @@
+"""Host-side logic of the drop-in model on the numpy C-ABI emulation (tests/cpu_backend.py) against
+the golden fixtures written by the unmodified reference.  No GPU, no CUDA kernels: this pins the
+orchestration (hoisted projections, batched teacher-forced phases, BPTT, strides, random-draw order).
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from polydis_b200.synth import synth_batch
+from polydis_b200.weights import make_state_dict, STATE_DICT_SPEC
+from tests import cpu_backend
+from tests.golden.make_golden_probe import probe_indices
+
+
+def _model(seed, gain=1.0, eos_bias=0.0):
+    from polydis_b200.model import DisentangleVAE
+    m = DisentangleVAE.init_model(device=torch.device("cpu"))
+    m.load_state_dict(make_state_dict(seed, gain=gain, eos_bias=eos_bias))
+    return m
+
+
+def test_state_dict_keys_match_reference_contract():
+    from polydis_b200.model import DisentangleVAE
+    m = DisentangleVAE.init_model(device=torch.device("cpu"))
+    sd = m.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in STATE_DICT_SPEC]
+    assert all(tuple(sd[k].shape) == s for k, s, _ in STATE_DICT_SPEC)
+
+
+@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555"])
+def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
+    cpu_backend.install(monkeypatch)
+    g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    B = int(g["B"])
+    x, c, pr = (torch.from_numpy(a) for a in synth_batch(B, int(g["data_seed"])))
+    m = _model(int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    m.train()
+    random.seed(int(g["rng_seed"]))
+    eps = (torch.from_numpy(g["eps_chd"]), torch.from_numpy(g["eps_rhy"]))
+    out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+    losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
+    np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(out[0].detach().numpy(), g["pitch"], atol=2e-5)
+    np.testing.assert_allclose(out[1].detach().numpy(), g["dur"], atol=2e-5)
+    np.testing.assert_allclose(out[3].scale.detach().numpy(), g["std_rhy"], atol=2e-5)
+    np.testing.assert_allclose(out[5].detach().numpy(), g["chroma"], atol=2e-5)
+    losses[0].backward()
+    params = dict(m.named_parameters())
+    for i, (name, _, _) in enumerate(STATE_DICT_SPEC):
+        gr = params[name].grad.reshape(-1).double()
+        assert abs(float(gr.norm()) - g["grad_norm"][i]) <= 1e-3 * g["grad_norm"][i] + 1e-9, name
+        got = gr[torch.from_numpy(probe_indices(name, gr.numel()))].numpy()
+        np.testing.assert_allclose(got, g["grad_probe"][i], rtol=5e-3,
+                                   atol=1e-4 * g["grad_norm"][i] + 1e-10, err_msg=name)
+    # python's random stream must be left exactly where the reference leaves it (487 draws)
+    random.seed(int(g["rng_seed"]))
+    for _ in range(487):
+        random.random()
+    expect = random.random()
+    random.seed(int(g["rng_seed"]))
+    m.run(x[:1], c[:1], pr[:1], *[float(v) for v in g["tfr"]], eps=(eps[0][:1], eps[1][:1]))
+    assert random.random() == expect
+
+
+@pytest.mark.parametrize("tag", ["w0", "w1"])
+def test_greedy_tokens_match_reference_golden(golden_dir, monkeypatch, tag):
+    cpu_backend.install(monkeypatch)
+    g = np.load(os.path.join(golden_dir, f"infer_{tag}.npz"))
+    x, c, pr = (torch.from_numpy(a) for a in synth_batch(int(g["B"]), int(g["data_seed"])))
+    m = _model(int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    est = m.inference(pr, c, sample=False)
+    assert est.dtype == np.int64 and est.shape == (int(g["B"]), 32, 15, 6)
+    assert (est == g["est_x"]).mean() >= 0.999
+    est2 = m.swap(pr, pr, c, c, True, True)
+    assert np.array_equal(est, est2)
+
+
+def test_forward_mode_dispatch(monkeypatch):
+    cpu_backend.install(monkeypatch)
+    x, c, pr = (torch.from_numpy(a) for a in synth_batch(2, 5))
+    m = _model(4)
+    random.seed(0)
+    a = m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5))
+    assert len(a) == 11 and all(v.dim() == 0 for v in a)
+    assert len(m('run', x, c, pr, 1., 1., 1.)) == 7
+    assert m(2, pr, c, False).shape == (2, 32, 15, 6)
+    with pytest.raises(NotImplementedError):
+        m('bogus')
