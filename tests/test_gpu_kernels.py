@@ -1,0 +1,242 @@
+"""-m gpu: every CUDA kernel of libpolydis_b200, called through the C-ABI, against the numpy
+restatement of the same entry point (tests/cpu_backend.py) on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests.cpu_backend import CpuBackend
+
+CPU = CpuBackend()
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _both(name, make_args):
+    """make_args(device) -> (args list with tensors, outputs list of tensors).  Runs the CUDA entry on
+    GPU tensors and the numpy emulation on CPU copies; returns [(gpu_out, cpu_out)]."""
+    from polydis_b200 import _lib
+    torch.manual_seed(0)
+    args, outs = make_args()
+    gargs = [a.cuda() if torch.is_tensor(a) else a for a in args]
+    gouts = [gargs[next(i for i, a in enumerate(args) if a is o)] for o in outs]
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call(name, *[_p(a) if torch.is_tensor(a) else a for a in gargs[:-1]], st)
+    torch.cuda.synchronize()
+    getattr(CPU, name)(*[_p(a) if torch.is_tensor(a) else a for a in args[:-1]], None)
+    return [(g.cpu(), o) for g, o in zip(gouts, outs)]
+
+
+@pytest.mark.parametrize("M,N,K,layout,acc,bias", [
+    (4, 3072, 36, "nt", 0, 1), (513, 130, 512, "nt", 0, 1), (96, 1000, 290, "nt", 0, 1),
+    (257, 300, 77, "nn", 1, 0), (1536, 512, 4000, "tn", 0, 0), (64, 5, 30000, "tn", 1, 0),
+    (1, 192, 0, "nt", 0, 1), (2048, 1536, 128, "nt", 0, 0), (300, 64, 642, "nn", 0, 0),
+])
+def test_gemm_f32(M, N, K, layout, acc, bias):
+    _dev()
+
+    def mk():
+        lda_pad, ldc = 8, N + 4
+        if layout == "tn":
+            A = torch.randn(K, M + lda_pad); sam, sak = 1, M + lda_pad
+        else:
+            A = torch.randn(M, K + lda_pad); sam, sak = K + lda_pad, 1
+        if layout == "nt":
+            Bm = torch.randn(N, K + 4); sbk, sbn = 1, K + 4
+        else:
+            Bm = torch.randn(K, N + 4); sbk, sbn = N + 4, 1
+        C = torch.randn(M, ldc)
+        b = torch.randn(N) if bias else None
+        return [A, sam, sak, Bm, sbk, sbn, C, ldc, b, M, N, K, acc, None], [C]
+    (g, c), = _both("pd_gemm_f32", mk)
+    tol = 2e-5 * max(1.0, np.sqrt(K))
+    assert torch.allclose(g, c, atol=tol, rtol=1e-4), float((g - c).abs().max())
+
+
+def test_colsum_and_transpose():
+    _dev()
+    (g, c), = _both("pd_colsum_f32",
+                    lambda: (lambda X, o: ([X, 200, 5000, 192, o, 1, None], [o]))(torch.randn(5000, 200), torch.randn(192)))
+    assert torch.allclose(g, c, atol=2e-3, rtol=1e-4)
+    (g, c), = _both("pd_transpose_f32",
+                    lambda: (lambda X, o: ([X, 135, 128, o, None], [o]))(torch.randn(135, 128), torch.zeros(128, 135)))
+    assert torch.equal(g, c)
+
+
+@pytest.mark.parametrize("B,H,masked,bcast,hprev", [(7, 64, False, False, True), (33, 1024, False, True, True),
+                                                   (130, 128, True, False, True), (130, 128, True, False, False)])
+def test_gru_gates_fwd_bwd(B, H, masked, bcast, hprev):
+    _dev()
+    t = 3
+
+    def mk_f():
+        gi, gh = torch.randn(B, 2, 3 * H), torch.randn(B, 3 * H)
+        gi2 = torch.randn(B, 3 * H) if bcast else None
+        hp = torch.randn(B, 2, H) if hprev else None
+        ho, rzn, hn = torch.zeros(B, 2, H), torch.zeros(B, 3 * H), torch.zeros(B, H)
+        ln = torch.randint(1, 8, (B,), dtype=torch.int32) if masked else None
+        return ([gi, 6 * H, gi2, 3 * H, gh, 3 * H, hp, 2 * H, ho, 2 * H, rzn, 3 * H, hn, H, ln, t, B, H, None],
+                [ho, rzn, hn])
+    for g, c in _both("pd_gru_gates_fwd", mk_f):
+        assert torch.allclose(g, c, atol=2e-6, rtol=1e-5), float((g - c).abs().max())
+
+    def mk_b():
+        dh, dh2 = torch.randn(B, H), torch.randn(B, 2, H)
+        rzn = torch.rand(B, 3 * H) * 0.98 + 0.01
+        rzn[:, 2 * H:] = rzn[:, 2 * H:] * 2 - 1
+        hn, hp = torch.randn(B, H), (torch.randn(B, H) if hprev else None)
+        dgi, dgh, dhp = torch.zeros(B, 2, 3 * H), torch.zeros(B, 3 * H), torch.zeros(B, H)
+        dgi2 = torch.randn(B, 3 * H) if bcast else None
+        ln = torch.randint(1, 8, (B,), dtype=torch.int32) if masked else None
+        return ([dh, H, dh2, 2 * H, rzn, 3 * H, hn, H, hp, H, dgi, 6 * H, dgh, 3 * H, dhp, H, dgi2, 3 * H, ln, t,
+                 B, H, None], [dgi, dgh, dhp] + ([dgi2] if bcast else []))
+    for g, c in _both("pd_gru_gates_bwd", mk_b):
+        assert torch.allclose(g, c, atol=2e-6, rtol=1e-5), float((g - c).abs().max())
+
+
+def _tokens(R):
+    tok = torch.zeros(R, 6, dtype=torch.int32)
+    tok[:, 0] = torch.randint(0, 131, (R,))
+    tok[:, 1:] = torch.randint(0, 3, (R, 5))
+    return tok
+
+
+def test_grid_prepare_and_note_embed():
+    _dev()
+    from polydis_b200.synth import synth_batch
+    x = torch.from_numpy(synth_batch(5, 2)[0])
+    n = 5 * 32
+
+    def mk():
+        tok, ln = torch.zeros(n * 16, 6, dtype=torch.int32), torch.zeros(n, dtype=torch.int32)
+        pt, dt = torch.zeros(n * 15, dtype=torch.int32), torch.zeros(n * 75, dtype=torch.int32)
+        return [x, n, tok, ln, pt, dt, None], [tok, ln, pt, dt]
+    for g, c in _both("pd_grid_prepare", mk):
+        assert torch.equal(g, c)
+    R = 3001
+
+    def mk_e():
+        out = torch.zeros(R, 2, 128)
+        return [_tokens(R), R, torch.randn(135, 128), torch.randn(128), out, 256, None], [out]
+    (g, c), = _both("pd_note_embed_fwd", mk_e)
+    assert torch.allclose(g, c, atol=1e-5)
+
+    def mk_b():
+        dwt, db = torch.randn(135, 128), torch.randn(128)
+        return [_tokens(R), R, torch.randn(R, 128), 128, dwt, db, None], [dwt, db]
+    for g, c in _both("pd_note_embed_bwd", mk_b):
+        assert torch.allclose(g, c, atol=2e-3, rtol=1e-4), float((g - c).abs().max())
+
+
+def test_greedy_pick_dur_token_chord():
+    _dev()
+    R = 1000
+
+    def mk():
+        p = torch.randn(R, 132)
+        p[::7, 129] = 50.0                     # force some EOS
+        p[5, 3] = p[5, 90] = 60.0              # tie -> first index
+        d = torch.randn(R, 10)
+        d[::3, 0] = d[::3, 1]                  # tie -> bit 0
+        tok, lens = torch.zeros(R, 6, dtype=torch.int32), torch.zeros(R, dtype=torch.int32)
+        lens[::14] = 2
+        return [p, 132, d, 10, R, 4, tok, 6, lens, None], [tok, lens]
+    for g, c in _both("pd_greedy_pick", mk):
+        assert torch.equal(g, c)
+
+    def mk15():
+        tok, lens = torch.zeros(R, 6, dtype=torch.int32), torch.zeros(R, dtype=torch.int32)
+        lens[::2] = 3
+        return [torch.randn(R, 130), 130, torch.randn(R, 10), 10, R, 15, tok, 6, lens, None], [tok, lens]
+    for g, c in _both("pd_greedy_pick", mk15):
+        assert torch.equal(g, c)
+    (g, c), = _both("pd_dur_token", lambda: (lambda t: ([torch.randn(R, 2), 2, R, t, None], [t]))(torch.zeros(R, 5)))
+    assert torch.equal(g, c)
+
+    def mkc():
+        tok = torch.zeros(9, 36)
+        return ([torch.randn(9, 12), 12, torch.randn(9, 24), 24, torch.randn(9, 12), 12, 9, torch.zeros(24), tok, 36,
+                 None], [tok])
+    (g, c), = _both("pd_chord_feedback", mkc)
+    assert torch.equal(g, c)
+    from polydis_b200.synth import synth_batch
+    cc = torch.from_numpy(synth_batch(6, 1)[1])
+
+    def mkt():
+        r, ch, b = (torch.zeros(48, dtype=torch.int32), torch.zeros(48 * 12, dtype=torch.int32),
+                    torch.zeros(48, dtype=torch.int32))
+        return [cc, 48, r, ch, b, None], [r, ch, b]
+    for g, c in _both("pd_chord_targets", mkt):
+        assert torch.equal(g, c)
+
+
+def test_texture_frontend():
+    _dev()
+    from polydis_b200.synth import synth_batch
+    pr = torch.from_numpy(synth_batch(6, 4)[2])
+
+    def mk():
+        out = torch.zeros(6, 10, 8, 29)
+        return [pr, torch.randn(10, 48) * 0.2, torch.randn(10) * 0.1, 6, 10, out, None], [out]
+    (g, c), = _both("pd_texture_frontend_fwd", mk)
+    assert torch.allclose(g, c, atol=1e-4), float((g - c).abs().max())
+
+    def mkb():
+        dw, db = torch.zeros(10, 48), torch.zeros(10)
+        return [pr, torch.randn(10, 48) * 0.2, torch.randn(10) * 0.1, 6, 10, torch.randn(6, 10, 8, 29), dw, db,
+                None], [dw, db]
+    for g, c in _both("pd_texture_frontend_bwd", mkb):
+        assert torch.allclose(g, c, atol=5e-3, rtol=1e-4), float((g - c).abs().max())
+
+
+@pytest.mark.parametrize("R,C,ignore", [(4001, 130, 130), (9000, 2, 2), (333, 12, -100)])
+def test_cross_entropy(R, C, ignore):
+    _dev()
+    tgt = torch.randint(0, C + (1 if ignore >= 0 else 0), (R,), dtype=torch.int32)
+    if ignore >= 0:
+        tgt[tgt == C] = ignore
+
+    def mk():
+        acc, loss = torch.zeros(2), torch.zeros(1)
+        return [torch.randn(R, C + 2) * 3, C + 2, tgt, R, C, ignore, acc, loss, None], [acc, loss]
+    (ga, ca), (gl, cl) = _both("pd_ce_fwd", mk)
+    assert torch.allclose(gl, cl, rtol=1e-5) and ga[1] == ca[1]
+
+    def mkb():
+        acc = torch.tensor([0.0, float((tgt != ignore).sum())])
+        d = torch.zeros(R, C)
+        return [torch.randn(R, C + 2) * 3, C + 2, tgt, R, C, ignore, acc, torch.tensor([0.7]), d, C, None], [d]
+    (g, c), = _both("pd_ce_bwd", mkb)
+    assert torch.allclose(g, c, atol=1e-8, rtol=1e-4)
+
+
+def test_posterior_kernels():
+    _dev()
+    B, D = 37, 256
+    (g, c), = _both("pd_exp_fwd", lambda: (lambda y: ([torch.randn(B * D), B * D, y, None], [y]))(torch.zeros(B * D)))
+    assert torch.allclose(g, c, rtol=1e-6)
+    (g, c), = _both("pd_mul_f32", lambda: (lambda y: ([torch.randn(B * D), torch.randn(B * D), B * D, y, None], [y]))(
+        torch.zeros(B * D)))
+    assert torch.allclose(g, c)
+    (g, c), = _both("pd_reparam_fwd", lambda: (lambda z: (
+        [torch.randn(B, D), torch.rand(B, D), torch.randn(B, D), B, D, z, 2 * D, None], [z]))(torch.zeros(B, 2 * D)))
+    assert torch.allclose(g, c, atol=1e-6)
+    for g, c in _both("pd_reparam_bwd", lambda: (lambda a, b: (
+            [torch.randn(B, 2 * D), 2 * D, torch.randn(B, D), B, D, a, b, None], [a, b]))(torch.zeros(B, D), torch.zeros(B, D))):
+        assert torch.allclose(g, c, atol=1e-6)
+    (g, c), = _both("pd_kl_fwd", lambda: (lambda o: (
+        [torch.randn(B * D), torch.rand(B * D) + 0.5, B * D, o, None], [o]))(torch.zeros(1)))
+    assert torch.allclose(g, c, rtol=1e-4)
+    for g, c in _both("pd_kl_bwd", lambda: (lambda a, b: (
+            [torch.randn(B * D), torch.rand(B * D) + 0.5, B * D, torch.tensor([1.3]), a, b, None], [a, b]))(
+            torch.zeros(B * D), torch.zeros(B * D))):
+        assert torch.allclose(g, c, rtol=1e-5, atol=1e-9)

@@ -1,0 +1,110 @@
+"""-m gpu: the drop-in model on the CUDA library against (a) the golden fixtures written by the
+unmodified reference and (b) the CPU oracle on fresh seeded inputs.
+
+Tolerances are the north-star's: losses <= 1e-3 relative, gradients <= 1e-2 relative (per parameter
+tensor, ||g - g_ref|| / ||g_ref||), greedy pitch/duration tokens identical in >= 99.9 % of positions.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from polydis_b200.synth import synth_batch
+from polydis_b200.weights import make_state_dict, STATE_DICT_SPEC
+from tests.golden.make_golden_probe import probe_indices
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _model(dev, seed, gain=1.0, eos_bias=0.0):
+    from polydis_b200.model import DisentangleVAE
+    m = DisentangleVAE.init_model(device=dev)
+    m.load_state_dict(make_state_dict(seed, gain=gain, eos_bias=eos_bias))
+    return m.to(dev)
+
+
+@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555"])
+def test_training_matches_reference_golden(golden_dir, tag):
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
+    B = int(g["B"])
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, int(g["data_seed"])))
+    m = _model(dev, int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    m.train()
+    random.seed(int(g["rng_seed"]))
+    eps = (torch.from_numpy(g["eps_chd"]).to(dev), torch.from_numpy(g["eps_rhy"]).to(dev))
+    out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+    losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
+    got = np.array([float(v.detach()) for v in losses])
+    np.testing.assert_allclose(got, g["losses"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out[0].detach().cpu().numpy(), g["pitch"], atol=2e-4)
+    np.testing.assert_allclose(out[1].detach().cpu().numpy(), g["dur"], atol=2e-4)
+    losses[0].backward()
+    params = dict(m.named_parameters())
+    for i, (name, _, _) in enumerate(STATE_DICT_SPEC):
+        gr = params[name].grad.reshape(-1).double().cpu()
+        assert abs(float(gr.norm()) - g["grad_norm"][i]) <= 1e-2 * g["grad_norm"][i] + 1e-9, name
+        probe = gr[torch.from_numpy(probe_indices(name, gr.numel()))].numpy()
+        err = np.linalg.norm(probe - g["grad_probe"][i]) / (np.linalg.norm(g["grad_probe"][i]) + 1e-12)
+        assert err <= 1e-2, (name, err)
+
+
+@pytest.mark.parametrize("tfr", [(1.0, 1.0, 1.0), (0.5, 0.5, 0.5)])
+def test_training_matches_oracle_full_gradients(tfr):
+    dev = _dev()
+    from oracle import polydis_oracle as O
+    B = 6
+    xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 21))
+    sd = {k: v.requires_grad_(True) for k, v in make_state_dict(9).items()}
+    torch.manual_seed(3)
+    e1, e2 = torch.randn(B, 256), torch.randn(B, 256)
+    random.seed(11)
+    plan = O.draw_plan(*tfr)
+    ref = O.loss(sd, xs, cs, prs, plan, e1, e2)
+    ref[0].backward()
+    m = _model(dev, 9)
+    m.train()
+    random.seed(11)
+    got = m.loss(xs.to(dev), cs.to(dev), prs.to(dev), *tfr, eps=(e1.to(dev), e2.to(dev)))
+    got[0].backward()
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 1e-3 * abs(float(b)) + 1e-6
+    for name, p in m.named_parameters():
+        gr, rf = p.grad.detach().cpu().double(), sd[name].grad.double()
+        err = float((gr - rf).norm() / (rf.norm() + 1e-20))
+        assert err <= 1e-2, (name, err)
+
+
+@pytest.mark.parametrize("tag", ["w0", "w1"])
+def test_greedy_tokens_match_reference_golden(golden_dir, tag):
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, f"infer_{tag}.npz"))
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(int(g["B"]), int(g["data_seed"])))
+    m = _model(dev, int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    est = m.inference(pr, c, sample=False)
+    assert est.dtype == np.int64 and est.shape == (int(g["B"]), 32, 15, 6)
+    match = (est == g["est_x"]).mean()
+    assert match >= 0.999, match
+
+
+def test_greedy_tokens_match_oracle_larger_batch():
+    dev = _dev()
+    from oracle import polydis_oracle as O
+    B = 48
+    xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 77))
+    sd = make_state_dict(5, gain=2.0, eos_bias=0.75)
+    ref = O.inference(sd, prs, cs)
+    m = _model(dev, 5, 2.0, 0.75)
+    est = m.swap(prs.to(dev), prs.to(dev), cs.to(dev), cs.to(dev), True, True)
+    match = (est == ref).mean()
+    pre = ref[..., 0] != 129
+    assert match >= 0.999, match
+    assert (est[pre] == ref[pre]).mean() >= 0.999
