@@ -160,7 +160,7 @@ def run_b200(args):
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
                                                         bucket_cap_mb=32)
     params = [p for p in model.parameters()]
-    opt = torch.optim.Adam(params, lr=1e-3, fused=True)
+    opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     xh, ch, ph = (torch.from_numpy(a).pin_memory() for a in synth_batch(B, 100 + rank))
     x, c, pr = xh.to(dev), ch.to(dev), ph.to(dev)
 
@@ -191,6 +191,15 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
+    graphed = None
+    if world == 1 and not args.eager:
+        from polydis_b200.graphs import GraphedTrainStep
+        c0 = _lib.call_count
+        graphed = GraphedTrainStep(model, opt, B).capture(x, c, pr)
+        calls_per_step = (_lib.call_count - c0) // (graphed._warm + 1)
+
+        def step(x, c, pr):  # noqa: F811
+            return graphed(x, c, pr)[0]
     for _ in range(args.warmup):
         step(x, c, pr)
     sampler = ClockSampler(local)
@@ -198,7 +207,7 @@ def run_b200(args):
         sampler.start()
     calls0 = _lib.call_count
     ms_step = timed(lambda: step(x, c, pr), args.steps)
-    launches = (_lib.call_count - calls0)
+    launches = (_lib.call_count - calls0) if graphed is None else calls_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
@@ -246,7 +255,7 @@ def run_b200(args):
                                   "teacher-forced PianoTree decoder, batch 512 per GPU (BASELINE configs[1])",
                       "batch_per_gpu": B, "global_batch": world * B, "tfr": [1, 1, 1],
                       "l2_policy": "working set per step (>5 GB of activations) exceeds the 126 MB L2; no explicit flush",
-                      "parallelism": f"dp{world}"},
+                      "parallelism": f"dp{world}", "cuda_graph": graphed is not None},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4},
            "gpu_launches": launches,
@@ -283,6 +292,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--decode-batch", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="issue the training step eagerly (no CUDA graph)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

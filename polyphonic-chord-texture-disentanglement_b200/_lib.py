@@ -13,10 +13,11 @@ _P, _L, _I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
 # name -> argument ctypes (every function returns int: 0 ok, cudaError_t > 0, -22 bad argument)
 SIGNATURES = {
     "pd_gemm_f32": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _P],
+    "pd_gemm_tf32": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _P],
     "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
-    "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I,
-                         _I, _P],
+    "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,
+                         _I, _I, _P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_note_embed_fwd": [_P, _L, _P, _P, _P, _L, _P],
     "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
@@ -31,6 +32,7 @@ SIGNATURES = {
     "pd_ce_bwd": [_P, _L, _P, _L, _I, _I, _P, _P, _P, _L, _P],
     "pd_exp_fwd": [_P, _L, _P, _P],
     "pd_mul_f32": [_P, _P, _L, _P, _P],
+    "pd_add_f32": [_P, _P, _L, _P, _P],
     "pd_reparam_fwd": [_P, _P, _P, _I, _I, _P, _L, _P],
     "pd_reparam_bwd": [_P, _L, _P, _I, _I, _P, _P, _P],
     "pd_kl_fwd": [_P, _P, _L, _P, _P],

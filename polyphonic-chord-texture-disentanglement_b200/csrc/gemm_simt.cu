@@ -112,8 +112,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_f32_kernel(GemmArgs g) {
             if (n >= g.N) continue;
             float v = acc[i][j] + (add_bias ? __ldg(g.bias + n) : 0.0f);
             float* c = g.C + (long)m * g.ldc + n;
-            if (g.atomic) atomicAdd(c, v);
-            else if (g.accumulate) *c += v;
+            if (g.atomic || g.accumulate) atomicAdd(c, v);   // RED at L2: no read round trip through the SM
             else *c = v;
         }
     }

@@ -1,0 +1,335 @@
+// Tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32, fp32 operands straight from HBM, fp32
+// accumulators in TMEM), operands staged by TMA through a 4-stage mbarrier ring, warp-specialised
+// (1 TMA warp, 1 MMA-issuing warp, 4 epilogue warps reading TMEM with tcgen05.ld).
+//
+//   C[m, n] (+)= sum_k A(m,k) * B(k,n) (+ bias[n])         fp32 in HBM, TF32 multiply, fp32 accumulate
+//
+// Operand layouts (the three GEMMs of a Linear / GRU layer, no transposed copies anywhere):
+//   A K-major : A[m*lda + k]   (activations as GEMM rows)       A MN-major: A[k*lda + m]  (dY^T for dW)
+//   B K-major : B[n*ldb + k]   (nn.Linear weight [N,K])         B MN-major: B[k*ldb + n]  (W for dX, X for dW)
+// K-major tiles are TMA boxes of 32 fp32 (128 B) x rows with the 128-byte swizzle; MN-major tiles are
+// boxes of 32 fp32 along M/N x 32 k-rows with the 32-byte-atom 128-byte swizzle
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout SWIZZLE_128B_BASE32B), the only MN-major
+// layout tcgen05 accepts for 4-byte operands.
+//
+// CTA tile 128 x BN (BN = 64/128/256, one tcgen05.mma M=128 N=BN K=8 per 32-byte k-slice), BK = 32.
+// Split-K over blockIdx.z with a red.global.add epilogue for the weight-gradient GEMMs, whose M x N is
+// tiny and whose K is the whole batch.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 4;
+constexpr int NUM_THREADS = 192;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46) | ((uint64_t)layout << 61);
+}
+
+struct TcArgs {
+    float* C; long ldc;
+    const float* bias;
+    int M, N, K;
+    int kb_per_split;   // k-blocks (of BK) per blockIdx.z
+    int atomic;         // accumulate into C (C += result, or split-K partial sums): red.global.add epilogue
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint64_t* full = (uint64_t*)(sB + STAGES * B_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_beg = blockIdx.z * g.kb_per_split;
+    const int kb_end = min(kb_total, kb_beg + g.kb_per_split);
+    const int nkb = kb_end - kb_beg;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, k0 = (kb_beg + i) * BK;
+                if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
+                mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                uint8_t* a = sA + s * A_BYTES;
+                uint8_t* b = sB + s * B_BYTES;
+                if (A_MN) {
+#pragma unroll
+                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
+                } else {
+                    tma_load_2d(&tmA, &full[s], a, k0, m0);
+                }
+                if (B_MN) {
+#pragma unroll
+                    for (int c = 0; c < BN / 32; ++c) tma_load_2d(&tmB, &full[s], b + c * (BK * 128), n0 + 32 * c, k0);
+                } else {
+                    tma_load_2d(&tmB, &full[s], b, k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (InstrDescriptor): D=f32 [4,6)=1, A/B format tf32=2 at [7,10)/[10,13),
+            // a_major [15], b_major [16], N>>3 at [17,23), M>>4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                mbar_wait(&full[s], (i / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, k-slice = +32 B inside the atom.
+                    // MN-major SW128_BASE32B: [k][128 B of M/N]; 32-wide M/N chunks BK*128 B apart (LBO),
+                    // 4-row k-atoms 512 B apart (SBO), k-slice of 8 rows = +1024 B.
+                    const uint64_t ad = A_MN ? make_desc(a + k * 1024, BK * 128, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
+                    const uint64_t bd = B_MN ? make_desc(b + k * 1024, BK * 128, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
+                    tc_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
+            }
+            tc_commit(tmem_full);                // accumulator complete
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread owns one output row
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        const bool add_bias = g.bias != nullptr && blockIdx.z == 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            if (n0 + c * 32 >= g.N) break;
+            uint32_t r[32];
+            if (nkb > 0) {
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (m < g.M) {
+                float* crow = g.C + (long)m * g.ldc + n0 + c * 32;
+                const int nvalid = min(32, g.N - (n0 + c * 32));
+                const bool vec = (nvalid == 32) && ((((uintptr_t)crow) & 15) == 0);
+                if (vec) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                               __uint_as_float(r[j + 3]));
+                        if (add_bias) {
+                            float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + c * 32 + j);
+                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        }
+                        if (g.atomic) {
+                            // accumulate / split-K: fire-and-forget vector reduction at L2 (no read-modify-write
+                            // round trip through the SM; a load+add+store epilogue here ran at ~30 GB/s)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v.x),
+                                         "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                        } else {
+                            *reinterpret_cast<float4*>(crow + j) = v;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j < nvalid) {
+                            float v = __uint_as_float(r[j]) + (add_bias ? g.bias[n0 + c * 32 + j] : 0.0f);
+                            if (g.atomic) atomicAdd(crow + j, v);
+                            else crow[j] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+    }
+}
+
+__global__ void zero_2d_tc_kernel(float* C, long ldc, int M, int N) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (long)M * N) C[(i / N) * ldc + (i % N)] = 0.0f;
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor [outer][inner] with row stride ld (floats); box = {32 inner, box_outer}.
+int make_map(CUtensorMap* map, const float* base, long inner, long outer, long ld, int box_outer, bool mn_major) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 801;   // cudaErrorNotSupported
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
+    constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
+    return pd_launch_status();
+}
+
+template <int BN>
+int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, g, grid, st);
+    if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, g, grid, st);
+    if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, g, grid, st);
+    return launch<BN, true, false>(ta, tb, g, grid, st);
+}
+
+}  // namespace
+
+// Same contract as pd_gemm_f32 (strides in floats) with TF32 multiplies on the tensor cores.
+// Requirements: operand base pointers 16-byte aligned, row strides multiples of 4 floats.  Returns
+// PD_BAD_ARG (-22) when a requirement does not hold so the caller can route to pd_gemm_f32.
+PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                        const float* bias, int M, int N, int K, int accumulate, void* stream) {
+    if (M <= 0 || N <= 0) return 0;
+    if (K <= 0 || (sak != 1 && sam != 1) || (sbk != 1 && sbn != 1)) return PD_BAD_ARG;
+    const bool a_mn = (sak != 1), b_mn = (sbk != 1);
+    const long lda = a_mn ? sak : sam, ldb = b_mn ? sbk : sbn;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3) || lda < 4 || ldb < 4) return PD_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles_m = (M + BM - 1) / BM;
+    int bn = 256;
+    if (N <= 64) bn = 64;
+    else if (N <= 128 || (long)tiles_m * ((N + 255) / 256) < PD_NUM_SMS) bn = 128;
+    if (bn == 128 && N > 64 && (long)tiles_m * ((N + 127) / 128) < PD_NUM_SMS / 2 && N % 128 != 0 && N % 64 == 0) bn = 64;
+    const int tiles_n = (N + bn - 1) / bn;
+    const long tiles = (long)tiles_m * tiles_n;
+    const int kb = (K + BK - 1) / BK;
+    int split = 1;
+    if (tiles < PD_NUM_SMS && kb >= 32) {
+        split = (int)((2 * PD_NUM_SMS + tiles - 1) / tiles);
+        if (split > kb / 8) split = kb / 8;
+        if (split < 1) split = 1;
+    }
+    int kb_per = (kb + split - 1) / split;
+    split = (kb + kb_per - 1) / kb_per;
+    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0};
+    CUtensorMap ta, tb;
+    int rc;
+    // K-major: [rows][K] -> dims {K, rows}, box {32, BM|bn}.  MN-major: [K][rows] -> dims {rows, K}, box {32, BK}.
+    rc = a_mn ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, BM, false);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&tb, B, N, K, ldb, BK, true) : make_map(&tb, B, K, N, ldb, bn, false);
+    if (rc) return rc;
+    if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
+    dim3 grid(tiles_m, tiles_n, split);
+    if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, g, grid, st);
+    if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, g, grid, st);
+    return launch_bn<64>(a_mn, b_mn, ta, tb, g, grid, st);
+}

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) gru_gates_fwd_kernel(GateFwd a) {
 struct GateBwd {
     const float* dh; long lddh;        // grad wrt this step's output state (recurrent part); may be NULL
     const float* dh2; long lddh2;      // extra grad source for the same state (output use); may be NULL
+    const float* dh3; long lddh3;      // third source (the dgh * W_hh product of the later step); may be NULL
     const float* rzn; long ldrzn;
     const float* hn; long ldhn;
     const float* hprev; long ldhp;     // may be NULL => zeros
@@ -92,6 +93,10 @@ __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
     float4 d = a.dh ? *reinterpret_cast<const float4*>(a.dh + (long)b * a.lddh + j) : make_float4(0, 0, 0, 0);
     if (a.dh2) {
         float4 e = *reinterpret_cast<const float4*>(a.dh2 + (long)b * a.lddh2 + j);
+        d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
+    }
+    if (a.dh3) {
+        float4 e = *reinterpret_cast<const float4*>(a.dh3 + (long)b * a.lddh3 + j);
         d.x += e.x; d.y += e.y; d.z += e.z; d.w += e.w;
     }
     float* dgi = a.dgi + (long)b * a.lddgi + j;
@@ -154,16 +159,17 @@ PD_API int pd_gru_gates_fwd(const float* gi, long ldgi, const float* gi2, long l
     return pd_launch_status();
 }
 
-PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* rzn,
-                            long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
+PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,
+                            long lddh3, const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
                             long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
                             long lddgi2, const int* lengths, int t, int B, int H, void* stream) {
     if (B <= 0) return 0;
-    if ((H & 3) || (dh && !al4(dh, lddh)) || (dh2 && !al4(dh2, lddh2)) || !al4(rzn, ldrzn) || !al4(hn, ldhn) ||
+    if ((H & 3) || (dh && !al4(dh, lddh)) || (dh2 && !al4(dh2, lddh2)) || (dh3 && !al4(dh3, lddh3)) ||
+        !al4(rzn, ldrzn) || !al4(hn, ldhn) ||
         (hprev && !al4(hprev, ldhp)) || !al4(dgi, lddgi) || !al4(dgh, lddgh) || !al4(dhprev, lddhp) ||
         (dgi2 && !al4(dgi2, lddgi2)))
         return PD_BAD_ARG;
-    GateBwd a{dh, lddh, dh2, lddh2, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh,
+    GateBwd a{dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh,
               dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H};
     long n = (long)B * (H >> 2);
     gru_gates_bwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a);

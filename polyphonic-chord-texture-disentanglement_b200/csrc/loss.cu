@@ -121,6 +121,10 @@ __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict_
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] * b[i];
 }
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, float* out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + b[i];
+}
 // z[b, j] = mu + std * eps, written with row stride ldz (into its half of dec_z)
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
                                    const float* __restrict__ eps, int B, int D, float* z, long ldz) {
@@ -203,6 +207,12 @@ PD_API int pd_exp_fwd(const float* x, long n, float* y, void* stream) {
 PD_API int pd_mul_f32(const float* a, const float* b, long n, float* out, void* stream) {
     if (n <= 0) return 0;
     mul_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    return pd_launch_status();
+}
+
+PD_API int pd_add_f32(const float* a, const float* b, long n, float* out, void* stream) {
+    if (n <= 0) return 0;
+    add_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
     return pd_launch_status();
 }
 

@@ -81,6 +81,10 @@ class DisentangleVAE(PytorchModel):
         self.decoder = decoder
         self.num_step = self.decoder.num_step
         self.chd_decoder = chd_decoder
+        #: GEMM arithmetic of the inference entry points: "fp32" (default) keeps greedy tokens identical
+        #: to the fp32 reference; "tf32" runs them on the tensor cores (faster, ~0.1 % of tokens of a
+        #: randomly initialised model may flip at near-tied argmaxes).
+        self.decode_precision = "fp32"
 
     # -- training ----------------------------------------------------------------------------------
     def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None):
@@ -124,7 +128,7 @@ class DisentangleVAE(PytorchModel):
     # -- inference ---------------------------------------------------------------------------------
     def inference_encode(self, pr_mat, c):
         self.eval()
-        with torch.no_grad():
+        with torch.no_grad(), ops.precision(self.decode_precision):
             dist_chd = self.chd_encoder(c)
             dist_rhy = self.rhy_encoder(pr_mat)
         return dist_chd, dist_rhy
@@ -132,7 +136,7 @@ class DisentangleVAE(PytorchModel):
     def decode_tokens(self, z_chd, z_rhy):
         """Greedy PianoTree decode -> (B,32,15,6) int32 tokens ON DEVICE (no host copy)."""
         self.eval()
-        with torch.no_grad():
+        with torch.no_grad(), ops.precision(self.decode_precision):
             return self.decoder.greedy_tokens(torch.cat([z_chd, z_rhy], dim=-1))
 
     def inference_decode(self, z_chd, z_rhy):
@@ -140,7 +144,7 @@ class DisentangleVAE(PytorchModel):
 
     def inference(self, pr_mat, c, sample, eps=None):
         self.eval()
-        with torch.no_grad():
+        with torch.no_grad(), ops.precision(self.decode_precision):
             dist_chd = self.chd_encoder(c)
             dist_rhy = self.rhy_encoder(pr_mat)
             z_chd = _sample(dist_chd, sample, None if eps is None else eps[0])

@@ -35,16 +35,48 @@ def _rows(t):
 
 
 # ------------------------------------------------------------------------------------------------
-# raw kernels
+# GEMM routing.  "tf32": tcgen05 tensor-core kernel (TF32 multiplies, fp32 accumulate) whenever TMA can
+# address the operands, else the fp32 FFMA kernel.  "fp32": always the FFMA kernel -- the fp32-faithful
+# arithmetic greedy decoding needs for token parity with the fp32 reference.
+PRECISION = "tf32"
+
+
+class precision:
+    """``with ops.precision("fp32"): ...`` selects the GEMM arithmetic for the enclosed calls."""
+
+    def __init__(self, mode):
+        assert mode in ("tf32", "fp32")
+        self.mode = mode
+
+    def __enter__(self):
+        global PRECISION
+        self.prev, PRECISION = PRECISION, self.mode
+
+    def __exit__(self, *exc):
+        global PRECISION
+        PRECISION = self.prev
+
+
+def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
+    name = "pd_gemm_f32"
+    if PRECISION == "tf32" and K >= 8 and N >= 16:
+        lda = sak if sak != 1 else sam
+        ldb = sbk if sbk != 1 else sbn
+        if a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0 \
+                and lda >= 4 and ldb >= 4:
+            name = "pd_gemm_tf32"
+    _call(name, _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
+          int(accumulate), _stream())
+    return out
+
+
 def gemm_nt(x, w, out, bias=None, accumulate=False):
     """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias)."""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape == (M, N) and x.stride(1) == 1 and out.stride(1) == 1
     assert w.stride(1) == 1 or K == 1
-    _call("pd_gemm_f32", _ptr(x), x.stride(0), 1, _ptr(w), 1, w.stride(0), _ptr(out), out.stride(0),
-          _ptr(bias), M, N, K, int(accumulate), _stream())
-    return out
+    return _gemm(x, x.stride(0), 1, w, 1, w.stride(0), out, bias, M, N, K, accumulate)
 
 
 def gemm_nn(x, w, out, accumulate=False):
@@ -52,9 +84,7 @@ def gemm_nn(x, w, out, accumulate=False):
     M, K = x.shape
     N = w.shape[1]
     assert w.shape[0] == K and out.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1
-    _call("pd_gemm_f32", _ptr(x), x.stride(0), 1, _ptr(w), w.stride(0), 1, _ptr(out), out.stride(0),
-          None, M, N, K, int(accumulate), _stream())
-    return out
+    return _gemm(x, x.stride(0), 1, w, w.stride(0), 1, out, None, M, N, K, accumulate)
 
 
 def gemm_tn(a, b, out, accumulate=False):
@@ -62,9 +92,7 @@ def gemm_tn(a, b, out, accumulate=False):
     R, M = a.shape
     N = b.shape[1]
     assert b.shape[0] == R and out.shape == (M, N) and a.stride(1) == 1 and b.stride(1) == 1
-    _call("pd_gemm_f32", _ptr(a), 1, a.stride(0), _ptr(b), b.stride(0), 1, _ptr(out), out.stride(0),
-          None, M, N, R, int(accumulate), _stream())
-    return out
+    return _gemm(a, 1, a.stride(0), b, b.stride(0), 1, out, None, M, N, R, accumulate)
 
 
 def colsum(x, out, accumulate=False):
@@ -114,6 +142,31 @@ class _Linear(torch.autograd.Function):
 
 def linear(x, w, b=None):
     return _Linear.apply(x, w, b)
+
+
+class _MatMulNN(torch.autograd.Function):
+    """c = a @ b for small weight-space products (a (M,K), b (K,N), both row-strided)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        c = torch.empty(a.shape[0], b.shape[1], device=a.device, dtype=torch.float32)
+        gemm_nn(a, b, c)
+        ctx.save_for_backward(a, b)
+        return c
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        dc = dc.contiguous()
+        da = torch.empty(a.shape, device=dc.device, dtype=torch.float32)
+        db = torch.empty(b.shape, device=dc.device, dtype=torch.float32)
+        gemm_nt(dc, b, da)             # da = dc b^T
+        gemm_tn(a, dc, db)             # db = a^T dc
+        return da, db
+
+
+def matmul_nn(a, b):
+    return _MatMulNN.apply(a, b)
 
 
 class _Linear2(torch.autograd.Function):
@@ -213,29 +266,60 @@ class _GruSeq(torch.autograd.Function):
         dgi = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
         dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
         dgi2 = torch.zeros(B, 3 * H, device=dev, dtype=torch.float32) if ctx.has_gi2 else None
-        dw = torch.zeros(w_hh.shape, device=dev, dtype=torch.float32)
-        dh_a = torch.empty(B, H, device=dev, dtype=torch.float32)
-        dh_b = torch.empty(B, H, device=dev, dtype=torch.float32)
+        # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
+        # and dgh @ W_hh (written by that step's GEMM); the next gate kernel sums both with dout[:, t]
+        dz_a = torch.empty(B, H, device=dev, dtype=torch.float32)
+        dz_b = torch.empty(B, H, device=dev, dtype=torch.float32)
+        dm_a = torch.empty(B, H, device=dev, dtype=torch.float32)
+        dm_b = torch.empty(B, H, device=dev, dtype=torch.float32)
         order = list(range(T - 1, -1, -1) if ctx.reverse else range(T))
-        dh = None
+        dz = dm = None
         st = _stream()
         for i in range(T - 1, -1, -1):
             t = order[i]
             hprev = h_all[:, order[i - 1]] if i > 0 else h0
-            nxt = dh_b if dh is dh_a else dh_a
-            _call("pd_gru_gates_bwd", _ptr(dh), 0 if dh is None else dh.stride(0), _ptr(dout[:, t]),
-                  dout.stride(0), _ptr(rzn[:, t]), rzn.stride(0), _ptr(hn[:, t]), hn.stride(0), _ptr(hprev),
-                  0 if hprev is None else hprev.stride(0), _ptr(dgi[:, t]), dgi.stride(0),
-                  _ptr(dgh[:, t]), dgh.stride(0), _ptr(nxt), nxt.stride(0), _ptr(dgi2),
-                  0 if dgi2 is None else dgi2.stride(0), _ptr(lengths), t, B, H, st)
+            nz = dz_b if dz is dz_a else dz_a
+            nm = dm_b if dm is dm_a else dm_a
+            _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
+                  dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+                  _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
+                  _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
+                  _ptr(dgi2), 0 if dgi2 is None else dgi2.stride(0), _ptr(lengths), t, B, H, st)
+            dz = nz
             if hprev is not None:
-                gemm_nn(dgh[:, t], w_hh, nxt, accumulate=True)        # dh_prev += dgh W_hh
-                gemm_tn(dgh[:, t], hprev, dw, accumulate=True)        # dW_hh += dgh^T h_prev
-            dh = nxt
+                gemm_nn(dgh[:, t], w_hh, nm)                          # dgh W_hh
+                dm = nm
+            else:
+                dm = None
+        dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)
-        colsum(dgh.view(B * T, 3 * H), db)
-        dh0 = dh if (h0 is not None and ctx.needs_input_grad[2]) else None
+        colsum(dgh_flat, db)
+        # dW_hh = sum_{b,t} dgh[b,t]^T h_prev[b,t] as ONE split-K GEMM over all (b,t) rows: h_prev of row r is
+        # row r-1 (r+1 when reversed) of the flattened state buffer, except at each sequence's first step,
+        # whose h_prev is h0 -- those rows are handled by a small GEMM and then zeroed in dgh.
+        dw = torch.empty(w_hh.shape, device=dev, dtype=torch.float32)
+        first = order[0]
+        if h0 is not None:
+            gemm_tn(dgh[:, first], h0, dw)
+        if T > 1:
+            dgh[:, first].zero_()
+            h_flat = h_all.view(B * T, H)
+            if ctx.reverse:
+                gemm_tn(dgh_flat[:-1], h_flat[1:], dw, accumulate=h0 is not None)
+            else:
+                gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
+        elif h0 is None:
+            dw.zero_()
+        dh0 = None
+        if h0 is not None and ctx.needs_input_grad[2]:
+            dh0 = dz if dm is None else _add(dz, dm)
         return dgi, dgi2, dh0, dw, db, None, None
+
+
+def _add(a, b):
+    out = torch.empty_like(a)
+    _call("pd_add_f32", _ptr(a), _ptr(b), a.numel(), _ptr(out), _stream())
+    return out
 
 
 def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False):

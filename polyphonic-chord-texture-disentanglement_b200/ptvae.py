@@ -212,11 +212,24 @@ class PtvaeDecoder(nn.Module):
         return _bigru_final(self.dec_notes_emb_gru, notes, lengths32)
 
     # -- duration level --------------------------------------------------------------------------
-    def _decode_durs(self, h_note, pitch):
+    def _dur_hid_folded(self):
+        """dur_hid_linear([h | pitch_logits]) with pitch_logits = W_p h + b_p folded into one 512-wide
+        projection: W_eff = W_a + W_b W_p, b_eff = b_d + W_b b_p (exact algebra; the reference feeds the raw
+        logits, ptvae.py:349-352).  Removes the 130-wide, TMA-unaligned operand from the hot loop; the
+        weight-space products are tiny (64x130x512) and differentiable."""
+        w_d, b_d = self.dur_hid_linear.weight, self.dur_hid_linear.bias
+        k = self.dec_notes_hid_size
+        w_b = w_d[:, k:]
+        w_eff = w_d[:, :k] + ops.matmul_nn(w_b, self.pitch_out_linear.weight)
+        b_eff = b_d + ops.linear(self.pitch_out_linear.bias.unsqueeze(0), w_b, None)[0]
+        return w_eff, b_eff
+
+    def _decode_durs(self, h_note, pitch, folded=None):
         """h_note (Q,512), pitch logits (Q,130) -> dur logits (Q,5,2).             ptvae.py:345-367"""
         Q = h_note.size(0)
         w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
-        dh = ops.linear_cat2(h_note, pitch, self.dur_hid_linear.weight, self.dur_hid_linear.bias)
+        w_eff, b_eff = folded if folded is not None else self._dur_hid_folded()
+        dh = ops.linear(h_note, w_eff, b_eff)
         tok = self.dur_sos_token.expand(Q, self.dur_width)
         outs = []
         for k in range(self.dur_width):
@@ -269,6 +282,7 @@ class PtvaeDecoder(nn.Module):
         gi_s = ops.linear(S, w_ih[:, :self.dec_time_hid_size], b_ih)
         w_tok = w_ih[:, self.dec_time_hid_size:]
         tok = sos_emb.expand(B, -1) if inference else notes[:, 0]
+        folded = self._dur_hid_folded()
         pred = [tok]
         lens = torch.zeros(B, device=S.device, dtype=torch.int32)
         pitches, durs = [], []
@@ -276,7 +290,7 @@ class PtvaeDecoder(nn.Module):
             gi = ops.linear(tok, w_tok, None)
             h = ops.gru_sequence(gi.view(B, 1, -1), gi_s, h, w_hh, b_hh)[:, 0]
             p = self.pitch_out_linear(h)
-            d = self._decode_durs(h, p)
+            d = self._decode_durs(h, p, folded)
             if keep_logits:
                 pitches.append(p)
                 durs.append(d)

@@ -50,6 +50,10 @@ class CpuBackend:
             r = r + _arr(bias, (N,), (1,))
         c[...] = c + r if acc else r
 
+    def pd_gemm_tf32(self, *a):
+        # same contract; the emulation keeps fp32 products (the GPU kernel rounds operands to TF32)
+        self.pd_gemm_f32(*a)
+
     def pd_colsum_f32(self, X, ldx, M, N, out, acc, st):
         o = _arr(out, (N,), (1,))
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0
@@ -80,13 +84,15 @@ class CpuBackend:
             Q = _arr(hn, (B, H), (ldhn, 1))
             Q[act] = GH[:, 2 * H:][act]
 
-    def pd_gru_gates_bwd(self, dh, lddh, dh2, lddh2, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+    def pd_gru_gates_bwd(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                          dhp, lddhp, dgi2, lddgi2, lengths, t, B, H, st):
         d = np.zeros((B, H), np.float32)
         if dh is not None:
             d = d + _arr(dh, (B, H), (lddh, 1))
         if dh2 is not None:
             d = d + _arr(dh2, (B, H), (lddh2, 1))
+        if dh3 is not None:
+            d = d + _arr(dh3, (B, H), (lddh3, 1))
         act = np.ones(B, bool) if lengths is None else (t < _arr(lengths, (B,), (1,), np.int32))
         S = _arr(rzn, (B, 3 * H), (ldrzn, 1))
         r, z, n = S[:, :H], S[:, H:2 * H], S[:, 2 * H:]
@@ -237,6 +243,9 @@ class CpuBackend:
 
     def pd_mul_f32(self, a, b, n, out, st):
         _arr(out, (n,), (1,))[...] = _arr(a, (n,), (1,)) * _arr(b, (n,), (1,))
+
+    def pd_add_f32(self, a, b, n, out, st):
+        _arr(out, (n,), (1,))[...] = _arr(a, (n,), (1,)) + _arr(b, (n,), (1,))
 
     def pd_reparam_fwd(self, mu, sd, eps, B, D, z, ldz, st):
         m = _arr(mu, (B, D), (D, 1))

@@ -62,6 +62,47 @@ def test_gemm_f32(M, N, K, layout, acc, bias):
     assert torch.allclose(g, c, atol=tol, rtol=1e-4), float((g - c).abs().max())
 
 
+@pytest.mark.parametrize("M,N,K,layout,acc,bias", [
+    (4, 3072, 36, "nt", 0, 1), (513, 136, 512, "nt", 1, 1), (2048, 1536, 128, "nt", 0, 0),
+    (257, 300, 77, "nn", 1, 0), (16384, 512, 1536, "nn", 0, 0), (1536, 512, 40000, "tn", 0, 0),
+    (64, 128, 30001, "tn", 1, 0), (130, 512, 7777, "tn", 0, 0), (1000, 1000, 292, "nt", 0, 1),
+])
+def test_gemm_tf32_tcgen05(M, N, K, layout, acc, bias):
+    """tcgen05 kernel (TF32 operands, fp32 accumulate) vs the fp32 restatement: error bounded by TF32
+    rounding of the operands (2^-11 each) -- checked relative to sqrt(K) * |a||b| scale."""
+    _dev()
+    r4 = lambda v: (v + 3) // 4 * 4          # TMA needs row strides that are multiples of 16 bytes
+
+    def mk():
+        ldc = N + 4
+        if layout == "tn":
+            A = torch.randn(K, r4(M) + 8); sam, sak = 1, r4(M) + 8
+        else:
+            A = torch.randn(M, r4(K) + 8); sam, sak = r4(K) + 8, 1
+        if layout == "nt":
+            Bm = torch.randn(N, r4(K) + 4); sbk, sbn = 1, r4(K) + 4
+        else:
+            Bm = torch.randn(K, r4(N) + 4); sbk, sbn = r4(N) + 4, 1
+        C = torch.randn(M, ldc)
+        b = torch.randn(N) if bias else None
+        return [A, sam, sak, Bm, sbk, sbn, C, ldc, b, M, N, K, acc, None], [C]
+    (g, c), = _both("pd_gemm_tf32", mk)
+    # TF32 round-to-nearest: per-product relative error ~4e-4 rms -> output error ~4e-4*sqrt(K) rms
+    tol = 3e-3 * np.sqrt(K) + 1e-5
+    assert torch.allclose(g, c, atol=tol, rtol=0), float((g - c).abs().max())
+    assert float((g - c).abs().mean()) < 0.6e-3 * np.sqrt(K) + 1e-5
+
+
+def test_gemm_tf32_rejects_unaligned_operands():
+    """Row strides that TMA cannot address are refused (-22) so the host routes to the FFMA kernel."""
+    _dev()
+    from polydis_b200 import _lib
+    A, Bm, C = torch.randn(64, 130).cuda(), torch.randn(32, 130).cuda(), torch.zeros(64, 32).cuda()
+    with pytest.raises(RuntimeError):
+        _lib.call("pd_gemm_tf32", A.data_ptr(), 130, 1, Bm.data_ptr(), 1, 130, C.data_ptr(), 32, None, 64, 32, 130, 0,
+                  torch.cuda.current_stream().cuda_stream)
+
+
 def test_colsum_and_transpose():
     _dev()
     (g, c), = _both("pd_colsum_f32",
@@ -97,7 +138,8 @@ def test_gru_gates_fwd_bwd(B, H, masked, bcast, hprev):
         dgi, dgh, dhp = torch.zeros(B, 2, 3 * H), torch.zeros(B, 3 * H), torch.zeros(B, H)
         dgi2 = torch.randn(B, 3 * H) if bcast else None
         ln = torch.randint(1, 8, (B,), dtype=torch.int32) if masked else None
-        return ([dh, H, dh2, 2 * H, rzn, 3 * H, hn, H, hp, H, dgi, 6 * H, dgh, 3 * H, dhp, H, dgi2, 3 * H, ln, t,
+        dh3 = torch.randn(B, H) if bcast else None
+        return ([dh, H, dh2, 2 * H, dh3, H, rzn, 3 * H, hn, H, hp, H, dgi, 6 * H, dgh, 3 * H, dhp, H, dgi2, 3 * H, ln, t,
                  B, H, None], [dgi, dgh, dhp] + ([dgi2] if bcast else []))
     for g, c in _both("pd_gru_gates_bwd", mk_b):
         assert torch.allclose(g, c, atol=2e-6, rtol=1e-5), float((g - c).abs().max())

@@ -31,9 +31,15 @@ def _model(dev, seed, gain=1.0, eos_bias=0.0):
     return m.to(dev)
 
 
-@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555"])
-def test_training_matches_reference_golden(golden_dir, tag):
+@pytest.mark.parametrize("tag,prec", [("tf111", "tf32"), ("tf111", "fp32"), ("tf000", "fp32"), ("tf555", "fp32"),
+                                      ("tf000", "tf32"), ("tf555", "tf32")])
+def test_training_matches_reference_golden(golden_dir, tag, prec):
+    """Teacher-forced training runs on the TF32 tensor-core path and must meet the north-star tolerances.
+    Scheduled-sampling runs (tf000 / tf555) feed argmax tokens back, so a TF32-flipped near-tie changes
+    later logits; their element-wise logit check is done in fp32 mode (exact logic parity) and the TF32 run
+    is held to the loss / gradient tolerances only."""
     dev = _dev()
+    from polydis_b200 import ops
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     B = int(g["B"])
     x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, int(g["data_seed"])))
@@ -41,13 +47,17 @@ def test_training_matches_reference_golden(golden_dir, tag):
     m.train()
     random.seed(int(g["rng_seed"]))
     eps = (torch.from_numpy(g["eps_chd"]).to(dev), torch.from_numpy(g["eps_rhy"]).to(dev))
-    out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
-    losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
-    got = np.array([float(v.detach()) for v in losses])
-    np.testing.assert_allclose(got, g["losses"], rtol=1e-3, atol=1e-6)
-    np.testing.assert_allclose(out[0].detach().cpu().numpy(), g["pitch"], atol=2e-4)
-    np.testing.assert_allclose(out[1].detach().cpu().numpy(), g["dur"], atol=2e-4)
-    losses[0].backward()
+    with ops.precision(prec):
+        out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+        losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
+        got = np.array([float(v.detach()) for v in losses])
+        np.testing.assert_allclose(got, g["losses"], rtol=1e-3, atol=1e-6)
+        if prec == "fp32" or tag == "tf111":
+            # logits ~0.3 in magnitude; TF32 operand rounding (2^-11) bounds the difference
+            atol = 2e-4 if prec == "fp32" else 3e-3
+            np.testing.assert_allclose(out[0].detach().cpu().numpy(), g["pitch"], atol=atol)
+            np.testing.assert_allclose(out[1].detach().cpu().numpy(), g["dur"], atol=atol)
+        losses[0].backward()
     params = dict(m.named_parameters())
     for i, (name, _, _) in enumerate(STATE_DICT_SPEC):
         gr = params[name].grad.reshape(-1).double().cpu()

@@ -15,8 +15,10 @@ for r in csv.DictReader(lines):
         rows.append((r["Kernel Name"], v))
 agg = defaultdict(lambda: [0, 0.0])
 for k, v in rows:
-    k = re.sub(r"<.*", "", k)
-    k = re.sub(r"^.*::", "", k)
+    k = k.replace("<unnamed>::", "").replace("void ", "")
+    k = re.sub(r"\(.*$", "", k)            # drop the argument list
+    k = re.sub(r"^at::native::", "torch:", k)
+    k = re.sub(r"<at::native.*", "<...>", k)
     agg[k][0] += 1
     agg[k][1] += v
 tot = sum(v for _, v in rows)
