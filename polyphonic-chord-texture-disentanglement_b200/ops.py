@@ -523,6 +523,52 @@ def dur_token(logit):
     return tok
 
 
+class _DurDecode(torch.autograd.Function):
+    """Fused 5-step duration GRU + head with greedy bit feedback (ptvae.py:353-367).  Forward: one
+    weight-resident kernel.  Backward: one kernel for the per-note BPTT plus ONE tensor-core GEMM
+    (GX^T . S) that produces every parameter gradient (layout in csrc/dur_decoder.cu)."""
+
+    @staticmethod
+    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
+        h2, _ = _rows(_chk(h0, "dur h0"))
+        Q = h2.shape[0]
+        dev = h2.device
+        logits = torch.empty(Q, 5, 2, device=dev, dtype=torch.float32)
+        need = any(ctx.needs_input_grad)
+        S = torch.empty(Q, 6, 72, device=dev, dtype=torch.float32) if need else None
+        params = [t.contiguous() for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)]
+        _call("pd_dur_decode_fwd", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
+              _stream())
+        ctx.save_for_backward(S, *params)
+        ctx.h_shape = h0.shape
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        S, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out = ctx.saved_tensors
+        Q = S.shape[0]
+        dev = S.device
+        dlogits = dlogits.contiguous()
+        GX = torch.empty(Q, 6, 264, device=dev, dtype=torch.float32)
+        dh0 = torch.empty(Q, 64, device=dev, dtype=torch.float32)
+        _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
+                                                                                 b_out)],
+              _ptr(GX), _ptr(dh0), dh0.stride(0), _stream())
+        G = torch.empty(264, 72, device=dev, dtype=torch.float32)
+        gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
+        gi_rows = torch.cat([G[0:128], G[192:256]], 0)            # [dr | dz | dn] x S columns
+        dw_hh, db_hh = G[0:192, 0:64], G[0:192, 69]
+        dw_ih, db_ih = gi_rows[:, 64:69], gi_rows[:, 69]
+        dsos = w_ih.t() @ gi_rows[:, 70]                           # (5,) from the step-0 input-gate grads
+        dw_out, db_out = G[256:258, 0:64], G[256:258, 69]
+        return (dh0.view(ctx.h_shape), dw_ih.contiguous(), db_ih.contiguous(), dw_hh.contiguous(),
+                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous())
+
+
+def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
+    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)
+
+
 def chord_feedback(root, chroma, bass):
     """(B,12), (B,12,2), (B,12) logits -> (B,36) feedback token (batch-union one-hots, ptvae.py:73-78)."""
     B = root.shape[0]

@@ -230,16 +230,8 @@ class PtvaeDecoder(nn.Module):
         w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
         w_eff, b_eff = folded if folded is not None else self._dur_hid_folded()
         dh = ops.linear(h_note, w_eff, b_eff)
-        tok = self.dur_sos_token.expand(Q, self.dur_width)
-        outs = []
-        for k in range(self.dur_width):
-            gi = ops.linear(tok, w_ih, b_ih)
-            dh = ops.gru_sequence(gi.view(Q, 1, -1), None, dh, w_hh, b_hh)[:, 0]
-            d = self.dur_out_linear(dh)
-            outs.append(d)
-            if k < self.dur_width - 1:
-                tok = ops.dur_token(d.detach())
-        return torch.stack(outs, 1)
+        return ops.dur_decode(dh, w_ih, b_ih, w_hh, b_hh, self.dur_sos_token, self.dur_out_linear.weight,
+                              self.dur_out_linear.bias)
 
     # -- teacher-forced (tfr1 = tfr2 = 1 decisions): batched phases -------------------------------
     def _time_inputs(self, z):

@@ -165,6 +165,73 @@ class CpuBackend:
         T[:, 0] = ~one
         T[:, 1] = one
 
+    # ---- fused duration decoder ----
+    @staticmethod
+    def _dur_tables(w_ih, b_ih, sos):
+        W = _arr(w_ih, (192, 5), (5, 1))
+        b = _arr(b_ih, (192,), (1,))
+        return np.stack([W @ _arr(sos, (5,), (1,)) + b, W[:, 0] + b, W[:, 1] + b])
+
+    def pd_dur_decode_fwd(self, h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, st):
+        h = _arr(h0, (Q, 64), (ldh0, 1)).copy()
+        gi_t = self._dur_tables(w_ih, b_ih, sos)
+        Whh, bhh = _arr(w_hh, (192, 64), (64, 1)), _arr(b_hh, (192,), (1,))
+        Wo, bo = _arr(w_out, (2, 64), (64, 1)), _arr(b_out, (2,), (1,))
+        L = _arr(logits, (Q, 5, 2), (10, 2, 1))
+        Sb = _arr(S, (Q, 6, 72), (432, 72, 1)) if S is not None else None
+        tok = np.zeros(Q, np.int64)
+        for k in range(5):
+            if Sb is not None:
+                Sb[:, k, :] = 0
+                Sb[:, k, :64] = h
+                if k == 0:
+                    Sb[:, 0, 64:69] = _arr(sos, (5,), (1,))
+                    Sb[:, 0, 70] = 1
+                else:
+                    Sb[np.arange(Q), k, 64 + tok - 1] = 1
+                Sb[:, k, 69] = 1
+            gi = gi_t[tok]
+            gh = h @ Whh.T + bhh
+            r = _sig(gi[:, :64] + gh[:, :64])
+            z = _sig(gi[:, 64:128] + gh[:, 64:128])
+            n = np.tanh(gi[:, 128:] + r * gh[:, 128:])
+            h = ((1 - z) * n + z * h).astype(np.float32)
+            lg = h @ Wo.T + bo
+            L[:, k, :] = lg
+            tok = np.where(lg[:, 1] > lg[:, 0], 2, 1)
+        if Sb is not None:
+            Sb[:, 5, :] = 0
+            Sb[:, 5, :64] = h
+            Sb[:, 5, 69] = 1
+
+    def pd_dur_decode_bwd(self, S, dlog, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, st):
+        Sb = _arr(S, (Q, 6, 72), (432, 72, 1))
+        dL = _arr(dlog, (Q, 5, 2), (10, 2, 1))
+        gi_t = self._dur_tables(w_ih, b_ih, sos)
+        Whh, bhh = _arr(w_hh, (192, 64), (64, 1)), _arr(b_hh, (192,), (1,))
+        Wo = _arr(w_out, (2, 64), (64, 1))
+        G = _arr(GX, (Q, 6, 264), (6 * 264, 264, 1))
+        G[...] = 0
+        dh = np.zeros((Q, 64), np.float32)
+        for k in range(4, -1, -1):
+            hp = Sb[:, k, :64]
+            tok = np.zeros(Q, np.int64) if k == 0 else np.where(Sb[:, k, 65] > 0.5, 2, 1)
+            G[:, k + 1, 256:258] = dL[:, k]
+            dh = dh + dL[:, k] @ Wo
+            gi = gi_t[tok]
+            gh = hp @ Whh.T + bhh
+            r = _sig(gi[:, :64] + gh[:, :64])
+            z = _sig(gi[:, 64:128] + gh[:, 64:128])
+            n = np.tanh(gi[:, 128:] + r * gh[:, 128:])
+            dn = dh * (1 - z) * (1 - n * n)
+            dz = dh * (hp - n) * z * (1 - z)
+            dr = dn * gh[:, 128:] * r * (1 - r)
+            dgh = np.concatenate([dr, dz, dn * r], 1)
+            G[:, k, :192] = dgh
+            G[:, k, 192:256] = dn
+            dh = (dh * z + dgh @ Whh).astype(np.float32)
+        _arr(dh0, (Q, 64), (lddh0, 1))[...] = dh
+
     def pd_chord_feedback(self, root, ldr, chroma, ldc, bass, ldb, B, flags, tok, ldt, st):
         Rt = _arr(root, (B, 12), (ldr, 1))
         Ch = _arr(chroma, (B, 12, 2), (ldc, 2, 1))
