@@ -1,0 +1,116 @@
+/* libpolydis_b200 -- C ABI of the PolyDis hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (ZZWaang/polyphonic-chord-texture-disentanglement) is pure Python on PyTorch ATen; it has
+ * no FFI of its own.  The entry points below are the native boundary a binding for its hot path needs:
+ * each one replaces an ATen call site of the reference (cited file:line), takes plain device pointers,
+ * element strides and sizes, launches on the given CUDA stream and returns immediately.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless noted); strides / leading dimensions are in ELEMENTS
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises or allocates device memory
+ *   - return value: 0 = launched; > 0 = cudaError_t; PD_BAD_ARG (-22) = argument contract violated
+ *     (for pd_gemm_tf32: operands TMA cannot address -- call pd_gemm_f32 instead)
+ *   - buffers documented "accumulated" must be initialised by the caller
+ *   - thread safety: entry points hold no mutable global state besides one-time function attributes;
+ *     concurrent calls on different streams are safe
+ */
+#ifndef POLYDIS_B200_H
+#define POLYDIS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_BAD_ARG (-22)
+
+/* ---- GEMM: nn.Linear / GRU projections (reference: every nn.Linear and the matmuls inside aten::gru,
+ * ptvae.py:26-27,63-68,115-120,343,349-352,361,374-375,396-398,435-437,461-462).
+ *   C[m*ldc+n] (+)= sum_k A(m,k) B(k,n) (+ bias[n]);  A(m,k)=A[m*sam+k*sak], B(k,n)=B[k*sbk+n*sbn];
+ *   one of (sam,sak) and one of (sbk,sbn) must be 1.  accumulate != 0 adds into C (L2 reductions).
+ * pd_gemm_f32 : fp32 FFMA, any shape/stride.   pd_gemm_tf32: tcgen05 tensor cores (TF32 x TF32 -> fp32),
+ * needs 16-byte aligned bases and row strides that are multiples of 4. */
+int pd_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                const float* bias, int M, int N, int K, int accumulate, void* stream);
+int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                 const float* bias, int M, int N, int K, int accumulate, void* stream);
+/* out[n] (+)= sum_m X[m*ldx+n]   (bias gradients) */
+int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int accumulate, void* stream);
+int pd_transpose_f32(const float* in, int rows, int cols, float* out, void* stream);
+
+/* ---- GRU cell gate math around the per-step W_hh GEMM (aten::gru at ptvae.py:63-65,359-360,396-398,
+ * 461-462; packed bi-GRU at :446-453,:480-486 through the per-row `lengths` mask).  Gate order r|z|n.
+ *   gi (B,3H) x-projection incl. b_ih; gi2 optional second term (same shape, e.g. the sequence-constant
+ *   half of the reference's torch.cat input); gh (B,3H) = W_hh h + b_hh; hprev NULL = zeros.
+ *   rzn/hn (may be NULL) receive r,z,n and (W_hn h + b_hn) for the backward pass.
+ *   Rows with t >= lengths[b] carry their state (lengths NULL = no mask). */
+int pd_gru_gates_fwd(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
+                     const float* hprev, long ldhp, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
+                     long ldhn, const int* lengths, int t, int B, int H, void* stream);
+/* d = dh + dh2 + dh3 (each optional): dgi=[dr,dz,dn], dgh=[dr,dz,dn*r], dhprev = d*z (the caller's GEMM adds
+ * dgh W_hh), dgi2 (optional) += dgi. */
+int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                     const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp,
+                     float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
+                     long lddgi2, const int* lengths, int t, int B, int H, void* stream);
+
+/* ---- PianoTree grid (ptvae.py:292-313,:498-511,:531-535).  x (n_steps,16,6) int64 -> tok int32 (same
+ * layout), lengths (n_steps) = 16 - #PAD, pitch targets (n_steps,15), duration targets (n_steps,15,5). */
+int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, int* pitch_tgt, int* dur_tgt,
+                    void* stream);
+/* note_embedding(multi-hot) as a gather: out[r] = bias + WT[pitch] (pitch < 130) + sum_k dur_k WT[130+k];
+ * tok int32 (R,6); WT = weight^T (135,128).   bwd accumulates dWT (135,128) and dbias (128). */
+int pd_note_embed_fwd(const int* tok, long R, const float* WT, const float* bias, float* out, long ldo,
+                      void* stream);
+int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, void* stream);
+/* greedy pick for note slot n (ptvae.py:408-416,:425): argmax pitch (first max) and duration bits -> tok row,
+ * lens[r] = first n with EOS (15 if none; lens must start at 0). */
+int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok, long ldtok,
+                   int* lens, void* stream);
+/* duration feedback token (ptvae.py:322-326): 5-wide, 1 at index == argmax bit */
+int pd_dur_token(const float* logit, long ldl, long R, float* tok, void* stream);
+/* fused duration decoder (ptvae.py:345-367): 5-step GRU(5->64) + Linear(64->2) with greedy bit feedback.
+ * logits (Q,5,2); S (Q,6,72) state buffer for the backward (NULL at inference); GX (Q,6,264) gradient buffer
+ * such that GX^T . S holds all parameter gradients (layout: csrc/dur_decoder.cu). */
+int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih, const float* w_hh,
+                      const float* b_hh, const float* sos, const float* w_out, const float* b_out, float* logits,
+                      float* S, void* stream);
+int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+                      const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                      const float* b_out, float* GX, float* dh0, long lddh0, void* stream);
+
+/* ---- chord decoder (ptvae.py:73-78; model.py:70-74).  Feedback token = [batch-UNION root one-hot |
+ * per-sample chroma argmax | batch-UNION bass one-hot] (the reference's indexing semantics). */
+int pd_chord_feedback(const float* root, long ldr, const float* chroma, long ldc, const float* bass, long ldb,
+                      int B, float* flags24, float* tok, long ldt, void* stream);
+int pd_chord_targets(const float* c, int rows, int* root, int* chroma, int* bass, void* stream);
+
+/* ---- texture encoder front end (ptvae.py:95-99,:114): Conv2d(1->C,(4,12),stride(4,1)) + ReLU +
+ * MaxPool(1,4) fused; out (B,C,8,29) channel-major (callers reinterpret as (B,8,29C) like the reference).
+ * bwd accumulates dw (C*48) and dbias (C). */
+int pd_texture_frontend_fwd(const float* pr_mat, const float* w, const float* bias, int B, int C, float* out,
+                            void* stream);
+int pd_texture_frontend_bwd(const float* pr_mat, const float* w, const float* bias, int B, int C,
+                            const float* gout, float* dw, float* dbias, void* stream);
+
+/* ---- losses (ptvae.py:498-511, model.py:70-90, train_utils.py:33-49).
+ * masked mean CE: targets int32, rows with target == ignore skipped; acc2 = {sum, count} kept for bwd. */
+int pd_ce_fwd(const float* logits, long ldl, const int* targets, long R, int C, int ignore, float* acc2,
+              float* loss, void* stream);
+int pd_ce_bwd(const float* logits, long ldl, const int* targets, long R, int C, int ignore, const float* acc2,
+              const float* gout, float* dlogits, long lddl, void* stream);
+int pd_exp_fwd(const float* x, long n, float* y, void* stream);
+int pd_mul_f32(const float* a, const float* b, long n, float* out, void* stream);
+int pd_add_f32(const float* a, const float* b, long n, float* out, void* stream);
+/* z = mu + sd*eps (eps NULL: z = mu), z row stride ldz;  bwd: dmu = dz, dsd = dz*eps */
+int pd_reparam_fwd(const float* mu, const float* sd, const float* eps, int B, int D, float* z, long ldz,
+                   void* stream);
+int pd_reparam_bwd(const float* dz, long lddz, const float* eps, int B, int D, float* dmu, float* dsd,
+                   void* stream);
+/* mean over n elements of KL(N(mu,sd) || N(0,1)) */
+int pd_kl_fwd(const float* mu, const float* sd, long n, float* out, void* stream);
+int pd_kl_bwd(const float* mu, const float* sd, long n, const float* gout, float* dmu, float* dsd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYDIS_B200_H */
