@@ -14,6 +14,7 @@ _P, _L, _I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
 SIGNATURES = {
     "pd_gemm_f32": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _P],
     "pd_gemm_tf32": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _P],
+    "pd_gemm_tf32_cfg": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P],
     "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 4;
+constexpr int BM = 128, BK = 32;
 constexpr int NUM_THREADS = 192;
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -88,8 +88,8 @@ struct TcArgs {
     int atomic;         // accumulate into C (C += result, or split-K partial sums): red.global.add epilogue
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
@@ -171,17 +171,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_commit(tmem_full);                // accumulator complete
         }
     } else {
-        // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32); thread owns one output row
+        // epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32).  tcgen05.ld hands each thread 32
+        // consecutive columns of ONE row; writing those straight out touches 32 different rows per store
+        // instruction.  Instead each warp transposes its 32x32 chunk through shared memory (the pipeline's
+        // stage-0 buffer is free once the accumulator is complete) and stores full 128-byte row segments.
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
         if (nkb > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
         }
+        constexpr int STG = 36;                                   // padded row stride (floats)
+        float* stg = reinterpret_cast<float*>(sA) + q * (32 * STG);
         const bool add_bias = g.bias != nullptr && blockIdx.z == 0;
+        const bool ldc_vec = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0);
+        const bool bias_vec = (((uintptr_t)g.bias) & 15) == 0;
+        const int sub_r = lane >> 3, colq = (lane & 7) * 4;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-            if (n0 + c * 32 >= g.N) break;
+            const int nb = n0 + c * 32;
+            if (nb >= g.N) break;
             uint32_t r[32];
             if (nkb > 0) {
                 tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
@@ -189,39 +197,48 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
             }
-            if (m < g.M) {
-                float* crow = g.C + (long)m * g.ldc + n0 + c * 32;
-                const int nvalid = min(32, g.N - (n0 + c * 32));
-                const bool vec = (nvalid == 32) && ((((uintptr_t)crow) & 15) == 0);
-                if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                               __uint_as_float(r[j + 3]));
-                        if (add_bias) {
-                            float4 bb = *reinterpret_cast<const float4*>(g.bias + n0 + c * 32 + j);
-                            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                        }
-                        if (g.atomic) {
-                            // accumulate / split-K: fire-and-forget vector reduction at L2 (no read-modify-write
-                            // round trip through the SM; a load+add+store epilogue here ran at ~30 GB/s)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + j), "f"(v.x),
-                                         "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                        } else {
-                            *reinterpret_cast<float4*>(crow + j) = v;
-                        }
-                    }
-                } else {
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(stg + lane * STG + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            __syncwarp();
+            const int n = nb + colq;
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_bias) {
+                if (n + 3 < g.N && bias_vec) bb = *reinterpret_cast<const float4*>(g.bias + n);
+                else {
+                    if (n < g.N) bb.x = g.bias[n];
+                    if (n + 1 < g.N) bb.y = g.bias[n + 1];
+                    if (n + 2 < g.N) bb.z = g.bias[n + 2];
+                }
+            }
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j < nvalid) {
-                            float v = __uint_as_float(r[j]) + (add_bias ? g.bias[n0 + c * 32 + j] : 0.0f);
-                            if (g.atomic) atomicAdd(crow + j, v);
-                            else crow[j] = v;
-                        }
+            for (int i = 0; i < 8; ++i) {
+                const int row = i * 4 + sub_r;
+                const int m = m0 + q * 32 + row;
+                float4 v = *reinterpret_cast<const float4*>(stg + row * STG + colq);
+                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                if (m < g.M && n < g.N) {
+                    float* dst = g.C + (long)m * g.ldc + n;
+                    if (ldc_vec && n + 3 < g.N) {
+                        if (g.atomic)
+                            // accumulate / split-K: fire-and-forget vector reduction at L2 (a load+add+store
+                            // epilogue here ran at ~30 GB/s)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                                         "f"(v.z), "f"(v.w) : "memory");
+                        else
+                            *reinterpret_cast<float4*>(dst) = v;
+                    } else {
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (n + j < g.N) {
+                                if (g.atomic) atomicAdd(dst + j, e[j]);
+                                else dst[j] = e[j];
+                            }
                     }
                 }
             }
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -269,45 +286,63 @@ int make_map(CUtensorMap* map, const float* base, long inner, long outer, long l
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
     constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, MINB, A_MN, B_MN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    gemm_tf32_kernel<BN, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
+    gemm_tf32_kernel<BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
     return pd_launch_status();
 }
 
-template <int BN>
-int launch_bn(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, g, grid, st);
-    if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, g, grid, st);
-    if (a_mn && b_mn) return launch<BN, true, true>(ta, tb, g, grid, st);
-    return launch<BN, true, false>(ta, tb, g, grid, st);
+template <int BN, int STAGES, int MINB>
+int launch_l(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch<BN, STAGES, MINB, false, false>(ta, tb, g, grid, st);
+    if (!a_mn && b_mn) return launch<BN, STAGES, MINB, false, true>(ta, tb, g, grid, st);
+    if (a_mn && b_mn) return launch<BN, STAGES, MINB, true, true>(ta, tb, g, grid, st);
+    return launch<BN, STAGES, MINB, true, false>(ta, tb, g, grid, st);
 }
 
-}  // namespace
+// config id = bn * 100 + stages * 10 + ctas_per_sm
+int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid,
+               cudaStream_t st) {
+    switch (cfg) {
+        case 25641: return launch_l<256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 25622: return launch_l<256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12841: return launch_l<128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12861: return launch_l<128, 6, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12832: return launch_l<128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12823: return launch_l<128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6441: return launch_l<64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6442: return launch_l<64, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6433: return launch_l<64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        default: return PD_BAD_ARG;
+    }
+}
 
-// Same contract as pd_gemm_f32 (strides in floats) with TF32 multiplies on the tensor cores.
-// Requirements: operand base pointers 16-byte aligned, row strides multiples of 4 floats.  Returns
-// PD_BAD_ARG (-22) when a requirement does not hold so the caller can route to pd_gemm_f32.
-PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
-                        const float* bias, int M, int N, int K, int accumulate, void* stream) {
+int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                   const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (sak != 1 && sam != 1) || (sbk != 1 && sbn != 1)) return PD_BAD_ARG;
     const bool a_mn = (sak != 1), b_mn = (sbk != 1);
     const long lda = a_mn ? sak : sam, ldb = b_mn ? sbk : sbn;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3) || lda < 4 || ldb < 4) return PD_BAD_ARG;
-    cudaStream_t st = (cudaStream_t)stream;
     const int tiles_m = (M + BM - 1) / BM;
-    int bn = 256;
-    if (N <= 64) bn = 64;
-    else if (N <= 128 || (long)tiles_m * ((N + 255) / 256) < PD_NUM_SMS) bn = 128;
-    if (bn == 128 && N > 64 && (long)tiles_m * ((N + 127) / 128) < PD_NUM_SMS / 2 && N % 128 != 0 && N % 64 == 0) bn = 64;
+    if (cfg == 0) {
+        // measured on B200 (tools/gemm_tune.py): wide tiles with 2 CTAs/SM when the grid fills the chip,
+        // 128-wide tiles for split-K weight gradients, 64-wide tiles for the small per-step recurrent GEMMs
+        const int kb0 = (K + BK - 1) / BK;
+        if (N <= 64) cfg = 6441;
+        else if ((long)tiles_m * ((N + 255) / 256) >= 2L * PD_NUM_SMS) cfg = 25622;
+        else if (kb0 >= 1024 || (long)tiles_m * ((N + 127) / 128) >= PD_NUM_SMS) cfg = 12823;
+        else cfg = 6441;
+    }
+    const int bn = cfg / 100;
     const int tiles_n = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tiles_n;
     const int kb = (K + BK - 1) / BK;
@@ -329,7 +364,21 @@ PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long
     if (rc) return rc;
     if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
     dim3 grid(tiles_m, tiles_n, split);
-    if (bn == 256) return launch_bn<256>(a_mn, b_mn, ta, tb, g, grid, st);
-    if (bn == 128) return launch_bn<128>(a_mn, b_mn, ta, tb, g, grid, st);
-    return launch_bn<64>(a_mn, b_mn, ta, tb, g, grid, st);
+    return launch_cfg(cfg, a_mn, b_mn, ta, tb, g, grid, st);
+}
+
+}  // namespace
+
+// Same contract as pd_gemm_f32 (strides in floats) with TF32 multiplies on the tensor cores.
+// Requirements: operand base pointers 16-byte aligned, row strides multiples of 4 floats.  Returns
+// PD_BAD_ARG (-22) when a requirement does not hold so the caller can route to pd_gemm_f32.
+PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                        const float* bias, int M, int N, int K, int accumulate, void* stream) {
+    return gemm_tf32_impl(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream);
+}
+
+// Tuning variant: cfg = BN*100 + stages*10 + CTAs/SM (one of the instantiated configurations), 0 = heuristic.
+PD_API int pd_gemm_tf32_cfg(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                            const float* bias, int M, int N, int K, int accumulate, int cfg, void* stream) {
+    return gemm_tf32_impl(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, cfg, (cudaStream_t)stream);
 }

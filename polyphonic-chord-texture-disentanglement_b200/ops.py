@@ -26,12 +26,34 @@ def _chk(t, name="tensor"):
 
 
 def _rows(t):
-    """View ``t`` as (rows, cols) with unit inner stride; returns (tensor2d, row_stride)."""
+    """View ``t`` as (rows, cols) with unit inner stride; returns (tensor2d, row_stride).  Tensors whose
+    leading dimensions collapse to one uniform row stride (e.g. a (...,130) view of a 136-padded buffer)
+    are re-strided in place, never copied."""
     if t.dim() != 2:
-        t = t.reshape(-1, t.shape[-1])
+        if t.dim() > 2 and t.stride(-1) == 1 and not t.is_contiguous():
+            sh, st = t.shape, t.stride()
+            if all(st[i] == st[i + 1] * sh[i + 1] for i in range(t.dim() - 2)):
+                rows = 1
+                for d in sh[:-1]:
+                    rows *= d
+                t = t.as_strided((rows, sh[-1]), (st[-2], 1))
+        if t.dim() != 2:
+            t = t.reshape(-1, t.shape[-1])
     if t.stride(1) != 1 and t.shape[1] != 1:
         t = t.contiguous()
     return t, (t.stride(0) if t.shape[0] > 1 else t.shape[1])
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def _empty_rows(rows, cols, dev):
+    """(rows, cols) fp32 buffer whose row stride is a multiple of 4 floats (TMA-addressable as a GEMM
+    operand) -- a view into a padded allocation when cols % 4 != 0."""
+    if cols % 4 == 0:
+        return torch.empty(rows, cols, device=dev, dtype=torch.float32)
+    return torch.empty(rows, _pad4(cols), device=dev, dtype=torch.float32)[:, :cols]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -115,12 +137,19 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
         x2, _ = _rows(_chk(x, "x"))
-        y = torch.empty(x2.shape[0], w.shape[0], device=x.device, dtype=torch.float32)
+        y = _empty_rows(x2.shape[0], w.shape[0], x.device)
         gemm_nt(x2, w, y, b)
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
         ctx.x_shape = x.shape
-        return y.view(*x.shape[:-1], w.shape[0])
+        if y.is_contiguous():
+            return y.view(*x.shape[:-1], w.shape[0])
+        lead = tuple(x.shape[:-1])
+        strides, acc = [], y.stride(0)
+        for d in reversed(lead):
+            strides.append(acc)
+            acc *= d
+        return y.as_strided(lead + (w.shape[0],), tuple(reversed(strides)) + (1,))
 
     @staticmethod
     def backward(ctx, dy):
@@ -214,12 +243,14 @@ def _gates_fwd(gi, gi2, gh, hprev, hout, rzn, hn, lengths, t):
           _ptr(hn), 0 if hn is None else hn.stride(0), _ptr(lengths), t, B, H, _stream())
 
 
-def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None):
-    """Run a GRU over precomputed input projections.  gi (B,T,3H) strided view, gi2 (B,3H) or None.
+def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None, n_steps=None):
+    """Run a GRU over precomputed input projections.  gi (B,T,3H) strided view, gi2 (B,3H) or None;
+    ``n_steps`` (<= T) uses only the first slots of gi (the note GRU consumes 15 of the 16 embedded slots).
 
-    Returns h_all (B,T,H).  ``save`` (dict) receives rzn / hn for the backward pass.
+    Returns h_all (B,n_steps,H).  ``save`` (dict) receives rzn / hn for the backward pass.
     """
     B, T, H3 = gi.shape
+    T = T if n_steps is None else n_steps
     H = H3 // 3
     dev = gi.device
     h_all = torch.empty(B, T, H, device=dev, dtype=torch.float32)
@@ -247,13 +278,14 @@ class _GruSeq(torch.autograd.Function):
     duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
 
     @staticmethod
-    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse):
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None):
         _chk(gi, "gi")
         save = {}
-        h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save)
+        h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
         ctx.reverse = reverse
         ctx.has_gi2 = gi2 is not None
+        ctx.t_full = gi.shape[1]
         return h_all
 
     @staticmethod
@@ -263,7 +295,9 @@ class _GruSeq(torch.autograd.Function):
         dev = dout.device
         if not dout.is_contiguous():
             dout = dout.contiguous()
-        dgi = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
+        dgi = torch.empty(B, ctx.t_full, 3 * H, device=dev, dtype=torch.float32)
+        if ctx.t_full > T:
+            dgi[:, T:].zero_()                     # unused input slots get no gradient
         dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
         dgi2 = torch.zeros(B, 3 * H, device=dev, dtype=torch.float32) if ctx.has_gi2 else None
         # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
@@ -313,7 +347,7 @@ class _GruSeq(torch.autograd.Function):
         dh0 = None
         if h0 is not None and ctx.needs_input_grad[2]:
             dh0 = dz if dm is None else _add(dz, dm)
-        return dgi, dgi2, dh0, dw, db, None, None
+        return dgi, dgi2, dh0, dw, db, None, None, None
 
 
 def _add(a, b):
@@ -322,13 +356,13 @@ def _add(a, b):
     return out
 
 
-def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False):
+def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None):
     """Autograd-aware GRU over (B,T,3H) input projections; falls to the no-grad loop when nothing
     requires grad (inference)."""
     if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
                                     (h0 is not None and h0.requires_grad)):
-        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse)
-    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse)
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps)
+    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -419,11 +453,18 @@ class _MaskedCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         l2, targets, acc = ctx.saved_tensors
-        d = torch.empty(l2.shape, device=l2.device, dtype=torch.float32)
+        d = _empty_rows(l2.shape[0], l2.shape[1], l2.device)
         g = g.contiguous()
         _call("pd_ce_bwd", _ptr(l2), l2.stride(0), _ptr(targets), l2.shape[0], l2.shape[1], ctx.ignore,
               _ptr(acc), _ptr(g), _ptr(d), d.stride(0), _stream())
-        return d.view(ctx.shape), None, None
+        if d.is_contiguous():
+            return d.view(ctx.shape), None, None
+        lead = tuple(ctx.shape[:-1])
+        strides, a = [], d.stride(0)
+        for k in reversed(lead):
+            strides.append(a)
+            a *= k
+        return d.as_strided(lead + (l2.shape[1],), tuple(reversed(strides)) + (1,)), None, None
 
 
 def masked_ce(logits, targets, ignore=-100):

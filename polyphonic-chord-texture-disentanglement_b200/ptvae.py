@@ -253,10 +253,10 @@ class PtvaeDecoder(nn.Module):
         h0 = self.dec_time_to_notes_hid(S)
         gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
         gi_tok = ops.linear(notes, wn_ih[:, self.dec_time_hid_size:], None)               # (R,16,1536)
-        h = ops.gru_sequence(gi_tok[:, :self.max_simu_note - 1], gi_s, h0, wn_hh, bn_hh)  # (R,15,512)
+        h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1)  # (R,15,512)
         pitch = self.pitch_out_linear(h)                                                  # (R,15,130)
         Q = R * (self.max_simu_note - 1)
-        dur = self._decode_durs(h.reshape(Q, -1), pitch.reshape(Q, -1))
+        dur = self._decode_durs(h.reshape(Q, -1), None)
         return pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), \
             dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
 

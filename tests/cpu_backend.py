@@ -54,6 +54,9 @@ class CpuBackend:
         # same contract; the emulation keeps fp32 products (the GPU kernel rounds operands to TF32)
         self.pd_gemm_f32(*a)
 
+    def pd_gemm_tf32_cfg(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, cfg, st):
+        self.pd_gemm_f32(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, st)
+
     def pd_colsum_f32(self, X, ldx, M, N, out, acc, st):
         o = _arr(out, (N,), (1,))
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0
