@@ -9,8 +9,8 @@ per GPU (config "PolyDisVAE training, batch=512 on 1 B200, teacher-forced PianoT
 greedy-decode segments/s reported beside it in the same JSON line (`decode`).  `value` is measured with
 the batch resident in HBM; `e2e` runs the same step through the public model API from pinned HOST
 buffers (H2D of x / c / pr_mat and D2H of the loss inside the timed region).  Under torchrun each rank
-runs the same per-GPU batch (weak scaling) with NCCL gradient all-reduce overlapped with backward
-(torch DDP buckets); timing is CUDA events, max over ranks.
+runs the same per-GPU batch (weak scaling) with bucketed NCCL gradient all-reduce overlapped with
+backward (polydis_b200.ddp, captured inside the step's CUDA graph); timing is CUDA events, max over ranks.
 
 `--impl reference` times the reference's CPU path: the oracle port (oracle/polydis_oracle.py, same op
 granularity as the reference, pinned to it by golden vectors) on all host cores, bounded batches.
@@ -156,18 +156,26 @@ def run_b200(args):
     random.seed(1234 + rank)
     model = DisentangleVAE.init_model(device=dev).to(dev)
     net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=32)
     params = [p for p in model.parameters()]
+    reducer = None
+    if world > 1:
+        from polydis_b200.ddp import BucketedGradAllReduce
+        for p in params:                                   # identical initial weights on every rank
+            dist.broadcast(p.data, 0)
+        reducer = BucketedGradAllReduce(params, bucket_mb=32)
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
     xh, ch, ph = (torch.from_numpy(a).pin_memory() for a in synth_batch(B, 100 + rank))
     x, c, pr = xh.to(dev), ch.to(dev), ph.to(dev)
 
     def step(x, c, pr):
-        opt.zero_grad(set_to_none=True)
+        if reducer is not None:
+            reducer.reset()
+        else:
+            opt.zero_grad(set_to_none=True)
         losses = net('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5))
         losses[0].backward()
+        if reducer is not None:
+            reducer.finish()
         torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
         opt.step()
         return losses[0]
@@ -192,10 +200,10 @@ def run_b200(args):
         return float(ms) / n
 
     graphed = None
-    if world == 1 and not args.eager:
+    if not args.eager:
         from polydis_b200.graphs import GraphedTrainStep
         c0 = _lib.call_count
-        graphed = GraphedTrainStep(model, opt, B).capture(x, c, pr)
+        graphed = GraphedTrainStep(model, opt, B, reducer=reducer, warmup=3 if world == 1 else 11).capture(x, c, pr)
         calls_per_step = (_lib.call_count - c0) // (graphed._warm + 1)
 
         def step(x, c, pr):  # noqa: F811
@@ -218,16 +226,20 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, max(2, args.steps // 2))
     h2d = xh.numel() * 8 + ch.numel() * 4 + ph.numel() * 4
 
-    # greedy decode (encode chord+texture -> means -> PianoTree decode -> int tokens on device)
+    # greedy decode (encode chord+texture -> means -> PianoTree decode -> int tokens on device), replayed
+    # from a CUDA graph; fp32-faithful GEMMs (token parity with the fp32 reference) and TF32 tensor cores
+    from polydis_b200.graphs import GraphedDecode
     Bd = args.decode_batch
     xd_, cd_, pd_ = (torch.from_numpy(a).to(dev) for a in synth_batch(Bd, 500 + rank))
-
-    def dec():
-        with torch.no_grad():
-            dc, dr = model.inference_encode(pd_, cd_)
-            return model.decode_tokens(dc.mean, dr.mean)
-    dec()
-    ms_dec = timed(dec, 2)
+    dec_ms = {}
+    for prec in ("fp32", "tf32"):
+        model.decode_precision = prec
+        gd = GraphedDecode(model, Bd).capture(pd_, cd_)
+        gd(pd_, cd_)
+        dec_ms[prec] = timed(lambda: gd(pd_, cd_), 3)
+        del gd
+    model.decode_precision = "fp32"
+    ms_dec = dec_ms["fp32"]
     model.train()
 
     # dominant kernel timed alone: the note-GRU recurrent GEMM [32B x 512] . [512 x 1536]
@@ -260,7 +272,8 @@ def run_b200(args):
                    "d2h_bytes_per_step": 4},
            "gpu_launches": launches,
            "decode": {"value": world * Bd / (ms_dec * 1e-3), "unit": "segments/s", "batch_per_gpu": Bd,
-                      "ms_per_batch": ms_dec},
+                      "ms_per_batch": ms_dec, "precision": "fp32 (token-parity mode)",
+                      "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
                         "what": "whole step: 5.45 algorithmic GFLOP/sample x batch / step time, vs sustained bf16 peak",
@@ -290,7 +303,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--decode-batch", type=int, default=2048)
+    ap.add_argument("--decode-batch", type=int, default=4096)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--eager", action="store_true", help="issue the training step eagerly (no CUDA graph)")
     args = ap.parse_args()

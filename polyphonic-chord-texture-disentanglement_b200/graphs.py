@@ -12,7 +12,7 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, batch, tfr=(1., 1., 1.), beta=0.1, weights=(1, 0.5), clip=1.0,
-                 warmup=3, grad_hook=None):
+                 warmup=3, reducer=None):
         assert tfr == (1., 1., 1.), "graph capture bakes the teacher-forcing plan; use eager steps for tfr < 1"
         dev = next(model.parameters()).device
         self.model, self.opt = model, optimizer
@@ -21,18 +21,21 @@ class GraphedTrainStep:
         self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
         self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
         self.tfr, self.beta, self.weights, self.clip = tfr, beta, weights, clip
-        self.grad_hook = grad_hook
+        self.reducer = reducer          # ddp.BucketedGradAllReduce: its all-reduces are captured in the graph
         self.losses = None
         self.graph = None
         self._warm = warmup
 
     def _step(self):
-        self.opt.zero_grad(set_to_none=True)
+        if self.reducer is not None:
+            self.reducer.reset()        # grads live in the reducer's flat buckets
+        else:
+            self.opt.zero_grad(set_to_none=True)
         losses = self.model('train', self.x, self.c, self.pr, tfr1=self.tfr[0], tfr2=self.tfr[1],
                             tfr3=self.tfr[2], beta=self.beta, weights=self.weights)
         losses[0].backward()
-        if self.grad_hook is not None:
-            self.grad_hook()
+        if self.reducer is not None:
+            self.reducer.finish()
         if self.clip:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.opt.step()
@@ -62,3 +65,47 @@ class GraphedTrainStep:
         self.pr.copy_(pr_mat, non_blocking=True)
         self.graph.replay()
         return self.losses
+
+
+class GraphedDecode:
+    """CUDA-graph replay of greedy inference: encode chord + texture -> posterior means -> PianoTree greedy
+    decode -> int tokens on device (``model.swap`` / ``inference(sample=False)`` semantics, model.py:133-149).
+    One segment batch = ~5,600 kernel launches captured once; replays take one launch each."""
+
+    def __init__(self, model, batch, warmup=1):
+        dev = next(model.parameters()).device
+        self.model = model
+        self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
+        self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
+        self.tokens, self.graph, self._warm = None, None, warmup
+
+    def _run(self):
+        from . import ops
+        m = self.model
+        m.eval()
+        with torch.no_grad(), ops.precision(m.decode_precision):
+            dc, dr = m.chd_encoder(self.c), m.rhy_encoder(self.pr)
+            return m.decoder.greedy_tokens(torch.cat([dc.mean, dr.mean], -1))
+
+    def capture(self, pr_mat, c):
+        self.pr.copy_(pr_mat); self.c.copy_(c)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(self._warm):
+                self._run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.tokens = self._run()
+        return self
+
+    def __call__(self, pr_mat, c):
+        """-> (B,32,15,6) int32 tokens on device (static buffer, overwritten by the next call)."""
+        if self.graph is None:
+            self.capture(pr_mat, c)
+        self.pr.copy_(pr_mat, non_blocking=True)
+        self.c.copy_(c, non_blocking=True)
+        self.graph.replay()
+        return self.tokens

@@ -356,11 +356,90 @@ class PtvaeDecoder(nn.Module):
 
     def greedy_tokens(self, z):
         """Greedy decode returning only the int tokens (B,32,15,6) int32 on device -- the logits the
-        reference copies to the host (ptvae.py:537-544) are never materialised."""
-        plan_note, plan_time = self._draw_plan(0., 0.)
+        reference copies to the host (ptvae.py:537-544) are never materialised.
+
+        Dedicated no-grad schedule of ptvae.py:430-491 at inference: fixed work buffers, states updated
+        in place, pitch + (folded) dur_hid heads as ONE GEMM, fused duration decoder, greedy pick and
+        embedding gather on device: 7 launches per note slot, no host synchronisation, capturable in a
+        CUDA graph (``graphs.GraphedDecode``)."""
+        self._draw_plan(0., 0.)                        # consume python's random like the reference
         with torch.no_grad():
-            self._decode_stepwise(z, True, None, None, plan_note, plan_time, keep_logits=False)
-        return self._last_tokens.permute(2, 0, 1, 3).contiguous()
+            return self._greedy_fast(z).permute(2, 0, 1, 3).contiguous()
+
+    def _greedy_fast(self, z):
+        B, dev = z.size(0), z.device
+        f32 = dict(device=dev, dtype=torch.float32)
+        T, NS, E = self.num_step, self.max_simu_note, self.note_emb_size
+        Ht, Hn = self.dec_time_hid_size, self.dec_notes_hid_size
+        emb_w, emb_b = self.note_embedding.weight, self.note_embedding.bias
+        emb_wt = ops.transpose(emb_w)
+        # constants of this decode
+        wt_ih, wt_hh, bt_ih, bt_hh = self.dec_time_gru.dir()
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        h_time = self.z2dec_hid_linear(z).contiguous()                                  # (B,1024), updated in place
+        gi_z = ops.linear(self.z2dec_in_linear(z), wt_ih[:, 2 * self.dec_emb_hid_size:], bt_ih)
+        w_tok_t = wt_ih[:, :2 * self.dec_emb_hid_size]
+        w_sum_n, w_tok_n = wn_ih[:, :Ht], wn_ih[:, Ht:]
+        w_eff, b_eff = self._dur_hid_folded()
+        w_heads = torch.cat([self.pitch_out_linear.weight, w_eff], 0).contiguous()      # (194,512)
+        b_heads = torch.cat([self.pitch_out_linear.bias, b_eff], 0).contiguous()
+        NH = w_heads.shape[0]
+        d_ih, d_hh, db_ih, db_hh = self.dec_dur_gru.dir()
+        dur_par = [t.contiguous() for t in (d_ih, db_ih, d_hh, db_hh, self.dur_sos_token,
+                                            self.dur_out_linear.weight, self.dur_out_linear.bias)]
+        sos_tok = torch.full((B, 6), 2, device=dev, dtype=torch.int32)     # device-side fills: graph-capturable
+        sos_tok[:, 0] = self.pitch_sos
+        eg = self.dec_notes_emb_gru
+        # work buffers
+        tokens = torch.empty(T, NS - 1, B, 6, device=dev, dtype=torch.int32)
+        lens = torch.empty(B, device=dev, dtype=torch.int32)
+        pred = torch.empty(B, NS, E, **f32)
+        tok_time = self.dec_init_input.expand(B, -1).contiguous()                       # (B,256)
+        gi_t, gh_t = torch.empty(B, 3 * Ht, **f32), torch.empty(B, 3 * Ht, **f32)
+        h_n, gi_s = torch.empty(B, Hn, **f32), torch.empty(B, 3 * Hn, **f32)
+        gi_n, gh_n = torch.empty(B, 3 * Hn, **f32), torch.empty(B, 3 * Hn, **f32)
+        heads = torch.empty(B, (NH + 3) // 4 * 4, **f32)
+        dlog = torch.empty(B, 5, 2, **f32)
+        He = self.dec_emb_hid_size
+        gi_e = [torch.empty(B, NS, 3 * He, **f32) for _ in range(2)]
+        gh_e, h_e = torch.empty(B, 3 * He, **f32), torch.empty(B, He, **f32)
+        st = ops._stream
+        for t in range(T):
+            ops.gemm_nt(tok_time, w_tok_t, gi_t)
+            ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh)
+            ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
+            ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias)
+            ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih)
+            ops._call("pd_note_embed_fwd", ops._ptr(sos_tok), B, ops._ptr(emb_wt), ops._ptr(emb_b), ops._ptr(pred),
+                      pred.stride(0), st())
+            lens.zero_()
+            for n in range(1, NS):
+                ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
+                ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh)
+                ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
+                ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads)
+                ops._call("pd_dur_decode_fwd", ops._ptr(heads[:, self.pitch_range:]), heads.stride(0), B,
+                          *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, st())
+                ops.greedy_pick(heads[:, :self.pitch_range], dlog, n, tokens[t, n - 1], lens)
+                ops._call("pd_note_embed_fwd", ops._ptr(tokens[t, n - 1]), B, ops._ptr(emb_wt), ops._ptr(emb_b),
+                          ops._ptr(pred[:, n]), pred.stride(0), st())
+            if t == T - 1:
+                break
+            # next time-step token: bi-GRU summary of the predicted notes with the predicted lengths
+            flat = pred.view(B * NS, E)
+            for d, rev in enumerate((False, True)):
+                w_ih, w_hh, b_ih, b_hh = eg.dir(rev)
+                ops.gemm_nt(flat, w_ih, gi_e[d].view(B * NS, 3 * He), b_ih)
+                out = tok_time[:, d * He:(d + 1) * He]
+                first = True
+                for k in (range(NS - 1, -1, -1) if rev else range(NS)):
+                    if first:
+                        ops.gemm_nt(h_e[:, :0], w_hh[:, :0], gh_e, b_hh)          # h = 0: gh = b_hh
+                    else:
+                        ops.gemm_nt(out, w_hh, gh_e, b_hh)
+                    ops._gates_fwd(gi_e[d][:, k], None, gh_e, None if first else out, out, None, None, lens, k)
+                    first = False
+        return tokens
 
     # -- losses / output formatting ---------------------------------------------------------------
     def recon_loss(self, x, recon_pitch, recon_dur, weights=(1, 0.5), weighted_dur=False):
