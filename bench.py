@@ -147,6 +147,11 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    verbose = bool(os.environ.get("PD_BENCH_VERBOSE"))
+
+    def mark(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -199,6 +204,7 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
+    mark("model + reducer ready")
     graphed = None
     if not args.eager:
         from polydis_b200.graphs import GraphedTrainStep
@@ -208,8 +214,10 @@ def run_b200(args):
 
         def step(x, c, pr):  # noqa: F811
             return graphed(x, c, pr)[0]
+    mark("graph captured" if graphed is not None else "eager mode")
     for _ in range(args.warmup):
         step(x, c, pr)
+    mark("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -218,6 +226,7 @@ def run_b200(args):
     launches = (_lib.call_count - calls0) if graphed is None else calls_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
 
+    mark(f"timed region done: {ms_step:.2f} ms/step")
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
     def e2e_step():
         xd, cd, pd = xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True), ph.to(dev, non_blocking=True)
@@ -226,6 +235,7 @@ def run_b200(args):
     ms_e2e = timed(e2e_step, max(2, args.steps // 2))
     h2d = xh.numel() * 8 + ch.numel() * 4 + ph.numel() * 4
 
+    mark("e2e done")
     # greedy decode (encode chord+texture -> means -> PianoTree decode -> int tokens on device), replayed
     # from a CUDA graph; fp32-faithful GEMMs (token parity with the fp32 reference) and TF32 tensor cores
     from polydis_b200.graphs import GraphedDecode
@@ -242,6 +252,7 @@ def run_b200(args):
     ms_dec = dec_ms["fp32"]
     model.train()
 
+    mark("decode done")
     # dominant kernel timed alone: the note-GRU recurrent GEMM [32B x 512] . [512 x 1536]
     from polydis_b200 import ops
     R = 32 * B
@@ -253,9 +264,19 @@ def run_b200(args):
     ms_gemm = timed(lambda: ops.gemm_nt(hA, wB, oC), 20)
     gemm_tflops = 2.0 * R * 512 * 1536 / (ms_gemm * 1e-3) / 1e12
 
-    if rank != 0:
+    def leave():
+        # a process group whose collectives were captured in CUDA graphs can block in
+        # destroy_process_group(); all results are out, so synchronise, rendezvous and exit hard
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        leave()
         return
     peak_tf, peak_hbm, peak_src = _peaks()
     sps = world * B / (ms_step * 1e-3)
@@ -292,8 +313,7 @@ def run_b200(args):
             out["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"failed: {e!r}"}
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 def main():
