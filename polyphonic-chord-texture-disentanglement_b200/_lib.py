@@ -24,8 +24,8 @@ SIGNATURES = {
     "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
     "pd_greedy_pick": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P],
     "pd_dur_token": [_P, _L, _L, _P, _P],
-    "pd_dur_decode_fwd": [_P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
-    "pd_dur_decode_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P],
+    "pd_dur_decode_fwd": [_P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "pd_dur_decode_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],
     "pd_transpose_f32": [_P, _I, _I, _P, _P],
     "pd_chord_feedback": [_P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P],
     "pd_chord_targets": [_P, _I, _P, _P, _P, _P],

@@ -578,8 +578,9 @@ class _DurDecode(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         S = torch.empty(Q, 6, 72, device=dev, dtype=torch.float32) if need else None
         params = [t.contiguous() for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)]
+        ctx.tf32 = int(PRECISION == "tf32")
         _call("pd_dur_decode_fwd", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
-              _stream())
+              ctx.tf32, _stream())
         ctx.save_for_backward(S, *params)
         ctx.h_shape = h0.shape
         return logits
@@ -594,7 +595,7 @@ class _DurDecode(torch.autograd.Function):
         dh0 = torch.empty(Q, 64, device=dev, dtype=torch.float32)
         _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
                                                                                  b_out)],
-              _ptr(GX), _ptr(dh0), dh0.stride(0), _stream())
+              _ptr(GX), _ptr(dh0), dh0.stride(0), ctx.tf32, _stream())
         G = torch.empty(264, 72, device=dev, dtype=torch.float32)
         gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
         gi_rows = torch.cat([G[0:128], G[192:256]], 0)            # [dr | dz | dn] x S columns

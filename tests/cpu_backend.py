@@ -175,7 +175,7 @@ class CpuBackend:
         b = _arr(b_ih, (192,), (1,))
         return np.stack([W @ _arr(sos, (5,), (1,)) + b, W[:, 0] + b, W[:, 1] + b])
 
-    def pd_dur_decode_fwd(self, h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, st):
+    def pd_dur_decode_fwd(self, h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, tf32, st):
         h = _arr(h0, (Q, 64), (ldh0, 1)).copy()
         gi_t = self._dur_tables(w_ih, b_ih, sos)
         Whh, bhh = _arr(w_hh, (192, 64), (64, 1)), _arr(b_hh, (192,), (1,))
@@ -207,7 +207,7 @@ class CpuBackend:
             Sb[:, 5, :64] = h
             Sb[:, 5, 69] = 1
 
-    def pd_dur_decode_bwd(self, S, dlog, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, st):
+    def pd_dur_decode_bwd(self, S, dlog, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, tf32, st):
         Sb = _arr(S, (Q, 6, 72), (432, 72, 1))
         dL = _arr(dlog, (Q, 5, 2), (10, 2, 1))
         gi_t = self._dur_tables(w_ih, b_ih, sos)

@@ -284,29 +284,31 @@ def test_posterior_kernels():
         assert torch.allclose(g, c, rtol=1e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("Q", [1, 33, 5000])
-def test_dur_decoder_fused(Q):
-    """Weight-resident fused duration GRU (fwd + bwd) vs the numpy restatement."""
+@pytest.mark.parametrize("Q,tf32", [(1, 0), (33, 0), (5000, 0), (33, 1), (5000, 1)])
+def test_dur_decoder_fused(Q, tf32):
+    """Weight-resident fused duration GRU (fwd + bwd) vs the numpy restatement; tf32=1 runs the recurrent
+    matvecs on the tensor cores (operands rounded to TF32, ~1e-3 relative)."""
     _dev()
+    tol = 3e-3 if tf32 else 2e-5
     par = lambda: [torch.randn(192, 5) * 0.3, torch.randn(192) * 0.1, torch.randn(192, 64) * 0.2, torch.randn(192) * 0.1,
                    torch.rand(5), torch.randn(2, 64) * 0.3, torch.randn(2) * 0.1]
 
     def mk():
         lg, S = torch.zeros(Q, 5, 2), torch.zeros(Q, 6, 72)
-        return [torch.randn(Q, 2, 64), 128, Q] + par() + [lg, S, None], [lg, S]
+        return [torch.randn(Q, 2, 64), 128, Q] + par() + [lg, S, tf32, None], [lg, S]
     (gl, cl), (gs, cs) = _both("pd_dur_decode_fwd", mk)
-    assert torch.allclose(gl, cl, atol=2e-5), float((gl - cl).abs().max())
     same_tok = (gs[:, :, 64:69] == cs[:, :, 64:69]).all(-1).all(-1)
-    assert same_tok.float().mean() > 0.995                      # a near-tied bit may flip by rounding
-    assert torch.allclose(gs[same_tok], cs[same_tok], atol=2e-5)
+    assert same_tok.float().mean() > (0.97 if tf32 else 0.995)   # a near-tied bit may flip by rounding
+    assert torch.allclose(gl[same_tok], cl[same_tok], atol=tol), float((gl - cl)[same_tok].abs().max())
+    assert torch.allclose(gs[same_tok], cs[same_tok], atol=tol)
 
     # backward on a state buffer produced by the emulation (so both sides see identical tokens)
     S = cs.clone()
 
     def mkb():
         GX, dh0 = torch.zeros(Q, 6, 264), torch.zeros(Q, 2, 64)
-        return [S, torch.randn(Q, 5, 2), Q] + par() + [GX, dh0, 128, None], [GX, dh0]
+        return [S, torch.randn(Q, 5, 2), Q] + par() + [GX, dh0, 128, tf32, None], [GX, dh0]
     for g, c in _both("pd_dur_decode_bwd", mkb):
         if g.dim() == 3 and g.shape[-1] == 64:
             g, c = g[:, 0], c[:, 0]
-        assert torch.allclose(g, c, atol=3e-5, rtol=1e-4), float((g - c).abs().max())
+        assert torch.allclose(g, c, atol=(5e-3 if tf32 else 3e-5), rtol=1e-4), float((g - c).abs().max())
