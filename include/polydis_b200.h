@@ -60,6 +60,11 @@ int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, c
  * layout), lengths (n_steps) = 16 - #PAD, pitch targets (n_steps,15), duration targets (n_steps,15,5). */
 int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, int* pitch_tgt, int* dur_tgt,
                     void* stream);
+/* data formats either side of the path: pr_mat (n_steps,128) -> grid x (n_steps,16,6) int64
+ * (converter.py:116-147 as called in dataset.py:98-104; *overflow set to 1 if a step holds > 14 onsets), and
+ * decoded tokens (n_steps,15,6) int32 -> pr_mat (n_steps,128) (ptvae.py:558-575). */
+int pd_prmat_to_grid(const float* pr_mat, long n_steps, long long* x, int* overflow, void* stream);
+int pd_grid_to_prmat(const int* tok, long n_steps, float* pr_mat, void* stream);
 /* note_embedding(multi-hot) as a gather: out[r] = bias + WT[pitch] (pitch < 130) + sum_k dur_k WT[130+k];
  * tok int32 (R,6); WT = weight^T (135,128).   bwd accumulates dWT (135,128) and dbias (128). */
 int pd_note_embed_fwd(const int* tok, long R, const float* WT, const float* bias, float* out, long ldo,

@@ -20,6 +20,8 @@ SIGNATURES = {
     "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,
                          _I, _I, _P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
+    "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
+    "pd_grid_to_prmat": [_P, _L, _P, _P],
     "pd_note_embed_fwd": [_P, _L, _P, _P, _P, _L, _P],
     "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
     "pd_greedy_pick": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P],

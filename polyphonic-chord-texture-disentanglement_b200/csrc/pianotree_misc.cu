@@ -185,7 +185,82 @@ __global__ void chord_targets_kernel(const float* __restrict__ c, int rows, int*
     for (int i = 0; i < 12; ++i) chroma[r * 12 + i] = (int)p[12 + i];
 }
 
+// ---- data formats either side of the path ---------------------------------
+// pr_mat (n_steps,128) durations-at-onset -> PianoTree grid x (n_steps,16,6) int64: the reference's
+// converter.target_to_3dtarget as called in dataset.py:98-104.  One warp per time step: each lane owns 4
+// pitches, a ballot + popc prefix gives every onset its slot (pitches ascending).  Steps with more than 14
+// onsets do not fit the grid (the reference indexes out of bounds); they raise *overflow and are clipped.
+__global__ void __launch_bounds__(256) prmat_to_grid_kernel(const float* __restrict__ pr, long n_steps,
+                                                            long long* __restrict__ x, int* overflow) {
+    long s = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= n_steps) return;
+    const int lane = threadIdx.x & 31;
+    float4 v = *reinterpret_cast<const float4*>(pr + s * 128 + lane * 4);
+    const float d[4] = {v.x, v.y, v.z, v.w};
+    long long* xs = x + s * NOTE_SLOTS * TOK_W;
+    for (int i = lane; i < NOTE_SLOTS * TOK_W; i += 32) xs[i] = (i % TOK_W == 0) ? (i == 0 ? 128 : P_PAD) : 2;
+    __syncwarp();
+    int mine = (d[0] != 0.f) + (d[1] != 0.f) + (d[2] != 0.f) + (d[3] != 0.f);
+    int pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    int slot = 1 + pre - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (d[k] != 0.f) {
+            if (slot <= NOTE_SLOTS - 2) {
+                int dur = (int)d[k] - 1;
+                xs[slot * TOK_W] = lane * 4 + k;
+#pragma unroll
+                for (int b = 0; b < 5; ++b) xs[slot * TOK_W + 1 + b] = (dur >> (4 - b)) & 1;
+            }
+            ++slot;
+        }
+    }
+    if (lane == 0) {
+        if (total > NOTE_SLOTS - 2) atomicExch(overflow, 1);
+        xs[(min(total, NOTE_SLOTS - 2) + 1) * TOK_W] = P_EOS;
+    }
+}
+
+// decoded tokens (n_steps,15,6) int32 [pitch, 5 duration bits] -> pr_mat (n_steps,128): the loop of
+// ptvae.py:558-575 (first 10 notes of a step, stop at EOS, duration = bits+1 clipped at the segment end).
+// step index inside its 32-step segment = s % 32.
+__global__ void grid_to_prmat_kernel(const int* __restrict__ tok, long n_steps, float* __restrict__ pr) {
+    long s = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_steps) return;
+    float* row = pr + s * 128;
+    for (int i = 0; i < 128; ++i) row[i] = 0.0f;
+    const int t = (int)(s % 32);
+    const int* ts = tok + s * 15 * TOK_W;
+    for (int n = 0; n < 10; ++n) {
+        int p = ts[n * TOK_W];
+        if (p == P_EOS) break;
+        int dur = 0;
+        for (int b = 0; b < 5; ++b) dur = dur * 2 + ts[n * TOK_W + 1 + b];
+        dur += 1;
+        if (p >= 0 && p < 128) row[p] = (float)min(dur, 32 - t);
+    }
+}
+
 }  // namespace
+
+PD_API int pd_prmat_to_grid(const float* pr_mat, long n_steps, long long* x, int* overflow, void* stream) {
+    if (n_steps <= 0) return 0;
+    if (((uintptr_t)pr_mat & 15)) return PD_BAD_ARG;
+    prmat_to_grid_kernel<<<pd_blocks(n_steps * 32, 256), 256, 0, (cudaStream_t)stream>>>(pr_mat, n_steps, x, overflow);
+    return pd_launch_status();
+}
+
+PD_API int pd_grid_to_prmat(const int* tok, long n_steps, float* pr_mat, void* stream) {
+    if (n_steps <= 0) return 0;
+    grid_to_prmat_kernel<<<pd_blocks(n_steps, 128), 128, 0, (cudaStream_t)stream>>>(tok, n_steps, pr_mat);
+    return pd_launch_status();
+}
 
 PD_API int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, int* pitch_tgt,
                            int* dur_tgt, void* stream) {

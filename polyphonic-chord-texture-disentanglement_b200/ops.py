@@ -380,6 +380,28 @@ def grid_prepare(x):
     return tok, lengths, pt, dt
 
 
+def pr_mat_to_grid(pr_mat):
+    """Device-side batch construction: pr_mat (B,32,128) fp32 -> PianoTree grid x
+    (B,32,16,6) int64, as converter.target_to_3dtarget does per item on the host (dataset.py:98-104).
+    Returns (x, overflow) where overflow is a device int32 flag set if any step held more than 14 onsets."""
+    pr = _chk(pr_mat, "pr_mat").contiguous()
+    B = pr.shape[0]
+    x = torch.empty(B, 32, 16, 6, device=pr.device, dtype=torch.int64)
+    overflow = torch.zeros(1, device=pr.device, dtype=torch.int32)
+    _call("pd_prmat_to_grid", _ptr(pr), B * 32, _ptr(x), _ptr(overflow), _stream())
+    return x, overflow
+
+
+def tokens_to_pr_mat(tokens):
+    """Decoded tokens (B,32,15,6) int32 -> pr_mat (B,32,128) fp32 on device (ptvae.py:558-575 without the
+    host loop and without moving the tokens off the GPU)."""
+    tok = _chk(tokens, "tokens").to(torch.int32).contiguous()
+    B = tok.shape[0]
+    pr = torch.empty(B, 32, 128, device=tok.device, dtype=torch.float32)
+    _call("pd_grid_to_prmat", _ptr(tok), B * 32, _ptr(pr), _stream())
+    return pr
+
+
 class _NoteEmbed(torch.autograd.Function):
     """note_embedding(multi-hot) as a 6-row gather-add (ptvae.py:299-313,:333); tok int32 (R,6)."""
 

@@ -118,6 +118,42 @@ class TextureEncoder(nn.Module):
         return _posterior(_bigru_final(self.gru, y), self.linear_mu, self.linear_var)
 
 
+class PtvaeEncoder(nn.Module):
+    """PianoTree encoder (the alternative texture encoder train.py:32 instantiates; ptvae.py:125-215):
+    note embedding -> packed bi-GRU(128->256) over each step's notes -> bi-GRU(512->512) over the 32 steps ->
+    Normal(mu, exp(std)).  Same kernel family as the decoder's note summariser."""
+
+    def __init__(self, device=None, max_simu_note=16, max_pitch=127, min_pitch=0, pitch_sos=128, pitch_eos=129,
+                 pitch_pad=130, dur_pad=2, dur_width=5, num_step=32, note_emb_size=128, enc_notes_hid_size=256,
+                 enc_time_hid_size=512, z_size=512):
+        super().__init__()
+        if (max_simu_note, max_pitch, min_pitch, pitch_pad, dur_width, num_step, note_emb_size) != \
+                (16, 127, 0, 130, 5, 32, 128):
+            raise NotImplementedError("libpolydis_b200 kernels are specialised to the PolyDis grid")
+        self.max_simu_note, self.num_step, self.note_emb_size = max_simu_note, num_step, note_emb_size
+        self.pitch_pad, self.pitch_range, self.dur_width = pitch_pad, max_pitch - min_pitch + 3, dur_width
+        self.note_size = self.pitch_range + dur_width
+        self.device = device if device is not None else 'cuda'
+        self.z_size, self.enc_notes_hid_size, self.enc_time_hid_size = z_size, enc_notes_hid_size, enc_time_hid_size
+        self.note_embedding = LinearParams(self.note_size, note_emb_size)
+        self.enc_notes_gru = GRUParams(note_emb_size, enc_notes_hid_size, bidirectional=True)
+        self.enc_time_gru = GRUParams(2 * enc_notes_hid_size, enc_time_hid_size, bidirectional=True)
+        self.linear_mu = LinearParams(2 * enc_time_hid_size, z_size)
+        self.linear_std = LinearParams(2 * enc_time_hid_size, z_size)
+
+    def forward(self, x, return_iterators=False):
+        B = x.size(0)
+        tok, lengths, _, _ = ops.grid_prepare(x)
+        emb = ops.note_embed(tok, self.note_embedding.weight, self.note_embedding.bias)
+        notes = _bigru_final(self.enc_notes_gru, emb.view(B * self.num_step, self.max_simu_note, -1), lengths)
+        h = _bigru_final(self.enc_time_gru, notes.view(B, self.num_step, -1))
+        dist = _posterior(h, self.linear_mu, self.linear_std)
+        embedded = emb.view(B, self.num_step, self.max_simu_note, self.note_emb_size)
+        if return_iterators:
+            return dist.mean, dist.scale, embedded
+        return dist, embedded, lengths.view(B, self.num_step).long()
+
+
 class RnnDecoder(nn.Module):
     """Chord decoder: 8 GRU steps with root / chroma / bass heads.  ptvae.py:32-87"""
 

@@ -127,6 +127,35 @@ class CpuBackend:
         if dt is not None:
             _arr(dt, (steps, 15, 5), (75, 5, 1), np.int32)[...] = X[:, 1:, 1:]
 
+    def pd_prmat_to_grid(self, pr, n_steps, x, overflow, st):
+        P = _arr(pr, (n_steps, 128), (128, 1))
+        X = _arr(x, (n_steps, 16, 6), (96, 6, 1), np.int64)
+        X[...] = 2
+        X[:, :, 0] = 130
+        X[:, 0, 0] = 128
+        for s in range(n_steps):
+            ps = np.nonzero(P[s])[0]
+            if len(ps) > 14:
+                _arr(overflow, (1,), (1,), np.int32)[0] = 1
+                ps = ps[:14]
+            for i, p in enumerate(ps):
+                d = int(P[s, p]) - 1
+                X[s, 1 + i] = [p] + [(d >> (4 - b)) & 1 for b in range(5)]
+            X[s, len(ps) + 1, 0] = 129
+
+    def pd_grid_to_prmat(self, tok, n_steps, pr, st):
+        T = _arr(tok, (n_steps, 15, 6), (90, 6, 1), np.int32)
+        P = _arr(pr, (n_steps, 128), (128, 1))
+        P[...] = 0
+        for s in range(n_steps):
+            for n in range(10):
+                p = T[s, n, 0]
+                if p == 129:
+                    break
+                dur = int("".join(str(int(b)) for b in T[s, n, 1:]), 2) + 1
+                if 0 <= p < 128:
+                    P[s, p] = min(dur, 32 - s % 32)
+
     def pd_note_embed_fwd(self, tok, R, WT, bias, out, ldo, st):
         T = _arr(tok, (R, 6), (6, 1), np.int32)
         W = _arr(WT, (135, 128), (128, 1))

@@ -312,3 +312,23 @@ def test_dur_decoder_fused(Q, tf32):
         if g.dim() == 3 and g.shape[-1] == 64:
             g, c = g[:, 0], c[:, 0]
         assert torch.allclose(g, c, atol=(5e-3 if tf32 else 3e-5), rtol=1e-4), float((g - c).abs().max())
+
+
+def test_prmat_grid_conversions():
+    _dev()
+    from polydis_b200.synth import synth_batch
+    x, c, pr = synth_batch(7, 13)
+    pr[0, 3, 20:37] = 2                                    # one overflowing step
+
+    def mk():
+        out, ovf = torch.zeros(7 * 32, 16, 6, dtype=torch.int64), torch.zeros(1, dtype=torch.int32)
+        return [torch.from_numpy(pr), 7 * 32, out, ovf, None], [out, ovf]
+    for g, c_ in _both("pd_prmat_to_grid", mk):
+        assert torch.equal(g, c_)
+    tok = torch.from_numpy(x[:, :, 1:, :].astype(np.int32)).contiguous()
+
+    def mk2():
+        out = torch.zeros(7 * 32, 128)
+        return [tok, 7 * 32, out, None], [out]
+    (g, c_), = _both("pd_grid_to_prmat", mk2)
+    assert torch.equal(g, c_)
