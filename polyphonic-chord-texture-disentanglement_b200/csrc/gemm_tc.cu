@@ -86,13 +86,17 @@ struct TcArgs {
     int M, N, K;
     int kb_per_split;   // k-blocks (of BK) per blockIdx.z
     int atomic;         // accumulate into C (C += result, or split-K partial sums): red.global.add epilogue
+    int dbg;            // tuning only: 1 = skip the epilogue stores, 2 = skip the MMAs, 3 = both
 };
 
-template <int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
+// MH = number of 128-row halves per CTA tile (1 or 2).  The per-step GEMMs of this path are L2->SM bandwidth
+// bound with fp32 operands (a 128x256 tile needs 96 B/clk against ~43 B/clk/SM of L2 fabric); MH = 2 reuses
+// every B (weight) stage for two accumulators in TMEM and cuts the traffic per MAC by a third.
+template <int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int A_BYTES = MH * BM * BK * 4, B_BYTES = BN * BK * 4;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -102,7 +106,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = blockIdx.x * (MH * BM), n0 = blockIdx.y * BN;
     const int kb_total = (g.K + BK - 1) / BK;
     const int kb_beg = blockIdx.z * g.kb_per_split;
     const int kb_end = min(kb_total, kb_beg + g.kb_per_split);
@@ -116,7 +120,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(MH * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -134,7 +138,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint8_t* b = sB + s * B_BYTES;
                 if (A_MN) {
 #pragma unroll
-                    for (int c = 0; c < BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
+                    for (int c = 0; c < MH * BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
                 } else {
                     tma_load_2d(&tmA, &full[s], a, k0, m0);
                 }
@@ -162,9 +166,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, k-slice = +32 B inside the atom.
                     // MN-major SW128_BASE32B: [k][128 B of M/N]; 32-wide M/N chunks BK*128 B apart (LBO),
                     // 4-row k-atoms 512 B apart (SBO), k-slice of 8 rows = +1024 B.
-                    const uint64_t ad = A_MN ? make_desc(a + k * 1024, BK * 128, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
                     const uint64_t bd = B_MN ? make_desc(b + k * 1024, BK * 128, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
-                    tc_mma_tf32(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int h = 0; h < MH; ++h) {       // the two 128-row halves share this B stage
+                        const uint32_t ah = a + h * (BM * BK * 4);
+                        const uint64_t ad = A_MN ? make_desc(ah + k * 1024, BK * 128, 512, 1) : make_desc(ah + k * 32, 16, 1024, 2);
+                        if (!(g.dbg & 2)) tc_mma_tf32(tmem_base + h * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 tc_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
             }
@@ -187,12 +195,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool bias_vec = (((uintptr_t)g.bias) & 15) == 0;
         const int sub_r = lane >> 3, colq = (lane & 7) * 4;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int hc = 0; hc < MH * (BN / 32); ++hc) {
+            const int h = hc / (BN / 32), c = hc % (BN / 32);
             const int nb = n0 + c * 32;
-            if (nb >= g.N) break;
+            if (nb >= g.N || m0 + h * BM >= g.M || (g.dbg & 1)) continue;
             uint32_t r[32];
             if (nkb > 0) {
-                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * BN + c * 32, r);
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
@@ -214,7 +223,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int row = i * 4 + sub_r;
-                const int m = m0 + q * 32 + row;
+                const int m = m0 + h * BM + q * 32 + row;
                 float4 v = *reinterpret_cast<const float4*>(stg + row * STG + colq);
                 v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                 if (m < g.M && n < g.N) {
@@ -245,7 +254,191 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(MH * BN));
+    }
+}
+
+// ---- persistent variant ---------------------------------------------------------------------------
+// One CTA per SM loops over (m-tile, n-tile, k-split) work items.  Two accumulators live in TMEM
+// (2 x BN columns): while the epilogue warps drain accumulator j%2 (tcgen05.ld -> smem transpose ->
+// coalesced stores) the MMA warp already fills the other one from the next item's TMA stages, so the
+// store phase -- 40 % of a K=512 tile in the one-shot kernel (tools/gemm_dissect.py) -- overlaps the
+// main loop instead of following it.  Barrier phases run across items (global k-block counter).
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g,
+                     int tiles_m, int tiles_n, int n_split) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STG = 36;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    float* stg_all = (float*)(sB + STAGES * B_BYTES);                 // 4 warps x 32 x STG floats
+    uint64_t* full = (uint64_t*)(stg_all + 4 * 32 * STG);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;                              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                              // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kb_total = (g.K + BK - 1) / BK;
+    const long n_items = (long)tiles_m * tiles_n * n_split;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // work item -> (m0, n0, k-block range); consecutive items share the A tile (same m, next n)
+    auto decode = [&](long item, int& m0, int& n0, int& kb_beg, int& nkb, int& z) {
+        z = (int)(item % n_split);
+        long t = item / n_split;
+        n0 = (int)(t % tiles_n) * BN;
+        m0 = (int)(t / tiles_n) * BM;
+        kb_beg = z * g.kb_per_split;
+        nkb = min(kb_total, kb_beg + g.kb_per_split) - kb_beg;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long cnt = 0;
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                int m0, n0, kb_beg, nkb, z;
+                decode(item, m0, n0, kb_beg, nkb, z);
+                for (int i = 0; i < nkb; ++i, ++cnt) {
+                    const int s = (int)(cnt % STAGES), k0 = (kb_beg + i) * BK;
+                    if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
+                    mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                    uint8_t* a = sA + s * A_BYTES;
+                    uint8_t* b = sB + s * B_BYTES;
+                    if (A_MN) {
+#pragma unroll
+                        for (int c = 0; c < BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
+                    } else {
+                        tma_load_2d(&tmA, &full[s], a, k0, m0);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c) tma_load_2d(&tmB, &full[s], b + c * (BK * 128), n0 + 32 * c, k0);
+                    } else {
+                        tma_load_2d(&tmB, &full[s], b, k0, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            long cnt = 0, j = 0;
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                int m0, n0, kb_beg, nkb, z;
+                decode(item, m0, n0, kb_beg, nkb, z);
+                const int acc = (int)(j & 1);
+                if (j >= 2) mbar_wait(&tmem_empty[acc], (uint32_t)((j >> 1) - 1) & 1);   // epilogue drained it
+                tc_fence_after();
+                for (int i = 0; i < nkb; ++i, ++cnt) {
+                    const int s = (int)(cnt % STAGES);
+                    mbar_wait(&full[s], (uint32_t)(cnt / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 8; ++k) {
+                        const uint64_t ad = A_MN ? make_desc(a + k * 1024, BK * 128, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
+                        const uint64_t bd = B_MN ? make_desc(b + k * 1024, BK * 128, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
+                        tc_mma_tf32(tmem_base + acc * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        float* stg = stg_all + q * (32 * STG);
+        const bool ldc_vec = ((g.ldc & 3) == 0) && ((((uintptr_t)g.C) & 15) == 0);
+        const bool bias_vec = (((uintptr_t)g.bias) & 15) == 0;
+        const int sub_r = lane >> 3, colq = (lane & 7) * 4;
+        long j = 0;
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            int m0, n0, kb_beg, nkb, z;
+            decode(item, m0, n0, kb_beg, nkb, z);
+            const int acc = (int)(j & 1);
+            mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1);
+            tc_fence_after();
+            const bool add_bias = g.bias != nullptr && z == 0;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                const int nb = n0 + c * 32;
+                if (nb >= g.N) break;
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+#pragma unroll
+                for (int jj = 0; jj < 32; jj += 4)
+                    *reinterpret_cast<uint4*>(stg + lane * STG + jj) = make_uint4(r[jj], r[jj + 1], r[jj + 2], r[jj + 3]);
+                __syncwarp();
+                const int n = nb + colq;
+                float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add_bias) {
+                    if (n + 3 < g.N && bias_vec) bb = *reinterpret_cast<const float4*>(g.bias + n);
+                    else {
+                        if (n < g.N) bb.x = g.bias[n];
+                        if (n + 1 < g.N) bb.y = g.bias[n + 1];
+                        if (n + 2 < g.N) bb.z = g.bias[n + 2];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + sub_r;
+                    const int m = m0 + q * 32 + row;
+                    float4 v = *reinterpret_cast<const float4*>(stg + row * STG + colq);
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                    if (m < g.M && n < g.N) {
+                        float* dst = g.C + (long)m * g.ldc + n;
+                        if (ldc_vec && n + 3 < g.N) {
+                            if (g.atomic)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y),
+                                             "f"(v.z), "f"(v.w) : "memory");
+                            else
+                                *reinterpret_cast<float4*>(dst) = v;
+                        } else {
+                            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj)
+                                if (n + jj < g.N) {
+                                    if (g.atomic) atomicAdd(dst + jj, e[jj]);
+                                    else dst[jj] = e[jj];
+                                }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // this warp's TMEM reads of accumulator `acc` are complete: hand it back to the MMA warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
     }
 }
 
@@ -286,63 +479,97 @@ int make_map(CUtensorMap* map, const float* base, long inner, long outer, long l
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-template <int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
+template <int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
-    constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 1024 + 256;
+    constexpr int smem = STAGES * (MH * BM * BK * 4 + BN * BK * 4) + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<BN, STAGES, MINB, A_MN, B_MN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<MH, BN, STAGES, MINB, A_MN, B_MN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    gemm_tf32_kernel<BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
+    gemm_tf32_kernel<MH, BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
     return pd_launch_status();
 }
 
-template <int BN, int STAGES, int MINB>
+template <int MH, int BN, int STAGES, int MINB>
 int launch_l(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<BN, STAGES, MINB, false, false>(ta, tb, g, grid, st);
-    if (!a_mn && b_mn) return launch<BN, STAGES, MINB, false, true>(ta, tb, g, grid, st);
-    if (a_mn && b_mn) return launch<BN, STAGES, MINB, true, true>(ta, tb, g, grid, st);
-    return launch<BN, STAGES, MINB, true, false>(ta, tb, g, grid, st);
+    if (!a_mn && !b_mn) return launch<MH, BN, STAGES, MINB, false, false>(ta, tb, g, grid, st);
+    if (!a_mn && b_mn) return launch<MH, BN, STAGES, MINB, false, true>(ta, tb, g, grid, st);
+    if (a_mn && b_mn) return launch<MH, BN, STAGES, MINB, true, true>(ta, tb, g, grid, st);
+    return launch<MH, BN, STAGES, MINB, true, false>(ta, tb, g, grid, st);
 }
 
-// config id = bn * 100 + stages * 10 + ctas_per_sm
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m, int tiles_n, int split,
+             cudaStream_t st) {
+    constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 4 * 32 * 36 * 4 + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<BN, STAGES, A_MN, B_MN>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    long items = (long)tiles_m * tiles_n * split;
+    int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    gemm_tf32_persistent<BN, STAGES, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g, tiles_m, tiles_n, split);
+    return pd_launch_status();
+}
+
+template <int BN, int STAGES>
+int launch_pl(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m,
+              int tiles_n, int split, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_p<BN, STAGES, false, false>(ta, tb, g, tiles_m, tiles_n, split, st);
+    if (!a_mn && b_mn) return launch_p<BN, STAGES, false, true>(ta, tb, g, tiles_m, tiles_n, split, st);
+    if (a_mn && b_mn) return launch_p<BN, STAGES, true, true>(ta, tb, g, tiles_m, tiles_n, split, st);
+    return launch_p<BN, STAGES, true, false>(ta, tb, g, tiles_m, tiles_n, split, st);
+}
+
+// config id = (m_halves - 1) * 100000 + bn * 100 + stages * 10 + ctas_per_sm; 9xxxxx = persistent kernel
 int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid,
                cudaStream_t st) {
     switch (cfg) {
-        case 25641: return launch_l<256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 25622: return launch_l<256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12841: return launch_l<128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12861: return launch_l<128, 6, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12832: return launch_l<128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12823: return launch_l<128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 6441: return launch_l<64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 6442: return launch_l<64, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 6433: return launch_l<64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 25641: return launch_l<1, 256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 25622: return launch_l<1, 256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12841: return launch_l<1, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12832: return launch_l<1, 128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12823: return launch_l<1, 128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6441: return launch_l<1, 64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6433: return launch_l<1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 125631: return launch_l<2, 256, 3, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 112841: return launch_l<2, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 112822: return launch_l<2, 128, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
         default: return PD_BAD_ARG;
     }
 }
 
 int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                    const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st) {
+    const int dbg = cfg / 1000000;
+    cfg %= 1000000;
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (sak != 1 && sam != 1) || (sbk != 1 && sbn != 1)) return PD_BAD_ARG;
     const bool a_mn = (sak != 1), b_mn = (sbk != 1);
     const long lda = a_mn ? sak : sam, ldb = b_mn ? sbk : sbn;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3) || lda < 4 || ldb < 4) return PD_BAD_ARG;
-    const int tiles_m = (M + BM - 1) / BM;
     if (cfg == 0) {
-        // measured on B200 (tools/gemm_tune.py): wide tiles with 2 CTAs/SM when the grid fills the chip,
-        // 128-wide tiles for split-K weight gradients, 64-wide tiles for the small per-step recurrent GEMMs
+        // measured on B200 (tools/gemm_tune.py, tools/gemm_dissect.py)
+        const int tiles_m = (M + BM - 1) / BM;
         const int kb0 = (K + BK - 1) / BK;
-        if (N <= 64) cfg = 6441;
-        else if ((long)tiles_m * ((N + 255) / 256) >= 2L * PD_NUM_SMS) cfg = 25622;
-        else if (kb0 >= 1024 || (long)tiles_m * ((N + 127) / 128) >= PD_NUM_SMS) cfg = 12823;
-        else cfg = 6441;
+        const long t256 = (long)tiles_m * ((N + 255) / 256), t128 = (long)tiles_m * ((N + 127) / 128);
+        if (N <= 64) cfg = 6441;                                     // narrow heads
+        else if (N <= 128) cfg = 12823;
+        else if (kb0 >= 1024 && t256 < PD_NUM_SMS) cfg = 12823;      // split-K weight gradients
+        else if (t256 >= 2L * PD_NUM_SMS && kb0 >= 8) cfg = 925641;  // persistent, epilogue overlapped
+        else if (t256 >= PD_NUM_SMS) cfg = 25622;                    // 2 CTAs/SM
+        else if (t128 >= PD_NUM_SMS) cfg = 12823;
+        else cfg = 6441;                                             // small per-step recurrent GEMMs
     }
-    const int bn = cfg / 100;
+    const int mh = (cfg >= 100000 && cfg < 900000) ? 2 : 1;
+    const int bn = (cfg % 100000) / 100;
+    const int tiles_m = (M + mh * BM - 1) / (mh * BM);
     const int tiles_n = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tiles_n;
     const int kb = (K + BK - 1) / BK;
@@ -354,15 +581,17 @@ int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk,
     }
     int kb_per = (kb + split - 1) / split;
     split = (kb + kb_per - 1) / kb_per;
-    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0};
+    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0, dbg};
     CUtensorMap ta, tb;
     int rc;
     // K-major: [rows][K] -> dims {K, rows}, box {32, BM|bn}.  MN-major: [K][rows] -> dims {rows, K}, box {32, BK}.
-    rc = a_mn ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, BM, false);
+    rc = a_mn ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, mh * BM, false);
     if (rc) return rc;
     rc = b_mn ? make_map(&tb, B, N, K, ldb, BK, true) : make_map(&tb, B, K, N, ldb, bn, false);
     if (rc) return rc;
     if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
+    if (cfg == 925641) return launch_pl<256, 4>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
+    if (cfg == 912861) return launch_pl<128, 6>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
     dim3 grid(tiles_m, tiles_n, split);
     return launch_cfg(cfg, a_mn, b_mn, ta, tb, g, grid, st);
 }

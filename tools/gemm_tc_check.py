@@ -7,6 +7,7 @@ import torch
 from polydis_b200 import _lib
 
 dev = torch.device("cuda:0")
+CFG = int(os.environ.get("PD_GEMM_CFG", "0"))
 st = lambda: torch.cuda.current_stream().cuda_stream
 
 
@@ -30,8 +31,12 @@ def run(name, M, N, K, layout, acc=0, bias=True, pad=4, time_it=False):
     if acc:
         ref = ref + C0[:, :N].double()
     try:
-        _lib.call(name, A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, C.data_ptr(), ldc,
-                  None if b is None else b.data_ptr(), M, N, K, acc, st())
+        if CFG and name == "pd_gemm_tf32":
+            _lib.call("pd_gemm_tf32_cfg", A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, C.data_ptr(), ldc,
+                      None if b is None else b.data_ptr(), M, N, K, acc, CFG, st())
+        else:
+            _lib.call(name, A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, C.data_ptr(), ldc,
+                      None if b is None else b.data_ptr(), M, N, K, acc, st())
         torch.cuda.synchronize()
     except RuntimeError as e:
         print(f"{name} {layout} M={M} N={N} K={K}: ERROR {e}")
