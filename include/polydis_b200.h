@@ -119,6 +119,14 @@ int pd_reparam_bwd(const float* dz, long lddz, const float* eps, int B, int D, f
 int pd_kl_fwd(const float* mu, const float* sd, long n, float* out, void* stream);
 int pd_kl_bwd(const float* mu, const float* sd, long n, const float* gout, float* dmu, float* dsd, void* stream);
 
+/* ---- optimizer tail (amc_dl/torch_plus/module.py:142-143, scheduler.py:69-74, example.py:4-12): global-norm
+ * clip + Adam + exponentially decayed LR with a floor on flat fp32 buffers; norm and step count live on the
+ * device.  pd_sumsq_f32 accumulates into out[0]. */
+int pd_sumsq_f32(const float* g, long n, float* out, void* stream);
+int pd_counter_inc(int* counter, void* stream);
+int pd_adam_clip_step(float* p, const float* g, float* m, float* v, long n, const float* sumsq, const int* step,
+                      float lr0, float gamma, float lr_min, float b1, float b2, float eps, float clip, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ import os
 
 from . import build as _build
 
-_P, _L, _I = ctypes.c_void_p, ctypes.c_long, ctypes.c_int
+_P, _L, _I, _F = ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_float
 
 # name -> argument ctypes (every function returns int: 0 ok, cudaError_t > 0, -22 bad argument)
 SIGNATURES = {
@@ -42,6 +42,9 @@ SIGNATURES = {
     "pd_reparam_bwd": [_P, _L, _P, _I, _I, _P, _P, _P],
     "pd_kl_fwd": [_P, _P, _L, _P, _P],
     "pd_kl_bwd": [_P, _P, _L, _P, _P, _P, _P],
+    "pd_sumsq_f32": [_P, _L, _P, _P],
+    "pd_counter_inc": [_P, _P],
+    "pd_adam_clip_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _F, _P],
 }
 
 LIB_PATH = _build.LIB_PATH

@@ -21,6 +21,10 @@ class GraphedTrainStep:
         self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
         self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
         self.tfr, self.beta, self.weights, self.clip = tfr, beta, weights, clip
+        from .optim import FusedClipAdam
+        self.fused = isinstance(optimizer, FusedClipAdam)     # clip + Adam + LR decay inside optimizer.step()
+        if self.fused:
+            reducer = optimizer.reducer
         self.reducer = reducer          # ddp.BucketedGradAllReduce: its all-reduces are captured in the graph
         self.losses = None
         self.graph = None
@@ -36,7 +40,7 @@ class GraphedTrainStep:
         losses[0].backward()
         if self.reducer is not None:
             self.reducer.finish()
-        if self.clip:
+        if self.clip and not self.fused:
             torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.opt.step()
         return torch.stack([l.detach() for l in losses])

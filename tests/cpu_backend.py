@@ -366,6 +366,25 @@ class CpuBackend:
         _arr(dsd, (n,), (1,))[...] = g * (s - 1 / s)
 
 
+    # ---- optimizer tail ----
+    def pd_sumsq_f32(self, g, n, out, st):
+        G = _arr(g, (n,), (1,))
+        _arr(out, (1,), (1,))[0] += np.float32((G.astype(np.float64) ** 2).sum())
+
+    def pd_counter_inc(self, c, st):
+        _arr(c, (1,), (1,), np.int32)[0] += 1
+
+    def pd_adam_clip_step(self, p, g, m, v, n, sumsq, step, lr0, gamma, lr_min, b1, b2, eps, clip, st):
+        P, G, M, V = (_arr(x, (n,), (1,)) for x in (p, g, m, v))
+        t = int(_arr(step, (1,), (1,), np.int32)[0])
+        coef = min(1.0, clip / (np.sqrt(_arr(sumsq, (1,), (1,))[0]) + 1e-6)) if clip > 0 else 1.0
+        lr = max(lr0 * gamma ** (t - 1), lr_min) if gamma > 0 else lr0
+        gi = G * np.float32(coef)
+        M[...] = b1 * M + (1 - b1) * gi
+        V[...] = b2 * V + (1 - b2) * gi * gi
+        P[...] -= (lr / (1 - b1 ** t)) * M / (np.sqrt(V) / np.sqrt(1 - b2 ** t) + eps)
+
+
 def install(monkeypatch):
     """Route polydis_b200's library calls to the numpy emulation for the duration of a test."""
     from polydis_b200 import _lib, ops
