@@ -90,14 +90,15 @@ class DisentangleVAE(PytorchModel):
     def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None):
         """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
         recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
-        embedded_x, lengths = self.decoder.emb_x(x)
-        dist_chd = self.chd_encoder(c)
-        dist_rhy = self.rhy_encoder(pr_mat)
+        # independent branches go to side streams (ops.fork_join); python-side order is the reference's
+        dist_chd, dist_rhy, (embedded_x, lengths) = ops.fork_join([
+            lambda: self.chd_encoder(c), lambda: self.rhy_encoder(pr_mat), lambda: self.decoder.emb_x(x)])
         z_chd = _sample(dist_chd, True, None if eps is None else eps[0])
         z_rhy = _sample(dist_rhy, True, None if eps is None else eps[1])
         dec_z = torch.cat([z_chd, z_rhy], dim=-1)
-        pitch_outs, dur_outs = self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2)
-        recon_root, recon_chroma, recon_bass = self.chd_decoder(z_chd, False, tfr3, c)
+        (pitch_outs, dur_outs), (recon_root, recon_chroma, recon_bass) = ops.fork_join([
+            lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2),
+            lambda: self.chd_decoder(z_chd, False, tfr3, c)])
         return pitch_outs, dur_outs, dist_chd, dist_rhy, recon_root, recon_chroma, recon_bass
 
     def loss_function(self, x, c, recon_pitch, recon_dur, dist_chd, dist_rhy, recon_root, recon_chroma,

@@ -57,6 +57,42 @@ def _empty_rows(rows, cols, dev):
 
 
 # ------------------------------------------------------------------------------------------------
+# Fork-join over CUDA streams.  The two encoders, the two directions of every bi-GRU and the chord decoder
+# are independent chains of small kernels (48-192 CTAs each on a 148-SM part); issuing them on side streams
+# lets them overlap -- also inside a captured CUDA graph, where the streams become parallel branches, and in
+# backward, because autograd replays each op on the stream its forward ran on.
+FORK_STREAMS = True
+_stream_pool = []
+_stream_depth = 0
+
+
+def fork_join(fns):
+    """Run the callables in list order (python side effects keep their order); all but the last go to side
+    streams forked from the current stream, the last runs on the current stream, then everything is joined."""
+    global _stream_depth
+    if not FORK_STREAMS or len(fns) < 2 or not torch.cuda.is_available():
+        return [f() for f in fns]
+    cur = torch.cuda.current_stream()
+    n_side = len(fns) - 1
+    while len(_stream_pool) < _stream_depth + n_side:
+        _stream_pool.append(torch.cuda.Stream())
+    side = _stream_pool[_stream_depth:_stream_depth + n_side]
+    _stream_depth += n_side
+    try:
+        outs = []
+        for f, st in zip(fns[:-1], side):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(f())
+        outs.append(fns[-1]())
+        for st in side:
+            cur.wait_stream(st)
+    finally:
+        _stream_depth -= n_side
+    return outs
+
+
+# ------------------------------------------------------------------------------------------------
 # GEMM routing.  "tf32": tcgen05 tensor-core kernel (TF32 multiplies, fp32 accumulate) whenever TMA can
 # address the operands, else the fp32 FFMA kernel.  "fp32": always the FFMA kernel -- the fp32-faithful
 # arithmetic greedy decoding needs for token parity with the fp32 reference (SURVEY.md 7.4-2).

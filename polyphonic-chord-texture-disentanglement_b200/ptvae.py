@@ -67,13 +67,12 @@ class ConvParams(nn.Module):
 
 def _bigru_final(gru, x, lengths=None):
     """Final hidden states [fwd | bwd] of a bi-GRU over x (R,T,I); ``lengths`` int32 (R,) = packed."""
-    outs = []
-    for rev in (False, True):
+    def one(rev):
         w_ih, w_hh, b_ih, b_hh = gru.dir(rev)
         gi = ops.linear(x, w_ih, b_ih)
         h = ops.gru_sequence(gi, None, None, w_hh, b_hh, lengths, rev)
-        outs.append(h[:, 0] if rev else h[:, -1])
-    return torch.cat(outs, -1)
+        return h[:, 0] if rev else h[:, -1]
+    return torch.cat(ops.fork_join([lambda: one(False), lambda: one(True)]), -1)
 
 
 def _posterior(h, linear_mu, linear_var):
