@@ -88,7 +88,7 @@ class GraphedDecode:
         m = self.model
         m.eval()
         with torch.no_grad(), ops.precision(m.decode_precision):
-            dc, dr = m.chd_encoder(self.c), m.rhy_encoder(self.pr)
+            dc, dr = ops.fork_join([lambda: m.chd_encoder(self.c), lambda: m.rhy_encoder(self.pr)])
             return m.decoder.greedy_tokens(torch.cat([dc.mean, dr.mean], -1))
 
     def capture(self, pr_mat, c):

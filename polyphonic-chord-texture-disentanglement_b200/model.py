@@ -130,8 +130,7 @@ class DisentangleVAE(PytorchModel):
     def inference_encode(self, pr_mat, c):
         self.eval()
         with torch.no_grad(), ops.precision(self.decode_precision):
-            dist_chd = self.chd_encoder(c)
-            dist_rhy = self.rhy_encoder(pr_mat)
+            dist_chd, dist_rhy = ops.fork_join([lambda: self.chd_encoder(c), lambda: self.rhy_encoder(pr_mat)])
         return dist_chd, dist_rhy
 
     def decode_tokens(self, z_chd, z_rhy):

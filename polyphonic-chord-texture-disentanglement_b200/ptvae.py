@@ -437,7 +437,7 @@ class PtvaeDecoder(nn.Module):
         dlog = torch.empty(B, 5, 2, **f32)
         He = self.dec_emb_hid_size
         gi_e = [torch.empty(B, NS, 3 * He, **f32) for _ in range(2)]
-        gh_e, h_e = torch.empty(B, 3 * He, **f32), torch.empty(B, He, **f32)
+        gh_e, h_e = [torch.empty(B, 3 * He, **f32) for _ in range(2)], torch.empty(B, He, **f32)
         st = ops._stream
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
@@ -462,18 +462,20 @@ class PtvaeDecoder(nn.Module):
                 break
             # next time-step token: bi-GRU summary of the predicted notes with the predicted lengths
             flat = pred.view(B * NS, E)
-            for d, rev in enumerate((False, True)):
+
+            def summarise(d, rev):
                 w_ih, w_hh, b_ih, b_hh = eg.dir(rev)
                 ops.gemm_nt(flat, w_ih, gi_e[d].view(B * NS, 3 * He), b_ih)
                 out = tok_time[:, d * He:(d + 1) * He]
                 first = True
                 for k in (range(NS - 1, -1, -1) if rev else range(NS)):
                     if first:
-                        ops.gemm_nt(h_e[:, :0], w_hh[:, :0], gh_e, b_hh)          # h = 0: gh = b_hh
+                        ops.gemm_nt(h_e[:, :0], w_hh[:, :0], gh_e[d], b_hh)          # h = 0: gh = b_hh
                     else:
-                        ops.gemm_nt(out, w_hh, gh_e, b_hh)
-                    ops._gates_fwd(gi_e[d][:, k], None, gh_e, None if first else out, out, None, None, lens, k)
+                        ops.gemm_nt(out, w_hh, gh_e[d], b_hh)
+                    ops._gates_fwd(gi_e[d][:, k], None, gh_e[d], None if first else out, out, None, None, lens, k)
                     first = False
+            ops.fork_join([lambda: summarise(0, False), lambda: summarise(1, True)])   # the two directions overlap
         return tokens
 
     # -- losses / output formatting ---------------------------------------------------------------
