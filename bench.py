@@ -250,14 +250,14 @@ def run_b200(args):
     Bd = args.decode_batch
     xd_, cd_, pd_ = (torch.from_numpy(a).to(dev) for a in synth_batch(Bd, 500 + rank))
     dec_ms = {}
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32x3", "tf32"):
         model.decode_precision = prec
         gd = GraphedDecode(model, Bd).capture(pd_, cd_)
         gd(pd_, cd_)
         dec_ms[prec] = timed(lambda: gd(pd_, cd_), 3)
         del gd
-    model.decode_precision = "fp32"
-    ms_dec = dec_ms["fp32"]
+    model.decode_precision = "tf32x3"
+    ms_dec = dec_ms["tf32x3"]
     model.train()
 
     mark("decode done")
@@ -302,7 +302,9 @@ def run_b200(args):
                    "d2h_bytes_per_step": 4},
            "gpu_launches": launches,
            "decode": {"value": world * Bd / (ms_dec * 1e-3), "unit": "segments/s", "batch_per_gpu": Bd,
-                      "ms_per_batch": ms_dec, "precision": "fp32 (token-parity mode)",
+                      "ms_per_batch": ms_dec,
+                      "precision": "tf32x3 (error-compensated tensor-core GEMMs; token parity with the fp32 reference)",
+                      "fp32_ffma_value": world * Bd / (dec_ms["fp32"] * 1e-3),
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,

@@ -125,6 +125,22 @@ __global__ void add_kernel(const float* __restrict__ a, const float* __restrict_
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + b[i];
 }
+// lo = x - rn_tf32(x): the part of an fp32 operand a TF32 tensor-core multiply drops (error-compensated
+// "3xTF32" GEMM: A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi, the hi parts being what TMA's TFLOAT32 load yields).
+// hi is written explicitly (fp32 with the 13 low mantissa bits cleared) so the result does not depend on how
+// the TMA / tensor-core path rounds an fp32 operand to TF32.
+__global__ void tf32_split_kernel(const float* __restrict__ x, long ldx, long rows, int cols, float* __restrict__ hi_out,
+                                  float* __restrict__ lo, long ldo) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    long r = i / cols;
+    int c = (int)(i % cols);
+    float v = x[r * ldx + c];
+    uint32_t hi;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    hi_out[r * ldo + c] = __uint_as_float(hi);
+    lo[r * ldo + c] = v - __uint_as_float(hi);
+}
 // z[b, j] = mu + std * eps, written with row stride ldz (into its half of dec_z)
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
                                    const float* __restrict__ eps, int B, int D, float* z, long ldz) {
@@ -213,6 +229,13 @@ PD_API int pd_mul_f32(const float* a, const float* b, long n, float* out, void* 
 PD_API int pd_add_f32(const float* a, const float* b, long n, float* out, void* stream) {
     if (n <= 0) return 0;
     add_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a, b, n, out);
+    return pd_launch_status();
+}
+
+// hi = round_to_tf32(x), lo = x - hi for x (rows, cols; row stride ldx); outputs with row stride ldo
+PD_API int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, float* lo, long ldo, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    tf32_split_kernel<<<pd_blocks(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, cols, hi, lo, ldo);
     return pd_launch_status();
 }
 

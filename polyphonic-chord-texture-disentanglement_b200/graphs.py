@@ -100,9 +100,12 @@ class GraphedDecode:
                 self._run()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        from . import ops
+        ops._lo_cache.clear()           # weight low parts ("tf32x3") must be (re)computed INSIDE the graph
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.tokens = self._run()
+        ops._lo_cache.clear()
         return self
 
     def __call__(self, pr_mat, c):

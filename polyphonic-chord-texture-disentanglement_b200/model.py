@@ -81,10 +81,10 @@ class DisentangleVAE(PytorchModel):
         self.decoder = decoder
         self.num_step = self.decoder.num_step
         self.chd_decoder = chd_decoder
-        #: GEMM arithmetic of the inference entry points: "fp32" (default) keeps greedy tokens identical
-        #: to the fp32 reference; "tf32" runs them on the tensor cores (faster, ~0.1 % of tokens of a
-        #: randomly initialised model may flip at near-tied argmaxes).
-        self.decode_precision = "fp32"
+        #: GEMM arithmetic of the inference entry points: "tf32x3" (default; error-compensated tensor-core GEMMs,
+        #: fp32-class accuracy) and "fp32" (FFMA) keep greedy tokens identical to the fp32 reference; "tf32"
+        #: is fastest but flips near-tied argmaxes of a randomly initialised model.
+        self.decode_precision = "tf32x3"
 
     # -- training ----------------------------------------------------------------------------------
     def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None):

@@ -96,33 +96,66 @@ def fork_join(fns):
 # GEMM routing.  "tf32": tcgen05 tensor-core kernel (TF32 multiplies, fp32 accumulate) whenever TMA can
 # address the operands, else the fp32 FFMA kernel.  "fp32": always the FFMA kernel -- the fp32-faithful
 # arithmetic greedy decoding needs for token parity with the fp32 reference.
+#   "tf32x3": error-compensated tensor-core GEMM -- A.B + A.B_lo + A_lo.B with TF32 multiplies and fp32
+#             accumulation (lo = x - rn_tf32(x)): ~2^-22 relative operand error, i.e. fp32-class results at
+#             tensor-core speed for the inference GEMMs (SURVEY.md 7.4-2 "TF32x3").
 PRECISION = "tf32"
+_lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
 
 
 class precision:
     """``with ops.precision("fp32"): ...`` selects the GEMM arithmetic for the enclosed calls."""
 
     def __init__(self, mode):
-        assert mode in ("tf32", "fp32")
+        assert mode in ("tf32", "fp32", "tf32x3")
         self.mode = mode
 
     def __enter__(self):
         global PRECISION
         self.prev, PRECISION = PRECISION, self.mode
+        _lo_cache.clear()       # weight hi/lo splits are only valid within one scope (pointers get reused)
 
     def __exit__(self, *exc):
         global PRECISION
         PRECISION = self.prev
+        _lo_cache.clear()
+
+
+def _split_hi_lo(t, cache):
+    """(hi, lo) with hi = rn_tf32(t), lo = t - hi, as row-padded tensors (cached for weights: they do not
+    change inside a decode)."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+    if cache and key in _lo_cache:
+        return _lo_cache[key]
+    rows, cols = t.shape
+    buf = torch.empty(2, rows, _pad4(cols), device=t.device, dtype=torch.float32)
+    hi, lo = buf[0, :, :cols], buf[1, :, :cols]
+    _call("pd_tf32_split", _ptr(t), t.stride(0), rows, cols, _ptr(hi), _ptr(lo), hi.stride(0), _stream())
+    if cache:
+        if len(_lo_cache) > 256:
+            _lo_cache.clear()
+        _lo_cache[key] = (hi, lo)
+    return hi, lo
 
 
 def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
     name = "pd_gemm_f32"
-    if PRECISION == "tf32" and K >= 8 and N >= 16:
+    tc_ok = False
+    if PRECISION != "fp32" and K >= 8 and N >= 16:
         lda = sak if sak != 1 else sam
         ldb = sbk if sbk != 1 else sbn
-        if a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0 \
-                and lda >= 4 and ldb >= 4:
-            name = "pd_gemm_tf32"
+        tc_ok = (a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
+                 and lda >= 4 and ldb >= 4)
+    if tc_ok and PRECISION == "tf32x3" and sak == 1 and sbk == 1 and a.dim() == 2 and b.dim() == 2:
+        # NT only (the inference GEMMs): three TF32 passes accumulated in fp32 by the L2-reduction epilogue
+        st = _stream()
+        (a_hi, a_lo), (b_hi, b_lo) = _split_hi_lo(a, False), _split_hi_lo(b, True)
+        for x_, w_, bias_, acc_ in ((a_hi, b_hi, bias, accumulate), (a_hi, b_lo, None, True), (a_lo, b_hi, None, True)):
+            _call("pd_gemm_tf32", _ptr(x_), x_.stride(0), 1, _ptr(w_), 1, w_.stride(0), _ptr(out), out.stride(0),
+                  _ptr(bias_), M, N, K, int(acc_), st)
+        return out
+    if tc_ok and PRECISION == "tf32":
+        name = "pd_gemm_tf32"
     _call(name, _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
           int(accumulate), _stream())
     return out

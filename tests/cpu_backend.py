@@ -57,6 +57,13 @@ class CpuBackend:
     def pd_gemm_tf32_cfg(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, cfg, st):
         self.pd_gemm_f32(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, st)
 
+    def pd_tf32_split(self, x, ldx, rows, cols, hi_out, lo, ldo, st):
+        X = _arr(x, (rows, cols), (ldx, 1)).astype(np.float32)
+        bits = X.view(np.uint32).astype(np.uint64)
+        hi = (((bits + 0x1000) >> 13) << 13).astype(np.uint32).view(np.float32)     # round-to-nearest (ties away)
+        _arr(hi_out, (rows, cols), (ldo, 1))[...] = hi
+        _arr(lo, (rows, cols), (ldo, 1))[...] = X - hi
+
     def pd_colsum_f32(self, X, ldx, M, N, out, acc, st):
         o = _arr(out, (N,), (1,))
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0

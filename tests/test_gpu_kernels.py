@@ -385,3 +385,20 @@ def test_graphed_train_step_matches_eager():
     # second-step loss depends on the first update; noise differs (eps drawn from different generator states)
     assert abs(losses[0][0] - losses[1][0]) < 5e-2 * abs(losses[0][0])
     assert losses[1][1] < losses[1][0] + 0.5 and losses[0][1] < losses[0][0] + 0.5
+
+
+def test_tf32x3_gemm_is_fp32_class():
+    """Error-compensated 3xTF32 GEMM (tensor cores) vs fp64: relative error ~1e-6, i.e. fp32-class, against
+    ~3e-4 for plain TF32."""
+    dev = _dev()
+    from polydis_b200 import ops
+    torch.manual_seed(0)
+    A, W, b = torch.randn(700, 512, device=dev), torch.randn(194, 512, device=dev), torch.randn(194, device=dev)
+    ref = A.double() @ W.double().t() + b.double()
+    errs = {}
+    for mode in ("tf32", "tf32x3", "fp32"):
+        out = torch.empty(700, 196, device=dev)[:, :194]
+        with ops.precision(mode):
+            ops.gemm_nt(A, W, out, b)
+        errs[mode] = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert errs["tf32x3"] < 3e-6 and errs["fp32"] < 1e-6 and errs["tf32"] > 10 * errs["tf32x3"], errs

@@ -98,19 +98,23 @@ def test_training_matches_oracle_full_gradients(tfr):
         assert err <= 1e-2, (name, err)
 
 
-@pytest.mark.parametrize("tag", ["w0", "w1"])
-def test_greedy_tokens_match_reference_golden(golden_dir, tag):
+@pytest.mark.parametrize("tag,prec", [("w0", "fp32"), ("w1", "fp32"), ("w0", "tf32x3"), ("w1", "tf32x3")])
+def test_greedy_tokens_match_reference_golden(golden_dir, tag, prec):
+    """fp32 FFMA GEMMs and the error-compensated 3xTF32 tensor-core GEMMs both reproduce the reference's
+    greedy tokens."""
     dev = _dev()
     g = np.load(os.path.join(golden_dir, f"infer_{tag}.npz"))
     x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(int(g["B"]), int(g["data_seed"])))
     m = _model(dev, int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    m.decode_precision = prec
     est = m.inference(pr, c, sample=False)
     assert est.dtype == np.int64 and est.shape == (int(g["B"]), 32, 15, 6)
     match = (est == g["est_x"]).mean()
     assert match >= 0.999, match
 
 
-def test_greedy_tokens_match_oracle_larger_batch():
+@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
+def test_greedy_tokens_match_oracle_larger_batch(prec):
     dev = _dev()
     from oracle import polydis_oracle as O
     B = 48
@@ -118,6 +122,7 @@ def test_greedy_tokens_match_oracle_larger_batch():
     sd = make_state_dict(5, gain=2.0, eos_bias=0.75)
     ref = O.inference(sd, prs, cs)
     m = _model(dev, 5, 2.0, 0.75)
+    m.decode_precision = prec
     est = m.swap(prs.to(dev), prs.to(dev), cs.to(dev), cs.to(dev), True, True)
     match = (est == ref).mean()
     pre = ref[..., 0] != 129
