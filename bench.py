@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 TRAIN_GFLOP_PER_SAMPLE = 5.45      # algorithmic minimum fwd+bwd, SURVEY.md 8(d)
 DECODE_GFLOP_PER_SEGMENT = 1.92
 METRIC = "polydis_train_samples_per_sec"
+NOTE_GEMM_DRAM_BYTES = 112.1e6     # ncu: 60.8 MB read + 51.4 MB written per note-GRU step GEMM at B=512
 
 
 def _peaks():
@@ -41,7 +42,7 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -52,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
         except OSError:
@@ -307,7 +308,9 @@ def run_b200(args):
                       "fp32_ffma_value": world * Bd / (dec_ms["fp32"] * 1e-3),
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                        "frac": achieved / peak_tf, "traffic": NOTE_GEMM_DRAM_BYTES, "peak_source": peak_src,
+                        "traffic_what": "dram read+write bytes per launch of the dominant GEMM from ncu --set full "
+                                        "(profiles/r01_ncu_full_kernels.md); algorithmic 137 MB, half of C stays in L2",
                         "what": "whole step: 5.45 algorithmic GFLOP/sample x batch / step time, vs sustained bf16 peak",
                         "dominant_kernel": {"name": "note-GRU recurrent GEMM [32B x 512].[512 x 1536]",
                                             "ms": ms_gemm, "achieved": gemm_tflops, "frac": gemm_tflops / peak_tf}},
@@ -330,7 +333,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512)
