@@ -259,6 +259,12 @@ def run_b200(args):
         del gd
     model.decode_precision = "tf32x3"
     ms_dec = dec_ms["tf32x3"]
+    # latency-bound corner (BASELINE configs[4]: a 256-bar arrangement = 128 segments over 8 GPUs = 16 per GPU)
+    xs_, cs_, ps_ = (torch.from_numpy(a).to(dev) for a in synth_batch(16, 900 + rank))
+    gd16 = GraphedDecode(model, 16).capture(ps_, cs_)
+    gd16(ps_, cs_)
+    ms_dec16 = timed(lambda: gd16(ps_, cs_), 3)
+    del gd16
     model.train()
 
     mark("decode done")
@@ -306,7 +312,8 @@ def run_b200(args):
                       "ms_per_batch": ms_dec,
                       "precision": "tf32x3 (error-compensated tensor-core GEMMs; token parity with the fp32 reference)",
                       "fp32_ffma_value": world * Bd / (dec_ms["fp32"] * 1e-3),
-                      "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True},
+                      "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True,
+                      "latency_16_segments_ms": ms_dec16},
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved / peak_tf, "traffic": NOTE_GEMM_DRAM_BYTES, "peak_source": peak_src,
                         "traffic_what": "dram read+write bytes per launch of the dominant GEMM from ncu --set full "
@@ -337,7 +344,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--decode-batch", type=int, default=4096)
+    ap.add_argument("--decode-batch", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--fused-optim", action="store_true",
                     help="polydis_b200.optim.FusedClipAdam (flat buckets) instead of torch clip_grad_norm_ + fused Adam; "
