@@ -236,6 +236,16 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     mark(f"timed region done: {ms_step:.2f} ms/step")
+    # free-running regime (tfr = 0,0,0: what train.py's schedule yields after its first step, scheduler.py:48-49):
+    # 32 x 15 sequential note steps with greedy feedback, same kernels step-wise, whole step in one CUDA graph
+    ms_tfr0 = None
+    if world == 1 and graphed is not None and not args.no_tfr0:
+        from polydis_b200.graphs import GraphedTrainStep
+        g0 = GraphedTrainStep(model, opt, B, tfr=(0., 0., 0.), warmup=1).capture(x, c, pr)
+        g0(x, c, pr)
+        ms_tfr0 = timed(lambda: g0(x, c, pr), 3)
+        del g0
+        mark(f"tfr=0 step: {ms_tfr0:.1f} ms")
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
     def e2e_step():
         xd, cd, pd = xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True), ph.to(dev, non_blocking=True)
@@ -308,6 +318,8 @@ def run_b200(args):
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4},
            "gpu_launches": launches,
+           "train_free_running": None if ms_tfr0 is None else
+           {"value": B / (ms_tfr0 * 1e-3), "unit": "samples/s", "ms_per_step": ms_tfr0, "tfr": [0, 0, 0], "cuda_graph": True},
            "decode": {"value": world * Bd / (ms_dec * 1e-3), "unit": "segments/s", "batch_per_gpu": Bd,
                       "ms_per_batch": ms_dec,
                       "precision": "tf32x3 (error-compensated tensor-core GEMMs; token parity with the fp32 reference)",
@@ -346,6 +358,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--decode-batch", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tfr0", action="store_true", help="skip the free-running (tfr=0) training measurement")
     ap.add_argument("--fused-optim", action="store_true",
                     help="polydis_b200.optim.FusedClipAdam (flat buckets) instead of torch clip_grad_norm_ + fused Adam; "
                          "measured 0.9 ms/step slower at 1 GPU because backward then accumulates into the flat buckets")

@@ -4,8 +4,10 @@ One teacher-forced training step is ~1,400 kernel launches issued from Python (G
 recurrent step, forwards and backwards); eager issue is CPU-bound.  ``GraphedTrainStep`` captures the
 whole step once (static input buffers, capturable Adam) and replays it with a single launch per
 step -- "CUDA graphs instead of a tracing compiler".  Valid while the host-side control flow is fixed:
-the teacher-forcing decisions drawn from python's ``random`` are baked in at capture, so it is used
-for tfr = (1,1,1) (every decision True regardless of the draw); scheduled sampling runs eagerly.
+the teacher-forcing decisions drawn from python's ``random`` are baked in at capture, so every ratio must
+be exactly 0 or 1 (decisions independent of the draw): tfr = (1,1,1) -- the batched teacher-forced path -- or
+tfr = (0,0,0), the free-running regime train.py's schedule settles into after its first step
+(scheduler.py:48-49); intermediate ratios run eagerly.
 """
 import torch
 
@@ -13,7 +15,9 @@ import torch
 class GraphedTrainStep:
     def __init__(self, model, optimizer, batch, tfr=(1., 1., 1.), beta=0.1, weights=(1, 0.5), clip=1.0,
                  warmup=3, reducer=None):
-        assert tfr == (1., 1., 1.), "graph capture bakes the teacher-forcing plan; use eager steps for tfr < 1"
+        assert all(t in (0., 1.) for t in tfr), \
+            "graph capture bakes the teacher-forcing plan: every ratio must be 0 or 1 (deterministic decisions); " \
+            "use eager steps for 0 < tfr < 1"
         dev = next(model.parameters()).device
         self.model, self.opt = model, optimizer
         self.params = [p for p in model.parameters()]
