@@ -146,8 +146,9 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
         ldb = sbk if sbk != 1 else sbn
         tc_ok = (a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
                  and lda >= 4 and ldb >= 4)
-    if tc_ok and PRECISION == "tf32x3" and sak == 1 and sbk == 1 and a.dim() == 2 and b.dim() == 2:
-        # NT only (the inference GEMMs): three TF32 passes accumulated in fp32 by the L2-reduction epilogue
+    if tc_ok and PRECISION == "tf32x3" and M >= 512 and sak == 1 and sbk == 1 and a.dim() == 2 and b.dim() == 2:
+        # NT only (the inference GEMMs): three TF32 passes accumulated in fp32 by the L2-reduction epilogue.
+        # Small batches (M < 512) stay on the single-launch FFMA kernel: they are launch-latency bound.
         st = _stream()
         (a_hi, a_lo), (b_hi, b_lo) = _split_hi_lo(a, False), _split_hi_lo(b, True)
         for x_, w_, bias_, acc_ in ((a_hi, b_hi, bias, accumulate), (a_hi, b_lo, None, True), (a_lo, b_hi, None, True)):
