@@ -36,6 +36,10 @@ int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, l
 /* tuning variant of pd_gemm_tf32: cfg = BN*100 + stages*10 + CTAs/SM of an instantiated tile config (0 = heuristic) */
 int pd_gemm_tf32_cfg(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                      const float* bias, int M, int N, int K, int accumulate, int cfg, void* stream);
+/* bf16 operands (bit patterns; strides in elements, multiples of 8), fp32 accumulate / output: kind::f16 MMAs */
+int pd_gemm_bf16(const void* A, long sam, long sak, const void* B, long sbk, long sbn, float* C, long ldc,
+                 const float* bias, int M, int N, int K, int accumulate, void* stream);
+int pd_f32_to_bf16(const float* x, long ldx, long rows, int cols, void* out, long ldo, void* stream);
 /* hi = round_to_nearest_tf32(x), lo = x - hi (row stride ldo): operands of the error-compensated "3xTF32" GEMM
  * A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi (TF32 multiplies, fp32 accumulation: ~fp32 accuracy on tensor cores) */
 int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, float* lo, long ldo, void* stream);

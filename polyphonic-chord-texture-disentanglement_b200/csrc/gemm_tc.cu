@@ -61,6 +61,30 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// Element-size dependent constants.  EB = 4: fp32 operands multiplied as TF32 (K = 8 per MMA, 32 elements per
+// 128-byte row, MN-major via SWIZZLE_128B_BASE32B).  EB = 2: bf16 operands (K = 16 per MMA, 64 elements per
+// row, MN-major via the ordinary SWIZZLE_128B layout).
+template <int EB> struct Elem {
+    static constexpr int BKE = 128 / EB;                        // elements per k-block (one 128-byte row)
+    static constexpr uint32_t FMT = EB == 4 ? 2u : 1u;          // instr-desc operand format: TF32 / BF16
+    static constexpr uint32_t MN_LAYOUT = EB == 4 ? 1u : 2u;    // SWIZZLE_128B_BASE32B / SWIZZLE_128B
+    static constexpr uint32_t MN_SBO = EB == 4 ? 512u : 1024u;  // bytes between k-atoms (4 / 8 rows of 128 B)
+    static constexpr uint32_t MN_KSTEP = EB == 4 ? 1024u : 2048u;   // bytes per MMA k-slice (8 / 16 rows)
+};
+template <int EB>
+__device__ __forceinline__ void tc_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    if (EB == 4) tc_mma_tf32(d, ad, bd, idesc, acc);
+    else tc_mma_bf16(d, ad, bd, idesc, acc);
+}
+
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -92,11 +116,12 @@ struct TcArgs {
 // MH = number of 128-row halves per CTA tile (1 or 2).  The per-step GEMMs of this path are L2->SM bandwidth
 // bound with fp32 operands (a 128x256 tile needs 96 B/clk against ~43 B/clk/SM of L2 fabric); MH = 2 reuses
 // every B (weight) stage for two accumulators in TMEM and cuts the traffic per MAC by a third.
-template <int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
+template <int EB, int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int A_BYTES = MH * BM * BK * 4, B_BYTES = BN * BK * 4;
+    constexpr int BKE = Elem<EB>::BKE, CW = 128 / EB;   // k-block elements; MN-major chunk width (elements per 128 B)
+    constexpr int A_BYTES = MH * BM * 128, B_BYTES = BN * 128;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -107,7 +132,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * (MH * BM), n0 = blockIdx.y * BN;
-    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_total = (g.K + BKE - 1) / BKE;
     const int kb_beg = blockIdx.z * g.kb_per_split;
     const int kb_end = min(kb_total, kb_beg + g.kb_per_split);
     const int nkb = kb_end - kb_beg;
@@ -131,20 +156,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0) {
         if (lane == 0) {
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES, k0 = (kb_beg + i) * BK;
+                const int s = i % STAGES, k0 = (kb_beg + i) * BKE;
                 if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                 uint8_t* a = sA + s * A_BYTES;
                 uint8_t* b = sB + s * B_BYTES;
                 if (A_MN) {
 #pragma unroll
-                    for (int c = 0; c < MH * BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
+                    for (int c = 0; c < MH * BM / CW; ++c) tma_load_2d(&tmA, &full[s], a + c * (BKE * 128), m0 + CW * c, k0);
                 } else {
                     tma_load_2d(&tmA, &full[s], a, k0, m0);
                 }
                 if (B_MN) {
 #pragma unroll
-                    for (int c = 0; c < BN / 32; ++c) tma_load_2d(&tmB, &full[s], b + c * (BK * 128), n0 + 32 * c, k0);
+                    for (int c = 0; c < BN / CW; ++c) tma_load_2d(&tmB, &full[s], b + c * (BKE * 128), n0 + CW * c, k0);
                 } else {
                     tma_load_2d(&tmB, &full[s], b, k0, n0);
                 }
@@ -154,7 +179,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             // instruction descriptor (InstrDescriptor): D=f32 [4,6)=1, A/B format tf32=2 at [7,10)/[10,13),
             // a_major [15], b_major [16], N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+            const uint32_t idesc = (1u << 4) | (Elem<EB>::FMT << 7) | (Elem<EB>::FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
@@ -162,16 +187,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
+                for (int k = 0; k < 4; ++k) {          // 4 MMA k-slices per 128-byte row
                     // K-major SW128: rows of 128 B, 8-row groups 1024 B apart, k-slice = +32 B inside the atom.
                     // MN-major SW128_BASE32B: [k][128 B of M/N]; 32-wide M/N chunks BK*128 B apart (LBO),
                     // 4-row k-atoms 512 B apart (SBO), k-slice of 8 rows = +1024 B.
-                    const uint64_t bd = B_MN ? make_desc(b + k * 1024, BK * 128, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
+                    const uint64_t bd = B_MN ? make_desc(b + k * Elem<EB>::MN_KSTEP, BKE * 128, Elem<EB>::MN_SBO, Elem<EB>::MN_LAYOUT)
+                                             : make_desc(b + k * 32, 16, 1024, 2);
 #pragma unroll
                     for (int h = 0; h < MH; ++h) {       // the two 128-row halves share this B stage
-                        const uint32_t ah = a + h * (BM * BK * 4);
-                        const uint64_t ad = A_MN ? make_desc(ah + k * 1024, BK * 128, 512, 1) : make_desc(ah + k * 32, 16, 1024, 2);
-                        if (!(g.dbg & 2)) tc_mma_tf32(tmem_base + h * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        const uint32_t ah = a + h * (BM * 128);
+                        const uint64_t ad = A_MN ? make_desc(ah + k * Elem<EB>::MN_KSTEP, BKE * 128, Elem<EB>::MN_SBO, Elem<EB>::MN_LAYOUT)
+                                                 : make_desc(ah + k * 32, 16, 1024, 2);
+                        if (!(g.dbg & 2)) tc_mma<EB>(tmem_base + h * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                 }
                 tc_commit(&empty[s]);            // frees the smem slot once these MMAs have read it
@@ -268,12 +295,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int EB, int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g,
                      int tiles_m, int tiles_n, int n_split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STG = 36;
+    constexpr int BKE = Elem<EB>::BKE, CW = 128 / EB;
+    constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STG = 36;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
@@ -285,7 +313,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kb_total = (g.K + BK - 1) / BK;
+    const int kb_total = (g.K + BKE - 1) / BKE;
     const long n_items = (long)tiles_m * tiles_n * n_split;
 
     if (warp == 0 && lane == 0) {
@@ -321,20 +349,20 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 int m0, n0, kb_beg, nkb, z;
                 decode(item, m0, n0, kb_beg, nkb, z);
                 for (int i = 0; i < nkb; ++i, ++cnt) {
-                    const int s = (int)(cnt % STAGES), k0 = (kb_beg + i) * BK;
+                    const int s = (int)(cnt % STAGES), k0 = (kb_beg + i) * BKE;
                     if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
                     mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                     uint8_t* a = sA + s * A_BYTES;
                     uint8_t* b = sB + s * B_BYTES;
                     if (A_MN) {
 #pragma unroll
-                        for (int c = 0; c < BM / 32; ++c) tma_load_2d(&tmA, &full[s], a + c * (BK * 128), m0 + 32 * c, k0);
+                        for (int c = 0; c < BM / CW; ++c) tma_load_2d(&tmA, &full[s], a + c * (BKE * 128), m0 + CW * c, k0);
                     } else {
                         tma_load_2d(&tmA, &full[s], a, k0, m0);
                     }
                     if (B_MN) {
 #pragma unroll
-                        for (int c = 0; c < BN / 32; ++c) tma_load_2d(&tmB, &full[s], b + c * (BK * 128), n0 + 32 * c, k0);
+                        for (int c = 0; c < BN / CW; ++c) tma_load_2d(&tmB, &full[s], b + c * (BKE * 128), n0 + CW * c, k0);
                     } else {
                         tma_load_2d(&tmB, &full[s], b, k0, n0);
                     }
@@ -343,7 +371,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+            const uint32_t idesc = (1u << 4) | (Elem<EB>::FMT << 7) | (Elem<EB>::FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             long cnt = 0, j = 0;
             for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
@@ -358,10 +386,12 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     tc_fence_after();
                     const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; ++k) {
-                        const uint64_t ad = A_MN ? make_desc(a + k * 1024, BK * 128, 512, 1) : make_desc(a + k * 32, 16, 1024, 2);
-                        const uint64_t bd = B_MN ? make_desc(b + k * 1024, BK * 128, 512, 1) : make_desc(b + k * 32, 16, 1024, 2);
-                        tc_mma_tf32(tmem_base + acc * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k) {          // 4 MMA k-slices per 128-byte row
+                        const uint64_t ad = A_MN ? make_desc(a + k * Elem<EB>::MN_KSTEP, BKE * 128, Elem<EB>::MN_SBO, Elem<EB>::MN_LAYOUT)
+                                                : make_desc(a + k * 32, 16, 1024, 2);
+                        const uint64_t bd = B_MN ? make_desc(b + k * Elem<EB>::MN_KSTEP, BKE * 128, Elem<EB>::MN_SBO, Elem<EB>::MN_LAYOUT)
+                                             : make_desc(b + k * 32, 16, 1024, 2);
+                        tc_mma<EB>(tmem_base + acc * BN, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[s]);
                 }
@@ -465,104 +495,115 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [outer][inner] with row stride ld (floats); box = {32 inner, box_outer}.
-int make_map(CUtensorMap* map, const float* base, long inner, long outer, long ld, int box_outer, bool mn_major) {
+int make_map(CUtensorMap* map, const void* base, int eb, long inner, long outer, long ld, int box_outer, bool mn_major) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return 801;   // cudaErrorNotSupported
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, (void*)base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = enc(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     (mn_major && eb == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
 
-template <int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
+template <int EB, int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
-    constexpr int smem = STAGES * (MH * BM * BK * 4 + BN * BK * 4) + 1024 + 256;
+    constexpr int smem = STAGES * (MH * BM * 128 + BN * 128) + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<MH, BN, STAGES, MINB, A_MN, B_MN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EB, MH, BN, STAGES, MINB, A_MN, B_MN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    gemm_tf32_kernel<MH, BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
+    gemm_tf32_kernel<EB, MH, BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
     return pd_launch_status();
 }
 
-template <int MH, int BN, int STAGES, int MINB>
+template <int EB, int MH, int BN, int STAGES, int MINB>
 int launch_l(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch<MH, BN, STAGES, MINB, false, false>(ta, tb, g, grid, st);
-    if (!a_mn && b_mn) return launch<MH, BN, STAGES, MINB, false, true>(ta, tb, g, grid, st);
-    if (a_mn && b_mn) return launch<MH, BN, STAGES, MINB, true, true>(ta, tb, g, grid, st);
-    return launch<MH, BN, STAGES, MINB, true, false>(ta, tb, g, grid, st);
+    if (!a_mn && !b_mn) return launch<EB, MH, BN, STAGES, MINB, false, false>(ta, tb, g, grid, st);
+    if (!a_mn && b_mn) return launch<EB, MH, BN, STAGES, MINB, false, true>(ta, tb, g, grid, st);
+    if (a_mn && b_mn) return launch<EB, MH, BN, STAGES, MINB, true, true>(ta, tb, g, grid, st);
+    return launch<EB, MH, BN, STAGES, MINB, true, false>(ta, tb, g, grid, st);
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int EB, int BN, int STAGES, bool A_MN, bool B_MN>
 int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m, int tiles_n, int split,
              cudaStream_t st) {
-    constexpr int smem = STAGES * (BM * BK * 4 + BN * BK * 4) + 4 * 32 * 36 * 4 + 1024 + 256;
+    constexpr int smem = STAGES * (BM * 128 + BN * 128) + 4 * 32 * 36 * 4 + 1024 + 256;
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<BN, STAGES, A_MN, B_MN>,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     long items = (long)tiles_m * tiles_n * split;
     int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
-    gemm_tf32_persistent<BN, STAGES, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g, tiles_m, tiles_n, split);
+    gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g, tiles_m, tiles_n, split);
     return pd_launch_status();
 }
 
-template <int BN, int STAGES>
+template <int EB, int BN, int STAGES>
 int launch_pl(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m,
               int tiles_n, int split, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_p<BN, STAGES, false, false>(ta, tb, g, tiles_m, tiles_n, split, st);
-    if (!a_mn && b_mn) return launch_p<BN, STAGES, false, true>(ta, tb, g, tiles_m, tiles_n, split, st);
-    if (a_mn && b_mn) return launch_p<BN, STAGES, true, true>(ta, tb, g, tiles_m, tiles_n, split, st);
-    return launch_p<BN, STAGES, true, false>(ta, tb, g, tiles_m, tiles_n, split, st);
+    if (!a_mn && !b_mn) return launch_p<EB, BN, STAGES, false, false>(ta, tb, g, tiles_m, tiles_n, split, st);
+    if (!a_mn && b_mn) return launch_p<EB, BN, STAGES, false, true>(ta, tb, g, tiles_m, tiles_n, split, st);
+    if (a_mn && b_mn) return launch_p<EB, BN, STAGES, true, true>(ta, tb, g, tiles_m, tiles_n, split, st);
+    return launch_p<EB, BN, STAGES, true, false>(ta, tb, g, tiles_m, tiles_n, split, st);
 }
 
 // config id = (m_halves - 1) * 100000 + bn * 100 + stages * 10 + ctas_per_sm; 9xxxxx = persistent kernel
+template <int EB>
 int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid,
                cudaStream_t st) {
     switch (cfg) {
-        case 25641: return launch_l<1, 256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 25622: return launch_l<1, 256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12841: return launch_l<1, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12832: return launch_l<1, 128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 12823: return launch_l<1, 128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 6441: return launch_l<1, 64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 6433: return launch_l<1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 125631: return launch_l<2, 256, 3, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 112841: return launch_l<2, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
-        case 112822: return launch_l<2, 128, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-        default: return PD_BAD_ARG;
+        case 25622: return launch_l<EB, 1, 256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 12823: return launch_l<EB, 1, 128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6441: return launch_l<EB, 1, 64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        default: break;
     }
+    if (EB == 4) {          // tuning-only configurations exist for the fp32/TF32 operand type
+        switch (cfg) {
+            case 25641: return launch_l<4, 1, 256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 12841: return launch_l<4, 1, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 12832: return launch_l<4, 1, 128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 6433: return launch_l<4, 1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 125631: return launch_l<4, 2, 256, 3, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 112841: return launch_l<4, 2, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 112822: return launch_l<4, 2, 128, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+            default: break;
+        }
+    }
+    return PD_BAD_ARG;
 }
 
-int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
-                   const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st) {
+// EB = 4: A, B fp32 (TF32 multiply).  EB = 2: A, B bf16.  Strides in elements; C / bias fp32.
+template <int EB>
+int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, long sbn, float* C, long ldc,
+                 const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st) {
+    constexpr int BKE = 128 / EB, ALIGN = 16 / EB;       // k-block elements; stride alignment in elements
     const int dbg = cfg / 1000000;
     cfg %= 1000000;
     if (M <= 0 || N <= 0) return 0;
     if (K <= 0 || (sak != 1 && sam != 1) || (sbk != 1 && sbn != 1)) return PD_BAD_ARG;
     const bool a_mn = (sak != 1), b_mn = (sbk != 1);
     const long lda = a_mn ? sak : sam, ldb = b_mn ? sbk : sbn;
-    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 3) || (ldb & 3) || lda < 4 || ldb < 4) return PD_BAD_ARG;
+    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda % ALIGN) || (ldb % ALIGN) || lda < ALIGN || ldb < ALIGN)
+        return PD_BAD_ARG;
     if (cfg == 0) {
         // measured on B200 (tools/gemm_tune.py, tools/gemm_dissect.py)
         const int tiles_m = (M + BM - 1) / BM;
-        const int kb0 = (K + BK - 1) / BK;
+        const int kb0 = (K + BKE - 1) / BKE;
         const long t256 = (long)tiles_m * ((N + 255) / 256), t128 = (long)tiles_m * ((N + 127) / 128);
         if (N <= 64) cfg = 6441;                                     // narrow heads
         else if (N <= 128) cfg = 12823;
-        else if (kb0 >= 1024 && t256 < PD_NUM_SMS) cfg = 12823;      // split-K weight gradients
-        else if (t256 >= 2L * PD_NUM_SMS && kb0 >= 8) cfg = 925641;  // persistent, epilogue overlapped
+        else if ((long)kb0 * BKE >= 32768 && t256 < PD_NUM_SMS) cfg = 12823;   // split-K weight gradients
+        else if (t256 >= 2L * PD_NUM_SMS && kb0 >= 4) cfg = 925641;  // persistent, epilogue overlapped
         else if (t256 >= PD_NUM_SMS) cfg = 25622;                    // 2 CTAs/SM
         else if (t128 >= PD_NUM_SMS) cfg = 12823;
         else cfg = 6441;                                             // small per-step recurrent GEMMs
@@ -572,7 +613,7 @@ int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk,
     const int tiles_m = (M + mh * BM - 1) / (mh * BM);
     const int tiles_n = (N + bn - 1) / bn;
     const long tiles = (long)tiles_m * tiles_n;
-    const int kb = (K + BK - 1) / BK;
+    const int kb = (K + BKE - 1) / BKE;
     int split = 1;
     if (tiles < PD_NUM_SMS && kb >= 32) {
         split = (int)((2 * PD_NUM_SMS + tiles - 1) / tiles);
@@ -584,16 +625,34 @@ int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk,
     TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0, dbg};
     CUtensorMap ta, tb;
     int rc;
-    // K-major: [rows][K] -> dims {K, rows}, box {32, BM|bn}.  MN-major: [K][rows] -> dims {rows, K}, box {32, BK}.
-    rc = a_mn ? make_map(&ta, A, M, K, lda, BK, true) : make_map(&ta, A, K, M, lda, mh * BM, false);
+    // K-major: [rows][K] -> dims {K, rows}, box {128 B, BM|bn rows}.  MN-major: [K][rows] -> dims {rows, K},
+    // box {128 B of M/N, BKE k-rows}.
+    rc = a_mn ? make_map(&ta, A, EB, M, K, lda, BKE, true) : make_map(&ta, A, EB, K, M, lda, mh * BM, false);
     if (rc) return rc;
-    rc = b_mn ? make_map(&tb, B, N, K, ldb, BK, true) : make_map(&tb, B, K, N, ldb, bn, false);
+    rc = b_mn ? make_map(&tb, B, EB, N, K, ldb, BKE, true) : make_map(&tb, B, EB, K, N, ldb, bn, false);
     if (rc) return rc;
     if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
-    if (cfg == 925641) return launch_pl<256, 4>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
-    if (cfg == 912861) return launch_pl<128, 6>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
+    if (cfg == 925641) return launch_pl<EB, 256, 4>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
+    if (cfg == 912861 && EB == 4) return launch_pl<4, 128, 6>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
     dim3 grid(tiles_m, tiles_n, split);
-    return launch_cfg(cfg, a_mn, b_mn, ta, tb, g, grid, st);
+    return launch_cfg<EB>(cfg, a_mn, b_mn, ta, tb, g, grid, st);
+}
+
+// fp32 (rows, cols; row stride ldx) -> bf16 (row stride ldo), round to nearest even
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, long ldx, long rows, int cols, uint16_t* __restrict__ out,
+                                   long ldo) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c2 = (cols + 1) >> 1;
+    if (i >= rows * c2) return;
+    const long r = i / c2;
+    const int c = (int)(i % c2) * 2;
+    const float a = x[r * ldx + c];
+    const float b = (c + 1 < cols) ? x[r * ldx + c + 1] : 0.0f;
+    uint32_t lo, hi;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(*reinterpret_cast<uint16_t*>(&lo)) : "f"(a));
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(*reinterpret_cast<uint16_t*>(&hi)) : "f"(b));
+    out[r * ldo + c] = (uint16_t)lo;
+    if (c + 1 < cols) out[r * ldo + c + 1] = (uint16_t)hi;
 }
 
 }  // namespace
@@ -603,11 +662,25 @@ int gemm_tf32_impl(const float* A, long sam, long sak, const float* B, long sbk,
 // PD_BAD_ARG (-22) when a requirement does not hold so the caller can route to pd_gemm_f32.
 PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                         const float* bias, int M, int N, int K, int accumulate, void* stream) {
-    return gemm_tf32_impl(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream);
+    return gemm_tc_impl<4>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream);
 }
 
 // Tuning variant: cfg = BN*100 + stages*10 + CTAs/SM (one of the instantiated configurations), 0 = heuristic.
 PD_API int pd_gemm_tf32_cfg(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                             const float* bias, int M, int N, int K, int accumulate, int cfg, void* stream) {
-    return gemm_tf32_impl(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, cfg, (cudaStream_t)stream);
+    return gemm_tc_impl<4>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, cfg, (cudaStream_t)stream);
+}
+
+// bf16 operands (A, B: uint16 bf16 bit patterns; strides in elements, multiples of 8; bases 16-byte aligned),
+// fp32 accumulate / output / bias: tcgen05.mma kind::f16.  Same layouts as pd_gemm_tf32.
+PD_API int pd_gemm_bf16(const void* A, long sam, long sak, const void* B, long sbk, long sbn, float* C, long ldc,
+                        const float* bias, int M, int N, int K, int accumulate, void* stream) {
+    return gemm_tc_impl<2>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream);
+}
+
+PD_API int pd_f32_to_bf16(const float* x, long ldx, long rows, int cols, void* out, long ldo, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    long n = rows * ((cols + 1) / 2);
+    f32_to_bf16_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, cols, (uint16_t*)out, ldo);
+    return pd_launch_status();
 }

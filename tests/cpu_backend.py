@@ -57,6 +57,28 @@ class CpuBackend:
     def pd_gemm_tf32_cfg(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, cfg, st):
         self.pd_gemm_f32(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, st)
 
+    @staticmethod
+    def _bf16_to_f32(ptr, shape, strides):
+        u = _arr(ptr, shape, strides, np.uint16).astype(np.uint32) << 16
+        return u.view(np.float32)
+
+    def pd_gemm_bf16(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, st):
+        if M <= 0 or N <= 0:
+            return
+        a = self._bf16_to_f32(A, (M, K), (sam, sak))
+        b = self._bf16_to_f32(B, (K, N), (sbk, sbn))
+        c = _arr(C, (M, N), (ldc, 1))
+        r = (a @ b).astype(np.float32)
+        if bias is not None:
+            r = r + _arr(bias, (N,), (1,))
+        c[...] = c + r if acc else r
+
+    def pd_f32_to_bf16(self, x, ldx, rows, cols, out, ldo, st):
+        X = _arr(x, (rows, cols), (ldx, 1)).astype(np.float32)
+        bits = X.view(np.uint32).astype(np.uint64)
+        rounded = (bits + 0x7FFF + ((bits >> 16) & 1)) >> 16                     # round to nearest even
+        _arr(out, (rows, cols), (ldo, 1), np.uint16)[...] = rounded.astype(np.uint16)
+
     def pd_tf32_split(self, x, ldx, rows, cols, hi_out, lo, ldo, st):
         X = _arr(x, (rows, cols), (ldx, 1)).astype(np.float32)
         bits = X.view(np.uint32).astype(np.uint64)

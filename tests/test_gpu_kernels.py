@@ -402,3 +402,37 @@ def test_tf32x3_gemm_is_fp32_class():
             ops.gemm_nt(A, W, out, b)
         errs[mode] = float((out.double() - ref).abs().max() / ref.abs().max())
     assert errs["tf32x3"] < 3e-6 and errs["fp32"] < 1e-6 and errs["tf32"] > 10 * errs["tf32x3"], errs
+
+
+@pytest.mark.parametrize("M,N,K,layout,acc", [(513, 136, 512, "nt", 1), (2048, 1536, 128, "nt", 0), (257, 304, 80, "nn", 1),
+                                              (1536, 512, 40000, "tn", 0), (64, 128, 30008, "tn", 1)])
+def test_gemm_bf16_tcgen05(M, N, K, layout, acc):
+    """bf16-operand tcgen05 GEMM (kind::f16, fp32 accumulate) and the fp32->bf16 conversion kernel vs the numpy
+    restatement (products of bf16 values are exact in fp32; only the summation order differs)."""
+    _dev()
+    from polydis_b200 import _lib
+    r8 = lambda v: (v + 7) // 8 * 8
+    torch.manual_seed(1)
+    if layout == "tn":
+        A32 = torch.randn(K, r8(M) + 8); sam, sak = 1, r8(M) + 8
+    else:
+        A32 = torch.randn(M, r8(K) + 8); sam, sak = r8(K) + 8, 1
+    if layout == "nt":
+        B32 = torch.randn(N, r8(K) + 8); sbk, sbn = 1, r8(K) + 8
+    else:
+        B32 = torch.randn(K, r8(N) + 8); sbk, sbn = r8(N) + 8, 1
+    outs = []
+    for X in (A32, B32):
+        def mk(X=X):
+            o = torch.zeros(X.shape, dtype=torch.int16)
+            return [X, X.shape[1], X.shape[0], X.shape[1], o, X.shape[1], None], [o]
+        (g, c), = _both("pd_f32_to_bf16", mk)
+        assert torch.equal(g, c)
+        assert torch.equal(g.view(torch.bfloat16), X.to(torch.bfloat16))
+        outs.append(c)
+
+    def mkg():
+        C = torch.randn(M, N + 4)
+        return [outs[0], sam, sak, outs[1], sbk, sbn, C, N + 4, torch.randn(N), M, N, K, acc, None], [C]
+    (g, c), = _both("pd_gemm_bf16", mkg)
+    assert torch.allclose(g, c, atol=2e-5 * max(1.0, np.sqrt(K)), rtol=1e-4), float((g - c).abs().max())
