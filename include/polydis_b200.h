@@ -63,6 +63,13 @@ int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, c
                      float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
                      long lddgi2, const int* lengths, int t, int B, int H, void* stream);
 
+/* fused GRU step on the tensor cores: hout = GRUCell(gi [+ gi2], hprev) with W_hh h computed by tcgen05.mma into
+ * TMEM and the gate math done in the epilogue (the (B,3H) h-projection never reaches HBM).  H % 64 == 0,
+ * hprev != NULL, hout != hprev, strides multiples of 4 floats, 16-byte aligned bases; else PD_BAD_ARG. */
+int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
+                     long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
+                     long ldhn, const int* lengths, int t, int B, int H, void* stream);
+
 /* ---- PianoTree grid (ptvae.py:292-313,:498-511,:531-535).  x (n_steps,16,6) int64 -> tok int32 (same
  * layout), lengths (n_steps) = 16 - #PAD, pitch targets (n_steps,15), duration targets (n_steps,15,5). */
 int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, int* pitch_tgt, int* dur_tgt,

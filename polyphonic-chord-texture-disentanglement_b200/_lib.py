@@ -22,6 +22,7 @@ SIGNATURES = {
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,
                          _I, _I, _P],
+    "pd_gru_step_tf32": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
     "pd_grid_to_prmat": [_P, _L, _P, _P],

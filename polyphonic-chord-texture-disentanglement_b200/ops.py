@@ -100,6 +100,11 @@ def fork_join(fns):
 #             accumulation (lo = x - rn_tf32(x)): ~2^-22 relative operand error, i.e. fp32-class results at
 #             tensor-core speed for the inference GEMMs (SURVEY.md 7.4-2 "TF32x3").
 PRECISION = "tf32"
+# Recurrent GEMM + gate math in one tcgen05 kernel (csrc/gru_step_tc.cu).  Correct (tests/test_gpu_kernels.py) but
+# measured SLOWER than GEMM + gate kernel on B200 (note-GRU step 246 vs 148 us cold, tools/gru_step_bench.py): its
+# row-per-thread epilogue reads gi / gi2 / h_prev and writes h / r|z|n / hn as 64-byte pieces per lane.  Off until
+# the epilogue is staged through shared memory.
+FUSED_GRU_STEP = False
 _lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
 
 
@@ -332,7 +337,21 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
         save["rzn"], save["hn"] = rzn, hn
     order = range(T - 1, -1, -1) if reverse else range(T)
     hprev = h0
+    # fused step (recurrent GEMM + gate math in one tcgen05 kernel) whenever TMA can address the operands
+    fused_ok = (FUSED_GRU_STEP and PRECISION == "tf32" and H % 64 == 0 and w_hh.stride(1) == 1
+                and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0 and b_hh.data_ptr() % 16 == 0
+                and gi.stride(2) == 1 and gi.stride(0) % 4 == 0 and gi.stride(1) % 4 == 0 and gi.data_ptr() % 16 == 0
+                and (gi2 is None or (gi2.stride(1) == 1 and gi2.stride(0) % 4 == 0 and gi2.data_ptr() % 16 == 0)))
     for t in order:
+        if (fused_ok and hprev is not None and hprev.stride(1) == 1 and hprev.stride(0) % 4 == 0
+                and hprev.data_ptr() % 16 == 0):
+            _call("pd_gru_step_tf32", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(b_hh),
+                  _ptr(gi[:, t]), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
+                  _ptr(h_all[:, t]), h_all.stride(0), None if rzn is None else _ptr(rzn[:, t]),
+                  0 if rzn is None else rzn.stride(0), None if hn is None else _ptr(hn[:, t]),
+                  0 if hn is None else hn.stride(0), _ptr(lengths), t, B, H, _stream())
+            hprev = h_all[:, t]
+            continue
         if hprev is None:
             gemm_nt(gh[:, :0], w_hh[:, :0], gh, b_hh)          # K = 0: gh = b_hh
         else:

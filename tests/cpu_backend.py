@@ -116,6 +116,14 @@ class CpuBackend:
             Q = _arr(hn, (B, H), (ldhn, 1))
             Q[act] = GH[:, 2 * H:][act]
 
+    def pd_gru_step_tf32(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
+                         B, H, st):
+        HP = _arr(hp, (B, H), (ldhp, 1))
+        gh = (HP @ _arr(w, (3 * H, H), (ldw, 1)).T + _arr(b_hh, (3 * H,), (1,))).astype(np.float32)
+        gh_ptr = gh.ctypes.data
+        self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh_ptr, 3 * H, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
+                              B, H, st)
+
     def pd_gru_gates_bwd(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                          dhp, lddhp, dgi2, lddgi2, lengths, t, B, H, st):
         d = np.zeros((B, H), np.float32)

@@ -436,3 +436,23 @@ def test_gemm_bf16_tcgen05(M, N, K, layout, acc):
         return [outs[0], sam, sak, outs[1], sbk, sbn, C, N + 4, torch.randn(N), M, N, K, acc, None], [C]
     (g, c), = _both("pd_gemm_bf16", mkg)
     assert torch.allclose(g, c, atol=2e-5 * max(1.0, np.sqrt(K)), rtol=1e-4), float((g - c).abs().max())
+
+
+@pytest.mark.parametrize("B,H,masked,bcast,save", [(7, 64, False, False, True), (300, 512, False, True, True),
+                                                   (130, 128, True, False, True), (513, 1024, False, True, False)])
+def test_gru_step_fused_tcgen05(B, H, masked, bcast, save):
+    """Fused recurrent GEMM + gate epilogue vs GEMM-then-gates in numpy (TF32 operand rounding on the GEMM)."""
+    _dev()
+    t = 3
+
+    def mk():
+        hp, w, b = torch.randn(B, 2, H) * 0.5, torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+        gi = torch.randn(B, 2, 3 * H)
+        gi2 = torch.randn(B, 3 * H) if bcast else None
+        ho = torch.zeros(B, 2, H)
+        rzn, hn = (torch.zeros(B, 3 * H), torch.zeros(B, H)) if save else (None, None)
+        ln = torch.randint(1, 8, (B,), dtype=torch.int32) if masked else None
+        return ([hp, 2 * H, w, H, b, gi, 6 * H, gi2, 3 * H, ho, 2 * H, rzn, 3 * H, hn, H, ln, t, B, H, None],
+                [ho] + ([rzn, hn] if save else []))
+    for g, c in _both("pd_gru_step_tf32", mk):
+        assert torch.allclose(g, c, atol=3e-3, rtol=0), float((g - c).abs().max())

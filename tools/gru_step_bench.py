@@ -1,0 +1,27 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from polydis_b200 import ops
+dev = torch.device("cuda:0")
+flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+def t(fn, n=10):
+    for _ in range(2): fn()
+    tot = 0.0
+    for _ in range(n):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); tot += e0.elapsed_time(e1)
+    return tot / n * 1e3
+for (B, T, H, bc) in [(16384, 15, 512, True), (512, 32, 1024, True), (16384, 16, 128, False), (512, 8, 512, True)]:
+    gi = torch.randn(B, T, 3 * H, device=dev); gi2 = torch.randn(B, 3 * H, device=dev) if bc else None
+    h_all = torch.randn(B, T, H, device=dev); w = torch.randn(3 * H, H, device=dev) * 0.03; b = torch.randn(3 * H, device=dev)
+    rzn = torch.empty(B, T, 3 * H, device=dev); hn = torch.empty(B, T, H, device=dev); gh = torch.empty(B, 3 * H, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    def fused():
+        ops._call("pd_gru_step_tf32", h_all[:, 2].data_ptr(), T * H, w.data_ptr(), H, b.data_ptr(), gi[:, 3].data_ptr(), T * 3 * H,
+                  None if gi2 is None else gi2.data_ptr(), 3 * H, h_all[:, 3].data_ptr(), T * H, rzn[:, 3].data_ptr(), T * 3 * H,
+                  hn[:, 3].data_ptr(), T * H, None, 3, B, H, st)
+    def split():
+        ops.gemm_nt(h_all[:, 2], w, gh, b)
+        ops._gates_fwd(gi[:, 3], gi2, gh, h_all[:, 2], h_all[:, 3], rzn[:, 3], hn[:, 3], None, 3)
+    print(f"B={B} H={H}: fused {t(fused):7.1f} us   gemm+gates {t(split):7.1f} us", flush=True)
