@@ -128,3 +128,29 @@ def test_greedy_tokens_match_oracle_larger_batch(prec):
     pre = ref[..., 0] != 129
     assert match >= 0.999, match
     assert (est[pre] == ref[pre]).mean() >= 0.999
+
+
+@pytest.mark.parametrize("B", [1, 130])
+def test_odd_batch_sizes_match_oracle(B):
+    """Batch sizes that are not multiples of any tile size (and the degenerate B = 1): teacher-forced losses and
+    greedy tokens against the CPU oracle."""
+    dev = _dev()
+    from oracle import polydis_oracle as O
+    xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 300 + B))
+    sd = make_state_dict(12, gain=2.0, eos_bias=0.75)
+    torch.manual_seed(B)
+    e1, e2 = torch.randn(B, 256), torch.randn(B, 256)
+    random.seed(2)
+    with torch.no_grad():
+        ref = O.loss(sd, xs, cs, prs, O.draw_plan(1., 1., 1.), e1, e2)
+    m = _model(dev, 12, 2.0, 0.75)
+    m.train()
+    random.seed(2)
+    got = m.loss(xs.to(dev), cs.to(dev), prs.to(dev), 1., 1., 1., eps=(e1.to(dev), e2.to(dev)))
+    got[0].backward()
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 1e-3 * abs(float(b)) + 1e-6
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+    nd = min(B, 24)
+    est = m.swap(prs[:nd].to(dev), prs[:nd].to(dev), cs[:nd].to(dev), cs[:nd].to(dev), True, True)
+    assert (est == O.inference(sd, prs[:nd], cs[:nd])).mean() >= 0.999
