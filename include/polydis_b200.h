@@ -46,6 +46,9 @@ int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, floa
 /* out[n] (+)= sum_m X[m*ldx+n]   (bias gradients) */
 int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int accumulate, void* stream);
 int pd_transpose_f32(const float* in, int rows, int cols, float* out, void* stream);
+/* out[r*ldo+c] = sum_t X[r*ldr + t*ldt + c]: gradient of a projection broadcast over a GRU's steps (the hoisted
+ * z / summary terms of ptvae.py:394-395,458-460) in one pass instead of a read-modify-write per step */
+int pd_sum_steps_f32(const float* X, long ldr, long ldt, int T, float* out, long ldo, long R, int C, void* stream);
 
 /* ---- GRU cell gate math around the per-step W_hh GEMM (aten::gru at ptvae.py:63-65,359-360,396-398,
  * 461-462; packed bi-GRU at :446-453,:480-486 through the per-row `lengths` mask).  Gate order r|z|n.
@@ -69,6 +72,17 @@ int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, c
 int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
                      long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                      long ldhn, const int* lengths, int t, int B, int H, void* stream);
+
+/* weight-resident variable-length GRU, hidden 128 (the note-summary bi-GRU, ptvae.py:446-453,:480-486): one kernel
+ * runs the whole recurrence of a tile of sequences with W_hh resident in shared memory and stops at the tile's
+ * longest sequence.  gi (R,T,384) incl. b_ih, lengths (R), h0 = 0; rows past their length carry their state.
+ * passes 1 = TF32, 3 = error-compensated TF32.  bwd: dgi / dgh (R,T,384) from dout (R,T,128) and the saves. */
+int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
+                  float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R, int T,
+                  int reverse, int passes, void* stream);
+int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn, long zr,
+                  long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh, float* dgi, long gr,
+                  long gt, float* dgh, long qr, long qt, long R, int T, int reverse, void* stream);
 
 /* ---- PianoTree grid (ptvae.py:292-313,:498-511,:531-535).  x (n_steps,16,6) int64 -> tok int32 (same
  * layout), lengths (n_steps) = 16 - #PAD, pitch targets (n_steps,15), duration targets (n_steps,15,5). */

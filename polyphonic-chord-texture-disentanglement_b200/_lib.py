@@ -19,10 +19,13 @@ SIGNATURES = {
     "pd_f32_to_bf16": [_P, _L, _L, _I, _P, _L, _P],
     "pd_tf32_split": [_P, _L, _L, _I, _P, _P, _L, _P],
     "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
+    "pd_sum_steps_f32": [_P, _L, _L, _I, _P, _L, _L, _I, _P],
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,
                          _I, _I, _P],
     "pd_gru_step_tf32": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
+    "pd_gru128_fwd": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P],
+    "pd_gru128_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
     "pd_grid_to_prmat": [_P, _L, _P, _P],

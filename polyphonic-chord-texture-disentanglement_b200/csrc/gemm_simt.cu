@@ -140,6 +140,69 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ldx, int M, int 
     atomicAdd(out + n, (s0 + s1) + (s2 + s3));
 }
 
+// Vector variant for 16-byte aligned inputs: a block sums one 128-column strip over its row range with 8 warps
+// striding the rows (lane = 4 columns, float4 loads, 4 rows in flight per thread), reduces the warps through
+// shared memory and issues one atomicAdd per column.
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict__ X, long ldx, int M, int N, float* out,
+                                                         int rows_per_blk) {
+    __shared__ float4 part[8][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.x * 128 + lane * 4;
+    const int mb = blockIdx.y * rows_per_blk, me = min(M, mb + rows_per_blk);
+    float4 s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n < N) {
+        int m = mb + warp;
+        for (; m + 24 < me; m += 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)(m + 8 * i) * ldx + n));
+                s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+            }
+        }
+        for (; m < me; m += 8) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)m * ldx + n));
+            s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        }
+    }
+    part[warp][lane] = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                                   (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int c = threadIdx.x, col = blockIdx.x * 128 + c;
+        if (col < N) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += reinterpret_cast<const float*>(&part[w][0])[c];
+            atomicAdd(out + col, t);
+        }
+    }
+}
+
+// out[r*ldo + c] = sum_t X[r*ldr + t*ldt + c]   (float4 lanes; C % 4 == 0)
+__global__ void __launch_bounds__(256) sum_steps_kernel(const float* __restrict__ X, long ldr, long ldt, int T, float* out,
+                                                        long ldo, long R, int C4) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= R * C4) return;
+    const long r = idx / C4;
+    const int c = (int)(idx % C4) * 4;
+    const float* p = X + r * ldr + c;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    int t = 0;
+    for (; t + 1 < T; t += 2) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p + (long)t * ldt));
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long)(t + 1) * ldt));
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+        b.x += v.x; b.y += v.y; b.z += v.z; b.w += v.w;
+    }
+    if (t < T) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(p + (long)t * ldt));
+        a.x += u.x; a.y += u.y; a.z += u.z; a.w += u.w;
+    }
+    *reinterpret_cast<float4*>(out + r * ldo + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
 }  // namespace
 
 PD_API int pd_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C,
@@ -182,10 +245,28 @@ PD_API int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int
     if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
     if (M <= 0) return pd_launch_status();
     int nbx = (N + 127) / 128;
+    if ((((uintptr_t)X) & 15) == 0 && (ldx & 3) == 0 && (N & 3) == 0 && M >= 256) {
+        int want = (6 * PD_NUM_SMS + nbx - 1) / nbx;
+        int rows = (M + want - 1) / want;
+        rows = ((rows < 64 ? 64 : rows) + 7) / 8 * 8;
+        dim3 gridv(nbx, (M + rows - 1) / rows);
+        colsum_vec_kernel<<<gridv, 256, 0, st>>>(X, ldx, M, N, out, rows);
+        return pd_launch_status();
+    }
     int want_y = (4 * PD_NUM_SMS + nbx - 1) / nbx;
     int rows_per = (M + want_y - 1) / want_y;
     if (rows_per < 32) rows_per = 32;
     dim3 grid(nbx, (M + rows_per - 1) / rows_per);
     colsum_kernel<<<grid, 128, 0, st>>>(X, ldx, M, N, out, rows_per);
+    return pd_launch_status();
+}
+
+// out (R,C; row stride ldo) = sum over the T steps of X (R,T,C; strides ldr, ldt in floats): the gradient of a
+// projection that is broadcast over a GRU's steps.  C % 4 == 0, strides % 4 == 0, 16-byte aligned bases.
+PD_API int pd_sum_steps_f32(const float* X, long ldr, long ldt, int T, float* out, long ldo, long R, int C, void* stream) {
+    if (R <= 0 || C <= 0) return 0;
+    if ((C & 3) || (ldr & 3) || (ldt & 3) || (ldo & 3) || (((uintptr_t)X | (uintptr_t)out) & 15) || T < 0) return PD_BAD_ARG;
+    const long n = R * (C / 4);
+    sum_steps_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(X, ldr, ldt, T, out, ldo, R, C / 4);
     return pd_launch_status();
 }

@@ -198,6 +198,14 @@ def colsum(x, out, accumulate=False):
     return out
 
 
+def sum_steps(x, T):
+    """(R,T',C) strided -> (R,C): sum over the first T steps."""
+    R, _, C = x.shape
+    out = torch.empty(R, C, device=x.device, dtype=torch.float32)
+    _call("pd_sum_steps_f32", _ptr(x), x.stride(0), x.stride(1), T, _ptr(out), out.stride(0), R, C, _stream())
+    return out
+
+
 def transpose(x):
     x = x.contiguous()
     out = torch.empty(x.shape[1], x.shape[0], device=x.device, dtype=x.dtype)
@@ -318,6 +326,23 @@ def _gates_fwd(gi, gi2, gh, hprev, hout, rzn, hn, lengths, t):
           _ptr(hn), 0 if hn is None else hn.stride(0), _ptr(lengths), t, B, H, _stream())
 
 
+# Weight-resident GRU128 kernel (csrc/gru128_resident.cu) for the note-summary bi-GRU.  Its matvecs run on
+# mma.sync, which B200 issues at about FFMA rate, so per row it only matches the tcgen05 GEMM + gate kernels --
+# but it is ONE launch instead of 32 (fwd) / 48 (bwd) and it occupies every SM.  Measured (B200, 16 steps):
+# 16384 sequences 423 vs 461 us forward, equal backward, but the teacher-forced step loses 0.3 ms because the
+# two directions no longer overlap the rest of the step; 512 sequences (free-running training, small-batch
+# decode) and the 3-pass tf32x3 decode win 6-12 %.  Hence the row limit in TF32 mode.
+RESIDENT_GRU128 = True
+RESIDENT_GRU128_MAX_ROWS_TF32 = 4096
+
+
+def _resident128_ok(gi, gi2, h0, lengths, H):
+    return (RESIDENT_GRU128 and H == 128 and lengths is not None and h0 is None and gi2 is None
+            and (PRECISION == "tf32x3" or (PRECISION == "tf32" and gi.shape[0] <= RESIDENT_GRU128_MAX_ROWS_TF32))
+            and gi.stride(2) == 1 and gi.stride(0) % 2 == 0
+            and gi.stride(1) % 2 == 0 and gi.data_ptr() % 8 == 0)
+
+
 def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None, n_steps=None):
     """Run a GRU over precomputed input projections.  gi (B,T,3H) strided view, gi2 (B,3H) or None;
     ``n_steps`` (<= T) uses only the first slots of gi (the note GRU consumes 15 of the 16 embedded slots).
@@ -329,6 +354,18 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
     H = H3 // 3
     dev = gi.device
     h_all = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    if _resident128_ok(gi, gi2, h0, lengths, H):
+        # weight-resident kernel: whole variable-length recurrence in one launch (csrc/gru128_resident.cu)
+        rzn = hn = None
+        if save is not None:
+            rzn = torch.empty(B, T, H3, device=dev, dtype=torch.float32)
+            hn = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+            save["rzn"], save["hn"], save["resident"] = rzn, hn, True
+        _call("pd_gru128_fwd", _ptr(gi), gi.stride(0), gi.stride(1), _ptr(lengths), _ptr(w_hh), _ptr(b_hh),
+              _ptr(h_all), h_all.stride(0), h_all.stride(1), _ptr(rzn), 0 if rzn is None else rzn.stride(0),
+              0 if rzn is None else rzn.stride(1), _ptr(hn), 0 if hn is None else hn.stride(0),
+              0 if hn is None else hn.stride(1), B, T, int(reverse), 3 if PRECISION == "tf32x3" else 1, _stream())
+        return h_all
     gh = torch.empty(B, H3, device=dev, dtype=torch.float32)
     rzn = hn = None
     if save is not None:
@@ -372,6 +409,7 @@ class _GruSeq(torch.autograd.Function):
         save = {}
         h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
+        ctx.resident = bool(save.get("resident"))
         ctx.reverse = reverse
         ctx.has_gi2 = gi2 is not None
         ctx.t_full = gi.shape[1]
@@ -388,7 +426,7 @@ class _GruSeq(torch.autograd.Function):
         if ctx.t_full > T:
             dgi[:, T:].zero_()                     # unused input slots get no gradient
         dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
-        dgi2 = torch.zeros(B, 3 * H, device=dev, dtype=torch.float32) if ctx.has_gi2 else None
+        dgi2 = None        # gradient of the step-constant projection: summed over the steps after the loop
         # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
         # and dgh @ W_hh (written by that step's GEMM); the next gate kernel sums both with dout[:, t]
         dz_a = torch.empty(B, H, device=dev, dtype=torch.float32)
@@ -398,7 +436,12 @@ class _GruSeq(torch.autograd.Function):
         order = list(range(T - 1, -1, -1) if ctx.reverse else range(T))
         dz = dm = None
         st = _stream()
-        for i in range(T - 1, -1, -1):
+        if ctx.resident:
+            _call("pd_gru128_bwd", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
+                  h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
+                  _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
+                  dgh.stride(1), B, T, int(ctx.reverse), st)
+        for i in (range(T - 1, -1, -1) if not ctx.resident else ()):
             t = order[i]
             hprev = h_all[:, order[i - 1]] if i > 0 else h0
             nz = dz_b if dz is dz_a else dz_a
@@ -416,7 +459,14 @@ class _GruSeq(torch.autograd.Function):
                 dm = None
         dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)
-        colsum(dgh_flat, db)
+        if ctx.has_gi2:
+            # one pass over dgi instead of a read-modify-write of (B,3H) in every step's gate kernel; the r and z
+            # thirds of db_hh equal those of sum(dgi) (dgh differs from dgi only in the n gate)
+            dgi2 = sum_steps(dgi, T)
+            colsum(dgi2[:, :2 * H], db[:2 * H])
+            colsum(dgh_flat[:, 2 * H:], db[2 * H:])
+        else:
+            colsum(dgh_flat, db)
         # dW_hh = sum_{b,t} dgh[b,t]^T h_prev[b,t] as ONE split-K GEMM over all (b,t) rows: h_prev of row r is
         # row r-1 (r+1 when reversed) of the flattened state buffer, except at each sequence's first step,
         # whose h_prev is h0 -- those rows are handled by a small GEMM and then zeroed in dgh.

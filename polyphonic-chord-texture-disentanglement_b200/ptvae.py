@@ -438,6 +438,7 @@ class PtvaeDecoder(nn.Module):
         He = self.dec_emb_hid_size
         gi_e = [torch.empty(B, NS, 3 * He, **f32) for _ in range(2)]
         gh_e, h_e = [torch.empty(B, 3 * He, **f32) for _ in range(2)], torch.empty(B, He, **f32)
+        h_sum = [torch.empty(B, NS, He, **f32) for _ in range(2)]
         st = ops._stream
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
@@ -467,6 +468,13 @@ class PtvaeDecoder(nn.Module):
                 w_ih, w_hh, b_ih, b_hh = eg.dir(rev)
                 ops.gemm_nt(flat, w_ih, gi_e[d].view(B * NS, 3 * He), b_ih)
                 out = tok_time[:, d * He:(d + 1) * He]
+                if ops._resident128_ok(gi_e[d], None, None, lens, He):
+                    # whole variable-length recurrence in one weight-resident kernel
+                    ops._call("pd_gru128_fwd", ops._ptr(gi_e[d]), gi_e[d].stride(0), gi_e[d].stride(1), ops._ptr(lens),
+                              ops._ptr(w_hh), ops._ptr(b_hh), ops._ptr(h_sum[d]), h_sum[d].stride(0), h_sum[d].stride(1),
+                              None, 0, 0, None, 0, 0, B, NS, int(rev), 3 if ops.PRECISION == "tf32x3" else 1, st())
+                    out.copy_(h_sum[d][:, 0 if rev else NS - 1])
+                    return
                 first = True
                 for k in (range(NS - 1, -1, -1) if rev else range(NS)):
                     if first:

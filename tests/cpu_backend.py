@@ -91,6 +91,9 @@ class CpuBackend:
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0
         o[...] = o + s if acc else s
 
+    def pd_sum_steps_f32(self, X, ldr, ldt, T, out, ldo, R, C, st):
+        _arr(out, (R, C), (ldo, 1))[...] = _arr(X, (R, T, C), (ldr, ldt, 1)).sum(1, dtype=np.float32)
+
     def pd_transpose_f32(self, inp, rows, cols, out, st):
         _arr(out, (cols, rows), (rows, 1))[...] = _arr(inp, (rows, cols), (cols, 1)).T
 
@@ -123,6 +126,60 @@ class CpuBackend:
         gh_ptr = gh.ctypes.data
         self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh_ptr, 3 * H, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
                               B, H, st)
+
+    def pd_gru128_fwd(self, gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse,
+                      passes, st):
+        H = 128
+        GI = _arr(gi, (R, T, 3 * H), (ldr, ldt, 1))
+        L = np.minimum(_arr(lengths, (R,), (1,), np.int32), T)
+        W, b = _arr(w_hh, (3 * H, H), (H, 1)), _arr(b_hh, (3 * H,), (1,))
+        HA = _arr(h_all, (R, T, H), (hr, ht, 1))
+        Z = _arr(rzn, (R, T, 3 * H), (zr, zt, 1)) if rzn is not None else None
+        N = _arr(hn, (R, T, H), (nr, nt, 1)) if hn is not None else None
+        h = np.zeros((R, H), np.float32)
+        for s_ in range(T):
+            t = T - 1 - s_ if reverse else s_
+            gh = (h @ W.T + b).astype(np.float32)
+            g = GI[:, t]
+            r = _sig(g[:, :H] + gh[:, :H])
+            z = _sig(g[:, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(g[:, 2 * H:] + r * gh[:, 2 * H:])
+            act = t < L
+            h = np.where(act[:, None], (1 - z) * n + z * h, h).astype(np.float32)
+            HA[:, t] = h
+            if Z is not None:
+                Z[act, t] = np.concatenate([r, z, n], 1)[act]
+            if N is not None:
+                N[act, t] = gh[:, 2 * H:][act]
+
+    def pd_gru128_bwd(self, dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr,
+                      qt, R, T, reverse, st):
+        H = 128
+        DO = _arr(dout, (R, T, H), (dr, dt, 1))
+        HA = _arr(h_all, (R, T, H), (hr, ht, 1))
+        Z = _arr(rzn, (R, T, 3 * H), (zr, zt, 1))
+        N = _arr(hn, (R, T, H), (nr, nt, 1))
+        L = np.minimum(_arr(lengths, (R,), (1,), np.int32), T)
+        W = _arr(w_hh, (3 * H, H), (H, 1))
+        GI = _arr(dgi, (R, T, 3 * H), (gr, gt, 1))
+        GH = _arr(dgh, (R, T, 3 * H), (qr, qt, 1))
+        dh = np.zeros((R, H), np.float32)
+        for s_ in range(T - 1, -1, -1):
+            t = T - 1 - s_ if reverse else s_
+            tp = t + 1 if reverse else t - 1
+            d = dh + DO[:, t]
+            act = (t < L)[:, None]
+            hp = HA[:, tp] if 0 <= tp < T else np.zeros((R, H), np.float32)
+            with np.errstate(all="ignore"):
+                r, z, n = Z[:, t, :H], Z[:, t, H:2 * H], Z[:, t, 2 * H:]
+                dn = d * (1 - z) * (1 - n * n)
+                dz = d * (hp - n) * z * (1 - z)
+                drr = dn * N[:, t] * r * (1 - r)
+                g_i = np.where(act, np.concatenate([drr, dz, dn], 1), 0).astype(np.float32)
+                g_h = np.where(act, np.concatenate([drr, dz, dn * r], 1), 0).astype(np.float32)
+            GI[:, t] = g_i
+            GH[:, t] = g_h
+            dh = (np.where(act, d * z, d) + g_h @ W).astype(np.float32)
 
     def pd_gru_gates_bwd(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                          dhp, lddhp, dgi2, lddgi2, lengths, t, B, H, st):

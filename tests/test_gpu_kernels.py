@@ -108,9 +108,19 @@ def test_colsum_and_transpose():
     (g, c), = _both("pd_colsum_f32",
                     lambda: (lambda X, o: ([X, 200, 5000, 192, o, 1, None], [o]))(torch.randn(5000, 200), torch.randn(192)))
     assert torch.allclose(g, c, atol=2e-3, rtol=1e-4)
+    (g, c), = _both("pd_colsum_f32",          # odd width / stride: scalar kernel; ragged row split
+                    lambda: (lambda X, o: ([X, 203, 4999, 190, o, 0, None], [o]))(torch.randn(4999, 203), torch.randn(190)))
+    assert torch.allclose(g, c, atol=2e-3, rtol=1e-4)
+    (g, c), = _both("pd_colsum_f32",          # vector kernel on a column slice of a wider matrix
+                    lambda: (lambda X, o: ([X, 384, 30001, 256, o, 0, None], [o]))(torch.randn(30001, 384), torch.zeros(256)))
+    assert torch.allclose(g, c, atol=5e-3, rtol=1e-4)
     (g, c), = _both("pd_transpose_f32",
                     lambda: (lambda X, o: ([X, 135, 128, o, None], [o]))(torch.randn(135, 128), torch.zeros(128, 135)))
     assert torch.equal(g, c)
+    for T in (1, 2, 15):
+        (g, c), = _both("pd_sum_steps_f32",
+                        lambda: (lambda X, o: ([X, 16 * 388, 388, T, o, 384, 77, 384, None], [o]))(torch.randn(77, 16, 388), torch.zeros(77, 384)))
+        assert torch.allclose(g, c, atol=1e-5, rtol=1e-5)
 
 
 @pytest.mark.parametrize("B,H,masked,bcast,hprev", [(7, 64, False, False, True), (33, 1024, False, True, True),
@@ -456,3 +466,32 @@ def test_gru_step_fused_tcgen05(B, H, masked, bcast, save):
                 [ho] + ([rzn, hn] if save else []))
     for g, c in _both("pd_gru_step_tf32", mk):
         assert torch.allclose(g, c, atol=3e-3, rtol=0), float((g - c).abs().max())
+
+
+@pytest.mark.parametrize("R,T,reverse,passes", [(5, 16, 0, 1), (1000, 16, 1, 1), (333, 16, 0, 3), (64, 7, 1, 3)])
+def test_gru128_resident(R, T, reverse, passes):
+    """Weight-resident variable-length GRU (fwd: TF32 / 3xTF32 matvecs; bwd: TF32) vs the numpy restatement."""
+    _dev()
+    H = 128
+    torch.manual_seed(4)
+    w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+    lengths = torch.randint(1, T + 1, (R,), dtype=torch.int32)
+    lengths[0] = T
+
+    def mk():
+        gi = torch.randn(R, T, 3 * H)
+        h_all, rzn, hn = torch.zeros(R, T, H), torch.zeros(R, T, 3 * H), torch.zeros(R, T, H)
+        return ([gi, T * 3 * H, 3 * H, lengths, w, b, h_all, T * H, H, rzn, T * 3 * H, 3 * H, hn, T * H, H, R, T, reverse,
+                 passes, None], [h_all, rzn, hn])
+    res = _both("pd_gru128_fwd", mk)
+    tol = 2e-5 if passes == 3 else 4e-3
+    for g, c in res:
+        assert torch.allclose(g, c, atol=tol, rtol=0), float((g - c).abs().max())
+    h_all, rzn, hn = (c for _, c in res)                 # emulation outputs feed the backward on both sides
+
+    def mkb():
+        dgi, dgh = torch.zeros(R, T, 3 * H), torch.zeros(R, T, 3 * H)
+        return ([torch.randn(R, T, H), T * H, H, h_all, T * H, H, rzn, T * 3 * H, 3 * H, hn, T * H, H, lengths, w, dgi,
+                 T * 3 * H, 3 * H, dgh, T * 3 * H, 3 * H, R, T, reverse, None], [dgi, dgh])
+    for g, c in _both("pd_gru128_bwd", mkb):
+        assert torch.allclose(g, c, atol=5e-3, rtol=1e-3), float((g - c).abs().max())
