@@ -19,6 +19,11 @@ static inline unsigned pd_blocks(long n, int per) { return (unsigned)((n + per -
 #define PD_NUM_SMS 148
 
 __device__ __forceinline__ float pd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// MUFU forms for the TF32-mode recurrent kernels, which are instruction-bound on the gate math: ex2.approx +
+// rcp.approx, absolute error ~1e-6 (three orders below the TF32 operand rounding of the matvec next to them);
+// saturate correctly (exp -> inf gives 1/inf = 0).  The fp32 / tf32x3 parity paths keep expf / tanhf.
+__device__ __forceinline__ float pd_sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float pd_tanh_fast(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

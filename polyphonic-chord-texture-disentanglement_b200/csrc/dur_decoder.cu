@@ -19,18 +19,20 @@
 //   col 69 -> db_ih, col 70 -> sum of step-0 input-gate grads (for d dur_sos_token);
 //   rows 256..257 x cols 0..63 -> dW_out, col 69 -> db_out.
 //
-// Two arithmetic modes (template TC): FFMA fp32 as described (the fp32-faithful mode greedy decoding needs
-// for token parity) and, for training, TF32 tensor-core matvecs: each warp keeps its slice of W_hh as
-// mma.sync m16n8k8 B-fragments in registers and multiplies the 32-note state tile straight out of shared
-// memory.  (tcgen05 is not used here on purpose: the 64-wide, 5-step recurrence is bound by gate
-// transcendentals and state traffic, the matvec is <10 % of the kernel once it is off the FFMA pipe, and
-// warp-level MMA keeps accumulators in registers next to the gate math instead of a TMEM round trip.)
+// Two arithmetic modes.  fp32 (tf32 = 0): the FFMA kernels described above -- the fp32-faithful path greedy
+// decoding needs for token parity.  TF32 (tf32 = 1, training): warp-autonomous kernels (dur_*_warp_kernel below):
+// every warp owns 16 notes for the whole recurrence, multiplies its state tile by W_hh (TF32-rounded, resident in
+// shared memory in a k-permuted layout so that one LDS.64 yields an mma B fragment) with mma.sync m16n8k8 into
+// register accumulators whose layout puts r, z and n of a unit in the same thread, does the gate math, the head
+// and the greedy bit in registers with quad shuffles, and synchronises with __syncwarp only -- no block barrier
+// in the step loop.  (ncu, 245,760 notes: the block-synchronous TF32 variant this replaces ran 0.97 / 1.86 ms
+// fwd / bwd at 43 % issue utilisation, stalled on barriers and fixed-latency waits with 11 % tensor-pipe use.)
 #include "common.cuh"
 
 namespace {
 
 constexpr int H = 64, G3 = 192, SW = 72, GXW = 264, NSLOT = 6, NSTEP = 5;
-constexpr int RT = 32;            // notes per CTA tile
+constexpr int RT = 32;            // notes per CTA tile (FFMA kernels)
 constexpr int HS = 68;            // padded row stride of 64-wide shared arrays (conflict-free LDS.128 per row)
 constexpr int GS = 196;           // padded row stride of 192-wide shared arrays
 constexpr int NTHR = 192;
@@ -56,62 +58,6 @@ __device__ __forceinline__ float dot64(const float (&w)[H], const float* __restr
     return (a0 + a1) + (a2 + a3);
 }
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// out[r][n] = bias[n] + sum_k in[r][k] * W[n][k] for a 32-row tile, W slice held as B fragments:
-// warp w owns output columns [32w, 32w+32) (4 n-tiles), K = 64 (8 k-steps).
-__device__ __forceinline__ void tile_matvec_rows_tc(const uint32_t (&bw)[4][8][2], const float (&bias)[4][2],
-                                                    const float (*in_s)[68], float (*out_s)[196], int warp, int lane) {
-    const int g = lane >> 2, tig = lane & 3;
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-        float acc[4][4];
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) { acc[nt][0] = acc[nt][2] = bias[nt][0]; acc[nt][1] = acc[nt][3] = bias[nt][1]; }
-#pragma unroll
-        for (int kt = 0; kt < 8; ++kt) {
-            uint32_t a[4];
-            a[0] = to_tf32(in_s[16 * m + g][8 * kt + tig]);
-            a[1] = to_tf32(in_s[16 * m + g + 8][8 * kt + tig]);
-            a[2] = to_tf32(in_s[16 * m + g][8 * kt + tig + 4]);
-            a[3] = to_tf32(in_s[16 * m + g + 8][8 * kt + tig + 4]);
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[nt], a, bw[nt][kt][0], bw[nt][kt][1]);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-            const int col = 32 * warp + 8 * nt + 2 * tig;
-            *reinterpret_cast<float2*>(&out_s[16 * m + g][col]) = make_float2(acc[nt][0], acc[nt][1]);
-            *reinterpret_cast<float2*>(&out_s[16 * m + g + 8][col]) = make_float2(acc[nt][2], acc[nt][3]);
-        }
-    }
-}
-
-__device__ __forceinline__ void load_row_frags(const float* __restrict__ w_hh, const float* __restrict__ b_hh,
-                                               uint32_t (&bw)[4][8][2], float (&bias)[4][2], int warp, int lane) {
-    const int g = lane >> 2, tig = lane & 3;
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-        const int n = 32 * warp + 8 * nt + g;
-#pragma unroll
-        for (int kt = 0; kt < 8; ++kt) {
-            bw[nt][kt][0] = to_tf32(w_hh[n * H + 8 * kt + tig]);
-            bw[nt][kt][1] = to_tf32(w_hh[n * H + 8 * kt + tig + 4]);
-        }
-        bias[nt][0] = b_hh[32 * warp + 8 * nt + 2 * tig];
-        bias[nt][1] = b_hh[32 * warp + 8 * nt + 2 * tig + 1];
-    }
-}
-
 // gi tables: [0] = W_ih sos + b_ih (step 0), [1] = W_ih[:,0] + b_ih (fed-back bit 0), [2] = W_ih[:,1] + b_ih
 __device__ __forceinline__ void build_gi_tables(const DurParams& p, float (*gi_t)[G3]) {
     for (int j = threadIdx.x; j < G3; j += blockDim.x) {
@@ -124,7 +70,7 @@ __device__ __forceinline__ void build_gi_tables(const DurParams& p, float (*gi_t
     }
 }
 
-template <bool TC>
+// ---- fp32 (FFMA) kernels ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHR) dur_fwd_kernel(const float* __restrict__ h0, long ldh0, long Q, DurParams p,
                                                        float* __restrict__ logits, float* __restrict__ S) {
     __shared__ __align__(16) float h_s[RT][HS];
@@ -134,21 +80,13 @@ __global__ void __launch_bounds__(NTHR) dur_fwd_kernel(const float* __restrict__
     __shared__ float lg_s[RT][2];
     __shared__ int tok_s[RT];
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    float w[H];                 // FFMA mode: row tid of W_hh        (dead in TC mode)
-    uint32_t bw[4][8][2];       // TC mode: this warp's B fragments  (dead in FFMA mode)
-    float bfrag[4][2];
-    float bh = 0.0f;
-    if (TC) {
-        load_row_frags(p.w_hh, p.b_hh, bw, bfrag, warp, lane);
-    } else {
+    float w[H];                 // row tid of W_hh
 #pragma unroll
-        for (int k = 0; k < H; k += 4) {
-            float4 v = *reinterpret_cast<const float4*>(p.w_hh + tid * H + k);
-            w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
-        }
-        bh = p.b_hh[tid];
+    for (int k = 0; k < H; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(p.w_hh + tid * H + k);
+        w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
     }
+    const float bh = p.b_hh[tid];
     build_gi_tables(p, gi_t);
     if (tid < 2 * H) wo_s[tid / H][tid % H] = p.w_out[tid];
     const float bo0 = p.b_out[0], bo1 = p.b_out[1];
@@ -179,12 +117,8 @@ __global__ void __launch_bounds__(NTHR) dur_fwd_kernel(const float* __restrict__
                 }
             }
             // phase A: gh[r][j] = b_hh[j] + W_hh[j] . h[r]
-            if (TC) {
-                tile_matvec_rows_tc(bw, bfrag, h_s, gh_s, warp, lane);
-            } else {
 #pragma unroll 2
-                for (int r = 0; r < RT; ++r) gh_s[r][tid] = bh + dot64(w, h_s[r]);
-            }
+            for (int r = 0; r < RT; ++r) gh_s[r][tid] = bh + dot64(w, h_s[r]);
             __syncthreads();
             // phase B: gates
             for (int i = tid; i < RT * H; i += NTHR) {
@@ -222,9 +156,6 @@ __global__ void __launch_bounds__(NTHR) dur_fwd_kernel(const float* __restrict__
     }
 }
 
-constexpr int WS = 72;            // padded row stride of the shared W_hh copy (conflict-free B-fragment loads)
-
-template <bool TC>
 __global__ void __launch_bounds__(NTHR) dur_bwd_kernel(const float* __restrict__ S, const float* __restrict__ dlog,
                                                        long Q, DurParams p, float* __restrict__ GX,
                                                        float* __restrict__ dh0, long lddh0) {
@@ -233,34 +164,23 @@ __global__ void __launch_bounds__(NTHR) dur_bwd_kernel(const float* __restrict__
     float (*dh_s)[HS] = reinterpret_cast<float (*)[HS]>(dyn_smem + RT * HS);       // grad wrt the step's output state
     float (*dn_s)[HS] = reinterpret_cast<float (*)[HS]>(dyn_smem + 2 * RT * HS);
     float (*g_s)[GS] = reinterpret_cast<float (*)[GS]>(dyn_smem + 3 * RT * HS);    // gh, then [dr | dz | dn*r]
-    // the tail of the dynamic buffer is the tf32 W_hh copy (TC mode) or the dh_prev partials (FFMA mode)
-    float (*w_s)[WS] = reinterpret_cast<float (*)[WS]>(dyn_smem + 3 * RT * HS + RT * GS);
-    float (*part_s)[RT][HS] = reinterpret_cast<float (*)[RT][HS]>(dyn_smem + 3 * RT * HS + RT * GS);
+    float (*part_s)[RT][HS] = reinterpret_cast<float (*)[RT][HS]>(dyn_smem + 3 * RT * HS + RT * GS);   // dh_prev partials
     __shared__ float gi_t[3][G3];
     __shared__ __align__(16) float wo_s[2][H];
     __shared__ float dl_s[RT][2];
     __shared__ int tok_s[RT];
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    float w[H];      // FFMA: row tid of W_hh               (recompute gh)
-    float wc[H];     // FFMA: column (tid%64), rows third*64.. (dh_prev = W_hh^T dgh)
-    uint32_t bw[4][8][2];
-    float bfrag[4][2];
+    float w[H];      // row tid of W_hh               (recompute gh)
+    float wc[H];     // column (tid%64), rows third*64.. (dh_prev = W_hh^T dgh)
     const int third = tid / H, kk = tid % H;
-    float bh = 0.0f;
-    if (TC) {
-        load_row_frags(p.w_hh, p.b_hh, bw, bfrag, warp, lane);
-        for (int i = tid; i < G3 * H; i += NTHR) w_s[i / H][i % H] = __uint_as_float(to_tf32(p.w_hh[i]));
-    } else {
 #pragma unroll
-        for (int k = 0; k < H; k += 4) {
-            float4 v = *reinterpret_cast<const float4*>(p.w_hh + tid * H + k);
-            w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
-        }
-#pragma unroll
-        for (int j = 0; j < H; ++j) wc[j] = p.w_hh[(third * H + j) * H + kk];
-        bh = p.b_hh[tid];
+    for (int k = 0; k < H; k += 4) {
+        float4 v = *reinterpret_cast<const float4*>(p.w_hh + tid * H + k);
+        w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
     }
+#pragma unroll
+    for (int j = 0; j < H; ++j) wc[j] = p.w_hh[(third * H + j) * H + kk];
+    const float bh = p.b_hh[tid];
     build_gi_tables(p, gi_t);
     if (tid < 2 * H) wo_s[tid / H][tid % H] = p.w_out[tid];
 
@@ -302,12 +222,8 @@ __global__ void __launch_bounds__(NTHR) dur_bwd_kernel(const float* __restrict__
                 dh_s[r][u] += wo_s[0][u] * dl_s[r][0] + wo_s[1][u] * dl_s[r][1];
             }
             // recompute gh
-            if (TC) {
-                tile_matvec_rows_tc(bw, bfrag, hp_s, g_s, warp, lane);
-            } else {
 #pragma unroll 2
-                for (int r = 0; r < RT; ++r) g_s[r][tid] = bh + dot64(w, hp_s[r]);
-            }
+            for (int r = 0; r < RT; ++r) g_s[r][tid] = bh + dot64(w, hp_s[r]);
             __syncthreads();
             // gate backward (in place: gh -> dgh)
             for (int i = tid; i < RT * H; i += NTHR) {
@@ -327,55 +243,18 @@ __global__ void __launch_bounds__(NTHR) dur_bwd_kernel(const float* __restrict__
                 dh_s[r][u] = d * zz;                 // direct path to the previous state
             }
             __syncthreads();
-            if (TC) {
-                // dh_prev[r][kk] += sum_j dgh[r][j] W_hh[j][kk]: warps 0..3 own 16 output columns each
-                // (2 n-tiles), K = 192 (24 k-steps), A from g_s, B fragments from the shared tf32 W copy;
-                // every dh_s element is owned by exactly one thread, so the product is added in place.
-                if (warp < 4) {
-                    const int g = lane >> 2, tig = lane & 3;
-#pragma unroll
-                    for (int m = 0; m < 2; ++m) {
-                        float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll 4
-                        for (int kt = 0; kt < 24; ++kt) {
-                            uint32_t a[4];
-                            a[0] = to_tf32(g_s[16 * m + g][8 * kt + tig]);
-                            a[1] = to_tf32(g_s[16 * m + g + 8][8 * kt + tig]);
-                            a[2] = to_tf32(g_s[16 * m + g][8 * kt + tig + 4]);
-                            a[3] = to_tf32(g_s[16 * m + g + 8][8 * kt + tig + 4]);
-#pragma unroll
-                            for (int nt = 0; nt < 2; ++nt) {
-                                const int n = 16 * warp + 8 * nt + g;
-                                mma_tf32(acc[nt], a, __float_as_uint(w_s[8 * kt + tig][n]),
-                                         __float_as_uint(w_s[8 * kt + tig + 4][n]));
-                            }
-                        }
-#pragma unroll
-                        for (int nt = 0; nt < 2; ++nt) {
-                            const int col = 16 * warp + 8 * nt + 2 * tig;
-                            dh_s[16 * m + g][col] += acc[nt][0];
-                            dh_s[16 * m + g][col + 1] += acc[nt][1];
-                            dh_s[16 * m + g + 8][col] += acc[nt][2];
-                            dh_s[16 * m + g + 8][col + 1] += acc[nt][3];
-                        }
-                    }
-                }
-            } else {
-                // dh_prev partials: part[third][r][kk] = sum_j W_hh[third*64+j][kk] * dgh[r][third*64+j]
+            // dh_prev partials: part[third][r][kk] = sum_j W_hh[third*64+j][kk] * dgh[r][third*64+j]
 #pragma unroll 2
-                for (int r = 0; r < RT; ++r) part_s[third][r][kk] = dot64(wc, &g_s[r][third * H]);
-            }
+            for (int r = 0; r < RT; ++r) part_s[third][r][kk] = dot64(wc, &g_s[r][third * H]);
             // gate gradients -> GX slot k
             for (int i = tid; i < rows * 256; i += NTHR) {
                 int r = i >> 8, c = i & 255;
                 GX[((q0 + r) * NSLOT + k) * GXW + c] = (c < G3) ? g_s[r][c] : dn_s[r][c - G3];
             }
-            if (!TC) {
-                __syncthreads();
-                for (int i = tid; i < RT * H; i += NTHR) {
-                    int r = i / H, u = i % H;
-                    dh_s[r][u] += part_s[0][r][u] + part_s[1][r][u] + part_s[2][r][u];
-                }
+            __syncthreads();
+            for (int i = tid; i < RT * H; i += NTHR) {
+                int r = i / H, u = i % H;
+                dh_s[r][u] += part_s[0][r][u] + part_s[1][r][u] + part_s[2][r][u];
             }
         }
         __syncthreads();
@@ -389,18 +268,369 @@ unsigned dur_grid(long Q) {
     return (unsigned)(tiles < cap ? tiles : cap);
 }
 
+// ---- TF32 warp-autonomous kernels ----------------------------------------------------------------------
+constexpr int WM = 16;            // notes per warp tile (one m16 MMA tile)
+constexpr int WSP = 72;           // row stride of the shared W_hh copy (== 8 mod 32: conflict-free fragment loads)
+constexpr int TS = 200;           // row stride of the gi tables (rows of different tokens on different banks)
+constexpr int FW_WARPS = 12, BW_WARPS = 8;
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// position of column k inside a W_hh row of the shared copy: (k, k+4) of every 8-group become neighbours, so the
+// B fragment {W[n][8kt+tig], W[n][8kt+tig+4]} of mma.m16n8k8 is ONE 8-byte shared load
+__device__ __forceinline__ int kperm(int k) { return (k & ~7) | ((k & 3) << 1) | ((k >> 2) & 1); }
+
+struct WarpShared {              // block-wide part of the dynamic shared memory
+    float w[G3 * WSP];           // TF32-rounded W_hh, k-permuted rows
+    float gi_t[3 * TS];          // x-projection per input token; b_hh of the r and z gates folded in
+    float bhn[H];                // b_hh of the n gate (multiplied by r, cannot be folded)
+    float wo[2 * H];
+    float sos[8];
+};
+
+__device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh) {
+    for (int i = threadIdx.x; i < G3 * H; i += blockDim.x) {
+        const int n = i / H, k = i % H;
+        sh->w[n * WSP + kperm(k)] = __uint_as_float(to_tf32(p.w_hh[i]));
+    }
+    for (int j = threadIdx.x; j < G3; j += blockDim.x) {
+        const float bh = j < 2 * H ? p.b_hh[j] : 0.0f;
+        float b = p.b_ih[j], s = b;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) s = fmaf(p.w_ih[j * 5 + c], p.sos[c], s);
+        sh->gi_t[j] = s + bh;
+        sh->gi_t[TS + j] = p.w_ih[j * 5 + 0] + b + bh;
+        sh->gi_t[2 * TS + j] = p.w_ih[j * 5 + 1] + b + bh;
+        if (j >= 2 * H) sh->bhn[j - 2 * H] = p.b_hh[j];
+    }
+    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) sh->wo[i] = p.w_out[i];
+    if (threadIdx.x < 8) sh->sos[threadIdx.x] = threadIdx.x < 5 ? p.sos[threadIdx.x] : 0.0f;
+}
+
+// gh (16 x 192, bias-free) = hw (16 x 64 state tile of this warp) . W_hh^T, as 24 n-tiles of accumulators:
+// acc[j] / acc[8+j] / acc[16+j] hold r / z / n of units 8j..8j+7; element [2*half+c] is row g+8*half, unit 8j+2*tig+c
+__device__ __forceinline__ void warp_matvec(const float* __restrict__ w_s, const float (*hw)[HS], float (&acc)[24][4],
+                                            int g, int tig) {
+#pragma unroll
+    for (int nt = 0; nt < 24; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+#pragma unroll
+    for (int kt = 0; kt < 8; ++kt) {
+        const uint32_t a[4] = {to_tf32(hw[g][8 * kt + tig]), to_tf32(hw[g + 8][8 * kt + tig]),
+                               to_tf32(hw[g][8 * kt + tig + 4]), to_tf32(hw[g + 8][8 * kt + tig + 4])};
+#pragma unroll
+        for (int nt = 0; nt < 24; ++nt) {
+            const float2 b = *reinterpret_cast<const float2*>(w_s + (8 * nt + g) * WSP + 8 * kt + 2 * tig);
+            mma_tf32(acc[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
+        }
+    }
+}
+
+// 16 rows x 64 floats (row stride ld) -> hw; rows >= rows are zero-filled.  al16: rows are 16-byte aligned
+// (else 8-byte: the decoder reads dur_hid out of a wider head buffer at an even column offset)
+__device__ __forceinline__ void warp_load_rows(const float* __restrict__ src, long ld, int rows, float (*hw)[HS], int lane,
+                                               bool al16 = true) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i, r = idx >> 4, c4 = (idx & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+            const float* q = src + (long)r * ld + c4;
+            if (al16) {
+                v = __ldg(reinterpret_cast<const float4*>(q));
+            } else {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(q)), b = __ldg(reinterpret_cast<const float2*>(q + 2));
+                v = make_float4(a.x, a.y, b.x, b.y);
+            }
+        }
+        *reinterpret_cast<float4*>(&hw[r][c4]) = v;
+    }
+}
+
+// asynchronous variant (cp.async, 16-byte aligned rows): the copy lands in hw without passing through registers,
+// so it can be issued a phase early; complete it with warp_async_wait() + __syncwarp()
+__device__ __forceinline__ void warp_load_rows_async(const float* __restrict__ src, long ld, int rows, float (*hw)[HS], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int idx = lane + 32 * i, r = idx >> 4, c4 = (idx & 15) * 4;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&hw[r][c4]);
+        const float* q = src + (long)(r < rows ? r : 0) * ld + c4;
+        const int bytes = r < rows ? 16 : 0;               // src-size 0: zero-fill
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(q), "r"(bytes) : "memory");
+    }
+}
+__device__ __forceinline__ void warp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// state tile + input tokens of step k -> S slot k (slot 5: final state, no token); 18 float4 per row
+__device__ __forceinline__ void warp_store_slot(float* __restrict__ S, long q0, int rows, int k, const float (*hw)[HS],
+                                                const int* tokw, const float* sos, int lane) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const int idx = lane + 32 * i, r = idx / 18, c = idx - 18 * r;
+        if (r >= rows) continue;
+        float4 v;
+        if (c < 16) {
+            v = *reinterpret_cast<const float4*>(&hw[r][4 * c]);
+        } else if (k == NSTEP) {
+            v = (c == 16) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(0.f, 1.f, 0.f, 0.f);
+        } else if (k == 0) {
+            v = (c == 16) ? make_float4(sos[0], sos[1], sos[2], sos[3]) : make_float4(sos[4], 1.f, 1.f, 0.f);
+        } else {
+            const int t = tokw[r];                                           // 1: bit 0, 2: bit 1
+            v = (c == 16) ? make_float4(t == 1 ? 1.f : 0.f, t == 2 ? 1.f : 0.f, 0.f, 0.f) : make_float4(0.f, 1.f, 0.f, 0.f);
+        }
+        *reinterpret_cast<float4*>(S + ((q0 + r) * NSLOT + k) * SW + 4 * c) = v;
+    }
+}
+
+__global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const float* __restrict__ h0, long ldh0, long Q,
+                                                                         DurParams p, float* __restrict__ logits,
+                                                                         float* __restrict__ S) {
+    extern __shared__ __align__(16) float dyn_smem[];
+    WarpShared* sh = reinterpret_cast<WarpShared*>(dyn_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    float* wbase = dyn_smem + sizeof(WarpShared) / 4 + warp * (WM * HS + WM);
+    float (*hw)[HS] = reinterpret_cast<float (*)[HS]>(wbase);                 // this warp's state tile
+    int* tokw = reinterpret_cast<int*>(wbase + WM * HS);                      // token (gi table index) per row
+    warp_setup(p, sh);
+    __syncthreads();
+    const bool al16 = (((uintptr_t)h0 & 15) == 0) && ((ldh0 & 3) == 0);
+    const float bo0 = p.b_out[0], bo1 = p.b_out[1];
+    const long n16 = (Q + WM - 1) / WM;
+    for (long t16 = blockIdx.x + (long)gridDim.x * warp; t16 < n16; t16 += (long)gridDim.x * FW_WARPS) {   // tiles spread over CTAs first
+        const long q0 = t16 * WM;
+        const int rows = (int)min((long)WM, Q - q0);
+        __syncwarp();
+        warp_load_rows(h0 + q0 * ldh0, ldh0, rows, hw, lane, al16);
+        if (lane < WM) tokw[lane] = 0;
+        int tok[2] = {0, 0};
+        for (int k = 0; k < NSTEP; ++k) {
+            __syncwarp();
+            if (S) warp_store_slot(S, q0, rows, k, hw, tokw, sh->sos, lane);
+            float acc[24][4];
+            warp_matvec(sh->w, hw, acc, g, tig);
+            __syncwarp();                                  // every lane is done reading the old state
+            float l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int u = 8 * j + 2 * tig;
+                const float2 bn = *reinterpret_cast<const float2*>(&sh->bhn[u]);
+                const float2 w0 = *reinterpret_cast<const float2*>(&sh->wo[u]);
+                const float2 w1 = *reinterpret_cast<const float2*>(&sh->wo[H + u]);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int row = g + 8 * half;
+                    const float* tb = sh->gi_t + tok[half] * TS + u;
+                    const float2 gr = *reinterpret_cast<const float2*>(tb);
+                    const float2 gz = *reinterpret_cast<const float2*>(tb + H);
+                    const float2 gn = *reinterpret_cast<const float2*>(tb + 2 * H);
+                    const float2 hp = *reinterpret_cast<const float2*>(&hw[row][u]);
+                    const float r0 = pd_sigmoid_fast(gr.x + acc[j][2 * half]), r1 = pd_sigmoid_fast(gr.y + acc[j][2 * half + 1]);
+                    const float z0 = pd_sigmoid_fast(gz.x + acc[8 + j][2 * half]), z1 = pd_sigmoid_fast(gz.y + acc[8 + j][2 * half + 1]);
+                    const float n0 = pd_tanh_fast(gn.x + r0 * (acc[16 + j][2 * half] + bn.x));
+                    const float n1 = pd_tanh_fast(gn.y + r1 * (acc[16 + j][2 * half + 1] + bn.y));
+                    const float2 hn = make_float2((1.0f - z0) * n0 + z0 * hp.x, (1.0f - z1) * n1 + z1 * hp.y);
+                    *reinterpret_cast<float2*>(&hw[row][u]) = hn;
+                    l0[half] = fmaf(hn.x, w0.x, fmaf(hn.y, w0.y, l0[half]));
+                    l1[half] = fmaf(hn.x, w1.x, fmaf(hn.y, w1.y, l1[half]));
+                }
+            }
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {         // duration head: finish the two dot products in the quad
+                l0[half] += __shfl_xor_sync(0xffffffffu, l0[half], 1);
+                l1[half] += __shfl_xor_sync(0xffffffffu, l1[half], 1);
+                l0[half] += __shfl_xor_sync(0xffffffffu, l0[half], 2);
+                l1[half] += __shfl_xor_sync(0xffffffffu, l1[half], 2);
+                const float a0 = l0[half] + bo0, a1 = l1[half] + bo1;
+                const int row = g + 8 * half;
+                tok[half] = a1 > a0 ? 2 : 1;               // table index of the fed-back bit
+                if (tig == 0) {
+                    tokw[row] = tok[half];
+                    if (row < rows) *reinterpret_cast<float2*>(logits + ((q0 + row) * NSTEP + k) * 2) = make_float2(a0, a1);
+                }
+            }
+        }
+        __syncwarp();
+        if (S) warp_store_slot(S, q0, rows, NSTEP, hw, tokw, sh->sos, lane);
+    }
+}
+
+__global__ void __launch_bounds__(BW_WARPS * 32, 1) dur_bwd_warp_kernel(const float* __restrict__ S,
+                                                                         const float* __restrict__ dlog, long Q, DurParams p,
+                                                                         float* __restrict__ GX, float* __restrict__ dh0,
+                                                                         long lddh0) {
+    extern __shared__ __align__(16) float dyn_smem[];
+    WarpShared* sh = reinterpret_cast<WarpShared*>(dyn_smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    float* wbase = dyn_smem + sizeof(WarpShared) / 4 + warp * (WM * HS + WM * GS + 3 * WM);
+    float (*hw)[HS] = reinterpret_cast<float (*)[HS]>(wbase);                 // state entering the step
+    float (*gw)[GS] = reinterpret_cast<float (*)[GS]>(wbase + WM * HS);       // [dr | dz | dn*r] of the step
+    int* tokw = reinterpret_cast<int*>(wbase + WM * HS + WM * GS);
+    float2* dlw = reinterpret_cast<float2*>(wbase + WM * HS + WM * GS + WM);  // dL/dlogits of the step per row
+    warp_setup(p, sh);
+    __syncthreads();
+    const long n16 = (Q + WM - 1) / WM;
+    for (long t16 = blockIdx.x + (long)gridDim.x * warp; t16 < n16; t16 += (long)gridDim.x * BW_WARPS) {
+        const long q0 = t16 * WM;
+        const int rows = (int)min((long)WM, Q - q0);
+        float dh[8][4];                                    // grad wrt the step's output state, accumulator layout
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dh[j][0] = dh[j][1] = dh[j][2] = dh[j][3] = 0.0f;
+        warp_load_rows_async(S + (q0 * NSLOT + NSTEP - 1) * SW, (long)NSLOT * SW, rows, hw, lane);
+        // GX slot 5: no gate gradient, logit gradient of step 4 in cols 256..257
+#pragma unroll
+        for (int i = 0; i < 33; ++i) {
+            const int idx = lane + 32 * i, r = idx / 66, c = idx - 66 * r;
+            if (r < rows) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c == 64) {
+                    const float2 d = __ldg(reinterpret_cast<const float2*>(dlog + ((q0 + r) * NSTEP + NSTEP - 1) * 2));
+                    v.x = d.x; v.y = d.y;
+                }
+                *reinterpret_cast<float4*>(GX + ((q0 + r) * NSLOT + NSTEP) * GXW + 4 * c) = v;
+            }
+        }
+        for (int k = NSTEP - 1; k >= 0; --k) {
+            if (lane < WM) {
+                int t = 0;
+                float2 d = make_float2(0.f, 0.f);
+                if (lane < rows) {
+                    if (k > 0) t = (__ldg(S + ((q0 + lane) * NSLOT + k) * SW + 65) > 0.5f) ? 2 : 1;
+                    d = __ldg(reinterpret_cast<const float2*>(dlog + ((q0 + lane) * NSTEP + k) * 2));
+                }
+                tokw[lane] = t;
+                dlw[lane] = d;
+            }
+            warp_async_wait();
+            __syncwarp();
+            float acc[24][4];
+            warp_matvec(sh->w, hw, acc, g, tig);           // recompute gh of the step
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = g + 8 * half;
+                const int tok = tokw[row];
+                const float2 dl = dlw[row];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int u = 8 * j + 2 * tig;
+                    const float2 bn = *reinterpret_cast<const float2*>(&sh->bhn[u]);
+                    const float2 w0 = *reinterpret_cast<const float2*>(&sh->wo[u]);
+                    const float2 w1 = *reinterpret_cast<const float2*>(&sh->wo[H + u]);
+                    const float* tb = sh->gi_t + tok * TS + u;
+                    const float2 gr = *reinterpret_cast<const float2*>(tb);
+                    const float2 gz = *reinterpret_cast<const float2*>(tb + H);
+                    const float2 gn = *reinterpret_cast<const float2*>(tb + 2 * H);
+                    const float2 hp = *reinterpret_cast<const float2*>(&hw[row][u]);
+                    float dr[2], dz[2], dnr[2], dn[2];
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const float ghn = acc[16 + j][2 * half + c] + (c ? bn.y : bn.x);
+                        const float rr = pd_sigmoid_fast((c ? gr.y : gr.x) + acc[j][2 * half + c]);
+                        const float zz = pd_sigmoid_fast((c ? gz.y : gz.x) + acc[8 + j][2 * half + c]);
+                        const float nn = pd_tanh_fast((c ? gn.y : gn.x) + rr * ghn);
+                        // head backward first: dh += W_out^T dlogits
+                        const float d = dh[j][2 * half + c] + (c ? w0.y : w0.x) * dl.x + (c ? w1.y : w1.x) * dl.y;
+                        dn[c] = d * (1.0f - zz) * (1.0f - nn * nn);
+                        dz[c] = d * ((c ? hp.y : hp.x) - nn) * zz * (1.0f - zz);
+                        dr[c] = dn[c] * ghn * rr * (1.0f - rr);
+                        dnr[c] = dn[c] * rr;
+                        dh[j][2 * half + c] = d * zz;      // direct path to the previous state
+                    }
+                    *reinterpret_cast<float2*>(&gw[row][u]) = make_float2(dr[0], dr[1]);
+                    *reinterpret_cast<float2*>(&gw[row][H + u]) = make_float2(dz[0], dz[1]);
+                    *reinterpret_cast<float2*>(&gw[row][2 * H + u]) = make_float2(dnr[0], dnr[1]);
+                    if (row < rows)
+                        *reinterpret_cast<float2*>(GX + ((q0 + row) * NSLOT + k) * GXW + G3 + u) = make_float2(dn[0], dn[1]);
+                }
+            }
+            __syncwarp();
+            // the state tile is dead until the next step: fetch the state entering step k-1 behind the rest of this one
+            if (k > 0) warp_load_rows_async(S + (q0 * NSLOT + k - 1) * SW, (long)NSLOT * SW, rows, hw, lane);
+            // GX slot k: cols 0..191 from the staged gate gradients; cols 256..263 = [dlogits of step k-1, 0...]
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+                const int idx = lane + 32 * i, r = idx / 48, c = idx - 48 * r;
+                if (r < rows)
+                    *reinterpret_cast<float4*>(GX + ((q0 + r) * NSLOT + k) * GXW + 4 * c) = *reinterpret_cast<const float4*>(&gw[r][4 * c]);
+            }
+            {
+                const int r = lane >> 1, c = lane & 1;
+                if (r < rows) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c == 0 && k > 0) {
+                        const float2 d = __ldg(reinterpret_cast<const float2*>(dlog + ((q0 + r) * NSTEP + k - 1) * 2));
+                        v.x = d.x; v.y = d.y;
+                    }
+                    *reinterpret_cast<float4*>(GX + ((q0 + r) * NSLOT + k) * GXW + 256 + 4 * c) = v;
+                }
+            }
+            // dh += dgh . W_hh: 8 n-tiles (units), K = 192 gate rows; B fragment = W_hh[8kt+tig (+4)][8nt+g]
+            float acc2[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) acc2[nt][0] = acc2[nt][1] = acc2[nt][2] = acc2[nt][3] = 0.0f;
+            const int pg = kperm(g);                       // column 8nt+g sits at 8nt + kperm(g) in the shared copy
+#pragma unroll 4
+            for (int kt = 0; kt < 24; ++kt) {
+                const uint32_t a[4] = {to_tf32(gw[g][8 * kt + tig]), to_tf32(gw[g + 8][8 * kt + tig]),
+                                       to_tf32(gw[g][8 * kt + tig + 4]), to_tf32(gw[g + 8][8 * kt + tig + 4])};
+                const float* wr = sh->w + (8 * kt + tig) * WSP + pg;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt)
+                    mma_tf32(acc2[nt], a, __float_as_uint(wr[8 * nt]), __float_as_uint(wr[4 * WSP + 8 * nt]));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dh[j][c] += acc2[j][c];
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int row = g + 8 * half;
+            if (row < rows)
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float2*>(dh0 + (q0 + row) * lddh0 + 8 * j + 2 * tig) = make_float2(dh[j][2 * half], dh[j][2 * half + 1]);
+        }
+    }
+}
+
+constexpr int FW_SMEM = (int)sizeof(WarpShared) + FW_WARPS * (WM * HS + WM) * 4;
+constexpr int BW_SMEM = (int)sizeof(WarpShared) + BW_WARPS * (WM * HS + WM * GS + 3 * WM) * 4;
+
+unsigned warp_grid(long Q) {
+    long tiles = (Q + WM - 1) / WM;
+    return (unsigned)(tiles < PD_NUM_SMS ? tiles : PD_NUM_SMS);
+}
+
 }  // namespace
 
 // logits (Q,5,2) <- 5-step greedy-feedback duration GRU from h0 (Q,64; row stride ldh0).  S (Q,6,72) may be
-// NULL (inference).
+// NULL (inference).  tf32 != 0: tensor-core (TF32) matvecs; then S must be 16-byte and h0 8-byte aligned, ldh0 even.
 PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
                              const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
                              const float* b_out, float* logits, float* S, int tf32, void* stream) {
     if (Q <= 0) return 0;
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
-    if (tf32) dur_fwd_kernel<true><<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
-    else dur_fwd_kernel<false><<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+    if (tf32) {
+        if (((uintptr_t)S & 15) || ((uintptr_t)h0 & 7) || (ldh0 & 1) || ((uintptr_t)logits & 7)) return PD_BAD_ARG;
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+            if (e != cudaSuccess) return (int)e;
+            attr = true;
+        }
+        dur_fwd_warp_kernel<<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+    } else {
+        dur_fwd_kernel<<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+    }
     return pd_launch_status();
 }
 
@@ -411,17 +641,19 @@ PD_API int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const
     if (Q <= 0) return 0;
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
-    constexpr int smem_tc = (3 * RT * HS + RT * GS + G3 * WS) * (int)sizeof(float);
     constexpr int smem_ff = (3 * RT * HS + RT * GS + 3 * RT * HS) * (int)sizeof(float);
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dur_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(dur_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ff);
+        cudaError_t e = cudaFuncSetAttribute(dur_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ff);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
-    if (tf32) dur_bwd_kernel<true><<<dur_grid(Q), NTHR, smem_tc, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
-    else dur_bwd_kernel<false><<<dur_grid(Q), NTHR, smem_ff, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
+    if (tf32) {
+        if ((((uintptr_t)S | (uintptr_t)GX) & 15) || (((uintptr_t)dlogits | (uintptr_t)dh0) & 7) || (lddh0 & 1)) return PD_BAD_ARG;
+        dur_bwd_warp_kernel<<<warp_grid(Q), BW_WARPS * 32, BW_SMEM, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
+    } else {
+        dur_bwd_kernel<<<dur_grid(Q), NTHR, smem_ff, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
+    }
     return pd_launch_status();
 }
