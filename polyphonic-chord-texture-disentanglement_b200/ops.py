@@ -366,19 +366,61 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
               0 if rzn is None else rzn.stride(1), _ptr(hn), 0 if hn is None else hn.stride(0),
               0 if hn is None else hn.stride(1), B, T, int(reverse), 3 if PRECISION == "tf32x3" else 1, _stream())
         return h_all
-    gh = torch.empty(B, H3, device=dev, dtype=torch.float32)
     rzn = hn = None
     if save is not None:
         rzn = torch.empty(B, T, H3, device=dev, dtype=torch.float32)
         hn = torch.empty(B, T, H, device=dev, dtype=torch.float32)
         save["rzn"], save["hn"] = rzn, hn
-    order = range(T - 1, -1, -1) if reverse else range(T)
-    hprev = h0
+    order = list(range(T - 1, -1, -1) if reverse else range(T))
     # fused step (recurrent GEMM + gate math in one tcgen05 kernel) whenever TMA can address the operands
     fused_ok = (FUSED_GRU_STEP and PRECISION == "tf32" and H % 64 == 0 and w_hh.stride(1) == 1
                 and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0 and b_hh.data_ptr() % 16 == 0
                 and gi.stride(2) == 1 and gi.stride(0) % 4 == 0 and gi.stride(1) % 4 == 0 and gi.data_ptr() % 16 == 0
                 and (gi2 is None or (gi2.stride(1) == 1 and gi2.stride(0) % 4 == 0 and gi2.data_ptr() % 16 == 0)))
+
+    def run(sl):
+        _gru_steps_fwd(gi[sl], _sl(gi2, sl), _sl(h0, sl), w_hh, b_hh, _sl(lengths, sl), order, h_all[sl], _sl(rzn, sl),
+                       _sl(hn, sl), fused_ok)
+    _over_row_chunks(B, H3, run)
+    return h_all
+
+
+def _sl(t, sl):
+    return None if t is None else t[sl]
+
+
+# Optional row chunking of the big recurrences (OFF: measured slower).  The note GRU runs 15 steps over 32*B
+# independent sequences; at B = 512 one step's h-projection is 100 MB, so step-major order streams ~630 MB per
+# step through HBM.  Chunk-major order (all steps of a row chunk before the next chunk, a few chunks side by side on
+# forked streams) was meant to keep a chunk's gh / gi2 / state in the 126 MB L2 across steps.  B200, graph-replayed
+# step at B = 512 (tools/chunk_sweep.py): unchunked 17.78 ms; 50 MB chunks x 2 lanes 17.84; 25 MB x 3 18.18;
+# 12 MB x 3 19.21; 6 MB x 4 19.73 -- the smaller GEMM / gate launches lose more than the L2 hits return.
+ROW_CHUNK_BYTES = 0               # target size of one chunk's (rows, 3H) fp32 slab; 0 = never chunk
+ROW_CHUNK_MIN_BYTES = 48 << 20    # recurrences whose slab is smaller than this run unchunked
+ROW_CHUNK_LANES = 2
+
+
+def _over_row_chunks(B, H3, run):
+    """Call run(slice) over row chunks (concurrently on ROW_CHUNK_LANES forked streams) or once over all rows."""
+    if not FORK_STREAMS or not ROW_CHUNK_BYTES or B * H3 * 4 < ROW_CHUNK_MIN_BYTES:
+        run(slice(0, B))
+        return
+    rows = max(128, ROW_CHUNK_BYTES // (H3 * 4) // 128 * 128)
+    starts = list(range(0, B, rows))
+
+    def lane(l):
+        def go():
+            for s0 in starts[l::ROW_CHUNK_LANES]:
+                run(slice(s0, min(B, s0 + rows)))
+        return go
+    fork_join([lane(l) for l in range(min(ROW_CHUNK_LANES, len(starts)))])
+
+
+def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fused_ok):
+    """All steps of the recurrence for one block of rows (every argument already row-sliced)."""
+    B, H = h_all.shape[0], h_all.shape[2]
+    gh = torch.empty(B, 3 * H, device=gi.device, dtype=torch.float32)
+    hprev = h0
     for t in order:
         if (fused_ok and hprev is not None and hprev.stride(1) == 1 and hprev.stride(0) % 4 == 0
                 and hprev.data_ptr() % 16 == 0):
@@ -396,7 +438,39 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
         _gates_fwd(gi[:, t], gi2, gh, hprev, h_all[:, t],
                    None if rzn is None else rzn[:, t], None if hn is None else hn[:, t], lengths, t)
         hprev = h_all[:, t]
-    return h_all
+
+
+def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0):
+    """BPTT over all steps for one block of rows; dh0 (or None) receives the gradient of the initial state."""
+    B, T, H = h_all.shape
+    dev = dout.device
+    # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
+    # and dgh @ W_hh (written by that step's GEMM); the next gate kernel sums both with dout[:, t]
+    bufs = torch.empty(4, B, H, device=dev, dtype=torch.float32)
+    dz_a, dz_b, dm_a, dm_b = bufs[0], bufs[1], bufs[2], bufs[3]
+    dz = dm = None
+    st = _stream()
+    for i in range(T - 1, -1, -1):
+        t = order[i]
+        hprev = h_all[:, order[i - 1]] if i > 0 else h0
+        nz = dz_b if dz is dz_a else dz_a
+        nm = dm_b if dm is dm_a else dm_a
+        _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
+              dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+              _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
+              _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
+              None, 0, _ptr(lengths), t, B, H, st)
+        dz = nz
+        if hprev is not None:
+            gemm_nn(dgh[:, t], w_hh, nm)                          # dgh W_hh
+            dm = nm
+        else:
+            dm = None
+    if dh0 is not None:
+        if dm is None:
+            dh0.copy_(dz)
+        else:
+            _call("pd_add_f32", _ptr(dz), _ptr(dm), dz.numel(), _ptr(dh0), st)
 
 
 class _GruSeq(torch.autograd.Function):
@@ -427,36 +501,19 @@ class _GruSeq(torch.autograd.Function):
             dgi[:, T:].zero_()                     # unused input slots get no gradient
         dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
         dgi2 = None        # gradient of the step-constant projection: summed over the steps after the loop
-        # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
-        # and dgh @ W_hh (written by that step's GEMM); the next gate kernel sums both with dout[:, t]
-        dz_a = torch.empty(B, H, device=dev, dtype=torch.float32)
-        dz_b = torch.empty(B, H, device=dev, dtype=torch.float32)
-        dm_a = torch.empty(B, H, device=dev, dtype=torch.float32)
-        dm_b = torch.empty(B, H, device=dev, dtype=torch.float32)
         order = list(range(T - 1, -1, -1) if ctx.reverse else range(T))
-        dz = dm = None
-        st = _stream()
+        want_dh0 = h0 is not None and ctx.needs_input_grad[2]
+        dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if want_dh0 else None
         if ctx.resident:
             _call("pd_gru128_bwd", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
                   h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
                   _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
-                  dgh.stride(1), B, T, int(ctx.reverse), st)
-        for i in (range(T - 1, -1, -1) if not ctx.resident else ()):
-            t = order[i]
-            hprev = h_all[:, order[i - 1]] if i > 0 else h0
-            nz = dz_b if dz is dz_a else dz_a
-            nm = dm_b if dm is dm_a else dm_a
-            _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
-                  dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
-                  _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
-                  _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
-                  _ptr(dgi2), 0 if dgi2 is None else dgi2.stride(0), _ptr(lengths), t, B, H, st)
-            dz = nz
-            if hprev is not None:
-                gemm_nn(dgh[:, t], w_hh, nm)                          # dgh W_hh
-                dm = nm
-            else:
-                dm = None
+                  dgh.stride(1), B, T, int(ctx.reverse), _stream())
+        else:
+            def run(sl):
+                _gru_steps_bwd(dout[sl], rzn[sl], hn[sl], h_all[sl], _sl(h0, sl), w_hh, _sl(lengths, sl), order,
+                               dgi[sl], dgh[sl], _sl(dh0, sl))
+            _over_row_chunks(B, 3 * H, run)
         dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)
         if ctx.has_gi2:
@@ -483,9 +540,6 @@ class _GruSeq(torch.autograd.Function):
                 gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
         elif h0 is None:
             dw.zero_()
-        dh0 = None
-        if h0 is not None and ctx.needs_input_grad[2]:
-            dh0 = dz if dm is None else _add(dz, dm)
         return dgi, dgi2, dh0, dw, db, None, None, None
 
 

@@ -30,9 +30,15 @@ def test_state_dict_keys_match_reference_contract():
     assert all(tuple(sd[k].shape) == s for k, s, _ in STATE_DICT_SPEC)
 
 
-@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555"])
+@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     cpu_backend.install(monkeypatch)
+    if tag.endswith("-chunked"):        # row-chunked recurrences (ops._over_row_chunks): 128-row chunks, ragged tail
+        from polydis_b200 import ops
+        monkeypatch.setattr(ops, "ROW_CHUNK_MIN_BYTES", 0)
+        monkeypatch.setattr(ops, "ROW_CHUNK_BYTES", 1)
+        monkeypatch.setattr(ops, "RESIDENT_GRU128", False)
+        tag = tag[:-len("-chunked")]
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     B = int(g["B"])
     x, c, pr = (torch.from_numpy(a) for a in synth_batch(B, int(g["data_seed"])))
