@@ -26,6 +26,7 @@ struct TcArgs {
     int kb_per_split;   // k-blocks (of BK) per blockIdx.z
     int atomic;         // accumulate into C (C += result, or split-K partial sums): red.global.add epilogue
     int dbg;            // tuning only: 1 = skip the epilogue stores, 2 = skip the MMAs, 3 = both
+    int tma_store;      // persistent kernel: write C tiles with TMA bulk stores (plain stores, aligned C)
 };
 
 // MH = number of 128-row halves per CTA tile (1 or 2).  The per-step GEMMs of this path are L2->SM bandwidth
@@ -212,16 +213,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int EB, int BN, int STAGES, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs g,
-                     int tiles_m, int tiles_n, int n_split) {
+gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, TcArgs g, int tiles_m, int tiles_n, int n_split) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int BKE = Elem<EB>::BKE, CW = 128 / EB;
     constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STG = 36;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    float* stg_all = (float*)(sB + STAGES * B_BYTES);                 // 4 warps x 32 x STG floats
-    uint64_t* full = (uint64_t*)(stg_all + 4 * 32 * STG);
+    // epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B) -- TMA-store tiles (128-byte swizzle), or one padded
+    // 32 x STG transpose buffer per warp on the plain-store path
+    float* stg_all = (float*)(sB + STAGES * B_BYTES);
+    uint64_t* full = (uint64_t*)((uint8_t*)stg_all + 4 * 2 * 4096);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;                              // [2]
     uint64_t* tmem_empty = tmem_full + 2;                              // [2]
@@ -320,6 +323,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const bool bias_vec = (((uintptr_t)g.bias) & 15) == 0;
         const int sub_r = lane >> 3, colq = (lane & 7) * 4;
         long j = 0;
+        int n_st = 0;                                     // bulk stores issued by this warp
         for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             int m0, n0, kb_beg, nkb, z;
             decode(item, m0, n0, kb_beg, nkb, z);
@@ -327,6 +331,40 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1);
             tc_fence_after();
             const bool add_bias = g.bias != nullptr && z == 0;
+            if (g.tma_store) {
+                // TMEM -> registers (+ bias) -> swizzled shared tile -> one bulk tensor store per 32 x 32 chunk; two
+                // tiles per warp so the next chunk's TMEM read overlaps the previous chunk's drain; M / N edges are
+                // clipped by the tensor map
+                uint8_t* tiles = (uint8_t*)stg_all + q * (2 * 4096);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    const int nb = n0 + c * 32;
+                    if (nb >= g.N) break;
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + c * 32, r);
+                    if (add_bias) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj)
+                            if (nb + jj < g.N) r[jj] = __float_as_uint(__uint_as_float(r[jj]) + __ldg(g.bias + nb + jj));
+                    }
+                    uint8_t* tile = tiles + (n_st & 1) * 4096;
+                    if (n_st >= 2) {                      // the store issued from this tile two chunks ago has read it
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && !(g.dbg & 1)) tma_store_2d(&tmC, tile, nb, m0 + q * 32);
+                    ++n_st;
+                }
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 const int nb = n0 + c * 32;
@@ -378,6 +416,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this warp landed
     }
     tc_fence_before();
     __syncthreads();
@@ -415,9 +454,9 @@ int launch_l(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
 }
 
 template <int EB, int BN, int STAGES, bool A_MN, bool B_MN>
-int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m, int tiles_n, int split,
-             cudaStream_t st) {
-    constexpr int smem = STAGES * (BM * 128 + BN * 128) + 4 * 32 * 36 * 4 + 1024 + 256;
+int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcArgs& g, int tiles_m, int tiles_n,
+             int split, cudaStream_t st) {
+    constexpr int smem = STAGES * (BM * 128 + BN * 128) + 4 * 2 * 4096 + 1024 + 256;
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN>,
@@ -427,17 +466,17 @@ int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int 
     }
     long items = (long)tiles_m * tiles_n * split;
     int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
-    gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g, tiles_m, tiles_n, split);
+    gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, tc, g, tiles_m, tiles_n, split);
     return pd_launch_status();
 }
 
 template <int EB, int BN, int STAGES>
-int launch_pl(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, int tiles_m,
-              int tiles_n, int split, cudaStream_t st) {
-    if (!a_mn && !b_mn) return launch_p<EB, BN, STAGES, false, false>(ta, tb, g, tiles_m, tiles_n, split, st);
-    if (!a_mn && b_mn) return launch_p<EB, BN, STAGES, false, true>(ta, tb, g, tiles_m, tiles_n, split, st);
-    if (a_mn && b_mn) return launch_p<EB, BN, STAGES, true, true>(ta, tb, g, tiles_m, tiles_n, split, st);
-    return launch_p<EB, BN, STAGES, true, false>(ta, tb, g, tiles_m, tiles_n, split, st);
+int launch_pl(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcArgs& g,
+              int tiles_m, int tiles_n, int split, cudaStream_t st) {
+    if (!a_mn && !b_mn) return launch_p<EB, BN, STAGES, false, false>(ta, tb, tc, g, tiles_m, tiles_n, split, st);
+    if (!a_mn && b_mn) return launch_p<EB, BN, STAGES, false, true>(ta, tb, tc, g, tiles_m, tiles_n, split, st);
+    if (a_mn && b_mn) return launch_p<EB, BN, STAGES, true, true>(ta, tb, tc, g, tiles_m, tiles_n, split, st);
+    return launch_p<EB, BN, STAGES, true, false>(ta, tb, tc, g, tiles_m, tiles_n, split, st);
 }
 
 // config id = (m_halves - 1) * 100000 + bn * 100 + stages * 10 + ctas_per_sm; 9xxxxx = persistent kernel
@@ -498,14 +537,16 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     const long tiles = (long)tiles_m * tiles_n;
     const int kb = (K + BKE - 1) / BKE;
     int split = 1;
-    if (tiles < PD_NUM_SMS && kb >= 32) {
+    // split K until ~2 CTAs per SM exist: always for few-tile GEMMs, and for deep ones (K >= 4096: weight gradients such
+    // as the time GRU's 3072x1024x16384, 192 tiles -> 318 us unsplit, 238 us split) also when tiles fill one wave only
+    if ((tiles < PD_NUM_SMS && kb >= 32) || (tiles < 2 * PD_NUM_SMS && kb >= 4096 / BKE)) {
         split = (int)((2 * PD_NUM_SMS + tiles - 1) / tiles);
         if (split > kb / 8) split = kb / 8;
         if (split < 1) split = 1;
     }
     int kb_per = (kb + split - 1) / split;
     split = (kb + kb_per - 1) / kb_per;
-    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0, dbg};
+    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0, dbg, 0};
     CUtensorMap ta, tb;
     int rc;
     // K-major: [rows][K] -> dims {K, rows}, box {128 B, BM|bn rows}.  MN-major: [K][rows] -> dims {rows, K},
@@ -515,8 +556,17 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     rc = b_mn ? make_map(&tb, B, EB, N, K, ldb, BKE, true) : make_map(&tb, B, EB, K, N, ldb, bn, false);
     if (rc) return rc;
     if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
-    if (cfg == 925641) return launch_pl<EB, 256, 4>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
-    if (cfg == 912861 && EB == 4) return launch_pl<4, 128, 6>(a_mn, b_mn, ta, tb, g, tiles_m, tiles_n, split, st);
+    if (cfg == 925641 || (cfg == 912861 && EB == 4)) {
+        // C tiles leave through TMA bulk stores when they are plain stores into a 16-byte aligned matrix
+        CUtensorMap tc = ta;
+        if (!g.atomic && (((uintptr_t)C) & 15) == 0 && (ldc & 3) == 0 && ldc >= 4 && !(dbg & 4)) {
+            rc = make_map(&tc, C, 4, N, M, ldc, 32, false, true);
+            if (rc) return rc;
+            g.tma_store = 1;
+        }
+        if (cfg == 925641) return launch_pl<EB, 256, 4>(a_mn, b_mn, ta, tb, tc, g, tiles_m, tiles_n, split, st);
+        return launch_pl<4, 128, 6>(a_mn, b_mn, ta, tb, tc, g, tiles_m, tiles_n, split, st);
+    }
     dim3 grid(tiles_m, tiles_n, split);
     return launch_cfg<EB>(cfg, a_mn, b_mn, ta, tb, g, grid, st);
 }

@@ -33,6 +33,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// shared -> global tile store (bulk async group); the issuing thread must have made the generic-proxy writes of
+// the tile visible to the async proxy first (fence.proxy.async.shared::cta after the warp's stores)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -106,15 +113,17 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D fp32 tensor [outer][inner] with row stride ld (floats); box = {32 inner, box_outer}.
-int make_map(CUtensorMap* map, const void* base, int eb, long inner, long outer, long ld, int box_outer, bool mn_major) {
+// 2-D tensor [outer][inner] with row stride ld (elements); box = {128 bytes inner, box_outer}.  plain_f32: the
+// map is used to STORE fp32 results (FLOAT32 data type; the TFLOAT32 type of the operand maps is for loads)
+int make_map(CUtensorMap* map, const void* base, int eb, long inner, long outer, long ld, int box_outer, bool mn_major,
+             bool plain_f32 = false) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return 801;   // cudaErrorNotSupported
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
     cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
     cuuint32_t box[2] = {(cuuint32_t)(128 / eb), (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base,
+    CUresult r = enc(map, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : eb == 4 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base,
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      (mn_major && eb == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

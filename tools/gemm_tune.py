@@ -36,15 +36,16 @@ def shape(name, M, N, K, layout, cfgs, acc=0):
             out.append(f"{cfg}:ERR")
     print(f"{name:34s} {layout} M={M:6d} N={N:5d} K={K:6d} | " + "  ".join(out), flush=True)
 
-big = [25622, 12823, 925641, 912861]
-shape("note fwd step", 16384, 1536, 512, "nt", big)
-shape("gi_tok (output-bound)", 262144, 1536, 128, "nt", big)
-shape("emb gi (output-bound)", 262144, 384, 128, "nt", big)
-shape("time fwd step", 512, 3072, 1024, "nt", [12823, 6441, 6433, 912861])
-shape("note bwd dh", 16384, 512, 1536, "nn", big)
-shape("time bwd dh", 512, 1024, 3072, "nn", [12823, 6441, 6433])
-shape("note dW (split-K)", 1536, 512, 245760, "tn", big)
-shape("pitch head", 245760, 136, 512, "nt", [25622, 12823, 925641, 912861])
-shape("pitch dX", 245760, 512, 136, "nn", big)
-shape("dur_hid (N=64)", 245760, 64, 512, "nt", [6441, 6433])
-shape("note dX tok", 262144, 128, 1536, "nn", [12823, 25622, 912861])
+if __name__ == "__main__":
+    big = [25622, 12823, 925641, 912861]
+    shape("note fwd step", 16384, 1536, 512, "nt", big)
+    shape("gi_tok (output-bound)", 262144, 1536, 128, "nt", big)
+    shape("emb gi (output-bound)", 262144, 384, 128, "nt", big)
+    shape("time fwd step", 512, 3072, 1024, "nt", [12823, 6441, 6433, 912861])
+    shape("note bwd dh", 16384, 512, 1536, "nn", big)
+    shape("time bwd dh", 512, 1024, 3072, "nn", [12823, 6441, 6433])
+    shape("note dW (split-K)", 1536, 512, 245760, "tn", big)
+    shape("pitch head", 245760, 136, 512, "nt", [25622, 12823, 925641, 912861])
+    shape("pitch dX", 245760, 512, 136, "nn", big)
+    shape("dur_hid (N=64)", 245760, 64, 512, "nt", [6441, 6433])
+    shape("note dX tok", 262144, 128, 1536, "nn", [12823, 25622, 912861])
