@@ -495,6 +495,9 @@ int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUten
             case 12841: return launch_l<4, 1, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
             case 12832: return launch_l<4, 1, 128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
             case 6433: return launch_l<4, 1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 6442: return launch_l<4, 1, 64, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 6462: return launch_l<4, 1, 64, 6, 2>(a_mn, b_mn, ta, tb, g, grid, st);
+            case 12842: return launch_l<4, 1, 128, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
             case 125631: return launch_l<4, 2, 256, 3, 1>(a_mn, b_mn, ta, tb, g, grid, st);
             case 112841: return launch_l<4, 2, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
             case 112822: return launch_l<4, 2, 128, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);

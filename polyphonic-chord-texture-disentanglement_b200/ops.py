@@ -256,6 +256,50 @@ def linear(x, w, b=None):
     return _Linear.apply(x, w, b)
 
 
+class _LinearSplit(torch.autograd.Function):
+    """(y1, y2) = split(x W^T + b, n1): two heads that read the same activations as ONE GEMM.  The pitch head and the
+    (folded) duration-hidden projection both consume the note-GRU states (ptvae.py:336-343); as separate Linears
+    their backward writes two (Q,512) input gradients that autograd then adds (1.5 GB of traffic at B = 512) and
+    reads the states twice for the two weight gradients."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, n1):
+        x2, _ = _rows(_chk(x, "x"))
+        y = _empty_rows(x2.shape[0], w.shape[0], x.device)
+        gemm_nt(x2, w, y, b)
+        ctx.save_for_backward(x2, w)
+        ctx.n1 = n1
+        ctx.x_shape = x.shape
+        return y[:, :n1], y[:, n1:]
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        x2, w = ctx.saved_tensors
+        n1 = ctx.n1
+        dy = _empty_rows(x2.shape[0], w.shape[0], x2.device)
+        for part, d in ((dy[:, :n1], d1), (dy[:, n1:], d2)):
+            if d is None:
+                part.zero_()
+            else:
+                part.copy_(d.reshape(part.shape))
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
+            gemm_nn(dy, w, dx)
+            dx = dx.view(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
+            gemm_tn(dy, x2, dw)
+        if ctx.needs_input_grad[2]:
+            db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
+            colsum(dy, db)
+        return dx, dw, db, None
+
+
+def linear_split(x, w, b, n1):
+    return _LinearSplit.apply(x, w, b, n1)
+
+
 class _MatMulNN(torch.autograd.Function):
     """c = a @ b for small weight-space products (a (M,K), b (K,N), both row-strided)."""
 

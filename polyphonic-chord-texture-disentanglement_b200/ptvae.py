@@ -289,9 +289,14 @@ class PtvaeDecoder(nn.Module):
         gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
         gi_tok = ops.linear(notes, wn_ih[:, self.dec_time_hid_size:], None)               # (R,16,1536)
         h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1)  # (R,15,512)
-        pitch = self.pitch_out_linear(h)                                                  # (R,15,130)
+        # pitch head and (folded) duration-hidden projection as one GEMM over the note states
         Q = R * (self.max_simu_note - 1)
-        dur = self._decode_durs(h.reshape(Q, -1), None)
+        w_eff, b_eff = self._dur_hid_folded()
+        pitch, dh = ops.linear_split(h.reshape(Q, -1), torch.cat([self.pitch_out_linear.weight, w_eff], 0),
+                                     torch.cat([self.pitch_out_linear.bias, b_eff], 0), self.pitch_range)
+        w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
+        dur = ops.dur_decode(dh, w_ih, b_ih, w_hh, b_hh, self.dur_sos_token, self.dur_out_linear.weight,
+                             self.dur_out_linear.bias)
         return pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), \
             dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
 
