@@ -43,6 +43,9 @@ int pd_f32_to_bf16(const float* x, long ldx, long rows, int cols, void* out, lon
 /* hi = round_to_nearest_tf32(x), lo = x - hi (row stride ldo): operands of the error-compensated "3xTF32" GEMM
  * A.B ~= A_hi.B_hi + A_hi.B_lo + A_lo.B_hi (TF32 multiplies, fp32 accumulation: ~fp32 accuracy on tensor cores) */
 int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, float* lo, long ldo, void* stream);
+/* single-launch form: out (rows, 3*kp), kp = cols rounded up to 4: [hi | hi | lo] (order 0, A side) or [hi | lo | hi]
+ * (order 1, B side); one pd_gemm_tf32 over K = 3*kp then equals the three-product sum */
+int pd_tf32_split3(const float* x, long ldx, long rows, int cols, float* out, long ldo, int order, void* stream);
 /* out[n] (+)= sum_m X[m*ldx+n]   (bias gradients) */
 int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int accumulate, void* stream);
 int pd_transpose_f32(const float* in, int rows, int cols, float* out, void* stream);

@@ -141,6 +141,24 @@ __global__ void tf32_split_kernel(const float* __restrict__ x, long ldx, long ro
     hi_out[r * ldo + c] = __uint_as_float(hi);
     lo[r * ldo + c] = v - __uint_as_float(hi);
 }
+// Operand of the single-launch 3xTF32 GEMM: out row = three K-segments of width kp (cols padded to a multiple of 4,
+// padding zero): order 0 (A side) [hi | hi | lo], order 1 (B side) [hi | lo | hi], so that ONE GEMM over K = 3*kp
+// accumulates A_hi.B_hi + A_hi.B_lo + A_lo.B_hi in TMEM instead of three launches meeting in an L2-reduction epilogue.
+__global__ void tf32_split3_kernel(const float* __restrict__ x, long ldx, long rows, int cols, int kp, float* __restrict__ out,
+                                   long ldo, int order) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * kp) return;
+    long r = i / kp;
+    int c = (int)(i % kp);
+    float v = c < cols ? x[r * ldx + c] : 0.0f;
+    uint32_t hb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(v));
+    const float hi = __uint_as_float(hb), lo = v - hi;
+    float* o = out + r * ldo + c;
+    o[0] = hi;
+    o[kp] = order ? lo : hi;
+    o[2 * kp] = order ? hi : lo;
+}
 // z[b, j] = mu + std * eps, written with row stride ldz (into its half of dec_z)
 __global__ void reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sd,
                                    const float* __restrict__ eps, int B, int D, float* z, long ldz) {
@@ -236,6 +254,16 @@ PD_API int pd_add_f32(const float* a, const float* b, long n, float* out, void* 
 PD_API int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, float* lo, long ldo, void* stream) {
     if (rows <= 0 || cols <= 0) return 0;
     tf32_split_kernel<<<pd_blocks(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, cols, hi, lo, ldo);
+    return pd_launch_status();
+}
+
+// out (rows, 3*kp; row stride ldo), kp = cols rounded up to a multiple of 4: [hi | hi | lo] (order 0) or [hi | lo | hi]
+// (order 1) of x (rows, cols; row stride ldx)
+PD_API int pd_tf32_split3(const float* x, long ldx, long rows, int cols, float* out, long ldo, int order, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    const int kp = (cols + 3) / 4 * 4;
+    if (ldo < 3L * kp) return PD_BAD_ARG;
+    tf32_split3_kernel<<<pd_blocks(rows * kp, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, cols, kp, out, ldo, order);
     return pd_launch_status();
 }
 

@@ -126,21 +126,20 @@ class precision:
         _lo_cache.clear()
 
 
-def _split_hi_lo(t, cache):
-    """(hi, lo) with hi = rn_tf32(t), lo = t - hi, as row-padded tensors (cached for weights: they do not
-    change inside a decode)."""
-    key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()))
+def _split3(t, order, cache):
+    """Operand of the single-launch 3xTF32 GEMM: (rows, 3*pad4(cols)) = [hi | hi | lo] (order 0, activations) or
+    [hi | lo | hi] (order 1, weights; cached -- they do not change inside a decode), hi = rn_tf32(t), lo = t - hi."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), order)
     if cache and key in _lo_cache:
         return _lo_cache[key]
     rows, cols = t.shape
-    buf = torch.empty(2, rows, _pad4(cols), device=t.device, dtype=torch.float32)
-    hi, lo = buf[0, :, :cols], buf[1, :, :cols]
-    _call("pd_tf32_split", _ptr(t), t.stride(0), rows, cols, _ptr(hi), _ptr(lo), hi.stride(0), _stream())
+    out = torch.empty(rows, 3 * _pad4(cols), device=t.device, dtype=torch.float32)
+    _call("pd_tf32_split3", _ptr(t), t.stride(0), rows, cols, _ptr(out), out.stride(0), order, _stream())
     if cache:
         if len(_lo_cache) > 256:
             _lo_cache.clear()
-        _lo_cache[key] = (hi, lo)
-    return hi, lo
+        _lo_cache[key] = out
+    return out
 
 
 def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
@@ -152,13 +151,12 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
         tc_ok = (a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
                  and lda >= 4 and ldb >= 4)
     if tc_ok and PRECISION == "tf32x3" and M >= 512 and sak == 1 and sbk == 1 and a.dim() == 2 and b.dim() == 2:
-        # NT only (the inference GEMMs): three TF32 passes accumulated in fp32 by the L2-reduction epilogue.
-        # Small batches (M < 512) stay on the single-launch FFMA kernel: they are launch-latency bound.
-        st = _stream()
-        (a_hi, a_lo), (b_hi, b_lo) = _split_hi_lo(a, False), _split_hi_lo(b, True)
-        for x_, w_, bias_, acc_ in ((a_hi, b_hi, bias, accumulate), (a_hi, b_lo, None, True), (a_lo, b_hi, None, True)):
-            _call("pd_gemm_tf32", _ptr(x_), x_.stride(0), 1, _ptr(w_), 1, w_.stride(0), _ptr(out), out.stride(0),
-                  _ptr(bias_), M, N, K, int(acc_), st)
+        # NT only (the inference GEMMs): the three TF32 products as ONE GEMM over the concatenated K = 3*pad4(K),
+        # accumulated in fp32 in TMEM.  Small batches (M < 512) stay on the single-launch FFMA kernel: they are
+        # launch-latency bound.
+        a3, b3 = _split3(a, 0, False), _split3(b, 1, True)
+        _call("pd_gemm_tf32", _ptr(a3), a3.stride(0), 1, _ptr(b3), 1, b3.stride(0), _ptr(out), out.stride(0),
+              _ptr(bias), M, N, a3.shape[1], int(accumulate), _stream())
         return out
     if tc_ok and PRECISION == "tf32":
         name = "pd_gemm_tf32"

@@ -86,6 +86,17 @@ class CpuBackend:
         _arr(hi_out, (rows, cols), (ldo, 1))[...] = hi
         _arr(lo, (rows, cols), (ldo, 1))[...] = X - hi
 
+    def pd_tf32_split3(self, x, ldx, rows, cols, out, ldo, order, st):
+        kp = (cols + 3) // 4 * 4
+        X = np.zeros((rows, kp), np.float32)
+        X[:, :cols] = _arr(x, (rows, cols), (ldx, 1))
+        bits = X.view(np.uint32).astype(np.uint64)
+        hi = (((bits + 0x1000) >> 13) << 13).astype(np.uint32).view(np.float32)
+        O = _arr(out, (rows, 3 * kp), (ldo, 1))
+        O[:, :kp] = hi
+        O[:, kp:2 * kp] = (X - hi) if order else hi
+        O[:, 2 * kp:] = hi if order else (X - hi)
+
     def pd_colsum_f32(self, X, ldx, M, N, out, acc, st):
         o = _arr(out, (N,), (1,))
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0

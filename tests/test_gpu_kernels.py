@@ -495,3 +495,17 @@ def test_gru128_resident(R, T, reverse, passes):
                  T * 3 * H, 3 * H, dgh, T * 3 * H, 3 * H, R, T, reverse, None], [dgi, dgh])
     for g, c in _both("pd_gru128_bwd", mkb):
         assert torch.allclose(g, c, atol=5e-3, rtol=1e-3), float((g - c).abs().max())
+
+
+@pytest.mark.parametrize("order", [0, 1])
+def test_tf32_split3(order):
+    """[hi | hi | lo] / [hi | lo | hi] operand builder of the single-launch 3xTF32 GEMM (zero padded to K % 4 == 0)."""
+    _dev()
+    (g, c), = _both("pd_tf32_split3",
+                    lambda: (lambda X, o: ([X, 136, 77, 130, o, 400, order, None], [o]))(torch.randn(77, 136), torch.full((77, 400), 7.0)))
+    assert torch.equal(g, c)
+    kp = 132
+    hi, x = c[:, :kp], torch.zeros(77, kp)
+    lo = c[:, kp:2 * kp] if order else c[:, 2 * kp:3 * kp]
+    assert torch.equal((hi.view(torch.int32) & 0x1FFF), torch.zeros(77, kp, dtype=torch.int32))   # 10-bit mantissa
+    assert float(lo.abs().max()) < 2 ** -10 * 6 and torch.equal(c[:, 3 * kp:], torch.full((77, 400 - 3 * kp), 7.0))
