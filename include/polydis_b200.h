@@ -109,8 +109,9 @@ int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long ldd, lon
 int pd_dur_token(const float* logit, long ldl, long R, float* tok, void* stream);
 /* fused duration decoder (ptvae.py:345-367): 5-step GRU(5->64) + Linear(64->2) with greedy bit feedback.
  * logits (Q,5,2); S (Q,6,72) state buffer for the backward (NULL at inference); GX (Q,6,264) gradient buffer
- * such that GX^T . S holds all parameter gradients (layout: csrc/dur_decoder.cu).  tf32 != 0: recurrent
- * matvecs on the tensor cores (TF32), else fp32 FFMA (the token-parity mode). */
+ * such that GX^T . S holds all parameter gradients (layout: csrc/dur_decoder.cu).  tf32: 0 = fp32 FFMA kernels;
+ * 1 = recurrent matvecs on the tensor cores (TF32, training); 3 = error-compensated 3xTF32 matvecs with expf / tanhf
+ * gates (fp32-class, the token-parity decode; forward only -- the backward treats any nonzero value as 1). */
 int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih, const float* w_hh,
                       const float* b_hh, const float* sos, const float* w_out, const float* b_out, float* logits,
                       float* S, int tf32, void* stream);

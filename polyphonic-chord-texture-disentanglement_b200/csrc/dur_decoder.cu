@@ -296,10 +296,10 @@ struct WarpShared {              // block-wide part of the dynamic shared memory
     float sos[8];
 };
 
-__device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh) {
+__device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh, bool round_w = true) {
     for (int i = threadIdx.x; i < G3 * H; i += blockDim.x) {
         const int n = i / H, k = i % H;
-        sh->w[n * WSP + kperm(k)] = __uint_as_float(to_tf32(p.w_hh[i]));
+        sh->w[n * WSP + kperm(k)] = round_w ? __uint_as_float(to_tf32(p.w_hh[i])) : p.w_hh[i];
     }
     for (int j = threadIdx.x; j < G3; j += blockDim.x) {
         const float bh = j < 2 * H ? p.b_hh[j] : 0.0f;
@@ -317,18 +317,33 @@ __device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh) {
 
 // gh (16 x 192, bias-free) = hw (16 x 64 state tile of this warp) . W_hh^T, as 24 n-tiles of accumulators:
 // acc[j] / acc[8+j] / acc[16+j] hold r / z / n of units 8j..8j+7; element [2*half+c] is row g+8*half, unit 8j+2*tig+c
+// PASSES = 3: error-compensated products hi*lo + lo*hi + hi*hi on unrounded shared weights (fp32-class accuracy for
+// the token-parity decode); PASSES = 1: the shared weights are already TF32.
+template <int PASSES = 1>
 __device__ __forceinline__ void warp_matvec(const float* __restrict__ w_s, const float (*hw)[HS], float (&acc)[24][4],
                                             int g, int tig) {
 #pragma unroll
     for (int nt = 0; nt < 24; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
 #pragma unroll
     for (int kt = 0; kt < 8; ++kt) {
-        const uint32_t a[4] = {to_tf32(hw[g][8 * kt + tig]), to_tf32(hw[g + 8][8 * kt + tig]),
-                               to_tf32(hw[g][8 * kt + tig + 4]), to_tf32(hw[g + 8][8 * kt + tig + 4])};
+        const float av[4] = {hw[g][8 * kt + tig], hw[g + 8][8 * kt + tig], hw[g][8 * kt + tig + 4], hw[g + 8][8 * kt + tig + 4]};
+        uint32_t a[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = to_tf32(av[i]);
+            if (PASSES == 3) al[i] = to_tf32(av[i] - __uint_as_float(a[i]));
+        }
 #pragma unroll
         for (int nt = 0; nt < 24; ++nt) {
             const float2 b = *reinterpret_cast<const float2*>(w_s + (8 * nt + g) * WSP + 8 * kt + 2 * tig);
-            mma_tf32(acc[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
+            if (PASSES == 3) {
+                const uint32_t b0 = to_tf32(b.x), b1 = to_tf32(b.y);
+                mma_tf32(acc[nt], a, to_tf32(b.x - __uint_as_float(b0)), to_tf32(b.y - __uint_as_float(b1)));
+                mma_tf32(acc[nt], al, b0, b1);
+                mma_tf32(acc[nt], a, b0, b1);
+            } else {
+                mma_tf32(acc[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
+            }
         }
     }
 }
@@ -390,6 +405,11 @@ __device__ __forceinline__ void warp_store_slot(float* __restrict__ S, long q0, 
     }
 }
 
+// gate functions: MUFU forms in TF32 mode, expf / tanhf in the fp32-class (3-pass) mode
+template <int PASSES> __device__ __forceinline__ float gate_sigmoid(float x) { return PASSES == 1 ? pd_sigmoid_fast(x) : pd_sigmoid(x); }
+template <int PASSES> __device__ __forceinline__ float gate_tanh(float x) { return PASSES == 1 ? pd_tanh_fast(x) : tanhf(x); }
+
+template <int PASSES>
 __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const float* __restrict__ h0, long ldh0, long Q,
                                                                          DurParams p, float* __restrict__ logits,
                                                                          float* __restrict__ S) {
@@ -399,7 +419,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
     float* wbase = dyn_smem + sizeof(WarpShared) / 4 + warp * (WM * HS + WM);
     float (*hw)[HS] = reinterpret_cast<float (*)[HS]>(wbase);                 // this warp's state tile
     int* tokw = reinterpret_cast<int*>(wbase + WM * HS);                      // token (gi table index) per row
-    warp_setup(p, sh);
+    warp_setup(p, sh, PASSES == 1);
     __syncthreads();
     const bool al16 = (((uintptr_t)h0 & 15) == 0) && ((ldh0 & 3) == 0);
     const float bo0 = p.b_out[0], bo1 = p.b_out[1];
@@ -415,7 +435,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
             __syncwarp();
             if (S) warp_store_slot(S, q0, rows, k, hw, tokw, sh->sos, lane);
             float acc[24][4];
-            warp_matvec(sh->w, hw, acc, g, tig);
+            warp_matvec<PASSES>(sh->w, hw, acc, g, tig);
             __syncwarp();                                  // every lane is done reading the old state
             float l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
 #pragma unroll
@@ -432,10 +452,10 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
                     const float2 gz = *reinterpret_cast<const float2*>(tb + H);
                     const float2 gn = *reinterpret_cast<const float2*>(tb + 2 * H);
                     const float2 hp = *reinterpret_cast<const float2*>(&hw[row][u]);
-                    const float r0 = pd_sigmoid_fast(gr.x + acc[j][2 * half]), r1 = pd_sigmoid_fast(gr.y + acc[j][2 * half + 1]);
-                    const float z0 = pd_sigmoid_fast(gz.x + acc[8 + j][2 * half]), z1 = pd_sigmoid_fast(gz.y + acc[8 + j][2 * half + 1]);
-                    const float n0 = pd_tanh_fast(gn.x + r0 * (acc[16 + j][2 * half] + bn.x));
-                    const float n1 = pd_tanh_fast(gn.y + r1 * (acc[16 + j][2 * half + 1] + bn.y));
+                    const float r0 = gate_sigmoid<PASSES>(gr.x + acc[j][2 * half]), r1 = gate_sigmoid<PASSES>(gr.y + acc[j][2 * half + 1]);
+                    const float z0 = gate_sigmoid<PASSES>(gz.x + acc[8 + j][2 * half]), z1 = gate_sigmoid<PASSES>(gz.y + acc[8 + j][2 * half + 1]);
+                    const float n0 = gate_tanh<PASSES>(gn.x + r0 * (acc[16 + j][2 * half] + bn.x));
+                    const float n1 = gate_tanh<PASSES>(gn.y + r1 * (acc[16 + j][2 * half + 1] + bn.y));
                     const float2 hn = make_float2((1.0f - z0) * n0 + z0 * hp.x, (1.0f - z1) * n1 + z1 * hp.y);
                     *reinterpret_cast<float2*>(&hw[row][u]) = hn;
                     l0[half] = fmaf(hn.x, w0.x, fmaf(hn.y, w0.y, l0[half]));
@@ -612,22 +632,28 @@ unsigned warp_grid(long Q) {
 }  // namespace
 
 // logits (Q,5,2) <- 5-step greedy-feedback duration GRU from h0 (Q,64; row stride ldh0).  S (Q,6,72) may be
-// NULL (inference).  tf32 != 0: tensor-core (TF32) matvecs; then S must be 16-byte and h0 8-byte aligned, ldh0 even.
+// NULL (inference).  tf32: 0 = fp32 FFMA kernels, 1 = TF32 tensor-core matvecs, 3 = error-compensated 3xTF32 matvecs with
+// expf / tanhf gates (fp32-class, forward only).  Nonzero: S must be 16-byte and h0 8-byte aligned, ldh0 even.
 PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
                              const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
                              const float* b_out, float* logits, float* S, int tf32, void* stream) {
     if (Q <= 0) return 0;
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
+    // small fp32-class calls (step-wise decode of a few segments) are latency bound: one warp per 16 notes doing
+    // three MMA passes loses to the FFMA kernel, which spreads a tile over six warps (16-segment decode: 82 vs 62 ms)
+    if (tf32 == 3 && Q < 4096) tf32 = 0;
     if (tf32) {
         if (((uintptr_t)S & 15) || ((uintptr_t)h0 & 7) || (ldh0 & 1) || ((uintptr_t)logits & 7)) return PD_BAD_ARG;
         static bool attr = false;
         if (!attr) {
-            cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+            cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_fwd_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
             if (e != cudaSuccess) return (int)e;
             attr = true;
         }
-        dur_fwd_warp_kernel<<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+        if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+        else dur_fwd_warp_kernel<1><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
     } else {
         dur_fwd_kernel<<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
     }

@@ -835,7 +835,7 @@ class _DurDecode(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         S = torch.empty(Q, 6, 72, device=dev, dtype=torch.float32) if need else None
         params = [t.contiguous() for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)]
-        ctx.tf32 = int(PRECISION == "tf32")
+        ctx.tf32 = dur_mode()
         _call("pd_dur_decode_fwd", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
               ctx.tf32, _stream())
         ctx.save_for_backward(S, *params)
@@ -862,6 +862,11 @@ class _DurDecode(torch.autograd.Function):
         dw_out, db_out = G[256:258, 0:64], G[256:258, 69]
         return (dh0.view(ctx.h_shape), dw_ih.contiguous(), db_ih.contiguous(), dw_hh.contiguous(),
                 db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous())
+
+
+def dur_mode():
+    """Arithmetic flag of the duration-decoder kernels for the current precision scope (csrc/dur_decoder.cu)."""
+    return {"fp32": 0, "tf32": 1, "tf32x3": 3}[PRECISION]
 
 
 def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):

@@ -294,12 +294,12 @@ def test_posterior_kernels():
         assert torch.allclose(g, c, rtol=1e-5, atol=1e-9)
 
 
-@pytest.mark.parametrize("Q,tf32", [(1, 0), (33, 0), (5000, 0), (33, 1), (5000, 1)])
+@pytest.mark.parametrize("Q,tf32", [(1, 0), (33, 0), (5000, 0), (33, 1), (5000, 1), (33, 3), (5000, 3)])
 def test_dur_decoder_fused(Q, tf32):
     """Weight-resident fused duration GRU (fwd + bwd) vs the numpy restatement; tf32=1 runs the recurrent
     matvecs on the tensor cores (operands rounded to TF32, ~1e-3 relative)."""
     _dev()
-    tol = 3e-3 if tf32 else 2e-5
+    tol = {0: 2e-5, 1: 3e-3, 3: 3e-5}[tf32]
     par = lambda: [torch.randn(192, 5) * 0.3, torch.randn(192) * 0.1, torch.randn(192, 64) * 0.2, torch.randn(192) * 0.1,
                    torch.rand(5), torch.randn(2, 64) * 0.3, torch.randn(2) * 0.1]
 
@@ -308,7 +308,7 @@ def test_dur_decoder_fused(Q, tf32):
         return [torch.randn(Q, 2, 64), 128, Q] + par() + [lg, S, tf32, None], [lg, S]
     (gl, cl), (gs, cs) = _both("pd_dur_decode_fwd", mk)
     same_tok = (gs[:, :, 64:69] == cs[:, :, 64:69]).all(-1).all(-1)
-    assert same_tok.float().mean() > (0.97 if tf32 else 0.995)   # a near-tied bit may flip by rounding
+    assert same_tok.float().mean() > (0.97 if tf32 == 1 else 0.995)   # a near-tied bit may flip by rounding
     assert torch.allclose(gl[same_tok], cl[same_tok], atol=tol), float((gl - cl)[same_tok].abs().max())
     assert torch.allclose(gs[same_tok], cs[same_tok], atol=tol)
 
@@ -321,7 +321,7 @@ def test_dur_decoder_fused(Q, tf32):
     for g, c in _both("pd_dur_decode_bwd", mkb):
         if g.dim() == 3 and g.shape[-1] == 64:
             g, c = g[:, 0], c[:, 0]
-        assert torch.allclose(g, c, atol=(5e-3 if tf32 else 3e-5), rtol=1e-4), float((g - c).abs().max())
+        assert torch.allclose(g, c, atol=(5e-3 if tf32 else 3e-5), rtol=1e-4), float((g - c).abs().max())   # bwd: 3 -> TF32
 
 
 def test_prmat_grid_conversions():
