@@ -289,17 +289,20 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ int kperm(int k) { return (k & ~7) | ((k & 3) << 1) | ((k >> 2) & 1); }
 
 struct WarpShared {              // block-wide part of the dynamic shared memory
-    float w[G3 * WSP];           // TF32-rounded W_hh, k-permuted rows
+    float w[G3 * WSP];           // TF32-rounded W_hh (hi part), k-permuted rows
     float gi_t[3 * TS];          // x-projection per input token; b_hh of the r and z gates folded in
     float bhn[H];                // b_hh of the n gate (multiplied by r, cannot be folded)
     float wo[2 * H];
     float sos[8];
 };
 
-__device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh, bool round_w = true) {
+// w_lo (3-pass mode only): TF32-rounded residual W_hh - hi, same layout, placed behind the per-warp tiles
+__device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh, float* w_lo = nullptr) {
     for (int i = threadIdx.x; i < G3 * H; i += blockDim.x) {
         const int n = i / H, k = i % H;
-        sh->w[n * WSP + kperm(k)] = round_w ? __uint_as_float(to_tf32(p.w_hh[i])) : p.w_hh[i];
+        const float v = p.w_hh[i], hi = __uint_as_float(to_tf32(v));
+        sh->w[n * WSP + kperm(k)] = hi;
+        if (w_lo) w_lo[n * WSP + kperm(k)] = __uint_as_float(to_tf32(v - hi));
     }
     for (int j = threadIdx.x; j < G3; j += blockDim.x) {
         const float bh = j < 2 * H ? p.b_hh[j] : 0.0f;
@@ -317,11 +320,11 @@ __device__ __forceinline__ void warp_setup(const DurParams& p, WarpShared* sh, b
 
 // gh (16 x 192, bias-free) = hw (16 x 64 state tile of this warp) . W_hh^T, as 24 n-tiles of accumulators:
 // acc[j] / acc[8+j] / acc[16+j] hold r / z / n of units 8j..8j+7; element [2*half+c] is row g+8*half, unit 8j+2*tig+c
-// PASSES = 3: error-compensated products hi*lo + lo*hi + hi*hi on unrounded shared weights (fp32-class accuracy for
-// the token-parity decode); PASSES = 1: the shared weights are already TF32.
+// PASSES = 3: error-compensated products hi*lo + lo*hi + hi*hi with a second shared copy holding the weights' low
+// parts (fp32-class accuracy for the token-parity decode); PASSES = 1: hi parts only.
 template <int PASSES = 1>
 __device__ __forceinline__ void warp_matvec(const float* __restrict__ w_s, const float (*hw)[HS], float (&acc)[24][4],
-                                            int g, int tig) {
+                                            int g, int tig, const float* __restrict__ w_lo = nullptr) {
 #pragma unroll
     for (int nt = 0; nt < 24; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
 #pragma unroll
@@ -337,10 +340,10 @@ __device__ __forceinline__ void warp_matvec(const float* __restrict__ w_s, const
         for (int nt = 0; nt < 24; ++nt) {
             const float2 b = *reinterpret_cast<const float2*>(w_s + (8 * nt + g) * WSP + 8 * kt + 2 * tig);
             if (PASSES == 3) {
-                const uint32_t b0 = to_tf32(b.x), b1 = to_tf32(b.y);
-                mma_tf32(acc[nt], a, to_tf32(b.x - __uint_as_float(b0)), to_tf32(b.y - __uint_as_float(b1)));
-                mma_tf32(acc[nt], al, b0, b1);
-                mma_tf32(acc[nt], a, b0, b1);
+                const float2 bl = *reinterpret_cast<const float2*>(w_lo + (8 * nt + g) * WSP + 8 * kt + 2 * tig);
+                mma_tf32(acc[nt], a, __float_as_uint(bl.x), __float_as_uint(bl.y));
+                mma_tf32(acc[nt], al, __float_as_uint(b.x), __float_as_uint(b.y));
+                mma_tf32(acc[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
             } else {
                 mma_tf32(acc[nt], a, __float_as_uint(b.x), __float_as_uint(b.y));
             }
@@ -405,9 +408,10 @@ __device__ __forceinline__ void warp_store_slot(float* __restrict__ S, long q0, 
     }
 }
 
-// gate functions: MUFU forms in TF32 mode, expf / tanhf in the fp32-class (3-pass) mode
-template <int PASSES> __device__ __forceinline__ float gate_sigmoid(float x) { return PASSES == 1 ? pd_sigmoid_fast(x) : pd_sigmoid(x); }
-template <int PASSES> __device__ __forceinline__ float gate_tanh(float x) { return PASSES == 1 ? pd_tanh_fast(x) : tanhf(x); }
+// gate functions: MUFU forms (abs error ~1e-6, the size of fp32 reassociation differences against the reference)
+constexpr bool FAST_GATES_3X = true;
+template <int PASSES> __device__ __forceinline__ float gate_sigmoid(float x) { return PASSES == 1 || FAST_GATES_3X ? pd_sigmoid_fast(x) : pd_sigmoid(x); }
+template <int PASSES> __device__ __forceinline__ float gate_tanh(float x) { return PASSES == 1 || FAST_GATES_3X ? pd_tanh_fast(x) : tanhf(x); }
 
 template <int PASSES>
 __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const float* __restrict__ h0, long ldh0, long Q,
@@ -419,7 +423,8 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
     float* wbase = dyn_smem + sizeof(WarpShared) / 4 + warp * (WM * HS + WM);
     float (*hw)[HS] = reinterpret_cast<float (*)[HS]>(wbase);                 // this warp's state tile
     int* tokw = reinterpret_cast<int*>(wbase + WM * HS);                      // token (gi table index) per row
-    warp_setup(p, sh, PASSES == 1);
+    float* w_lo = PASSES == 3 ? dyn_smem + sizeof(WarpShared) / 4 + FW_WARPS * (WM * HS + WM) : nullptr;
+    warp_setup(p, sh, w_lo);
     __syncthreads();
     const bool al16 = (((uintptr_t)h0 & 15) == 0) && ((ldh0 & 3) == 0);
     const float bo0 = p.b_out[0], bo1 = p.b_out[1];
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
             __syncwarp();
             if (S) warp_store_slot(S, q0, rows, k, hw, tokw, sh->sos, lane);
             float acc[24][4];
-            warp_matvec<PASSES>(sh->w, hw, acc, g, tig);
+            warp_matvec<PASSES>(sh->w, hw, acc, g, tig, w_lo);
             __syncwarp();                                  // every lane is done reading the old state
             float l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
 #pragma unroll
@@ -622,6 +627,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, 1) dur_bwd_warp_kernel(const fl
 }
 
 constexpr int FW_SMEM = (int)sizeof(WarpShared) + FW_WARPS * (WM * HS + WM) * 4;
+constexpr int FW_SMEM3 = FW_SMEM + G3 * WSP * 4;          // + low parts of W_hh
 constexpr int BW_SMEM = (int)sizeof(WarpShared) + BW_WARPS * (WM * HS + WM * GS + 3 * WM) * 4;
 
 unsigned warp_grid(long Q) {
@@ -648,11 +654,11 @@ PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_
         static bool attr = false;
         if (!attr) {
             cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_fwd_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_fwd_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM3);
             if (e != cudaSuccess) return (int)e;
             attr = true;
         }
-        if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+        if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM3, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
         else dur_fwd_warp_kernel<1><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
     } else {
         dur_fwd_kernel<<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);

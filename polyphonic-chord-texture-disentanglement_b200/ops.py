@@ -142,7 +142,7 @@ def _split3(t, order, cache):
     return out
 
 
-def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
+def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None):
     name = "pd_gemm_f32"
     tc_ok = False
     if PRECISION != "fp32" and K >= 8 and N >= 16:
@@ -154,7 +154,7 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
         # NT only (the inference GEMMs): the three TF32 products as ONE GEMM over the concatenated K = 3*pad4(K),
         # accumulated in fp32 in TMEM.  Small batches (M < 512) stay on the single-launch FFMA kernel: they are
         # launch-latency bound.
-        a3, b3 = _split3(a, 0, False), _split3(b, 1, True)
+        a3, b3 = (_split3(a, 0, False) if a3 is None else a3), _split3(b, 1, True)
         _call("pd_gemm_tf32", _ptr(a3), a3.stride(0), 1, _ptr(b3), 1, b3.stride(0), _ptr(out), out.stride(0),
               _ptr(bias), M, N, a3.shape[1], int(accumulate), _stream())
         return out
@@ -165,13 +165,23 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate):
     return out
 
 
-def gemm_nt(x, w, out, bias=None, accumulate=False):
-    """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias)."""
+def split3_act(x):
+    """The [hi | hi | lo] operand of activations x for the 3xTF32 GEMM path, or None when that path does not apply
+    (other precision mode, small batch).  Lets a caller split a tensor ONCE for several GEMMs (``gemm_nt(..., a3=)``)."""
+    if PRECISION != "tf32x3" or x.dim() != 2 or x.shape[0] < 512 or x.stride(1) != 1 or x.shape[1] < 8:
+        return None
+    if x.data_ptr() % 16 or x.stride(0) % 4 or x.stride(0) < 4:
+        return None
+    return _split3(x, 0, False)
+
+
+def gemm_nt(x, w, out, bias=None, accumulate=False, a3=None):
+    """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias).  a3: ``split3_act(x)`` computed by the caller (optional)."""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape == (M, N) and x.stride(1) == 1 and out.stride(1) == 1
     assert w.stride(1) == 1 or K == 1
-    return _gemm(x, x.stride(0), 1, w, 1, w.stride(0), out, bias, M, N, K, accumulate)
+    return _gemm(x, x.stride(0), 1, w, 1, w.stride(0), out, bias, M, N, K, accumulate, a3)
 
 
 def gemm_nn(x, w, out, accumulate=False):

@@ -445,20 +445,24 @@ class PtvaeDecoder(nn.Module):
         gh_e, h_e = [torch.empty(B, 3 * He, **f32) for _ in range(2)], torch.empty(B, He, **f32)
         h_sum = [torch.empty(B, NS, He, **f32) for _ in range(2)]
         st = ops._stream
+        # (3xTF32 mode: a state that feeds several GEMMs is split into its hi / lo operand once -- ops.split3_act)
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
             ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh)
             ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
-            ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias)
-            ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih)
+            a_t = ops.split3_act(h_time)
+            ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias, a3=a_t)
+            ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih, a3=a_t)
             ops._call("pd_note_embed_fwd", ops._ptr(sos_tok), B, ops._ptr(emb_wt), ops._ptr(emb_b), ops._ptr(pred),
                       pred.stride(0), st())
             lens.zero_()
+            a_n = ops.split3_act(h_n)
             for n in range(1, NS):
                 ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
-                ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh)
+                ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)
                 ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
-                ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads)
+                a_n = ops.split3_act(h_n)              # serves the heads now and the recurrent GEMM of the next slot
+                ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads, a3=a_n)
                 ops._call("pd_dur_decode_fwd", ops._ptr(heads[:, self.pitch_range:]), heads.stride(0), B,
                           *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, ops.dur_mode(), st())
                 ops.greedy_pick(heads[:, :self.pitch_range], dlog, n, tokens[t, n - 1], lens)
