@@ -62,6 +62,11 @@ int pd_sum_steps_f32(const float* X, long ldr, long ldt, int T, float* out, long
 int pd_gru_gates_fwd(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
                      const float* hprev, long ldhp, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                      long ldhn, const int* lengths, int t, int B, int H, void* stream);
+/* inference variant: also writes h3 (B, 3H; row stride ldh3) = [hi | hi | lo] TF32 split of the new state, i.e. the
+ * pd_tf32_split3 (order 0) operand of the 3xTF32 GEMMs that consume the state next; no backward saves */
+int pd_gru_gates_fwd_split3(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
+                            const float* hprev, long ldhp, float* hout, long ldho, const int* lengths, int t, int B, int H,
+                            float* h3, long ldh3, void* stream);
 /* d = dh + dh2 + dh3 (each optional): dgi=[dr,dz,dn], dgh=[dr,dz,dn*r], dhprev = d*z (the caller's GEMM adds
  * dgh W_hh), dgi2 (optional) += dgi. */
 int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,

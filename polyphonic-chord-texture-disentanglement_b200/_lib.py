@@ -22,6 +22,7 @@ SIGNATURES = {
     "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
     "pd_sum_steps_f32": [_P, _L, _L, _I, _P, _L, _L, _I, _P],
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
+    "pd_gru_gates_fwd_split3": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P],
     "pd_gru_gates_bwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I,
                          _I, _I, _P],
     "pd_gru_step_tf32": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],

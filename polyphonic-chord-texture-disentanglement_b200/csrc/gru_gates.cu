@@ -25,7 +25,19 @@ struct GateFwd {
     float* hn; long ldhn;            // may be NULL
     const int* lengths; int t;       // may be NULL
     int B, H;
+    float* h3; long ldh3;            // may be NULL: [hi | hi | lo] TF32 split of the new state (3xTF32 GEMM operand)
 };
+
+// the new state as the A operand of the single-launch 3xTF32 GEMM (pd_tf32_split3 order 0), written by the producer
+__device__ __forceinline__ void store_split3(float* p, int H, float4 v) {
+    float4 hi, lo;
+#define PD_SPLIT(c) { uint32_t b; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(v.c)); hi.c = __uint_as_float(b); lo.c = v.c - hi.c; }
+    PD_SPLIT(x) PD_SPLIT(y) PD_SPLIT(z) PD_SPLIT(w)
+#undef PD_SPLIT
+    *reinterpret_cast<float4*>(p) = hi;
+    *reinterpret_cast<float4*>(p + H) = hi;
+    *reinterpret_cast<float4*>(p + 2 * H) = lo;
+}
 
 __global__ void __launch_bounds__(256) gru_gates_fwd_kernel(GateFwd a) {
     const int hq = a.H >> 2;
@@ -36,6 +48,7 @@ __global__ void __launch_bounds__(256) gru_gates_fwd_kernel(GateFwd a) {
                         : make_float4(0.f, 0.f, 0.f, 0.f);
     if (a.lengths && a.t >= a.lengths[b]) {   // past the end of this sequence: carry the state
         *reinterpret_cast<float4*>(a.hout + (long)b * a.ldho + j) = hp;
+        if (a.h3) store_split3(a.h3 + (long)b * a.ldh3 + j, a.H, hp);
         return;
     }
     const float* gi = a.gi + (long)b * a.ldgi + j;
@@ -68,6 +81,7 @@ __global__ void __launch_bounds__(256) gru_gates_fwd_kernel(GateFwd a) {
         *reinterpret_cast<float4*>(s + 2 * a.H) = n;
     }
     if (a.hn) *reinterpret_cast<float4*>(a.hn + (long)b * a.ldhn + j) = hnn;
+    if (a.h3) store_split3(a.h3 + (long)b * a.ldh3 + j, a.H, ho);
 }
 
 struct GateBwd {
@@ -146,17 +160,34 @@ inline bool al4(const void* p, long ld) { return ((uintptr_t)p & 15) == 0 && (ld
 
 }  // namespace
 
-PD_API int pd_gru_gates_fwd(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
-                            const float* hprev, long ldhp, float* hout, long ldho, float* rzn, long ldrzn,
-                            float* hn, long ldhn, const int* lengths, int t, int B, int H, void* stream) {
+static int gates_fwd_launch(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
+                            const float* hprev, long ldhp, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
+                            long ldhn, const int* lengths, int t, int B, int H, float* h3, long ldh3, void* stream) {
     if (B <= 0) return 0;
     if ((H & 3) || !al4(gi, ldgi) || !al4(gh, ldgh) || !al4(hout, ldho) || (gi2 && !al4(gi2, ldgi2)) ||
-        (hprev && !al4(hprev, ldhp)) || (rzn && !al4(rzn, ldrzn)) || (hn && !al4(hn, ldhn)))
+        (hprev && !al4(hprev, ldhp)) || (rzn && !al4(rzn, ldrzn)) || (hn && !al4(hn, ldhn)) ||
+        (h3 && (!al4(h3, ldh3) || ldh3 < 3L * H)))
         return PD_BAD_ARG;
-    GateFwd a{gi, ldgi, gi2, ldgi2, gh, ldgh, hprev, ldhp, hout, ldho, rzn, ldrzn, hn, ldhn, lengths, t, B, H};
+    GateFwd a{gi, ldgi, gi2, ldgi2, gh, ldgh, hprev, ldhp, hout, ldho, rzn, ldrzn, hn, ldhn, lengths, t, B, H, h3, ldh3};
     long n = (long)B * (H >> 2);
     gru_gates_fwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return pd_launch_status();
+}
+
+PD_API int pd_gru_gates_fwd(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
+                            const float* hprev, long ldhp, float* hout, long ldho, float* rzn, long ldrzn,
+                            float* hn, long ldhn, const int* lengths, int t, int B, int H, void* stream) {
+    return gates_fwd_launch(gi, ldgi, gi2, ldgi2, gh, ldgh, hprev, ldhp, hout, ldho, rzn, ldrzn, hn, ldhn, lengths, t, B, H,
+                            nullptr, 0, stream);
+}
+
+// Inference variant: additionally writes h3 (B, 3H; row stride ldh3) = [hi | hi | lo] of the new state, the A operand
+// of the single-launch 3xTF32 GEMMs that consume it next (saves a pd_tf32_split3 pass per step of the greedy decode).
+PD_API int pd_gru_gates_fwd_split3(const float* gi, long ldgi, const float* gi2, long ldgi2, const float* gh, long ldgh,
+                                   const float* hprev, long ldhp, float* hout, long ldho, const int* lengths, int t, int B,
+                                   int H, float* h3, long ldh3, void* stream) {
+    return gates_fwd_launch(gi, ldgi, gi2, ldgi2, gh, ldgh, hprev, ldhp, hout, ldho, nullptr, 0, nullptr, 0, lengths, t, B, H,
+                            h3, ldh3, stream);
 }
 
 PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,

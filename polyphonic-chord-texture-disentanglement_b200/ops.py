@@ -168,11 +168,7 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None):
 def split3_act(x):
     """The [hi | hi | lo] operand of activations x for the 3xTF32 GEMM path, or None when that path does not apply
     (other precision mode, small batch).  Lets a caller split a tensor ONCE for several GEMMs (``gemm_nt(..., a3=)``)."""
-    if PRECISION != "tf32x3" or x.dim() != 2 or x.shape[0] < 512 or x.stride(1) != 1 or x.shape[1] < 8:
-        return None
-    if x.data_ptr() % 16 or x.stride(0) % 4 or x.stride(0) < 4:
-        return None
-    return _split3(x, 0, False)
+    return _split3(x, 0, False) if split3_applies(x) else None
 
 
 def gemm_nt(x, w, out, bias=None, accumulate=False, a3=None):
@@ -376,6 +372,19 @@ def _gates_fwd(gi, gi2, gh, hprev, hout, rzn, hn, lengths, t):
           _ptr(gh), gh.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
           _ptr(hout), hout.stride(0), _ptr(rzn), 0 if rzn is None else rzn.stride(0),
           _ptr(hn), 0 if hn is None else hn.stride(0), _ptr(lengths), t, B, H, _stream())
+
+
+def gates_fwd_split3(gi, gi2, gh, h, h3):
+    """In-place inference GRU step on h (B,H) that also emits h3 = [hi | hi | lo] of the new state (3xTF32 operand)."""
+    B, H = h.shape
+    _call("pd_gru_gates_fwd_split3", _ptr(gi), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0), _ptr(gh),
+          gh.stride(0), _ptr(h), h.stride(0), _ptr(h), h.stride(0), None, 0, B, H, _ptr(h3), h3.stride(0), _stream())
+
+
+def split3_applies(x):
+    """Would ``split3_act(x)`` return an operand (3xTF32 tensor-core GEMM path) for this tensor?"""
+    return (PRECISION == "tf32x3" and x.dim() == 2 and x.shape[0] >= 512 and x.stride(1) == 1 and x.shape[1] >= 8
+            and x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0 and x.stride(0) >= 4)
 
 
 # Weight-resident GRU128 kernel (csrc/gru128_resident.cu) for the note-summary bi-GRU.  Its matvecs run on

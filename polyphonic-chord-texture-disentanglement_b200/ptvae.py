@@ -445,14 +445,20 @@ class PtvaeDecoder(nn.Module):
         gh_e, h_e = [torch.empty(B, 3 * He, **f32) for _ in range(2)], torch.empty(B, He, **f32)
         h_sum = [torch.empty(B, NS, He, **f32) for _ in range(2)]
         st = ops._stream
-        # (3xTF32 mode: a state that feeds several GEMMs is split into its hi / lo operand once -- ops.split3_act)
+        # 3xTF32 mode: a state that feeds several GEMMs is split into its [hi | hi | lo] operand once, by the gate
+        # kernel that produces it (ops.gates_fwd_split3) or by ops.split3_act
+        x3 = ops.split3_applies(h_time)
+        t3 = torch.empty(B, 3 * Ht, **f32) if x3 else None
+        n3 = torch.empty(B, 3 * Hn, **f32) if x3 else None
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
-            ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh)
-            ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
-            a_t = ops.split3_act(h_time)
-            ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias, a3=a_t)
-            ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih, a3=a_t)
+            ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh, a3=t3 if t > 0 else None)
+            if x3:
+                ops.gates_fwd_split3(gi_t, gi_z, gh_t, h_time, t3)
+            else:
+                ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
+            ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias, a3=t3)
+            ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih, a3=t3)
             ops._call("pd_note_embed_fwd", ops._ptr(sos_tok), B, ops._ptr(emb_wt), ops._ptr(emb_b), ops._ptr(pred),
                       pred.stride(0), st())
             lens.zero_()
@@ -460,8 +466,11 @@ class PtvaeDecoder(nn.Module):
             for n in range(1, NS):
                 ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
                 ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)
-                ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
-                a_n = ops.split3_act(h_n)              # serves the heads now and the recurrent GEMM of the next slot
+                if x3:                                 # n3 serves the heads now and the recurrent GEMM of the next slot
+                    ops.gates_fwd_split3(gi_n, gi_s, gh_n, h_n, n3)
+                    a_n = n3
+                else:
+                    ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
                 ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads, a3=a_n)
                 ops._call("pd_dur_decode_fwd", ops._ptr(heads[:, self.pitch_range:]), heads.stride(0), B,
                           *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, ops.dur_mode(), st())

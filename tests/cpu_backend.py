@@ -109,6 +109,10 @@ class CpuBackend:
         _arr(out, (cols, rows), (rows, 1))[...] = _arr(inp, (rows, cols), (cols, 1)).T
 
     # ---- gru gates ----
+    def pd_gru_gates_fwd_split3(self, gi, ldgi, gi2, ldgi2, gh, ldgh, hp, ldhp, ho, ldho, lengths, t, B, H, h3, ldh3, st):
+        self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh, ldgh, hp, ldhp, ho, ldho, None, 0, None, 0, lengths, t, B, H, st)
+        self.pd_tf32_split3(ho, ldho, B, H, h3, ldh3, 0, st)
+
     def pd_gru_gates_fwd(self, gi, ldgi, gi2, ldgi2, gh, ldgh, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn,
                          lengths, t, B, H, st):
         GI = _arr(gi, (B, 3 * H), (ldgi, 1)).copy()

@@ -509,3 +509,20 @@ def test_tf32_split3(order):
     lo = c[:, kp:2 * kp] if order else c[:, 2 * kp:3 * kp]
     assert torch.equal((hi.view(torch.int32) & 0x1FFF), torch.zeros(77, kp, dtype=torch.int32))   # 10-bit mantissa
     assert float(lo.abs().max()) < 2 ** -10 * 6 and torch.equal(c[:, 3 * kp:], torch.full((77, 400 - 3 * kp), 7.0))
+
+
+def test_gru_gates_fwd_split3():
+    """Inference gate kernel that also emits the [hi | hi | lo] operand of the new state."""
+    _dev()
+    B, H = 70, 128
+
+    def mk():
+        hp, h, h3 = torch.randn(B, H), torch.zeros(B, H), torch.zeros(B, 3 * H + 4)
+        return ([torch.randn(B, 3 * H), 3 * H, torch.randn(B, 3 * H), 3 * H, torch.randn(B, 3 * H), 3 * H, hp, H, h, H, None, 0, B, H,
+                 h3, 3 * H + 4, None], [h, h3])
+    (gh_, ch_), (g3, c3) = _both("pd_gru_gates_fwd_split3", mk)
+    assert torch.allclose(gh_, ch_, atol=2e-6)
+    hi, lo = g3[:, :H], g3[:, 2 * H:3 * H]
+    assert torch.equal(hi, g3[:, H:2 * H]) and torch.equal((hi + lo), gh_)          # exact split of the GPU state
+    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros(B, H, dtype=torch.int32))
+    assert torch.allclose(g3, c3, atol=3e-6)
