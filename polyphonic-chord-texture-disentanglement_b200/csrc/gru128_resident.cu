@@ -10,6 +10,7 @@
 // stops at the tile's longest sequence.  PASSES = 3 runs every product as hi*hi + hi*lo + lo*hi (error
 // compensated TF32, fp32-class accuracy) for the token-parity inference mode.
 // Outputs keep the masked-step semantics of pd_gru_gates_fwd: rows past their length carry their state.
+// Gate functions are the MUFU forms of common.cuh (abs error ~1e-6): the kernels are instruction bound.
 #include "common.cuh"
 
 namespace {
@@ -158,9 +159,9 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
                             if (t < len) {
                                 const float2 ir = xi[nt][half][0], iz = xi[nt][half][1], in = xi[nt][half][2];
                                 const float g0 = acc[2][nt][half * 2], g1 = acc[2][nt][half * 2 + 1];
-                                const float r_0 = pd_sigmoid(ir.x + acc[0][nt][half * 2]), r_1 = pd_sigmoid(ir.y + acc[0][nt][half * 2 + 1]);
-                                const float z_0 = pd_sigmoid(iz.x + acc[1][nt][half * 2]), z_1 = pd_sigmoid(iz.y + acc[1][nt][half * 2 + 1]);
-                                const float n_0 = tanhf(in.x + r_0 * g0), n_1 = tanhf(in.y + r_1 * g1);
+                                const float r_0 = pd_sigmoid_fast(ir.x + acc[0][nt][half * 2]), r_1 = pd_sigmoid_fast(ir.y + acc[0][nt][half * 2 + 1]);
+                                const float z_0 = pd_sigmoid_fast(iz.x + acc[1][nt][half * 2]), z_1 = pd_sigmoid_fast(iz.y + acc[1][nt][half * 2 + 1]);
+                                const float n_0 = pd_tanh_fast(in.x + r_0 * g0), n_1 = pd_tanh_fast(in.y + r_1 * g1);
                                 ho.x = (1.0f - z_0) * n_0 + z_0 * hp.x;
                                 ho.y = (1.0f - z_1) * n_1 + z_1 * hp.y;
                                 if (a.rzn) {
