@@ -247,9 +247,17 @@ def run_b200(args):
         del g0
         mark(f"tfr=0 step: {ms_tfr0:.1f} ms")
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
-    def e2e_step():
-        xd, cd, pd = xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True), ph.to(dev, non_blocking=True)
-        return float(step(xd, cd, pd))
+    # (graph mode: double-buffered -- every step copies one full batch from pinned host memory, the one the NEXT
+    # step trains on, behind the current replay, as a training loop's prefetcher does; eager mode: copy, then step)
+    if graphed is not None:
+        graphed.prefetch(xh, ch, ph)
+
+        def e2e_step():
+            return float(graphed.step_prefetched(next_batch=(xh, ch, ph))[0])
+    else:
+        def e2e_step():
+            xd, cd, pd = xh.to(dev, non_blocking=True), ch.to(dev, non_blocking=True), ph.to(dev, non_blocking=True)
+            return float(step(xd, cd, pd))
     e2e_step()
     ms_e2e = timed(e2e_step, max(2, args.steps // 2))
     h2d = xh.numel() * 8 + ch.numel() * 4 + ph.numel() * 4
@@ -316,7 +324,10 @@ def run_b200(args):
                       "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
                       "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else "torch clip_grad_norm_ + Adam(fused)"},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
-                   "d2h_bytes_per_step": 4},
+                   "d2h_bytes_per_step": 4,
+                   "how": ("GraphedTrainStep.prefetch/step_prefetched: each step copies one full batch from pinned host "
+                           "memory (the next step's, overlapped with the replay) and reads the loss back"
+                           if graphed is not None else "copy, step, read the loss back")},
            "gpu_launches": launches,
            "train_free_running": None if ms_tfr0 is None else
            {"value": B / (ms_tfr0 * 1e-3), "unit": "samples/s", "ms_per_step": ms_tfr0, "tfr": [0, 0, 0], "cuda_graph": True},

@@ -74,6 +74,33 @@ class GraphedTrainStep:
         self.graph.replay()
         return self.losses
 
+    # -- pipelined input feeding: the host->device copy of the NEXT batch overlaps the replay of the current one --
+    def prefetch(self, x, c, pr_mat):
+        """Start the asynchronous copy of a (pinned host) batch into the staging buffers on a side stream."""
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty_like(t) for t in (self.x, self.c, self.pr)]
+            self._copy_stream = torch.cuda.Stream()
+            self._staged, self._consumed = torch.cuda.Event(), torch.cuda.Event()
+            self._consumed.record()
+        self._copy_stream.wait_event(self._consumed)          # the previous staged batch has been taken over
+        with torch.cuda.stream(self._copy_stream):
+            for dst, src in zip(self._stage, (x, c, pr_mat)):
+                dst.copy_(src, non_blocking=True)
+            self._staged.record()
+
+    def step_prefetched(self, next_batch=None):
+        """Train on the batch staged by ``prefetch`` and (optionally) start fetching ``next_batch`` behind the
+        replay.  Returns the 11 losses as one device tensor."""
+        cur = torch.cuda.current_stream()
+        cur.wait_event(self._staged)
+        for dst, src in zip((self.x, self.c, self.pr), self._stage):
+            dst.copy_(src, non_blocking=True)                 # device-to-device, microseconds
+        self._consumed.record()
+        if next_batch is not None:
+            self.prefetch(*next_batch)
+        self.graph.replay()
+        return self.losses
+
 
 class GraphedDecode:
     """CUDA-graph replay of greedy inference: encode chord + texture -> posterior means -> PianoTree greedy

@@ -397,6 +397,26 @@ def test_graphed_train_step_matches_eager():
     assert losses[1][1] < losses[1][0] + 0.5 and losses[0][1] < losses[0][0] + 0.5
 
 
+def test_graphed_train_step_prefetch_pipeline():
+    """prefetch / step_prefetched: the batch staged from pinned host memory is the one the replay trains on, and
+    the next batch is copied behind it."""
+    dev = _dev()
+    from polydis_b200.graphs import GraphedTrainStep
+    from polydis_b200.model import DisentangleVAE
+    from polydis_b200.synth import synth_batch
+    host = [[torch.from_numpy(a).pin_memory() for a in synth_batch(8, seed)] for seed in (31, 32)]
+    m = DisentangleVAE.init_model(device=dev).to(dev).train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True, capturable=True)
+    g = GraphedTrainStep(m, opt, 8, warmup=1).capture(*[t.to(dev) for t in host[0]])
+    g.prefetch(*host[1])
+    l1 = g.step_prefetched(next_batch=host[0])
+    torch.cuda.synchronize()
+    assert torch.equal(g.x.cpu(), host[1][0]) and torch.equal(g.pr.cpu(), host[1][2]) and torch.isfinite(l1).all()
+    l2 = g.step_prefetched()
+    torch.cuda.synchronize()
+    assert torch.equal(g.x.cpu(), host[0][0]) and torch.equal(g.c.cpu(), host[0][1]) and torch.isfinite(l2).all()
+
+
 def test_tf32x3_gemm_is_fp32_class():
     """Error-compensated 3xTF32 GEMM (tensor cores) vs fp64: relative error ~1e-6, i.e. fp32-class, against
     ~3e-4 for plain TF32."""
