@@ -260,32 +260,72 @@ def linear(x, w, b=None):
     return _Linear.apply(x, w, b)
 
 
+class GradSlab:
+    """The (M, N) gradient matrix of a multi-head projection (``linear_split``), allocated by whichever backward
+    touches it first.  Consumers that know their input came from ``linear_split`` (the GRU recurrences) write their
+    input gradient straight into their column block, so the projection's backward needs no gather copies and the
+    heads' input gradients never exist separately (no autograd add over the shared activations)."""
+
+    def __init__(self):
+        self.M = self.N = self.dev = self.buf = None
+
+    def get(self):
+        if self.buf is None:
+            self.buf = _empty_rows(self.M, self.N, self.dev)
+        return self.buf
+
+    def block(self, off, n, lead):
+        """Column block [off, off+n) viewed as (*lead, n) (rows = prod(lead))."""
+        part = self.get()[:, off:off + n]
+        strides, acc = [], part.stride(0)
+        for d in reversed(lead):
+            strides.append(acc)
+            acc *= d
+        return part.as_strided(tuple(lead) + (n,), tuple(reversed(strides)) + (1,))
+
+
 class _LinearSplit(torch.autograd.Function):
-    """(y1, y2) = split(x W^T + b, n1): two heads that read the same activations as ONE GEMM.  The pitch head and the
-    (folded) duration-hidden projection both consume the note-GRU states (ptvae.py:336-343); as separate Linears
-    their backward writes two (Q,512) input gradients that autograd then adds (1.5 GB of traffic at B = 512) and
-    reads the states twice for the two weight gradients."""
+    """(y1, y2, ...) = split(x W^T + b, sizes): several heads that read the same activations as ONE GEMM.
+    E.g. the pitch head and the (folded) duration-hidden projection both consume the note-GRU states
+    (ptvae.py:336-343); as separate Linears their backward writes two (Q,512) input gradients that autograd then
+    adds (1.5 GB of traffic at B = 512) and reads the states twice for the two weight gradients.  Likewise the note
+    embeddings feed both directions of the summary bi-GRU and the note GRU (ptvae.py:446-453, :396)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, n1):
+    def forward(ctx, x, w, b, sizes, bias_cols, slab):
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
         gemm_nt(x2, w, y, b)
         ctx.save_for_backward(x2, w)
-        ctx.n1 = n1
-        ctx.x_shape = x.shape
-        return y[:, :n1], y[:, n1:]
+        ctx.sizes, ctx.bias_cols, ctx.slab, ctx.x_shape = sizes, bias_cols, slab, x.shape
+        slab.M, slab.N, slab.dev = x2.shape[0], w.shape[0], x.device
+        lead = tuple(x.shape[:-1])
+        outs, off = [], 0
+        for n in sizes:
+            part = y[:, off:off + n]
+            if len(lead) > 1:
+                strides, acc = [], part.stride(0)
+                for d in reversed(lead):
+                    strides.append(acc)
+                    acc *= d
+                part = part.as_strided(lead + (n,), tuple(reversed(strides)) + (1,))
+            outs.append(part)
+            off += n
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, d1, d2):
+    def backward(ctx, *ds):
         x2, w = ctx.saved_tensors
-        n1 = ctx.n1
-        dy = _empty_rows(x2.shape[0], w.shape[0], x2.device)
-        for part, d in ((dy[:, :n1], d1), (dy[:, n1:], d2)):
+        dy = ctx.slab.get()
+        ctx.slab.buf = None                                   # the slab is consumed by this backward
+        off = 0
+        for n, d in zip(ctx.sizes, ds):
+            part = dy[:, off:off + n]
+            off += n
             if d is None:
                 part.zero_()
-            else:
-                part.copy_(d.reshape(part.shape))
+            elif not (d.data_ptr() == part.data_ptr() and d.stride(-1) == 1 and d.stride(-2) == part.stride(0)):
+                part.copy_(d.reshape(part.shape))             # a consumer that did not write into the slab
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
@@ -295,13 +335,26 @@ class _LinearSplit(torch.autograd.Function):
             dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
             gemm_tn(dy, x2, dw)
         if ctx.needs_input_grad[2]:
-            db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
-            colsum(dy, db)
-        return dx, dw, db, None
+            db = torch.zeros(w.shape[0], device=dy.device, dtype=torch.float32)
+            nb = ctx.bias_cols
+            colsum(dy[:, :nb], db[:nb])
+        return dx, dw, db, None, None, None
 
 
-def linear_split(x, w, b, n1):
-    return _LinearSplit.apply(x, w, b, n1)
+def linear_split(x, w, b, sizes, bias_cols=None):
+    """Heads of widths ``sizes`` over the same input as one GEMM; outputs are shaped (*x.shape[:-1], n).  Only the
+    first ``bias_cols`` columns carry a trainable bias (default: all)."""
+    if isinstance(sizes, int):
+        sizes = (sizes, w.shape[0] - sizes)
+    sizes = tuple(sizes)
+    assert sum(sizes) == w.shape[0]
+    slab = GradSlab()
+    outs = _LinearSplit.apply(x, w, b, sizes, w.shape[0] if bias_cols is None else bias_cols, slab)
+    off = 0
+    for o, n in zip(outs, sizes):
+        o._pd_slab = (slab, off, n)                           # lets slab-aware consumers write their gradient in place
+        off += n
+    return outs
 
 
 class _MatMulNN(torch.autograd.Function):
@@ -539,8 +592,9 @@ class _GruSeq(torch.autograd.Function):
     duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
 
     @staticmethod
-    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None):
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None):
         _chk(gi, "gi")
+        ctx.slab = slab
         save = {}
         h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
@@ -557,7 +611,10 @@ class _GruSeq(torch.autograd.Function):
         dev = dout.device
         if not dout.is_contiguous():
             dout = dout.contiguous()
-        dgi = torch.empty(B, ctx.t_full, 3 * H, device=dev, dtype=torch.float32)
+        if ctx.slab is not None:       # gi is a head of a linear_split: its gradient goes straight into that op's slab
+            dgi = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (B, ctx.t_full))
+        else:
+            dgi = torch.empty(B, ctx.t_full, 3 * H, device=dev, dtype=torch.float32)
         if ctx.t_full > T:
             dgi[:, T:].zero_()                     # unused input slots get no gradient
         dgh = torch.empty(B, T, 3 * H, device=dev, dtype=torch.float32)
@@ -601,7 +658,7 @@ class _GruSeq(torch.autograd.Function):
                 gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
         elif h0 is None:
             dw.zero_()
-        return dgi, dgi2, dh0, dw, db, None, None, None
+        return dgi, dgi2, dh0, dw, db, None, None, None, None
 
 
 def _add(a, b):
@@ -615,7 +672,7 @@ def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=N
     requires grad (inference)."""
     if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
                                     (h0 is not None and h0.requires_grad)):
-        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps)
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]))
     return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps)
 
 
@@ -715,8 +772,9 @@ class _MaskedCE(torch.autograd.Function):
     """mean CE over rows whose int32 target != ignore (nn.CrossEntropyLoss(ignore_index))."""
 
     @staticmethod
-    def forward(ctx, logits, targets, ignore):
+    def forward(ctx, logits, targets, ignore, slab=None):
         l2, _ = _rows(_chk(logits, "logits"))
+        ctx.slab = slab
         acc = torch.empty(2, device=l2.device, dtype=torch.float32)
         loss = torch.empty((), device=l2.device, dtype=torch.float32)
         _call("pd_ce_fwd", _ptr(l2), l2.stride(0), _ptr(targets), l2.shape[0], l2.shape[1], ignore,
@@ -729,22 +787,38 @@ class _MaskedCE(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         l2, targets, acc = ctx.saved_tensors
-        d = _empty_rows(l2.shape[0], l2.shape[1], l2.device)
+        if ctx.slab is not None:        # logits are a head of a linear_split: write into that op's gradient slab
+            d = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (l2.shape[0],))
+        else:
+            d = _empty_rows(l2.shape[0], l2.shape[1], l2.device)
         g = g.contiguous()
         _call("pd_ce_bwd", _ptr(l2), l2.stride(0), _ptr(targets), l2.shape[0], l2.shape[1], ctx.ignore,
               _ptr(acc), _ptr(g), _ptr(d), d.stride(0), _stream())
         if d.is_contiguous():
-            return d.view(ctx.shape), None, None
+            return d.view(ctx.shape), None, None, None
         lead = tuple(ctx.shape[:-1])
         strides, a = [], d.stride(0)
         for k in reversed(lead):
             strides.append(a)
             a *= k
-        return d.as_strided(lead + (l2.shape[1],), tuple(reversed(strides)) + (1,)), None, None
+        return d.as_strided(lead + (l2.shape[1],), tuple(reversed(strides)) + (1,)), None, None, None
+
+
+def _slab_of(t, width):
+    slab = getattr(t, "_pd_slab", None)
+    return slab if slab is not None and slab[2] == width else None
+
+
+def keep_slab(new, old):
+    """Carry the linear_split gradient-slab tag of ``old`` over to a reshaped view of it."""
+    tag = getattr(old, "_pd_slab", None)
+    if tag is not None:
+        new._pd_slab = tag
+    return new
 
 
 def masked_ce(logits, targets, ignore=-100):
-    return _MaskedCE.apply(logits, targets, ignore)
+    return _MaskedCE.apply(logits, targets, ignore, _slab_of(logits, logits.shape[-1]) if logits.dim() == 2 else None)
 
 
 class _Exp(torch.autograd.Function):
@@ -846,8 +920,9 @@ class _DurDecode(torch.autograd.Function):
     (GX^T . S) that produces every parameter gradient (layout in csrc/dur_decoder.cu)."""
 
     @staticmethod
-    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
+    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab=None):
         h2, _ = _rows(_chk(h0, "dur h0"))
+        ctx.slab = slab
         Q = h2.shape[0]
         dev = h2.device
         logits = torch.empty(Q, 5, 2, device=dev, dtype=torch.float32)
@@ -868,7 +943,10 @@ class _DurDecode(torch.autograd.Function):
         dev = S.device
         dlogits = dlogits.contiguous()
         GX = torch.empty(Q, 6, 264, device=dev, dtype=torch.float32)
-        dh0 = torch.empty(Q, 64, device=dev, dtype=torch.float32)
+        if ctx.slab is not None:
+            dh0 = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (Q,))
+        else:
+            dh0 = torch.empty(Q, 64, device=dev, dtype=torch.float32)
         _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
                                                                                  b_out)],
               _ptr(GX), _ptr(dh0), dh0.stride(0), ctx.tf32, _stream())
@@ -880,7 +958,7 @@ class _DurDecode(torch.autograd.Function):
         dsos = w_ih.t() @ gi_rows[:, 70]                           # (5,) from the step-0 input-gate grads
         dw_out, db_out = G[256:258, 0:64], G[256:258, 69]
         return (dh0.view(ctx.h_shape), dw_ih.contiguous(), db_ih.contiguous(), dw_hh.contiguous(),
-                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous())
+                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None)
 
 
 def dur_mode():
@@ -889,7 +967,7 @@ def dur_mode():
 
 
 def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
-    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)
+    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, _slab_of(h0, 64) if h0.dim() == 2 else None)
 
 
 def chord_feedback(root, chroma, bass):

@@ -65,12 +65,13 @@ class ConvParams(nn.Module):
         self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-k, k))
 
 
-def _bigru_final(gru, x, lengths=None):
-    """Final hidden states [fwd | bwd] of a bi-GRU over x (R,T,I); ``lengths`` int32 (R,) = packed."""
+def _bigru_final(gru, x, lengths=None, gi=None):
+    """Final hidden states [fwd | bwd] of a bi-GRU over x (R,T,I); ``lengths`` int32 (R,) = packed.
+    ``gi`` = (gi_fwd, gi_bwd): x-projections computed by the caller (as heads of one wider GEMM)."""
     def one(rev):
         w_ih, w_hh, b_ih, b_hh = gru.dir(rev)
-        gi = ops.linear(x, w_ih, b_ih)
-        h = ops.gru_sequence(gi, None, None, w_hh, b_hh, lengths, rev)
+        g = ops.linear(x, w_ih, b_ih) if gi is None else gi[int(rev)]
+        h = ops.gru_sequence(g, None, None, w_hh, b_hh, lengths, rev)
         return h[:, 0] if rev else h[:, -1]
     return torch.cat(ops.fork_join([lambda: one(False), lambda: one(True)]), -1)
 
@@ -280,14 +281,21 @@ class PtvaeDecoder(nn.Module):
         R = B * self.num_step
         z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
         notes = x.reshape(R, self.max_simu_note, self.note_emb_size)
-        summ = self._summarize(notes, lengths32).view(B, self.num_step, -1)
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        # the note embeddings feed three x-projections (both directions of the summary bi-GRU and the note GRU):
+        # one GEMM, one input gradient (ops.linear_split)
+        eg = self.dec_notes_emb_gru
+        (wf, _, bf, _), (wb, _, bb, _) = eg.dir(False), eg.dir(True)
+        w_tok_n = wn_ih[:, self.dec_time_hid_size:]
+        gi_f, gi_b, gi_tok = ops.linear_split(                                            # gi_tok (R,16,1536)
+            notes, torch.cat([wf, wb, w_tok_n], 0), torch.cat([bf, bb, bf.new_zeros(w_tok_n.shape[0])], 0),
+            (wf.shape[0], wb.shape[0], w_tok_n.shape[0]), bias_cols=wf.shape[0] + wb.shape[0])
+        summ = _bigru_final(eg, notes, lengths32, gi=(gi_f, gi_b)).view(B, self.num_step, -1)
         tok = torch.cat([self.dec_init_input.expand(B, 1, -1), summ[:, :-1]], 1)
         summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
         S = summary.reshape(R, self.dec_time_hid_size)
-        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
         h0 = self.dec_time_to_notes_hid(S)
         gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
-        gi_tok = ops.linear(notes, wn_ih[:, self.dec_time_hid_size:], None)               # (R,16,1536)
         h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1)  # (R,15,512)
         # pitch head and (folded) duration-hidden projection as one GEMM over the note states
         Q = R * (self.max_simu_note - 1)
@@ -297,7 +305,7 @@ class PtvaeDecoder(nn.Module):
         w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
         dur = ops.dur_decode(dh, w_ih, b_ih, w_hh, b_hh, self.dur_sos_token, self.dur_out_linear.weight,
                              self.dur_out_linear.bias)
-        return pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), \
+        return ops.keep_slab(pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), pitch), \
             dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
 
     # -- general step-wise path (scheduled sampling / inference) ----------------------------------
@@ -508,7 +516,8 @@ class PtvaeDecoder(nn.Module):
     def recon_loss(self, x, recon_pitch, recon_dur, weights=(1, 0.5), weighted_dur=False):
         """Pitch CE (ignore PAD 130) + duration CE (ignore 2).                    ptvae.py:498-529"""
         _, _, pitch_tgt, dur_tgt = ops.grid_prepare(x)
-        pitch_loss = ops.masked_ce(recon_pitch.reshape(-1, recon_pitch.size(-1)), pitch_tgt, self.pitch_pad)
+        pitch_loss = ops.masked_ce(ops.keep_slab(recon_pitch.reshape(-1, recon_pitch.size(-1)), recon_pitch), pitch_tgt,
+                                   self.pitch_pad)
         if not weighted_dur:
             dur_loss = ops.masked_ce(recon_dur.reshape(-1, 2), dur_tgt, self.dur_pad)
         else:
