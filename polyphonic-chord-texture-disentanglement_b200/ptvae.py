@@ -176,17 +176,27 @@ class RnnDecoder(nn.Module):
         w_ih, w_hh, b_ih, b_hh = self.gru.dir()
         h = self.z2dec_hid(z_chd)
         gi_z = ops.linear(self.z2dec_in(z_chd), w_ih[:, self.input_dim:], b_ih)   # constant over steps
+        n = int(self.num_step / 4)
+        plan = [random.random() < tfr for _ in range(n)]      # drawn in the reference's order (ptvae.py:72)
+        if not inference and all(plan[:-1]):
+            # every fed-back token is the ground truth: the 8 steps are one GRU sequence over known inputs and the
+            # three heads one GEMM over all states (the reference's per-step loop, batched)
+            toks = torch.cat([self.init_input.expand(bs, 1, self.input_dim), c[:, :n - 1]], 1).contiguous()
+            hs = ops.gru_sequence(ops.linear(toks, w_ih[:, :self.input_dim], None), gi_z, h, w_hh, b_hh)
+            r, ch, b = ops.linear_split(
+                hs, torch.cat([self.root_out.weight, self.chroma_out.weight, self.bass_out.weight], 0),
+                torch.cat([self.root_out.bias, self.chroma_out.bias, self.bass_out.bias], 0), (12, 24, 12))
+            return r, ch.view(bs, n, 12, 2), b
         tok = self.init_input.expand(bs, self.input_dim)
         roots, chromas, basses = [], [], []
-        for t in range(int(self.num_step / 4)):
+        for t in range(n):
             gi = ops.linear(tok, w_ih[:, :self.input_dim], None)
             h = ops.gru_sequence(gi.view(bs, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
             r, ch, b = self.root_out(h), self.chroma_out(h).view(bs, 12, 2), self.bass_out(h)
             roots.append(r.unsqueeze(1))
             chromas.append(ch.unsqueeze(1))
             basses.append(b.unsqueeze(1))
-            teacher_force = random.random() < tfr
-            if teacher_force and not inference:
+            if plan[t] and not inference:
                 tok = c[:, t]
             else:
                 tok = ops.chord_feedback(r.detach(), ch.detach(), b.detach())

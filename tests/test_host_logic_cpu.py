@@ -95,3 +95,52 @@ def test_forward_mode_dispatch(monkeypatch):
     assert m(2, pr, c, False).shape == (2, 32, 15, 6)
     with pytest.raises(NotImplementedError):
         m('bogus')
+
+
+def test_linear_split_gradients(monkeypatch):
+    """ops.linear_split (several heads as one GEMM with a shared gradient slab) against plain torch autograd:
+    slab-aware consumer (GRU recurrence writes its input gradient in place), ordinary consumer (gather copy) and
+    an unused head (zero block); bias gradient restricted to the leading ``bias_cols`` columns."""
+    cpu_backend.install(monkeypatch)
+    from polydis_b200 import ops
+    torch.manual_seed(3)
+    R, T, K, H = 9, 4, 12, 8
+    x = torch.randn(R, T, K, requires_grad=True)
+    w = torch.randn(3 * H + 6 + 5, K, requires_grad=True)
+    b = torch.randn(3 * H + 6 + 5, requires_grad=True)
+    w_hh, b_hh = torch.randn(3 * H, H, requires_grad=True), torch.randn(3 * H, requires_grad=True)
+    lengths = torch.tensor([4, 1, 3, 2, 4, 4, 1, 2, 3], dtype=torch.int32)
+
+    def loss_ours():
+        gi, mid, _unused = ops.linear_split(x, w, b, (3 * H, 6, 5), bias_cols=3 * H + 6)
+        h = ops.gru_sequence(gi, None, None, w_hh, b_hh, lengths, False)
+        return (h[:, -1] ** 2).sum() + (mid * torch.arange(6.0)).sin().sum()
+
+    def loss_ref():
+        y = x @ w.t() + b
+        gi, mid = y[..., :3 * H], y[..., 3 * H:3 * H + 6]
+        gru = torch.nn.GRU(K, H, batch_first=True)            # only its cell math is used
+        h = torch.zeros(R, H)
+        for t in range(T):
+            gh = h @ w_hh.t() + b_hh
+            r = torch.sigmoid(gi[:, t, :H] + gh[:, :H])
+            z = torch.sigmoid(gi[:, t, H:2 * H] + gh[:, H:2 * H])
+            n = torch.tanh(gi[:, t, 2 * H:] + r * gh[:, 2 * H:])
+            hn = (1 - z) * n + z * h
+            h = torch.where((t < lengths)[:, None], hn, h)
+        del gru
+        return (h ** 2).sum() + (mid * torch.arange(6.0)).sin().sum()
+
+    grads = []
+    for fn in (loss_ours, loss_ref):
+        for p in (x, w, b, w_hh, b_hh):
+            p.grad = None
+        l = fn()
+        l.backward()
+        grads.append([float(l.detach())] + [p.grad.clone() for p in (x, w, b, w_hh, b_hh)])
+    assert abs(grads[0][0] - grads[1][0]) < 1e-4 * abs(grads[1][0])
+    for name, g, r in zip("x w b w_hh b_hh".split(), grads[0][1:], grads[1][1:]):
+        if name == "b":                                        # columns past bias_cols carry no bias gradient by contract
+            assert torch.equal(g[3 * H + 6:], torch.zeros(5))
+            g, r = g[:3 * H + 6], r[:3 * H + 6]
+        assert torch.allclose(g, r, atol=2e-4, rtol=1e-4), name

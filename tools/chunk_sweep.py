@@ -25,7 +25,8 @@ def timed(name):
     del g, m, opt
 
 
-for mb, lanes in [(0, 1), (12, 3), (25, 2), (25, 3), (50, 2), (6, 4), (12, 2), (25, 1), (50, 1)]:
-    ops.ROW_CHUNK_BYTES = mb << 20
-    ops.ROW_CHUNK_LANES = lanes
-    timed(f"chunk {mb} MB x {lanes} lanes")
+if __name__ == "__main__":
+    for mb, lanes in [(0, 1), (12, 3), (25, 2), (25, 3), (50, 2), (6, 4), (12, 2), (25, 1), (50, 1)]:
+        ops.ROW_CHUNK_BYTES = mb << 20
+        ops.ROW_CHUNK_LANES = lanes
+        timed(f"chunk {mb} MB x {lanes} lanes")
