@@ -558,7 +558,10 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     if (rc) return rc;
     rc = b_mn ? make_map(&tb, B, EB, N, K, ldb, BKE, true) : make_map(&tb, B, EB, K, N, ldb, bn, false);
     if (rc) return rc;
-    if (split > 1 && !accumulate) zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
+    if (split > 1 && !accumulate) {
+        if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);      // dense C: a memset node
+        else zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
+    }
     if (cfg == 925641 || (cfg == 912861 && EB == 4)) {
         // C tiles leave through TMA bulk stores when they are plain stores into a 16-byte aligned matrix
         CUtensorMap tc = ta;

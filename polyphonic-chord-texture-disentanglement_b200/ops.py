@@ -225,6 +225,17 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, w, b):
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
+        K = x2.shape[1]
+        ctx.k = K
+        if PRECISION == "tf32" and K % 4 and K >= 64 and x2.shape[0] >= 256:
+            # an input width TMA cannot address (row pitch not a multiple of 16 bytes: fc1 of the texture encoder,
+            # 290 -> 1000) would send all three GEMMs of the layer to the FFMA kernel; zero-padded copies of the two
+            # small operands keep them on the tensor cores
+            xp = torch.zeros(x2.shape[0], _pad4(K), device=x.device, dtype=torch.float32)
+            wp = torch.zeros(w.shape[0], _pad4(K), device=x.device, dtype=torch.float32)
+            xp[:, :K].copy_(x2)
+            wp[:, :K].copy_(w)
+            x2, w = xp, wp
         gemm_nt(x2, w, y, b)
         ctx.save_for_backward(x2, w)
         ctx.has_bias = b is not None
@@ -246,10 +257,12 @@ class _Linear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
             gemm_nn(dy2, w, dx)
-            dx = dx.view(ctx.x_shape)
+            dx = dx[:, :ctx.k].reshape(ctx.x_shape)           # (drops the zero-padding columns, if any)
         if ctx.needs_input_grad[1]:
             dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
             gemm_tn(dy2, x2, dw)
+            if ctx.k != w.shape[1]:
+                dw = dw[:, :ctx.k].contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
             colsum(dy2, db)
