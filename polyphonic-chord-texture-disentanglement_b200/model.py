@@ -91,13 +91,19 @@ class DisentangleVAE(PytorchModel):
         """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
         recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
         # independent branches go to side streams (ops.fork_join); python-side order is the reference's
-        dist_chd, dist_rhy, (embedded_x, lengths) = ops.fork_join([
-            lambda: self.chd_encoder(c), lambda: self.rhy_encoder(pr_mat), lambda: self.decoder.emb_x(x)])
+        def embed():
+            embedded_x, lengths = self.decoder.emb_x(x)
+            # with full teacher forcing (every draw < 1) the decoder's z-independent prologue runs here, beside the
+            # encoders, instead of after them
+            pre = self.decoder.teacher_forced_prologue(embedded_x, lengths) if tfr1 >= 1. and tfr2 >= 1. else None
+            return embedded_x, lengths, pre
+        dist_chd, dist_rhy, (embedded_x, lengths, pre) = ops.fork_join([
+            lambda: self.chd_encoder(c), lambda: self.rhy_encoder(pr_mat), embed])
         z_chd = _sample(dist_chd, True, None if eps is None else eps[0])
         z_rhy = _sample(dist_rhy, True, None if eps is None else eps[1])
         dec_z = torch.cat([z_chd, z_rhy], dim=-1)
         (pitch_outs, dur_outs), (recon_root, recon_chroma, recon_bass) = ops.fork_join([
-            lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2),
+            lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2, pre=pre),
             lambda: self.chd_decoder(z_chd, False, tfr3, c)])
         return pitch_outs, dur_outs, dist_chd, dist_rhy, recon_root, recon_chroma, recon_bass
 

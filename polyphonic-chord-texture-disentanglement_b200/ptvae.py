@@ -286,12 +286,15 @@ class PtvaeDecoder(nn.Module):
         gi_z = ops.linear(self.z2dec_in_linear(z), w_ih[:, 2 * self.dec_emb_hid_size:], b_ih)
         return z_hid, gi_z, w_ih[:, :2 * self.dec_emb_hid_size], w_hh, b_hh
 
-    def _decode_teacher_forced(self, z, x, lengths32):
-        B = z.size(0)
+    def teacher_forced_prologue(self, x, lengths):
+        """The part of the teacher-forced decoder that does not depend on z: x-projections of the ground-truth note
+        embeddings and their bi-GRU summaries (ptvae.py:446-453).  ``DisentangleVAE.run`` issues it next to the
+        encoders (other streams), which takes it off the serial encoder -> z -> decoder chain."""
+        B = x.size(0)
         R = B * self.num_step
-        z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
+        lengths32 = lengths.reshape(-1).to(torch.int32)
         notes = x.reshape(R, self.max_simu_note, self.note_emb_size)
-        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        wn_ih = self.dec_notes_gru.dir()[0]
         # the note embeddings feed three x-projections (both directions of the summary bi-GRU and the note GRU):
         # one GEMM, one input gradient (ops.linear_split)
         eg = self.dec_notes_emb_gru
@@ -301,6 +304,14 @@ class PtvaeDecoder(nn.Module):
             notes, torch.cat([wf, wb, w_tok_n], 0), torch.cat([bf, bb, bf.new_zeros(w_tok_n.shape[0])], 0),
             (wf.shape[0], wb.shape[0], w_tok_n.shape[0]), bias_cols=wf.shape[0] + wb.shape[0])
         summ = _bigru_final(eg, notes, lengths32, gi=(gi_f, gi_b)).view(B, self.num_step, -1)
+        return summ, gi_tok
+
+    def _decode_teacher_forced(self, z, x, lengths32, pre=None):
+        B = z.size(0)
+        R = B * self.num_step
+        z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        summ, gi_tok = pre if pre is not None else self.teacher_forced_prologue(x, lengths32)
         tok = torch.cat([self.dec_init_input.expand(B, 1, -1), summ[:, :-1]], 1)
         summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
         S = summary.reshape(R, self.dec_time_hid_size)
@@ -395,9 +406,10 @@ class PtvaeDecoder(nn.Module):
                 plan_time.append(random.random() < tfr1)
         return plan_note, plan_time
 
-    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2):
+    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None):
         """z (B,512); x embedded grid (B,32,16,128) + lengths (B,32), or None/None at inference.
-        -> pitch logits (B,32,15,130), dur logits (B,32,15,5,2).               ptvae.py:430-491"""
+        -> pitch logits (B,32,15,130), dur logits (B,32,15,5,2).               ptvae.py:430-491
+        ``pre``: result of ``teacher_forced_prologue`` computed ahead by the caller (optional)."""
         if inference:
             assert x is None
             assert lengths is None
@@ -406,11 +418,11 @@ class PtvaeDecoder(nn.Module):
         plan_note, plan_time = self._draw_plan(teacher_forcing_ratio1, teacher_forcing_ratio2)
         lengths32 = None if lengths is None else lengths.reshape(-1).to(torch.int32)
         if not inference and all(plan_time) and all(all(r) for r in plan_note):
-            return self._decode_teacher_forced(z, x, lengths32)
+            return self._decode_teacher_forced(z, x, lengths32, pre)
         return self._decode_stepwise(z, inference, x, lengths32, plan_note, plan_time)
 
-    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2):
-        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2)
+    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None):
+        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre)
 
     def greedy_tokens(self, z):
         """Greedy decode returning only the int tokens (B,32,15,6) int32 on device -- the logits the
