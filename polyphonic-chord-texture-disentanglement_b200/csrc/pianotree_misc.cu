@@ -70,31 +70,17 @@ __global__ void __launch_bounds__(EMB) note_embed_bwd_kernel(const int* __restri
     const int j = threadIdx.x;
     for (int i = 0; i <= NOTE_SIZE; ++i) acc[i * EMB + j] = 0.0f;
     long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
-    // rows in groups of 4 with all loads issued first: one row at a time left the CTA waiting on a dependent
-    // global load per row (191 us for 262,144 rows)
-    constexpr int U = 4;
-    for (long rb = r0; rb < r1; rb += U) {
-        float v[U];
-        int t[U][TOK_W];
+    for (long r = r0; r < r1; ++r) {
+        const int* t = tok + r * TOK_W;
+        float v = g[r * ldg + j];
+        int p = t[0];
+        if (p >= 0 && p < P_RANGE) acc[p * EMB + j] += v;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long r = rb + u;
-            const bool ok = r < r1;
-            v[u] = ok ? g[r * ldg + j] : 0.0f;
-#pragma unroll
-            for (int k = 0; k < TOK_W; ++k) t[u][k] = ok ? tok[r * TOK_W + k] : (k == 0 ? -1 : 0);
+        for (int k = 0; k < 5; ++k) {
+            float d = (float)t[1 + k];
+            if (d != 0.0f) acc[(P_RANGE + k) * EMB + j] += d * v;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int p = t[u][0];
-            if (p >= 0 && p < P_RANGE) acc[p * EMB + j] += v[u];
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const float d = (float)t[u][1 + k];
-                if (d != 0.0f) acc[(P_RANGE + k) * EMB + j] += d * v[u];
-            }
-            acc[NOTE_SIZE * EMB + j] += v[u];
-        }
+        acc[NOTE_SIZE * EMB + j] += v;
     }
     for (int i = 0; i < NOTE_SIZE; ++i) {
         float v = acc[i * EMB + j];

@@ -44,48 +44,42 @@ __global__ void __launch_bounds__(320) texture_fwd_kernel(const float* __restric
 
 __global__ void __launch_bounds__(320) texture_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int C,
-                                                          const float* __restrict__ gout, float* dw, float* dbias,
-                                                          int n_tiles) {
+                                                          const float* __restrict__ gout, float* dw, float* dbias) {
     __shared__ float band[KH][W_IN];
     __shared__ float ws[MAXC * KH * KW];
     __shared__ float bs[MAXC];
     __shared__ float dws[MAXC * KH * KW];
     __shared__ float dbs[MAXC];
-    // a CTA walks many (sample, 4-row band) tiles and keeps its weight-gradient partials in shared memory: one global
-    // atomicAdd per cell per CTA (with a CTA per tile, 4096 CTAs piled 2 M atomics onto 490 addresses: 204 us)
+    const int b = blockIdx.x >> 3, i = blockIdx.x & 7;
+    const float* src = pr + ((long)b * 32 + i * 4) * W_IN;
+    for (int k = threadIdx.x; k < KH * W_IN; k += blockDim.x) band[k / W_IN][k % W_IN] = src[k];
     for (int k = threadIdx.x; k < C * KH * KW; k += blockDim.x) { ws[k] = w[k]; dws[k] = 0.0f; }
     if (threadIdx.x < C) { bs[threadIdx.x] = bias[threadIdx.x]; dbs[threadIdx.x] = 0.0f; }
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int b = tile >> 3, i = tile & 7;
-        const float* src = pr + ((long)b * 32 + i * 4) * W_IN;
-        __syncthreads();                                   // previous tile done with the band
-        for (int k = threadIdx.x; k < KH * W_IN; k += blockDim.x) band[k / W_IN][k % W_IN] = src[k];
-        __syncthreads();
-        for (int o = threadIdx.x; o < C * W_POOL; o += blockDim.x) {
-            const int ch = o / W_POOL, wp = o % W_POOL;
-            const float g = gout[(((long)b * C + ch) * 8 + i) * W_POOL + wp];
-            if (g == 0.0f) continue;
-            const float* f = ws + ch * KH * KW;
-            float best = 0.0f;
-            int bq = -1;          // -1: relu inactive everywhere -> no gradient
-            for (int q = 0; q < 4; ++q) {
-                float s = bs[ch];
-                const int w0 = wp * 4 + q;
+    __syncthreads();
+    for (int o = threadIdx.x; o < C * W_POOL; o += blockDim.x) {
+        const int ch = o / W_POOL, wp = o % W_POOL;
+        const float g = gout[(((long)b * C + ch) * 8 + i) * W_POOL + wp];
+        if (g == 0.0f) continue;
+        const float* f = ws + ch * KH * KW;
+        float best = 0.0f;
+        int bq = -1;          // -1: relu inactive everywhere -> no gradient
+        for (int q = 0; q < 4; ++q) {
+            float s = bs[ch];
+            const int w0 = wp * 4 + q;
 #pragma unroll
-                for (int dr = 0; dr < KH; ++dr)
-#pragma unroll
-                    for (int dc = 0; dc < KW; ++dc) s = fmaf(f[dr * KW + dc], band[dr][w0 + dc], s);
-                if (s > best) { best = s; bq = q; }   // first maximum wins (max_pool2d backward convention)
-            }
-            if (bq < 0) continue;
-            const int w0 = wp * 4 + bq;
-            atomicAdd(&dbs[ch], g);
             for (int dr = 0; dr < KH; ++dr)
-                for (int dc = 0; dc < KW; ++dc) {
-                    float v = band[dr][w0 + dc];
-                    if (v != 0.0f) atomicAdd(&dws[ch * KH * KW + dr * KW + dc], g * v);
-                }
+#pragma unroll
+                for (int dc = 0; dc < KW; ++dc) s = fmaf(f[dr * KW + dc], band[dr][w0 + dc], s);
+            if (s > best) { best = s; bq = q; }   // first maximum wins (max_pool2d backward convention)
         }
+        if (bq < 0) continue;
+        const int w0 = wp * 4 + bq;
+        atomicAdd(&dbs[ch], g);
+        for (int dr = 0; dr < KH; ++dr)
+            for (int dc = 0; dc < KW; ++dc) {
+                float v = band[dr][w0 + dc];
+                if (v != 0.0f) atomicAdd(&dws[ch * KH * KW + dr * KW + dc], g * v);
+            }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < C * KH * KW; k += blockDim.x)
@@ -108,7 +102,6 @@ PD_API int pd_texture_frontend_bwd(const float* pr_mat, const float* w, const fl
                                    const float* gout, float* dw, float* dbias, void* stream) {
     if (B <= 0) return 0;
     if (C < 1 || C > MAXC) return PD_BAD_ARG;
-    const int n_tiles = B * 8, grid = n_tiles < 3 * PD_NUM_SMS ? n_tiles : 3 * PD_NUM_SMS;
-    texture_bwd_kernel<<<grid, 320, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C, gout, dw, dbias, n_tiles);
+    texture_bwd_kernel<<<B * 8, 320, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C, gout, dw, dbias);
     return pd_launch_status();
 }
