@@ -395,42 +395,6 @@ def matmul_nn(a, b):
     return _MatMulNN.apply(a, b)
 
 
-class _Linear2(torch.autograd.Function):
-    """y = [x1 | x2] W^T + b without materialising the concatenation (dur_hid_linear, ptvae.py:349-352)."""
-
-    @staticmethod
-    def forward(ctx, x1, x2, w, b):
-        a, _ = _rows(_chk(x1))
-        c, _ = _rows(_chk(x2))
-        k1 = a.shape[1]
-        y = torch.empty(a.shape[0], w.shape[0], device=a.device, dtype=torch.float32)
-        gemm_nt(a, w[:, :k1], y, b)
-        gemm_nt(c, w[:, k1:], y, None, accumulate=True)
-        ctx.save_for_backward(a, c, w)
-        ctx.shapes = (x1.shape, x2.shape)
-        return y.view(*x1.shape[:-1], w.shape[0])
-
-    @staticmethod
-    def backward(ctx, dy):
-        a, c, w = ctx.saved_tensors
-        k1 = a.shape[1]
-        dy2, _ = _rows(dy)
-        d1 = torch.empty(a.shape, device=dy.device, dtype=torch.float32)
-        d2 = torch.empty(c.shape, device=dy.device, dtype=torch.float32)
-        gemm_nn(dy2, w[:, :k1], d1)
-        gemm_nn(dy2, w[:, k1:], d2)
-        dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
-        gemm_tn(dy2, a, dw[:, :k1])
-        gemm_tn(dy2, c, dw[:, k1:])
-        db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
-        colsum(dy2, db)
-        return d1.view(ctx.shapes[0]), d2.view(ctx.shapes[1]), dw, db
-
-
-def linear_cat2(x1, x2, w, b):
-    return _Linear2.apply(x1, x2, w, b)
-
-
 # ------------------------------------------------------------------------------------------------
 def _gates_fwd(gi, gi2, gh, hprev, hout, rzn, hn, lengths, t):
     B, H = hout.shape
@@ -672,12 +636,6 @@ class _GruSeq(torch.autograd.Function):
         elif h0 is None:
             dw.zero_()
         return dgi, dgi2, dh0, dw, db, None, None, None, None
-
-
-def _add(a, b):
-    out = torch.empty_like(a)
-    _call("pd_add_f32", _ptr(a), _ptr(b), a.numel(), _ptr(out), _stream())
-    return out
 
 
 def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None):
