@@ -334,24 +334,34 @@ class PtvaeDecoder(nn.Module):
         tok = torch.tensor([[self.pitch_sos, 2, 2, 2, 2, 2]], device=dev, dtype=torch.int32)
         return ops.note_embed(tok, self.note_embedding.weight, self.note_embedding.bias)
 
-    def _decode_step_notes(self, S, notes, inference, tf_row, sos_emb, tok_store, keep_logits):
+    def _step_weights(self):
+        """Per-forward constants of the step-wise path: [time->notes hidden | summary x-projection] and
+        [pitch head | folded duration-hidden projection] as merged weight matrices (one GEMM each per use)."""
+        w_ih, _, b_ih, _ = self.dec_notes_gru.dir()
+        t2n = self.dec_time_to_notes_hid
+        w_eff, b_eff = self._dur_hid_folded()
+        return (torch.cat([t2n.weight, w_ih[:, :self.dec_time_hid_size]], 0), torch.cat([t2n.bias, b_ih], 0),
+                torch.cat([self.pitch_out_linear.weight, w_eff], 0), torch.cat([self.pitch_out_linear.bias, b_eff], 0))
+
+    def _decode_step_notes(self, S, notes, inference, tf_row, sos_emb, tok_store, keep_logits, consts=None):
         """One time step's 15 note slots.  S (B,1024); notes (B,16,128) ground truth or None.
         ptvae.py:370-428"""
         B = S.size(0)
         w_ih, w_hh, b_ih, b_hh = self.dec_notes_gru.dir()
-        h = self.dec_time_to_notes_hid(S)
-        gi_s = ops.linear(S, w_ih[:, :self.dec_time_hid_size], b_ih)
+        w_s, b_s, w_heads, b_heads = consts if consts is not None else self._step_weights()
+        h, gi_s = ops.linear_split(S, w_s, b_s, self.dec_notes_hid_size)      # initial state | summary projection
         w_tok = w_ih[:, self.dec_time_hid_size:]
         tok = sos_emb.expand(B, -1) if inference else notes[:, 0]
-        folded = self._dur_hid_folded()
+        d_ih, d_hh, db_ih, db_hh = self.dec_dur_gru.dir()
         pred = [tok]
         lens = torch.zeros(B, device=S.device, dtype=torch.int32)
         pitches, durs = [], []
         for n in range(1, self.max_simu_note):
             gi = ops.linear(tok, w_tok, None)
             h = ops.gru_sequence(gi.view(B, 1, -1), gi_s, h, w_hh, b_hh)[:, 0]
-            p = self.pitch_out_linear(h)
-            d = self._decode_durs(h, p, folded)
+            p, dh = ops.linear_split(h, w_heads, b_heads, self.pitch_range)   # pitch logits | duration-GRU h0
+            d = ops.dur_decode(dh, d_ih, db_ih, d_hh, db_hh, self.dur_sos_token, self.dur_out_linear.weight,
+                               self.dur_out_linear.bias)
             if keep_logits:
                 pitches.append(p)
                 durs.append(d)
@@ -377,12 +387,13 @@ class PtvaeDecoder(nn.Module):
         # greedy tokens [t][n-1] -> (B,6) int32 rows (pitch, 5 duration bits)
         tokens = torch.empty(self.num_step, self.max_simu_note - 1, B, 6, device=dev, dtype=torch.int32)
         tok, h = self.dec_init_input.expand(B, -1), z_hid
+        consts = self._step_weights()                  # merged head / projection weights, once per forward
         pitches, durs = [], []
         for t in range(self.num_step):
             gi = ops.linear(tok, w_tok, None)
             h = ops.gru_sequence(gi.view(B, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
             p, d, pred, plen = self._decode_step_notes(h, None if inference else x[:, t], inference,
-                                                       plan_note[t], sos_emb, tokens[t], keep_logits)
+                                                       plan_note[t], sos_emb, tokens[t], keep_logits, consts)
             if keep_logits:
                 pitches.append(p)
                 durs.append(d)
