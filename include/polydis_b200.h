@@ -80,6 +80,12 @@ int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, c
 int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
                      long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                      long ldhn, const int* lengths, int t, int B, int H, void* stream);
+/* EXPERIMENTAL -- compiled and exported, not yet validated on hardware, nothing routes to it: persistent variant of the
+ * fused step (4-stage ring, two TMEM accumulators, every epilogue operand / result moved as a 32x16 TMA box).  Same
+ * contract without the length mask; hout must not alias hprev. */
+int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
+                    long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
+                    long ldhn, int B, int H, void* stream);
 
 /* weight-resident variable-length GRU, hidden 128 (the note-summary bi-GRU, ptvae.py:446-453,:480-486): one kernel
  * runs the whole recurrence of a tile of sequences with W_hh resident in shared memory and stops at the tile's

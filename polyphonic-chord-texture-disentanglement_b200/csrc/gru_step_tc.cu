@@ -180,6 +180,242 @@ gru_step_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
+// ---- persistent variant with TMA epilogue I/O (EXPERIMENTAL: written at the end of round 1 without GPU time left;
+// compiled and exported, not routed to -- ops.FUSED_GRU_STEP_TMA stays False until it is validated on a B200) -------------
+// Lessons applied: (1) the first fused kernel above lost to GEMM + gate kernel on its row-per-thread global I/O (seven
+// arrays read / written as 64-byte pieces per lane) and its 2-stage, one-tile-per-CTA main loop; (2) the TMA bulk-store
+// epilogue of the persistent GEMM took output-bound GEMMs to the HBM roofline.  Here: persistent CTAs, 4-stage
+// TMA -> mbarrier ring, two TMEM accumulators (epilogue of item j overlaps the main loop of item j+1), and ALL
+// epilogue traffic as 32-row x 16-column TMA boxes (64-byte swizzle): each epilogue warp TMA-loads gi (r|z|n), gi2
+// (r|z|n) and h_prev of a 16-unit chunk into seven 2 KB buffers, computes the gates from TMEM + those buffers, writes
+// r, z, n, h', W_hn h + b_hn back INTO the same buffers and hands them to TMA stores; the loads of the next chunk are
+// issued once the stores have drained the buffers.  Unmasked steps only (lengths == NULL).
+__device__ __forceinline__ void mbar_arrive1(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct StepIo {
+    const float* b_hh;
+    int has_gi2, has_rzn, has_hn;
+    int B, H;
+};
+
+constexpr int IOB = 2048;          // one epilogue buffer: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
+constexpr int N_IOB = 7;           // gi r,z,n | gi2 r,z,n | h_prev
+
+// 16 floats of row `lane` of a 64-byte-swizzled 32 x 16 tile: 16-byte chunk j sits at j ^ ((row >> 1) & 3)
+__device__ __forceinline__ void io_read(const uint8_t* buf, int lane, float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 q = *reinterpret_cast<const float4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4));
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+    }
+}
+__device__ __forceinline__ void io_write(uint8_t* buf, int lane, const float (&v)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(buf + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
+                    const __grid_constant__ CUtensorMap tmHp, const __grid_constant__ CUtensorMap tmHo,
+                    const __grid_constant__ CUtensorMap tmRzn, const __grid_constant__ CUtensorMap tmHn, StepIo g,
+                    int tiles_m, int tiles_u) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    constexpr int A_BYTES = BM * 128, B_BYTES = BN3 * 128;
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_BYTES;
+    uint8_t* io = sB + STAGES * B_BYTES;                               // 4 warps x 7 buffers x 2 KB
+    uint64_t* full = (uint64_t*)(io + 4 * N_IOB * IOB);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;                              // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                              // [2]
+    uint64_t* io_bar = tmem_empty + 2;                                 // [4]: epilogue operands of a warp landed
+    uint32_t* tmem_slot = (uint32_t*)(io_bar + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = (g.H + 31) / 32;
+    const long n_items = (long)tiles_m * tiles_u;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        for (int q = 0; q < 4; ++q) mbar_init(&io_bar[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            long cnt = 0;
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int m0 = (int)(item / tiles_u) * BM, u0 = (int)(item % tiles_u) * UN;
+                for (int i = 0; i < nkb; ++i, ++cnt) {
+                    const int s = (int)(cnt % STAGES), k0 = i * 32;
+                    if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
+                    mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                    tma_load_2d(&tmA, &full[s], sA + s * A_BYTES, k0, m0);
+#pragma unroll
+                    for (int gate = 0; gate < 3; ++gate)      // r, z, n rows of the same 64 units
+                        tma_load_2d(&tmB, &full[s], sB + s * B_BYTES + gate * (UN * 128), k0, gate * g.H + u0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN3 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            long cnt = 0, j = 0;
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+                const int acc = (int)(j & 1);
+                if (j >= 2) mbar_wait(&tmem_empty[acc], (uint32_t)((j >> 1) - 1) & 1);   // epilogue drained it
+                tc_fence_after();
+                for (int i = 0; i < nkb; ++i, ++cnt) {
+                    const int s = (int)(cnt % STAGES);
+                    mbar_wait(&full[s], (uint32_t)(cnt / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_tf32(tmem_base + acc * BN3, make_desc(a + k * 32, 16, 1024, 2), make_desc(b + k * 32, 16, 1024, 2),
+                                    idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(&empty[s]);
+                }
+                tc_commit(&tmem_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;                                        // TMEM lane quarter == rows q*32.. of the tile
+        uint8_t* bufs = io + q * (N_IOB * IOB);
+        uint64_t* lbar = &io_bar[q];
+        const int H = g.H;
+        uint32_t lphase = 0;
+        // lane 0 of each epilogue warp is the producer of its own epilogue operands
+        auto issue_loads = [&](int m0, int u0, int c) {
+            const int col = u0 + c * 16, row = m0 + q * 32;
+            mbar_expect_tx(lbar, (uint32_t)((g.has_gi2 ? 7 : 4) * IOB));
+#pragma unroll
+            for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi, lbar, bufs + gate * IOB, gate * H + col, row);
+            if (g.has_gi2) {
+#pragma unroll
+                for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi2, lbar, bufs + (3 + gate) * IOB, gate * H + col, row);
+            }
+            tma_load_2d(&tmHp, lbar, bufs + 6 * IOB, col, row);
+        };
+        long j = 0;
+        if (lane == 0 && (long)blockIdx.x < n_items)
+            issue_loads((int)(blockIdx.x / tiles_u) * BM, (int)(blockIdx.x % tiles_u) * UN, 0);
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            const int m0 = (int)(item / tiles_u) * BM, u0 = (int)(item % tiles_u) * UN;
+            const int acc = (int)(j & 1);
+            mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < UN / 16; ++c) {
+                const int col = u0 + c * 16, row = m0 + q * 32;
+                float ghr[16], ghz[16], ghn[16];
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN3 + c * 16;
+                tc_ld16(tbase, ghr);
+                tc_ld16(tbase + UN, ghz);
+                tc_ld16(tbase + 2 * UN, ghn);
+                mbar_wait(lbar, lphase);                               // this chunk's gi / gi2 / h_prev boxes landed
+                lphase ^= 1;
+                float ir[16], iz[16], in[16], hp[16];
+                io_read(bufs, lane, ir);
+                io_read(bufs + IOB, lane, iz);
+                io_read(bufs + 2 * IOB, lane, in);
+                io_read(bufs + 6 * IOB, lane, hp);
+                if (g.has_gi2) {
+                    float t[16];
+                    io_read(bufs + 3 * IOB, lane, t);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ir[i] += t[i];
+                    io_read(bufs + 4 * IOB, lane, t);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) iz[i] += t[i];
+                    io_read(bufs + 5 * IOB, lane, t);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) in[i] += t[i];
+                }
+                add16(g.b_hh + col, ghr); add16(g.b_hh + H + col, ghz); add16(g.b_hh + 2 * H + col, ghn);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float r = pd_sigmoid_fast(ir[i] + ghr[i]);
+                    const float z = pd_sigmoid_fast(iz[i] + ghz[i]);
+                    const float n = pd_tanh_fast(in[i] + r * ghn[i]);
+                    hp[i] = (1.0f - z) * n + z * hp[i];
+                    ir[i] = r; iz[i] = z; in[i] = n;
+                }
+                // results go back into the buffers their operands came from and leave through TMA stores
+                io_write(bufs + 6 * IOB, lane, hp);
+                if (g.has_rzn) { io_write(bufs, lane, ir); io_write(bufs + IOB, lane, iz); io_write(bufs + 2 * IOB, lane, in); }
+                if (g.has_hn) io_write(bufs + 3 * IOB, lane, ghn);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&tmHo), "r"(smem_u32(bufs + 6 * IOB)), "r"(col), "r"(row) : "memory");
+                    if (g.has_rzn) {
+#pragma unroll
+                        for (int gate = 0; gate < 3; ++gate)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(&tmRzn), "r"(smem_u32(bufs + gate * IOB)), "r"(gate * H + col), "r"(row) : "memory");
+                    }
+                    if (g.has_hn)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&tmHn), "r"(smem_u32(bufs + 3 * IOB)), "r"(col), "r"(row) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the stores have read the buffers
+                    // operands of the next chunk (of this item, or chunk 0 of this CTA's next item)
+                    if (c + 1 < UN / 16) {
+                        issue_loads(m0, u0, c + 1);
+                    } else if (item + gridDim.x < n_items) {
+                        const long nx = item + gridDim.x;
+                        issue_loads((int)(nx / tiles_u) * BM, (int)(nx % tiles_u) * UN, 0);
+                    }
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            if (lane == 0) mbar_arrive1(&tmem_empty[acc]);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    }
+}
+
+// 2-D fp32 tensor [outer][inner] (row stride ld floats) as 16-column x 32-row boxes with the 64-byte swizzle:
+// the epilogue operand / result tiles of gru_step_tma_kernel (plain FLOAT32: no TF32 rounding on the way)
+int make_map_io(CUtensorMap* map, const void* base, long inner, long outer, long ld) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return 801;
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
+}
+
 inline bool al16(const void* p, long ld) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0; }
 
 }  // namespace
@@ -212,5 +448,44 @@ PD_API int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, lo
         attr = true;
     }
     gru_step_tf32_kernel<STAGES, 2><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, g);
+    return pd_launch_status();
+}
+
+// EXPERIMENTAL (not validated on hardware yet; nothing routes to it): persistent fused GRU step with TMA epilogue I/O.
+// Same contract as pd_gru_step_tf32 without the length mask; hout must not alias hprev.  gi: (B,3H) rows of the step
+// (row stride ldgi), gi2 / rzn / hn optional.
+PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
+                           long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
+                           long ldhn, int B, int H, void* stream) {
+    if (B <= 0) return 0;
+    if (H % UN != 0 || hprev == nullptr || hout == hprev) return PD_BAD_ARG;
+    if (!al16(hprev, ldhp) || !al16(w_hh, ldw) || !al16(gi, ldgi) || (gi2 && !al16(gi2, ldgi2)) || !al16(hout, ldho) ||
+        (rzn && !al16(rzn, ldrzn)) || (hn && !al16(hn, ldhn)) || ((uintptr_t)b_hh & 15) || ldhp < 4 || ldw < 4)
+        return PD_BAD_ARG;
+    CUtensorMap ta, tb, tgi, tgi2, thp, tho, trzn, thn;
+    int rc = make_map(&ta, hprev, 4, H, B, ldhp, BM, false);
+    if (!rc) rc = make_map(&tb, w_hh, 4, H, 3L * H, ldw, UN, false);
+    if (!rc) rc = make_map_io(&tgi, gi, 3L * H, B, ldgi);
+    if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
+    if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
+    tgi2 = tgi; trzn = tho; thn = tho;
+    if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
+    if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
+    if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
+    if (rc) return rc;
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H};
+    constexpr int STAGES = 4;
+    constexpr int smem = STAGES * (BM * 128 + BN3 * 128) + 4 * N_IOB * IOB + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    const long items = (long)tiles_m * tiles_u;
+    const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    gru_step_tma_kernel<STAGES><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn, g,
+                                                                                   tiles_m, tiles_u);
     return pd_launch_status();
 }

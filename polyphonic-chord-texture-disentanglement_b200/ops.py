@@ -105,6 +105,10 @@ PRECISION = "tf32"
 # row-per-thread epilogue reads gi / gi2 / h_prev and writes h / r|z|n / hn as 64-byte pieces per lane.  Off until
 # the epilogue is staged through shared memory.
 FUSED_GRU_STEP = False
+# Second-generation fused step (persistent, 4-stage ring, two TMEM accumulators, all epilogue I/O as TMA boxes;
+# csrc/gru_step_tc.cu gru_step_tma_kernel).  EXPERIMENTAL: written when round 1 had no GPU time left -- it compiles and
+# has a guarded test (POLYDIS_TEST_EXPERIMENTAL=1) but has never run on hardware.  Do not enable before it passes.
+FUSED_GRU_STEP_TMA = False
 _lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
 
 
@@ -464,7 +468,8 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
         save["rzn"], save["hn"] = rzn, hn
     order = list(range(T - 1, -1, -1) if reverse else range(T))
     # fused step (recurrent GEMM + gate math in one tcgen05 kernel) whenever TMA can address the operands
-    fused_ok = (FUSED_GRU_STEP and PRECISION == "tf32" and H % 64 == 0 and w_hh.stride(1) == 1
+    fused_ok = ((FUSED_GRU_STEP or (FUSED_GRU_STEP_TMA and lengths is None)) and PRECISION == "tf32" and H % 64 == 0
+                and w_hh.stride(1) == 1
                 and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0 and b_hh.data_ptr() % 16 == 0
                 and gi.stride(2) == 1 and gi.stride(0) % 4 == 0 and gi.stride(1) % 4 == 0 and gi.data_ptr() % 16 == 0
                 and (gi2 is None or (gi2.stride(1) == 1 and gi2.stride(0) % 4 == 0 and gi2.data_ptr() % 16 == 0)))
@@ -515,6 +520,14 @@ def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fuse
     for t in order:
         if (fused_ok and hprev is not None and hprev.stride(1) == 1 and hprev.stride(0) % 4 == 0
                 and hprev.data_ptr() % 16 == 0):
+            if FUSED_GRU_STEP_TMA and lengths is None:
+                _call("pd_gru_step_tma", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(b_hh),
+                      _ptr(gi[:, t]), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
+                      _ptr(h_all[:, t]), h_all.stride(0), None if rzn is None else _ptr(rzn[:, t]),
+                      0 if rzn is None else rzn.stride(0), None if hn is None else _ptr(hn[:, t]),
+                      0 if hn is None else hn.stride(0), B, H, _stream())
+                hprev = h_all[:, t]
+                continue
             _call("pd_gru_step_tf32", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(b_hh),
                   _ptr(gi[:, t]), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
                   _ptr(h_all[:, t]), h_all.stride(0), None if rzn is None else _ptr(rzn[:, t]),

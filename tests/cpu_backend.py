@@ -134,6 +134,9 @@ class CpuBackend:
             Q = _arr(hn, (B, H), (ldhn, 1))
             Q[act] = GH[:, 2 * H:][act]
 
+    def pd_gru_step_tma(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, B, H, st):
+        self.pd_gru_step_tf32(hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, None, 0, B, H, st)
+
     def pd_gru_step_tf32(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
                          B, H, st):
         HP = _arr(hp, (B, H), (ldhp, 1))

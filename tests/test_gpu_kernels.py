@@ -1,5 +1,7 @@
 """-m gpu: every CUDA kernel of libpolydis_b200, called through the C-ABI, against the numpy
 restatement of the same entry point (tests/cpu_backend.py) on seeded inputs."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -547,3 +549,21 @@ def test_gru_gates_fwd_split3():
     assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros(B, H, dtype=torch.int32))
     # (hi itself may differ from the emulation's by one TF32 ulp where the two states straddle a rounding boundary)
     assert torch.allclose(hi + lo, c3[:, :H] + c3[:, 2 * H:3 * H], atol=3e-6) and torch.equal(g3[:, 3 * H:], c3[:, 3 * H:])
+
+
+@pytest.mark.skipif(not os.environ.get("POLYDIS_TEST_EXPERIMENTAL"), reason="experimental kernel, not validated yet")
+@pytest.mark.parametrize("B,H,bcast,save", [(300, 128, True, True), (4100, 512, True, True), (129, 64, False, False)])
+def test_gru_step_tma_experimental(B, H, bcast, save):
+    """Persistent fused GRU step with TMA epilogue I/O (pd_gru_step_tma) vs the numpy restatement."""
+    _dev()
+    torch.manual_seed(5)
+    w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+
+    def mk():
+        ho = torch.zeros(B, H)
+        rzn = torch.zeros(B, 3 * H) if save else None
+        hn = torch.zeros(B, H) if save else None
+        return ([torch.randn(B, H), H, w, H, b, torch.randn(B, 3 * H), 3 * H, torch.randn(B, 3 * H) if bcast else None, 3 * H, ho, H,
+                 rzn, 3 * H, hn, H, B, H, None], [ho] + ([rzn, hn] if save else []))
+    for g, c in _both("pd_gru_step_tma", mk):
+        assert torch.allclose(g, c, atol=4e-3, rtol=0), float((g - c).abs().max())
