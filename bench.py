@@ -340,7 +340,9 @@ def run_b200(args):
            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": achieved / peak_tf, "traffic": NOTE_GEMM_DRAM_BYTES, "peak_source": peak_src,
                         "traffic_what": "dram read+write bytes per launch of the dominant GEMM from ncu --set full "
-                                        "(profiles/r01_ncu_full_kernels.md); algorithmic 137 MB, half of C stays in L2",
+                                        "(profiles/r01_ncu_full_kernels.md, captured with the one-shot 256-wide tile; the "
+                                        "persistent TMA-store variant timed here moves the same bytes); algorithmic 137 MB, "
+                                        "half of C stays in L2",
                         "what": "whole step: 5.45 algorithmic GFLOP/sample x batch / step time, vs sustained bf16 peak",
                         "dominant_kernel": {"name": "note-GRU recurrent GEMM [32B x 512].[512 x 1536]",
                                             "ms": ms_gemm, "achieved": gemm_tflops, "frac": gemm_tflops / peak_tf}},
