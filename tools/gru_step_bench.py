@@ -21,7 +21,17 @@ for (B, T, H, bc) in [(16384, 15, 512, True), (512, 32, 1024, True), (16384, 16,
         ops._call("pd_gru_step_tf32", h_all[:, 2].data_ptr(), T * H, w.data_ptr(), H, b.data_ptr(), gi[:, 3].data_ptr(), T * 3 * H,
                   None if gi2 is None else gi2.data_ptr(), 3 * H, h_all[:, 3].data_ptr(), T * H, rzn[:, 3].data_ptr(), T * 3 * H,
                   hn[:, 3].data_ptr(), T * H, None, 3, B, H, st)
+    def fused_tma():     # experimental persistent variant with TMA epilogue I/O (no length mask)
+        ops._call("pd_gru_step_tma", h_all[:, 2].data_ptr(), T * H, w.data_ptr(), H, b.data_ptr(), gi[:, 3].data_ptr(), T * 3 * H,
+                  None if gi2 is None else gi2.data_ptr(), 3 * H, h_all[:, 3].data_ptr(), T * H, rzn[:, 3].data_ptr(), T * 3 * H,
+                  hn[:, 3].data_ptr(), T * H, B, H, st)
     def split():
         ops.gemm_nt(h_all[:, 2], w, gh, b)
         ops._gates_fwd(gi[:, 3], gi2, gh, h_all[:, 2], h_all[:, 3], rzn[:, 3], hn[:, 3], None, 3)
-    print(f"B={B} H={H}: fused {t(fused):7.1f} us   gemm+gates {t(split):7.1f} us", flush=True)
+    line = f"B={B} H={H}: fused {t(fused):7.1f} us   gemm+gates {t(split):7.1f} us"
+    if os.environ.get("POLYDIS_TEST_EXPERIMENTAL"):
+        split(); ref = h_all[:, 3].clone(); ref_rzn = rzn[:, 3].clone()
+        h_all[:, 3].zero_(); fused_tma(); torch.cuda.synchronize()
+        err = float((h_all[:, 3] - ref).abs().max()); err_s = float((rzn[:, 3] - ref_rzn).abs().max())
+        line += f"   fused-TMA {t(fused_tma):7.1f} us (max |dh| {err:.2e}, |d rzn| {err_s:.2e} vs gemm+gates)"
+    print(line, flush=True)
