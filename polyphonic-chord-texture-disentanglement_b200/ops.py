@@ -110,6 +110,7 @@ FUSED_GRU_STEP = False
 # has a guarded test (POLYDIS_TEST_EXPERIMENTAL=1) but has never run on hardware.  Do not enable before it passes.
 FUSED_GRU_STEP_TMA = False
 _lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
+TF32X3_MIN_ROWS = 512   # smaller 3xTF32 GEMMs are launch-latency bound: they run on the single-launch FFMA kernel
 
 
 class precision:
@@ -154,7 +155,8 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None):
         ldb = sbk if sbk != 1 else sbn
         tc_ok = (a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0 and lda % 4 == 0 and ldb % 4 == 0
                  and lda >= 4 and ldb >= 4)
-    if tc_ok and PRECISION == "tf32x3" and M >= 512 and sak == 1 and sbk == 1 and a.dim() == 2 and b.dim() == 2:
+    if (tc_ok and PRECISION == "tf32x3" and M >= TF32X3_MIN_ROWS and sak == 1 and sbk == 1 and a.dim() == 2
+            and b.dim() == 2):
         # NT only (the inference GEMMs): the three TF32 products as ONE GEMM over the concatenated K = 3*pad4(K),
         # accumulated in fp32 in TMEM.  Small batches (M < 512) stay on the single-launch FFMA kernel: they are
         # launch-latency bound.
@@ -417,7 +419,7 @@ def gates_fwd_split3(gi, gi2, gh, h, h3):
 
 def split3_applies(x):
     """Would ``split3_act(x)`` return an operand (3xTF32 tensor-core GEMM path) for this tensor?"""
-    return (PRECISION == "tf32x3" and x.dim() == 2 and x.shape[0] >= 512 and x.stride(1) == 1 and x.shape[1] >= 8
+    return (PRECISION == "tf32x3" and x.dim() == 2 and x.shape[0] >= TF32X3_MIN_ROWS and x.stride(1) == 1 and x.shape[1] >= 8
             and x.data_ptr() % 16 == 0 and x.stride(0) % 4 == 0 and x.stride(0) >= 4)
 
 

@@ -71,9 +71,13 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     assert random.random() == expect
 
 
-@pytest.mark.parametrize("tag", ["w0", "w1"])
+@pytest.mark.parametrize("tag", ["w0", "w1", "w1-3xtf32"])
 def test_greedy_tokens_match_reference_golden(golden_dir, monkeypatch, tag):
     cpu_backend.install(monkeypatch)
+    if tag.endswith("-3xtf32"):     # force the large-batch route: [hi|hi|lo].[hi|lo|hi] GEMMs, operands split once per
+        from polydis_b200 import ops  # state (by the gate kernel), 3-pass duration decoder flag
+        monkeypatch.setattr(ops, "TF32X3_MIN_ROWS", 1)
+        tag = tag[:-len("-3xtf32")]
     g = np.load(os.path.join(golden_dir, f"infer_{tag}.npz"))
     x, c, pr = (torch.from_numpy(a) for a in synth_batch(int(g["B"]), int(g["data_seed"])))
     m = _model(int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
