@@ -153,6 +153,12 @@ int pd_ce_bwd(const float* logits, long ldl, const int* targets, long R, int C, 
 int pd_exp_fwd(const float* x, long n, float* y, void* stream);
 int pd_mul_f32(const float* a, const float* b, long n, float* out, void* stream);
 int pd_add_f32(const float* a, const float* b, long n, float* out, void* stream);
+/* scheduled sampling with a device-resident teacher-forcing plan (ptvae.py:420-424,:476-486,:84-86): out = *flag ? a : b
+ * (one int32 decision per step for the whole batch) and its gradient routing (the branch not taken gets zeros) */
+int pd_select_rows(const float* a, long lda, const float* b, long ldb, const int* flag, float* out, long ldo, long rows,
+                   int cols, void* stream);
+int pd_select_rows_bwd(const float* dout, long ldd, const int* flag, float* da, long ldda, float* db, long lddb, long rows,
+                       int cols, void* stream);
 /* z = mu + sd*eps (eps NULL: z = mu), z row stride ldz;  bwd: dmu = dz, dsd = dz*eps */
 int pd_reparam_fwd(const float* mu, const float* sd, const float* eps, int B, int D, float* z, long ldz,
                    void* stream);

@@ -48,6 +48,8 @@ SIGNATURES = {
     "pd_exp_fwd": [_P, _L, _P, _P],
     "pd_mul_f32": [_P, _P, _L, _P, _P],
     "pd_add_f32": [_P, _P, _L, _P, _P],
+    "pd_select_rows": [_P, _L, _P, _L, _P, _P, _L, _L, _I, _P],
+    "pd_select_rows_bwd": [_P, _L, _P, _P, _L, _P, _L, _L, _I, _P],
     "pd_reparam_fwd": [_P, _P, _P, _I, _I, _P, _L, _P],
     "pd_reparam_bwd": [_P, _L, _P, _I, _I, _P, _P, _P],
     "pd_kl_fwd": [_P, _P, _L, _P, _P],

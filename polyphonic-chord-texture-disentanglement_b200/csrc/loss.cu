@@ -203,6 +203,31 @@ __global__ void kl_bwd_kernel(const float* __restrict__ mu, const float* __restr
     dsd[i] = g * (s - 1.0f / s);
 }
 
+// Scheduled sampling with a DEVICE-resident teacher-forcing plan (one CUDA graph for every ratio): the next input is
+// the ground-truth row if *flag != 0, else the predicted row (ptvae.py:420-424, :476-486, :84-86); one decision per
+// step for the whole batch, like the reference's single random.random() per step.
+__global__ void select_rows_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb,
+                                   const int* __restrict__ flag, float* __restrict__ out, long ldo, long rows, int cols) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long r = i / cols;
+    const int c = (int)(i % cols);
+    out[r * ldo + c] = (*flag != 0) ? a[r * lda + c] : b[r * ldb + c];
+}
+// gradient routing of the select: the branch that was not taken gets zeros
+__global__ void select_rows_bwd_kernel(const float* __restrict__ dout, long ldd, const int* __restrict__ flag,
+                                       float* __restrict__ da, long ldda, float* __restrict__ db, long lddb, long rows,
+                                       int cols) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const long r = i / cols;
+    const int c = (int)(i % cols);
+    const float g = dout[r * ldd + c];
+    const bool take_a = *flag != 0;
+    if (da) da[r * ldda + c] = take_a ? g : 0.0f;
+    if (db) db[r * lddb + c] = take_a ? 0.0f : g;
+}
+
 }  // namespace
 
 // loss[0] = mean over rows with target != ignore of CE(logits[r], target[r]); acc2 = {sum, count} scratch
@@ -294,5 +319,22 @@ PD_API int pd_kl_bwd(const float* mu, const float* sd, long n, const float* gout
                      void* stream) {
     if (n <= 0) return 0;
     kl_bwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(mu, sd, n, 1.0f / (float)n, gout, dmu, dsd);
+    return pd_launch_status();
+}
+
+// out (rows, cols) = *flag ? a : b  (row strides in floats; flag: one int32 on the device)
+PD_API int pd_select_rows(const float* a, long lda, const float* b, long ldb, const int* flag, float* out, long ldo,
+                          long rows, int cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    select_rows_kernel<<<pd_blocks(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, flag, out, ldo, rows, cols);
+    return pd_launch_status();
+}
+
+// da = *flag ? dout : 0, db = *flag ? 0 : dout  (either may be NULL)
+PD_API int pd_select_rows_bwd(const float* dout, long ldd, const int* flag, float* da, long ldda, float* db, long lddb,
+                              long rows, int cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return 0;
+    select_rows_bwd_kernel<<<pd_blocks(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dout, ldd, flag, da, ldda, db, lddb,
+                                                                                         rows, cols);
     return pd_launch_status();
 }

@@ -7,18 +7,28 @@ step -- "CUDA graphs instead of a tracing compiler".  Valid while the host-side 
 the teacher-forcing decisions drawn from python's ``random`` are baked in at capture, so every ratio must
 be exactly 0 or 1 (decisions independent of the draw): tfr = (1,1,1) -- the batched teacher-forced path -- or
 tfr = (0,0,0), the free-running regime train.py's schedule settles into after its first step
-(scheduler.py:48-49); intermediate ratios run eagerly.
+(scheduler.py:48-49); intermediate ratios run eagerly -- or, with ``device_plan=True``, from ONE graph whose
+487 teacher-forcing decisions are device data: they are drawn from python ``random`` in the reference's order before
+every replay and uploaded, and the step-wise decoder picks ground-truth or predicted rows with a select kernel
+(``ops.select_rows``).  (device_plan was written after round 1's GPU budget was spent: its host logic is pinned to the
+reference goldens on the CPU emulation, the captured path has not run on hardware yet.)
 """
 import torch
 
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, batch, tfr=(1., 1., 1.), beta=0.1, weights=(1, 0.5), clip=1.0,
-                 warmup=3, reducer=None):
-        assert all(t in (0., 1.) for t in tfr), \
+                 warmup=3, reducer=None, device_plan=False):
+        assert device_plan or all(t in (0., 1.) for t in tfr), \
             "graph capture bakes the teacher-forcing plan: every ratio must be 0 or 1 (deterministic decisions); " \
-            "use eager steps for 0 < tfr < 1"
+            "use device_plan=True (decisions as device data) or eager steps for 0 < tfr < 1"
         dev = next(model.parameters()).device
+        self.device_plan = device_plan
+        if device_plan:
+            self.plan = torch.zeros(model.N_PLAN, device=dev, dtype=torch.int32)
+            self._plan_host = torch.zeros(model.N_PLAN, dtype=torch.int32).pin_memory()
+            self._plan_copied = torch.cuda.Event()
+            self._plan_copied.record()
         self.model, self.opt = model, optimizer
         self.params = [p for p in model.parameters()]
         self.x = torch.zeros(batch, 32, 16, 6, device=dev, dtype=torch.int64)
@@ -40,7 +50,8 @@ class GraphedTrainStep:
         else:
             self.opt.zero_grad(set_to_none=True)
         losses = self.model('train', self.x, self.c, self.pr, tfr1=self.tfr[0], tfr2=self.tfr[1],
-                            tfr3=self.tfr[2], beta=self.beta, weights=self.weights)
+                            tfr3=self.tfr[2], beta=self.beta, weights=self.weights,
+                            **({"plan_dev": self.plan} if self.device_plan else {}))
         losses[0].backward()
         if self.reducer is not None:
             self.reducer.finish()
@@ -49,8 +60,22 @@ class GraphedTrainStep:
         self.opt.step()
         return torch.stack([l.detach() for l in losses])
 
+    def set_tfr(self, tfr1, tfr2, tfr3):
+        """New teacher-forcing ratios for the following steps (device_plan graphs only: a schedule without re-capture)."""
+        assert self.device_plan
+        self.tfr = (tfr1, tfr2, tfr3)
+
+    def _upload_plan(self):
+        """Draw this step's 487 decisions (python ``random``, reference order) and copy them to the device."""
+        self._plan_copied.synchronize()                       # the previous upload has left the pinned buffer
+        self._plan_host.copy_(torch.tensor(self.model.draw_plan(*self.tfr), dtype=torch.int32))
+        self.plan.copy_(self._plan_host, non_blocking=True)
+        self._plan_copied.record()
+
     def capture(self, x, c, pr_mat):
         self.x.copy_(x); self.c.copy_(c); self.pr.copy_(pr_mat)
+        if self.device_plan:
+            self._upload_plan()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -71,6 +96,8 @@ class GraphedTrainStep:
         self.x.copy_(x, non_blocking=True)
         self.c.copy_(c, non_blocking=True)
         self.pr.copy_(pr_mat, non_blocking=True)
+        if self.device_plan:
+            self._upload_plan()
         self.graph.replay()
         return self.losses
 
@@ -98,6 +125,8 @@ class GraphedTrainStep:
         self._consumed.record()
         if next_batch is not None:
             self.prefetch(*next_batch)
+        if self.device_plan:
+            self._upload_plan()
         self.graph.replay()
         return self.losses
 

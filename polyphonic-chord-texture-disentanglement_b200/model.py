@@ -87,7 +87,23 @@ class DisentangleVAE(PytorchModel):
         self.decode_precision = "tf32x3"
 
     # -- training ----------------------------------------------------------------------------------
-    def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None):
+    N_PLAN = 487          # teacher-forcing decisions of one training forward: 479 PianoTree + 8 chord (ptvae.py:420,476,72)
+
+    def draw_plan(self, tfr1, tfr2, tfr3):
+        """The 487 teacher-forcing decisions of one training forward, drawn from python ``random`` in the reference's
+        order, as a list of 0/1 (for ``run(..., plan_dev=)``: scheduled sampling with the plan as device data)."""
+        import random
+        plan_note, plan_time = self.decoder._draw_plan(tfr1, tfr2)
+        flat = []
+        for t, row in enumerate(plan_note):
+            flat += [int(v) for v in row]
+            if t < len(plan_time):
+                flat.append(int(plan_time[t]))
+        flat += [int(random.random() < tfr3) for _ in range(int(self.chd_decoder.num_step / 4))]
+        assert len(flat) == self.N_PLAN
+        return flat
+
+    def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None, plan_dev=None):
         """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
         recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
         # independent branches go to side streams (ops.fork_join); python-side order is the reference's
@@ -95,7 +111,8 @@ class DisentangleVAE(PytorchModel):
             embedded_x, lengths = self.decoder.emb_x(x)
             # with full teacher forcing (every draw < 1) the decoder's z-independent prologue runs here, beside the
             # encoders, instead of after them
-            pre = self.decoder.teacher_forced_prologue(embedded_x, lengths) if tfr1 >= 1. and tfr2 >= 1. else None
+            pre = (self.decoder.teacher_forced_prologue(embedded_x, lengths)
+                   if tfr1 >= 1. and tfr2 >= 1. and plan_dev is None else None)
             return embedded_x, lengths, pre
         dist_chd, dist_rhy, (embedded_x, lengths, pre) = ops.fork_join([
             lambda: self.chd_encoder(c), lambda: self.rhy_encoder(pr_mat), embed])
@@ -103,8 +120,9 @@ class DisentangleVAE(PytorchModel):
         z_rhy = _sample(dist_rhy, True, None if eps is None else eps[1])
         dec_z = torch.cat([z_chd, z_rhy], dim=-1)
         (pitch_outs, dur_outs), (recon_root, recon_chroma, recon_bass) = ops.fork_join([
-            lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2, pre=pre),
-            lambda: self.chd_decoder(z_chd, False, tfr3, c)])
+            lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2, pre=pre,
+                                 plan_dev=None if plan_dev is None else plan_dev[:479]),
+            lambda: self.chd_decoder(z_chd, False, tfr3, c, plan_dev=None if plan_dev is None else plan_dev[479:])])
         return pitch_outs, dur_outs, dist_chd, dist_rhy, recon_root, recon_chroma, recon_bass
 
     def loss_function(self, x, c, recon_pitch, recon_dur, dist_chd, dist_rhy, recon_root, recon_chroma,
@@ -128,8 +146,8 @@ class DisentangleVAE(PytorchModel):
         kl_rhy = ops.kl_std_normal(dists[1].mean, dists[1].scale)
         return kl_chd + kl_rhy, kl_chd, kl_rhy
 
-    def loss(self, x, c, pr_mat, tfr1=0., tfr2=0., tfr3=0., beta=0.1, weights=(1, 0.5), eps=None):
-        outputs = self.run(x, c, pr_mat, tfr1, tfr2, tfr3, eps=eps)
+    def loss(self, x, c, pr_mat, tfr1=0., tfr2=0., tfr3=0., beta=0.1, weights=(1, 0.5), eps=None, plan_dev=None):
+        outputs = self.run(x, c, pr_mat, tfr1, tfr2, tfr3, eps=eps, plan_dev=plan_dev)
         return self.loss_function(x, c, *outputs, beta, weights)
 
     # -- inference ---------------------------------------------------------------------------------

@@ -956,6 +956,37 @@ def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
     return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, _slab_of(h0, 64) if h0.dim() == 2 else None)
 
 
+class _SelectRows(torch.autograd.Function):
+    """out = flag ? a : b with the decision read from DEVICE memory (one int32): scheduled sampling whose
+    teacher-forcing plan is data, not host control flow, so one captured CUDA graph serves every ratio."""
+
+    @staticmethod
+    def forward(ctx, a, b, flag):
+        a2, _ = _rows(_chk(a, "a"))
+        b2, _ = _rows(_chk(b, "b"))
+        out = torch.empty(a2.shape[0], a2.shape[1], device=a2.device, dtype=torch.float32)
+        _call("pd_select_rows", _ptr(a2), a2.stride(0), _ptr(b2), b2.stride(0), _ptr(flag), _ptr(out), out.stride(0),
+              a2.shape[0], a2.shape[1], _stream())
+        ctx.save_for_backward(flag)
+        ctx.shapes = (a.shape, b.shape)
+        return out.view(a.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        (flag,) = ctx.saved_tensors
+        g2, _ = _rows(g)
+        da = torch.empty(g2.shape, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        db = torch.empty(g2.shape, device=g.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        _call("pd_select_rows_bwd", _ptr(g2), g2.stride(0), _ptr(flag), _ptr(da), 0 if da is None else da.stride(0),
+              _ptr(db), 0 if db is None else db.stride(0), g2.shape[0], g2.shape[1], _stream())
+        return (None if da is None else da.view(ctx.shapes[0]), None if db is None else db.view(ctx.shapes[1]), None)
+
+
+def select_rows(a, b, flag):
+    """``flag`` (int32 device tensor, 1 element): nonzero -> a, zero -> b.  a, b: same shape, unit inner stride."""
+    return _SelectRows.apply(a, b, flag)
+
+
 def chord_feedback(root, chroma, bass):
     """(B,12), (B,12,2), (B,12) logits -> (B,36) feedback token (batch-union one-hots, ptvae.py:73-78)."""
     B = root.shape[0]

@@ -169,7 +169,9 @@ class RnnDecoder(nn.Module):
         self.bass_out = LinearParams(hidden_dim, 12)
         self.num_step = num_step
 
-    def forward(self, z_chd, inference, tfr, c=None):
+    def forward(self, z_chd, inference, tfr, c=None, plan_dev=None):
+        """``plan_dev``: int32 device tensor with this decoder's 8 teacher-forcing decisions (drawn by the caller, see
+        ``DisentangleVAE.draw_plan``): the decisions become data and python ``random`` is not touched here."""
         bs = z_chd.size(0)
         if inference:
             tfr = 0.
@@ -177,8 +179,11 @@ class RnnDecoder(nn.Module):
         h = self.z2dec_hid(z_chd)
         gi_z = ops.linear(self.z2dec_in(z_chd), w_ih[:, self.input_dim:], b_ih)   # constant over steps
         n = int(self.num_step / 4)
-        plan = [random.random() < tfr for _ in range(n)]      # drawn in the reference's order (ptvae.py:72)
-        if not inference and all(plan[:-1]):
+        if plan_dev is not None:
+            plan = None
+        else:
+            plan = [random.random() < tfr for _ in range(n)]  # drawn in the reference's order (ptvae.py:72)
+        if plan is not None and not inference and all(plan[:-1]):
             # every fed-back token is the ground truth: the 8 steps are one GRU sequence over known inputs and the
             # three heads one GEMM over all states (the reference's per-step loop, batched)
             toks = torch.cat([self.init_input.expand(bs, 1, self.input_dim), c[:, :n - 1]], 1).contiguous()
@@ -196,7 +201,11 @@ class RnnDecoder(nn.Module):
             roots.append(r.unsqueeze(1))
             chromas.append(ch.unsqueeze(1))
             basses.append(b.unsqueeze(1))
-            if plan[t] and not inference:
+            if t == n - 1:
+                break
+            if plan is None:                                  # decision read on the device
+                tok = ops.select_rows(c[:, t], ops.chord_feedback(r.detach(), ch.detach(), b.detach()), plan_dev[t:t + 1])
+            elif plan[t] and not inference:
                 tok = c[:, t]
             else:
                 tok = ops.chord_feedback(r.detach(), ch.detach(), b.detach())
@@ -343,7 +352,7 @@ class PtvaeDecoder(nn.Module):
         return (torch.cat([t2n.weight, w_ih[:, :self.dec_time_hid_size]], 0), torch.cat([t2n.bias, b_ih], 0),
                 torch.cat([self.pitch_out_linear.weight, w_eff], 0), torch.cat([self.pitch_out_linear.bias, b_eff], 0))
 
-    def _decode_step_notes(self, S, notes, inference, tf_row, sos_emb, tok_store, keep_logits, consts=None):
+    def _decode_step_notes(self, S, notes, inference, tf_row, sos_emb, tok_store, keep_logits, consts=None, flags=None):
         """One time step's 15 note slots.  S (B,1024); notes (B,16,128) ground truth or None.
         ptvae.py:370-428"""
         B = S.size(0)
@@ -370,12 +379,15 @@ class PtvaeDecoder(nn.Module):
             pred.append(emb)
             if n == self.max_simu_note - 1:
                 break
-            tok = emb if (inference or not tf_row[n - 1]) else notes[:, n]
+            if flags is not None:                             # device-resident plan: decision n-1 of this time step
+                tok = ops.select_rows(notes[:, n], emb, flags[n - 1:n])
+            else:
+                tok = emb if (inference or not tf_row[n - 1]) else notes[:, n]
         pitch = torch.stack(pitches, 1) if keep_logits else None
         dur = torch.stack(durs, 1) if keep_logits else None
         return pitch, dur, torch.stack(pred, 1), lens
 
-    def _decode_stepwise(self, z, inference, x, lengths32, plan_note, plan_time, keep_logits=True):
+    def _decode_stepwise(self, z, inference, x, lengths32, plan_note, plan_time, keep_logits=True, plan_dev=None):
         B = z.size(0)
         dev = z.device
         z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
@@ -392,14 +404,19 @@ class PtvaeDecoder(nn.Module):
         for t in range(self.num_step):
             gi = ops.linear(tok, w_tok, None)
             h = ops.gru_sequence(gi.view(B, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
+            W = self.max_simu_note - 1                       # plan layout per time step: 14 note decisions + 1 time decision
             p, d, pred, plen = self._decode_step_notes(h, None if inference else x[:, t], inference,
-                                                       plan_note[t], sos_emb, tokens[t], keep_logits, consts)
+                                                       None if plan_dev is not None else plan_note[t], sos_emb, tokens[t],
+                                                       keep_logits, consts,
+                                                       None if plan_dev is None else plan_dev[t * W:t * W + W - 1])
             if keep_logits:
                 pitches.append(p)
                 durs.append(d)
             if t == self.num_step - 1:
                 break
-            if plan_time[t] and not inference:
+            if plan_dev is not None:
+                tok = ops.select_rows(summ[:, t], self._summarize(pred, plen), plan_dev[t * W + W - 1:t * W + W])
+            elif plan_time[t] and not inference:
                 tok = summ[:, t]
             else:
                 tok = self._summarize(pred, plen)
@@ -417,7 +434,7 @@ class PtvaeDecoder(nn.Module):
                 plan_time.append(random.random() < tfr1)
         return plan_note, plan_time
 
-    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None):
+    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None):
         """z (B,512); x embedded grid (B,32,16,128) + lengths (B,32), or None/None at inference.
         -> pitch logits (B,32,15,130), dur logits (B,32,15,5,2).               ptvae.py:430-491
         ``pre``: result of ``teacher_forced_prologue`` computed ahead by the caller (optional)."""
@@ -426,14 +443,19 @@ class PtvaeDecoder(nn.Module):
             assert lengths is None
             assert teacher_forcing_ratio1 == 0
             assert teacher_forcing_ratio2 == 0
-        plan_note, plan_time = self._draw_plan(teacher_forcing_ratio1, teacher_forcing_ratio2)
         lengths32 = None if lengths is None else lengths.reshape(-1).to(torch.int32)
+        if plan_dev is not None:
+            # teacher-forcing decisions as device data (479 int32 in draw order: per time step 14 note decisions, then
+            # the time decision); the caller drew them, python ``random`` is not consumed here
+            assert not inference
+            return self._decode_stepwise(z, False, x, lengths32, None, None, plan_dev=plan_dev)
+        plan_note, plan_time = self._draw_plan(teacher_forcing_ratio1, teacher_forcing_ratio2)
         if not inference and all(plan_time) and all(all(r) for r in plan_note):
             return self._decode_teacher_forced(z, x, lengths32, pre)
         return self._decode_stepwise(z, inference, x, lengths32, plan_note, plan_time)
 
-    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None):
-        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre)
+    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None):
+        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre, plan_dev)
 
     def greedy_tokens(self, z):
         """Greedy decode returning only the int tokens (B,32,15,6) int32 on device -- the logits the

@@ -455,6 +455,18 @@ class CpuBackend:
     def pd_mul_f32(self, a, b, n, out, st):
         _arr(out, (n,), (1,))[...] = _arr(a, (n,), (1,)) * _arr(b, (n,), (1,))
 
+    def pd_select_rows(self, a, lda, b, ldb, flag, out, ldo, rows, cols, st):
+        f = int(_arr(flag, (1,), (1,), np.int32)[0])
+        _arr(out, (rows, cols), (ldo, 1))[...] = _arr(a, (rows, cols), (lda, 1)) if f else _arr(b, (rows, cols), (ldb, 1))
+
+    def pd_select_rows_bwd(self, dout, ldd, flag, da, ldda, db, lddb, rows, cols, st):
+        f = int(_arr(flag, (1,), (1,), np.int32)[0])
+        g = _arr(dout, (rows, cols), (ldd, 1))
+        if da is not None:
+            _arr(da, (rows, cols), (ldda, 1))[...] = g if f else 0.0
+        if db is not None:
+            _arr(db, (rows, cols), (lddb, 1))[...] = 0.0 if f else g
+
     def pd_add_f32(self, a, b, n, out, st):
         _arr(out, (n,), (1,))[...] = _arr(a, (n,), (1,)) + _arr(b, (n,), (1,))
 

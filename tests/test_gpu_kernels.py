@@ -567,3 +567,40 @@ def test_gru_step_tma_experimental(B, H, bcast, save):
                  rzn, 3 * H, hn, H, B, H, None], [ho] + ([rzn, hn] if save else []))
     for g, c in _both("pd_gru_step_tma", mk):
         assert torch.allclose(g, c, atol=4e-3, rtol=0), float((g - c).abs().max())
+
+
+def test_select_rows_kernels():
+    """Device-flag row select (scheduled sampling with the plan as device data) and its gradient routing."""
+    _dev()
+    for flag in (0, 1):
+        def mk2():
+            a, out = torch.randn(37, 132), torch.zeros(37, 128)
+            return [a, 132, torch.randn(37, 128), 128, torch.tensor([flag], dtype=torch.int32), out, 128, 37, 128, None], [out]
+        (g, c), = _both("pd_select_rows", mk2)
+        assert torch.equal(g, c)
+
+        def mkb():
+            da, db = torch.ones(37, 128), torch.ones(37, 128)
+            return [torch.randn(37, 128), 128, torch.tensor([flag], dtype=torch.int32), da, 128, db, 128, 37, 128, None], [da, db]
+        for g, c in _both("pd_select_rows_bwd", mkb):
+            assert torch.equal(g, c)
+
+
+@pytest.mark.skipif(not os.environ.get("POLYDIS_TEST_EXPERIMENTAL"), reason="captured device-plan path not run on hardware yet")
+def test_graphed_train_step_device_plan():
+    """One CUDA graph for every teacher-forcing ratio: decisions uploaded per step, selected on the device."""
+    dev = _dev()
+    import random
+    from polydis_b200.graphs import GraphedTrainStep
+    from polydis_b200.model import DisentangleVAE
+    from polydis_b200.synth import synth_batch
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(8, 31))
+    m = DisentangleVAE.init_model(device=dev).to(dev).train()
+    opt = torch.optim.Adam(m.parameters(), lr=0.0, fused=True, capturable=True)
+    random.seed(3)
+    g = GraphedTrainStep(m, opt, 8, tfr=(0.5, 0.5, 0.5), warmup=1, device_plan=True).capture(x, c, pr)
+    l_mixed = float(g(x, c, pr)[0])
+    g.set_tfr(1., 1., 1.)
+    l_tf = float(g(x, c, pr)[0])
+    ref = float(m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5))[0])
+    assert np.isfinite(l_mixed) and abs(l_tf - ref) < 5e-2 * abs(ref)      # same decisions, different noise draw

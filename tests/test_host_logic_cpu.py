@@ -30,7 +30,7 @@ def test_state_dict_keys_match_reference_contract():
     assert all(tuple(sd[k].shape) == s for k, s, _ in STATE_DICT_SPEC)
 
 
-@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked"])
+@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     cpu_backend.install(monkeypatch)
     if tag.endswith("-chunked"):        # row-chunked recurrences (ops._over_row_chunks): 128-row chunks, ragged tail
@@ -39,6 +39,8 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
         monkeypatch.setattr(ops, "ROW_CHUNK_BYTES", 1)
         monkeypatch.setattr(ops, "RESIDENT_GRU128", False)
         tag = tag[:-len("-chunked")]
+    devplan = tag.endswith("-devplan")
+    tag = tag[:-len("-devplan")] if devplan else tag
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
     B = int(g["B"])
     x, c, pr = (torch.from_numpy(a) for a in synth_batch(B, int(g["data_seed"])))
@@ -46,7 +48,11 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     m.train()
     random.seed(int(g["rng_seed"]))
     eps = (torch.from_numpy(g["eps_chd"]), torch.from_numpy(g["eps_rhy"]))
-    out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+    if devplan:     # teacher-forcing decisions as device data (one CUDA graph for every ratio): same draws, same result
+        plan = torch.tensor(m.draw_plan(*[float(v) for v in g["tfr"]]), dtype=torch.int32)
+        out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps, plan_dev=plan)
+    else:
+        out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
     losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
     np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(out[0].detach().numpy(), g["pitch"], atol=2e-5)
