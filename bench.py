@@ -241,10 +241,15 @@ def run_b200(args):
     ms_tfr0 = None
     if world == 1 and graphed is not None and not args.no_tfr0:
         from polydis_b200.graphs import GraphedTrainStep
+        if args.batched_sampling:       # opt-in: greedy pass + batched teacher-forced phases (ptvae.PtvaeDecoder)
+            from polydis_b200.ptvae import PtvaeDecoder
+            PtvaeDecoder.batched_sampling = True
         g0 = GraphedTrainStep(model, opt, B, tfr=(0., 0., 0.), warmup=1).capture(x, c, pr)
         g0(x, c, pr)
         ms_tfr0 = timed(lambda: g0(x, c, pr), 3)
         del g0
+        if args.batched_sampling:
+            PtvaeDecoder.batched_sampling = False
         mark(f"tfr=0 step: {ms_tfr0:.1f} ms")
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
     # (graph mode: double-buffered -- every step copies one full batch from pinned host memory, the one the NEXT
@@ -330,7 +335,8 @@ def run_b200(args):
                            if graphed is not None else "copy, step, read the loss back")},
            "gpu_launches": launches,
            "train_free_running": None if ms_tfr0 is None else
-           {"value": B / (ms_tfr0 * 1e-3), "unit": "samples/s", "ms_per_step": ms_tfr0, "tfr": [0, 0, 0], "cuda_graph": True},
+           {"value": B / (ms_tfr0 * 1e-3), "unit": "samples/s", "ms_per_step": ms_tfr0, "tfr": [0, 0, 0], "cuda_graph": True,
+            "path": "greedy pass + batched phases" if args.batched_sampling else "step-wise"},
            "decode": {"value": world * Bd / (ms_dec * 1e-3), "unit": "segments/s", "batch_per_gpu": Bd,
                       "ms_per_batch": ms_dec,
                       "precision": "tf32x3 (error-compensated tensor-core GEMMs; token parity with the fp32 reference)",
@@ -372,6 +378,8 @@ def main():
     ap.add_argument("--decode-batch", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tfr0", action="store_true", help="skip the free-running (tfr=0) training measurement")
+    ap.add_argument("--batched-sampling", action="store_true",
+                    help="free-running measurement through the opt-in batched scheduled-sampling path (not yet run on hardware)")
     ap.add_argument("--fused-optim", action="store_true",
                     help="polydis_b200.optim.FusedClipAdam (flat buckets) instead of torch clip_grad_norm_ + fused Adam; "
                          "measured 0.9 ms/step slower at 1 GPU because backward then accumulates into the flat buckets")

@@ -259,8 +259,9 @@ class PtvaeDecoder(nn.Module):
         """x (B,32,16,6) int64 -> embedded (B,32,16,128), lengths (B,32) int64.   ptvae.py:531-535"""
         tok, lengths, _, _ = ops.grid_prepare(x)
         emb = ops.note_embed(tok, self.note_embedding.weight, self.note_embedding.bias)
-        return emb.view(x.size(0), self.num_step, self.max_simu_note, self.note_emb_size), \
-            lengths.view(x.size(0), self.num_step).long()
+        emb = emb.view(x.size(0), self.num_step, self.max_simu_note, self.note_emb_size)
+        emb._pd_tok = tok                                  # int32 (B*512,6) tokens of this grid (batched_sampling)
+        return emb, lengths.view(x.size(0), self.num_step).long()
 
     def _summarize(self, notes, lengths32):
         """(R,16,128) note embeddings with lengths -> (R,256) bi-GRU summary.  ptvae.py:446-453,:480-486"""
@@ -338,6 +339,47 @@ class PtvaeDecoder(nn.Module):
         return ops.keep_slab(pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), pitch), \
             dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
 
+    # -- scheduled sampling / free-running training, batched (opt-in) ------------------------------
+    #: Greedy feedback carries no gradient (argmax), so a training forward with 0 <= tfr < 1 is exactly the
+    #: teacher-forced computation evaluated on MIXED inputs: note slot n is fed the ground-truth or the predicted
+    #: token according to the plan, time step t the summary of the ground-truth or of the predicted notes.  With this
+    #: switch on, the decoder first runs a no-grad greedy pass that follows the plan to obtain the predicted tokens and
+    #: lengths, then the batched teacher-forced phases (32 + 15 + 5 steps, one GEMM per weight gradient) over the mixed
+    #: inputs -- instead of 480 sequential note steps each with its own autograd nodes and weight-gradient GEMMs.
+    #: Pinned to the reference goldens (tfr = 0/0/0 and 0.5/0.5/0.5) on the CPU emulation; OFF by default until it has
+    #: run on hardware (written after round 1's GPU budget was spent).
+    batched_sampling = False
+
+    def _decode_sampled_batched(self, z, x, lengths32, plan_note, plan_time):
+        B, T, NS = z.size(0), self.num_step, self.max_simu_note
+        R = B * T
+        gt_tok = x._pd_tok.view(B, T, NS, 6)                                        # int32 ground-truth tokens
+        with torch.no_grad():                                                        # 1) predicted tokens / lengths
+            self._decode_stepwise(z.detach(), False, x.detach(), lengths32, plan_note, plan_time, keep_logits=False)
+        pred_tok = torch.cat([gt_tok[:, :, :1], self._last_tokens.permute(2, 0, 1, 3)], 2)      # slot 0 = SOS
+        plen32 = torch.stack(self._last_lens, 1).reshape(-1).to(torch.int32)         # (R,) in (b, t) order
+        dev = z.device
+        w, b = self.note_embedding.weight, self.note_embedding.bias
+        pred_emb = ops.note_embed(pred_tok.reshape(R * NS, 6).contiguous(), w, b).view(R, NS, -1)
+        if any(any(r) for r in plan_note):                 # some slots are fed the ground truth (host-side test: the
+            # free-running case builds no masks, so it stays capturable in a CUDA graph)
+            m_note = torch.tensor([[True] + list(r) + [False] for r in plan_note], device=dev)   # (T, NS) slots fed GT
+            mix_tok = torch.where(m_note.view(1, T, NS, 1), gt_tok, pred_tok)
+            mix_emb = ops.note_embed(mix_tok.reshape(R * NS, 6).contiguous(), w, b).view(R, NS, -1)
+        else:
+            mix_emb = pred_emb                             # slot 0 is the SOS token in both grids
+        # 2) teacher-forced phases over the mixed inputs
+        summ_pred = self._summarize(pred_emb, plen32).view(B, T, -1)
+        if any(plan_time):
+            summ_gt = self._summarize(x.reshape(R, NS, -1), lengths32).view(B, T, -1)
+            m_time = torch.tensor(list(plan_time) + [False], device=dev).view(1, T, 1)
+            summ = torch.where(m_time, summ_gt, summ_pred)
+        else:
+            summ = summ_pred
+        wn_ih = self.dec_notes_gru.dir()[0]
+        gi_tok = ops.linear(mix_emb, wn_ih[:, self.dec_time_hid_size:], None)
+        return self._decode_teacher_forced(z, None, None, pre=(summ, gi_tok))
+
     # -- general step-wise path (scheduled sampling / inference) ----------------------------------
     def _sos_embedding(self, dev):
         tok = torch.tensor([[self.pitch_sos, 2, 2, 2, 2, 2]], device=dev, dtype=torch.int32)
@@ -400,7 +442,7 @@ class PtvaeDecoder(nn.Module):
         tokens = torch.empty(self.num_step, self.max_simu_note - 1, B, 6, device=dev, dtype=torch.int32)
         tok, h = self.dec_init_input.expand(B, -1), z_hid
         consts = self._step_weights()                  # merged head / projection weights, once per forward
-        pitches, durs = [], []
+        pitches, durs, lens_all = [], [], []
         for t in range(self.num_step):
             gi = ops.linear(tok, w_tok, None)
             h = ops.gru_sequence(gi.view(B, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
@@ -412,6 +454,7 @@ class PtvaeDecoder(nn.Module):
             if keep_logits:
                 pitches.append(p)
                 durs.append(d)
+            lens_all.append(plen)
             if t == self.num_step - 1:
                 break
             if plan_dev is not None:
@@ -420,7 +463,7 @@ class PtvaeDecoder(nn.Module):
                 tok = summ[:, t]
             else:
                 tok = self._summarize(pred, plen)
-        self._last_tokens = tokens
+        self._last_tokens, self._last_lens = tokens, lens_all
         if not keep_logits:
             return None, None
         return torch.stack(pitches, 1), torch.stack(durs, 1)
@@ -452,6 +495,9 @@ class PtvaeDecoder(nn.Module):
         plan_note, plan_time = self._draw_plan(teacher_forcing_ratio1, teacher_forcing_ratio2)
         if not inference and all(plan_time) and all(all(r) for r in plan_note):
             return self._decode_teacher_forced(z, x, lengths32, pre)
+        if (self.batched_sampling and not inference and torch.is_grad_enabled()
+                and getattr(x, "_pd_tok", None) is not None):
+            return self._decode_sampled_batched(z, x, lengths32, plan_note, plan_time)
         return self._decode_stepwise(z, inference, x, lengths32, plan_note, plan_time)
 
     def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None):

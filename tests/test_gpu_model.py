@@ -176,3 +176,12 @@ def test_large_batch_3xtf32_decode_matches_fp32_decode():
         m.decode_precision = prec
         out[prec] = m.inference(pr, c, sample=False)
     assert (out["fp32"] == out["tf32x3"]).mean() >= 0.999
+
+
+@pytest.mark.skipif(not os.environ.get("POLYDIS_TEST_EXPERIMENTAL"),
+                    reason="opt-in batched scheduled-sampling path, pinned on the CPU emulation, not run on hardware yet")
+@pytest.mark.parametrize("tag", ["tf000", "tf555"])
+def test_batched_sampling_matches_reference_golden(golden_dir, monkeypatch, tag):
+    from polydis_b200.ptvae import PtvaeDecoder
+    monkeypatch.setattr(PtvaeDecoder, "batched_sampling", True)
+    test_training_matches_reference_golden(golden_dir, tag, "fp32")

@@ -30,7 +30,8 @@ def test_state_dict_keys_match_reference_contract():
     assert all(tuple(sd[k].shape) == s for k, s, _ in STATE_DICT_SPEC)
 
 
-@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan"])
+@pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan",
+                                 "tf000-batched", "tf555-batched"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     cpu_backend.install(monkeypatch)
     if tag.endswith("-chunked"):        # row-chunked recurrences (ops._over_row_chunks): 128-row chunks, ragged tail
@@ -39,6 +40,10 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
         monkeypatch.setattr(ops, "ROW_CHUNK_BYTES", 1)
         monkeypatch.setattr(ops, "RESIDENT_GRU128", False)
         tag = tag[:-len("-chunked")]
+    if tag.endswith("-batched"):        # scheduled sampling as greedy pass + batched teacher-forced phases on mixed inputs
+        from polydis_b200.ptvae import PtvaeDecoder
+        monkeypatch.setattr(PtvaeDecoder, "batched_sampling", True)
+        tag = tag[:-len("-batched")]
     devplan = tag.endswith("-devplan")
     tag = tag[:-len("-devplan")] if devplan else tag
     g = np.load(os.path.join(golden_dir, f"train_{tag}.npz"))
