@@ -355,9 +355,18 @@ class PtvaeDecoder(nn.Module):
         R = B * T
         gt_tok = x._pd_tok.view(B, T, NS, 6)                                        # int32 ground-truth tokens
         with torch.no_grad():                                                        # 1) predicted tokens / lengths
-            self._decode_stepwise(z.detach(), False, x.detach(), lengths32, plan_note, plan_time, keep_logits=False)
-        pred_tok = torch.cat([gt_tok[:, :, :1], self._last_tokens.permute(2, 0, 1, 3)], 2)      # slot 0 = SOS
-        plen32 = torch.stack(self._last_lens, 1).reshape(-1).to(torch.int32)         # (R,) in (b, t) order
+            if not any(plan_time) and not any(any(r) for r in plan_note):
+                # free-running: the dedicated greedy schedule (fixed buffers, 7 launches per note slot); the first
+                # slot of every step is the SOS token in the data grid as well (ptvae.py:437-439)
+                lens_tb = torch.empty(T, B, device=z.device, dtype=torch.int32)
+                tokens = self._greedy_fast(z.detach(), lens_out=lens_tb)
+                self._last_tokens = tokens
+                plen32 = lens_tb.t().reshape(-1)                                     # (R,) in (b, t) order
+            else:
+                self._decode_stepwise(z.detach(), False, x.detach(), lengths32, plan_note, plan_time, keep_logits=False)
+                tokens = self._last_tokens
+                plen32 = torch.stack(self._last_lens, 1).reshape(-1).to(torch.int32)
+        pred_tok = torch.cat([gt_tok[:, :, :1], tokens.permute(2, 0, 1, 3)], 2)      # slot 0 = SOS
         dev = z.device
         w, b = self.note_embedding.weight, self.note_embedding.bias
         pred_emb = ops.note_embed(pred_tok.reshape(R * NS, 6).contiguous(), w, b).view(R, NS, -1)
@@ -515,7 +524,8 @@ class PtvaeDecoder(nn.Module):
         with torch.no_grad():
             return self._greedy_fast(z).permute(2, 0, 1, 3).contiguous()
 
-    def _greedy_fast(self, z):
+    def _greedy_fast(self, z, lens_out=None):
+        """``lens_out`` (T,B) int32, optional: receives the predicted note count of every time step."""
         B, dev = z.size(0), z.device
         f32 = dict(device=dev, dtype=torch.float32)
         T, NS, E = self.num_step, self.max_simu_note, self.note_emb_size
@@ -586,6 +596,8 @@ class PtvaeDecoder(nn.Module):
                 ops.greedy_pick(heads[:, :self.pitch_range], dlog, n, tokens[t, n - 1], lens)
                 ops._call("pd_note_embed_fwd", ops._ptr(tokens[t, n - 1]), B, ops._ptr(emb_wt), ops._ptr(emb_b),
                           ops._ptr(pred[:, n]), pred.stride(0), st())
+            if lens_out is not None:
+                lens_out[t].copy_(lens)
             if t == T - 1:
                 break
             # next time-step token: bi-GRU summary of the predicted notes with the predicted lengths
