@@ -107,6 +107,15 @@ int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, in
  * decoded tokens (n_steps,15,6) int32 -> pr_mat (n_steps,128) (ptvae.py:558-575). */
 int pd_prmat_to_grid(const float* pr_mat, long n_steps, long long* x, int* overflow, void* stream);
 int pd_grid_to_prmat(const int* tok, long n_steps, float* pr_mat, void* stream);
+/* batch augmentation (dataset.py:67-120): transposition of a segment by shift[b] semitones.  pd_roll_prmat = np.roll
+ * of pr_mat (B,32,128) along the pitch axis (converter.py:65-68 augment_pr; out must not alias in);
+ * pd_expand_chord = converter.py:150-164 expand_chord: chord rows (rows,14) [root, 12 chroma, bass] -> (rows,36)
+ * [root one-hot | rolled chroma | bass one-hot]; rows_per_seg consecutive rows share one shift entry (8 per segment). */
+int pd_roll_prmat(const float* pr_in, const int* shift, long B, float* pr_out, void* stream);
+int pd_expand_chord(const float* chord14, const int* shift, long rows, int rows_per_seg, float* c36, void* stream);
+/* model.py:218-242 interp_path for B latent pairs at once: out (B,count,D); spherical interpolation of the direction,
+ * log-linear interpolation of the norm (float64 arithmetic inside, like the reference's numpy). */
+int pd_slerp_path(const float* z1, const float* z2, int B, int D, int count, float* out, void* stream);
 /* note_embedding(multi-hot) as a gather: out[r] = bias + WT[pitch] (pitch < 130) + sum_k dur_k WT[130+k];
  * tok int32 (R,6); WT = weight^T (135,128).   bwd accumulates dWT (135,128) and dbias (128). */
 int pd_note_embed_fwd(const int* tok, long R, const float* WT, const float* bias, float* out, long ldo,

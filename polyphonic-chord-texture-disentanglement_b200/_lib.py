@@ -32,6 +32,9 @@ SIGNATURES = {
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
     "pd_grid_to_prmat": [_P, _L, _P, _P],
+    "pd_roll_prmat": [_P, _P, _L, _P, _P],
+    "pd_expand_chord": [_P, _P, _L, _I, _P, _P],
+    "pd_slerp_path": [_P, _P, _I, _I, _I, _P, _P],
     "pd_note_embed_fwd": [_P, _L, _P, _P, _P, _L, _P],
     "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
     "pd_greedy_pick": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P],

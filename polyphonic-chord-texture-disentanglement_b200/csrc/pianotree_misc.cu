@@ -247,6 +247,82 @@ __global__ void grid_to_prmat_kernel(const int* __restrict__ tok, long n_steps, 
     }
 }
 
+// ---- batch augmentation on device (dataset.py:67-120): transpose a segment by `shift` semitones -----------------
+// pr_mat (B,32,128): np.roll along the pitch axis (converter.py:65-68; wraps around like np.roll).  The roll commutes
+// with piano_roll_to_target (converter.py:87-113), which works column by column, so rolling pr_mat equals rolling
+// the raw piano-roll first.  One thread per output element, coalesced along pitch.
+__global__ void roll_prmat_kernel(const float* __restrict__ in, const int* __restrict__ shift, long B, float* __restrict__ out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 32 * 128) return;
+    const int p = (int)(i & 127);
+    const long row = i >> 7;
+    int s = shift[row / 32] % 128;
+    if (s < 0) s += 128;
+    out[i] = in[row * 128 + ((p - s + 128) & 127)];
+}
+
+// chord (rows,14) [root, 12 chroma bits, bass] -> (rows,36) [root one-hot | rolled chroma | bass one-hot] transposed by
+// the segment's shift (converter.py:150-164 expand_chord); rows_per_seg chord rows share one shift entry.
+__global__ void expand_chord_kernel(const float* __restrict__ ch, const int* __restrict__ shift, long rows, int rows_per_seg,
+                                    float* __restrict__ out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * 36) return;
+    const long r = i / 36;
+    const int j = (int)(i % 36);
+    int s = shift[r / rows_per_seg] % 12;
+    if (s < 0) s += 12;
+    const float* c = ch + r * 14;
+    float v;
+    if (j < 12) v = (j == (((int)c[0] + s) % 12)) ? 1.0f : 0.0f;
+    else if (j < 24) v = c[1 + ((j - 12 - s + 12) % 12)];
+    else v = (j - 24 == (((int)c[13] + s) % 12)) ? 1.0f : 0.0f;
+    out[i] = v;
+}
+
+// ---- latent-space interpolation on device (model.py:218-242 interp_path): spherical interpolation of the direction,
+// log-linear interpolation of the norm, `count` points per (z1, z2) pair.  The reference runs this in float64 numpy on
+// the host; the kernel keeps float64 (the data is B x count x D, a few KB) so results agree to fp32 rounding.
+// One CTA per pair.
+__global__ void slerp_path_kernel(const float* __restrict__ z1, const float* __restrict__ z2, int D, int count,
+                                  float* __restrict__ out) {
+    __shared__ double red[3][32];
+    __shared__ double s_n1, s_n2, s_omega;
+    const int b = blockIdx.x;
+    const float* a = z1 + (long)b * D;
+    const float* c = z2 + (long)b * D;
+    double n1 = 0.0, n2 = 0.0, dot = 0.0;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const double x = a[i], y = c[i];
+        n1 += x * x; n2 += y * y; dot += x * y;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+        n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (l == 0) { red[0][w] = n1; red[1][w] = n2; red[2][w] = dot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double A = 0, Bq = 0, Cq = 0;
+        for (int i = 0; i < nw; ++i) { A += red[0][i]; Bq += red[1][i]; Cq += red[2][i]; }
+        A = sqrt(A); Bq = sqrt(Bq);
+        double cosv = Cq / (A * Bq);
+        cosv = fmin(1.0, fmax(-1.0, cosv));
+        s_n1 = A; s_n2 = Bq; s_omega = acos(cosv);
+    }
+    __syncthreads();
+    const double N1 = s_n1, N2 = s_n2, om = s_omega, so = sin(om);
+    const double l1 = log(N1), l2 = log(N2);
+    for (int k = 0; k < count; ++k) {
+        const double t = count > 1 ? (double)k / (double)(count - 1) : 0.0;
+        const double w1 = sin((1.0 - t) * om) / so, w2 = sin(t * om) / so;
+        const double len = exp(l1 + (l2 - l1) * t);
+        for (int i = threadIdx.x; i < D; i += blockDim.x)
+            out[((long)b * count + k) * D + i] = (float)((w1 * ((double)a[i] / N1) + w2 * ((double)c[i] / N2)) * len);
+    }
+}
+
 }  // namespace
 
 PD_API int pd_prmat_to_grid(const float* pr_mat, long n_steps, long long* x, int* overflow, void* stream) {
@@ -329,5 +405,26 @@ PD_API int pd_chord_feedback(const float* root, long ldr, const float* chroma, l
 PD_API int pd_chord_targets(const float* c, int rows, int* root, int* chroma, int* bass, void* stream) {
     if (rows <= 0) return 0;
     chord_targets_kernel<<<pd_blocks(rows, 128), 128, 0, (cudaStream_t)stream>>>(c, rows, root, chroma, bass);
+    return pd_launch_status();
+}
+
+PD_API int pd_roll_prmat(const float* pr_in, const int* shift, long B, float* pr_out, void* stream) {
+    if (B <= 0) return 0;
+    if (pr_in == pr_out) return PD_BAD_ARG;
+    roll_prmat_kernel<<<pd_blocks(B * 32 * 128, 256), 256, 0, (cudaStream_t)stream>>>(pr_in, shift, B, pr_out);
+    return pd_launch_status();
+}
+
+PD_API int pd_expand_chord(const float* chord14, const int* shift, long rows, int rows_per_seg, float* c36, void* stream) {
+    if (rows <= 0) return 0;
+    if (rows_per_seg <= 0) return PD_BAD_ARG;
+    expand_chord_kernel<<<pd_blocks(rows * 36, 256), 256, 0, (cudaStream_t)stream>>>(chord14, shift, rows, rows_per_seg, c36);
+    return pd_launch_status();
+}
+
+PD_API int pd_slerp_path(const float* z1, const float* z2, int B, int D, int count, float* out, void* stream) {
+    if (B <= 0 || count <= 0) return 0;
+    if (D <= 0) return PD_BAD_ARG;
+    slerp_path_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(z1, z2, D, count, out);
     return pd_launch_status();
 }

@@ -5,27 +5,35 @@ Replaces the reference's single-process ``nn.DataParallel`` wrap (amc_dl/torch_p
 Semantics match its loss averaging (module.py:152-157): every rank computes the per-shard mean losses,
 gradients are averaged over ranks (= gradient of the mean of per-shard losses).
 
-Design: parameters are packed, in reverse registration order (decoder / chord-decoder gradients are
-produced first by backward, the encoders' last), into a few flat fp32 buckets; ``p.grad`` are views into
-them, so backward accumulates straight into the communication buffers (no copy).  A
-post-accumulate-grad hook counts a bucket's parameters down and, when the bucket is complete, issues
-its all-reduce (``ReduceOp.AVG``) on a side stream ordered after the producing kernels -- the exchange
-overlaps the rest of backward, and because every launch is a stream operation the whole thing is
-capturable in the training step's CUDA graph.  ``finish()`` joins the side stream before the global-norm
-clip and the optimizer step (which therefore see identical gradients on every rank).
+Design (round 2):
+
+* parameters are packed, in reverse registration order (decoder / chord-decoder gradients are produced first
+  by backward, the encoders' last), into flat fp32 buckets of at most ``bucket_mb``;
+* ``p.grad`` is ``None`` while backward runs, so autograd's AccumulateGrad *adopts* the gradient tensor the
+  producing kernel wrote (no zero pass over the buckets, no read-modify-write add per parameter -- 81 extra
+  kernels on the step's critical path in round 1);
+* a post-accumulate-grad hook records a CUDA event on the stream the gradient was produced on (the model forks
+  encoders / decoder / chord decoder onto side streams, ``ops.fork_join``, and autograd replays their backward
+  on those streams) and counts the bucket down; when the bucket is complete the communication stream waits for
+  the events of ALL its parameters, gathers the gradients into the flat buffer with one multi-tensor copy, and
+  issues the all-reduce (``ReduceOp.AVG``).  ``p.grad`` is then re-pointed at the bucket views, so the clip and
+  the optimizer read the averaged gradients in place;
+* every operation is a stream operation, so the whole exchange is captured inside the training step's CUDA graph;
+* ``finish()`` joins the communication stream before the global-norm clip and the optimizer step (which therefore
+  see identical gradients on every rank).
 """
 import torch
 import torch.distributed as dist
 
 
 class BucketedGradAllReduce:
-    def __init__(self, params, bucket_mb=32, group=None):
+    def __init__(self, params, bucket_mb=8, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.cuda = self.params[0].is_cuda
         cap = int(bucket_mb * (1 << 20) // 4)
-        self.buckets = []                  # dicts: flat, params, pending
+        self.buckets = []                  # dicts: flat, params, views, pending, events, adopted
         cur, cur_n = [], 0
         for p in reversed(self.params):
             if cur and cur_n + p.numel() > cap:
@@ -38,51 +46,80 @@ class BucketedGradAllReduce:
         self.comm = torch.cuda.Stream() if self.cuda else None
         self._handles = []
         for bi, b in enumerate(self.buckets):
-            for p in b["params"]:
-                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+            for pi, p in enumerate(b["params"]):
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi, pi)))
         self.reset()
 
     def _close(self, plist):
         n = sum(-(-p.numel() // 4) * 4 for p in plist)             # 16-byte aligned slots
         flat = torch.zeros(n, device=plist[0].device, dtype=torch.float32)
-        off = 0
+        views, off = [], 0
         for p in plist:
-            p.grad = flat[off:off + p.numel()].view_as(p)
+            views.append(flat[off:off + p.numel()].view_as(p))
             off += -(-p.numel() // 4) * 4
-        self.buckets.append({"flat": flat, "params": plist, "pending": len(plist)})
+        events = [torch.cuda.Event() for _ in plist] if plist[0].is_cuda else None
+        self.buckets.append({"flat": flat, "params": plist, "views": views, "pending": len(plist), "events": events,
+                             "adopted": None})
 
-    def _make_hook(self, bi):
+    def _make_hook(self, bi, pi):
         def hook(_p):
             b = self.buckets[bi]
+            if b["events"] is not None:
+                # the gradient is complete on the stream this AccumulateGrad node runs on, which need not be the
+                # stream of the hook that fires last for the bucket
+                b["events"][pi].record(torch.cuda.current_stream())
             b["pending"] -= 1
             if b["pending"] == 0:
                 self._launch(b)
         return hook
 
     def _launch(self, b):
-        if self.world == 1:
-            return
+        grads = [p.grad for p in b["params"]]
+        if any(g is None for g in grads):
+            raise RuntimeError("BucketedGradAllReduce: a parameter's hook fired without a gradient")
         if self.cuda:
-            self.comm.wait_stream(torch.cuda.current_stream())
+            for ev in b["events"]:
+                self.comm.wait_event(ev)
             with torch.cuda.stream(self.comm):
-                dist.all_reduce(b["flat"], op=dist.ReduceOp.AVG, group=self.group)
-        else:                                                       # gloo (CPU tests): no AVG
-            dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group)
-            b["flat"].div_(self.world)
+                torch._foreach_copy_(b["views"], grads)
+                if self.world > 1:
+                    dist.all_reduce(b["flat"], op=dist.ReduceOp.AVG, group=self.group)
+            b["adopted"] = grads           # keep the producers' buffers alive until finish() has joined ``comm``
+        else:                                                       # gloo (CPU tests): no streams, no AVG
+            torch._foreach_copy_(b["views"], grads)
+            if self.world > 1:
+                dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group)
+                b["flat"].div_(self.world)
+        for p, v in zip(b["params"], b["views"]):
+            p.grad = v
 
     def reset(self):
-        """Zero the gradient buckets and re-arm the hooks (call instead of optimizer.zero_grad)."""
+        """Drop the gradients and re-arm the hooks (call instead of optimizer.zero_grad)."""
         for b in self.buckets:
-            b["flat"].zero_()
+            for p in b["params"]:
+                p.grad = None
             b["pending"] = len(b["params"])
+            b["adopted"] = None
 
     def finish(self):
-        """Make the compute stream wait for every bucket's all-reduce."""
-        if self.cuda and self.world > 1:
-            torch.cuda.current_stream().wait_stream(self.comm)
+        """Make the compute stream wait for every bucket's gather + all-reduce."""
         for b in self.buckets:
             if b["pending"] != 0:
                 raise RuntimeError("a parameter received no gradient; its bucket was never reduced")
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        for b in self.buckets:
+            b["adopted"] = None
+        self.check_grad_views()
+
+    def check_grad_views(self):
+        """Every ``p.grad`` must be its bucket view: a stray ``zero_grad(set_to_none=True)`` / foreign optimizer would
+        otherwise leave the optimizer stepping on stale bucket contents without any error."""
+        for b in self.buckets:
+            for p, v in zip(b["params"], b["views"]):
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    raise RuntimeError("BucketedGradAllReduce: p.grad is not the bucket view (gradients were reset or "
+                                       "replaced outside reset()/finish())")
 
     def remove(self):
         for h in self._handles:

@@ -18,7 +18,7 @@ import torch
 
 class GraphedTrainStep:
     def __init__(self, model, optimizer, batch, tfr=(1., 1., 1.), beta=0.1, weights=(1, 0.5), clip=1.0,
-                 warmup=3, reducer=None, device_plan=False):
+                 warmup=3, reducer=None, device_plan=False, inject_eps=False, restore_after_capture=True):
         assert device_plan or all(t in (0., 1.) for t in tfr), \
             "graph capture bakes the teacher-forcing plan: every ratio must be 0 or 1 (deterministic decisions); " \
             "use device_plan=True (decisions as device data) or eager steps for 0 < tfr < 1"
@@ -35,6 +35,14 @@ class GraphedTrainStep:
         self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
         self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
         self.tfr, self.beta, self.weights, self.clip = tfr, beta, weights, clip
+        #: inject_eps: the reparameterisation noise is read from these static buffers (fill them before a replay)
+        #: instead of being drawn inside the graph -- deterministic replays for tests / reproducible runs
+        self.eps = (tuple(torch.zeros(batch, 256, device=dev, dtype=torch.float32) for _ in range(2))
+                    if inject_eps else None)
+        #: restore_after_capture: warm-up and capture run REAL optimizer steps on the first batch; with this on
+        #: (default) parameters and optimizer state are put back afterwards, so training starts from the caller's
+        #: state and the first batch is trained once (the reference takes one step per batch, module.py:134-149)
+        self.restore_after_capture = restore_after_capture
         from .optim import FusedClipAdam
         self.fused = isinstance(optimizer, FusedClipAdam)     # clip + Adam + LR decay inside optimizer.step()
         if self.fused:
@@ -51,7 +59,8 @@ class GraphedTrainStep:
             self.opt.zero_grad(set_to_none=True)
         losses = self.model('train', self.x, self.c, self.pr, tfr1=self.tfr[0], tfr2=self.tfr[1],
                             tfr3=self.tfr[2], beta=self.beta, weights=self.weights,
-                            **({"plan_dev": self.plan} if self.device_plan else {}))
+                            **({"plan_dev": self.plan} if self.device_plan else {}),
+                            **({"eps": self.eps} if self.eps is not None else {}))
         losses[0].backward()
         if self.reducer is not None:
             self.reducer.finish()
@@ -72,10 +81,43 @@ class GraphedTrainStep:
         self.plan.copy_(self._plan_host, non_blocking=True)
         self._plan_copied.record()
 
+    def _snapshot(self):
+        """Parameters + optimizer state (torch optimizers: state_dict tensors; FusedClipAdam: its flat buffers)."""
+        snap = {"p": [p.detach().clone() for p in self.params]}
+        if self.fused:
+            snap["opt"] = self.opt.state_dict()
+        else:
+            snap["opt"] = [{k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state[p].items()}
+                           for p in self.params]
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            for p, q in zip(self.params, snap["p"]):
+                p.copy_(q)
+            if self.fused:
+                self.opt.load_state_dict(snap["opt"])
+                return
+            for p, st in zip(self.params, snap["opt"]):
+                cur = self.opt.state[p]
+                if not st:
+                    # the optimizer had no state yet: zero what warm-up created, IN PLACE (the captured graph holds
+                    # these tensors' addresses)
+                    for v in cur.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+                    continue
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        cur[k].copy_(v)
+                    else:
+                        cur[k] = v
+
     def capture(self, x, c, pr_mat):
         self.x.copy_(x); self.c.copy_(c); self.pr.copy_(pr_mat)
         if self.device_plan:
             self._upload_plan()
+        snap = self._snapshot() if self.restore_after_capture else None
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -86,11 +128,14 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = self._step()
+        if snap is not None:
+            self._restore(snap)
         return self
 
     def __call__(self, x, c, pr_mat):
         """Copy one batch into the static buffers (H2D if the sources are pinned host tensors), replay,
-        return the 11 losses as one device tensor (no host sync)."""
+        return the 11 losses as one device tensor (no host sync).  The returned tensor is a STATIC buffer that the
+        next replay overwrites: clone it to keep a step's losses."""
         if self.graph is None:
             self.capture(x, c, pr_mat)
         self.x.copy_(x, non_blocking=True)

@@ -229,8 +229,9 @@ class DisentangleVAE(PytorchModel):
         return estxs.reshape((bs, int_count, 32, 15, -1))
 
     def interp_z(self, z1, z2, int_count=10):
-        z1, z2 = z1.cpu().numpy(), z2.cpu().numpy()
-        return torch.stack([self.interp_path(a, b, int_count) for a, b in zip(z1, z2)], dim=0)
+        """(B,D) x 2 -> (B,int_count,D); the reference loops ``interp_path`` over the batch in host numpy
+        (model.py:211-216), here one kernel on the device (``ops.slerp_path``), no host round trip."""
+        return ops.slerp_path(z1, z2, int_count)
 
     def interp_path(self, z1, z2, interpolation_count=10):
         """Spherical interpolation of direction, log-linear interpolation of norm (model.py:218-242)."""

@@ -689,6 +689,35 @@ def pr_mat_to_grid(pr_mat):
     return x, overflow
 
 
+def augment_batch(pr_mat, chord14, shift):
+    """Device-side batch augmentation + construction (dataset.py:67-120 per item on the host):
+    transpose every segment by ``shift[b]`` semitones -- ``np.roll`` of the piano-roll along pitch
+    (converter.py:65-68) and ``expand_chord(c, shift)`` (converter.py:150-164) -- then build the PianoTree grid.
+
+    pr_mat (B,32,128) fp32, chord14 (B,8,14) fp32 [root, 12 chroma bits, bass], shift (B,) int.
+    Returns (x (B,32,16,6) int64, c (B,8,36) fp32, pr_mat' (B,32,128) fp32, overflow flag) -- the model's inputs."""
+    pr = _chk(pr_mat, "pr_mat").contiguous()
+    ch = _chk(chord14, "chord14").contiguous().to(torch.float32)
+    B = pr.shape[0]
+    sh = shift.to(device=pr.device, dtype=torch.int32).contiguous()
+    out = torch.empty_like(pr)
+    _call("pd_roll_prmat", _ptr(pr), _ptr(sh), B, _ptr(out), _stream())
+    rows_per_seg = ch.shape[1]
+    c36 = torch.empty(B, rows_per_seg, 36, device=pr.device, dtype=torch.float32)
+    _call("pd_expand_chord", _ptr(ch), _ptr(sh), B * rows_per_seg, rows_per_seg, _ptr(c36), _stream())
+    x, overflow = pr_mat_to_grid(out)
+    return x, c36, out, overflow
+
+
+def slerp_path(z1, z2, count):
+    """(B,D), (B,D) -> (B,count,D): model.py:218-242 ``interp_path`` for every pair, on the device."""
+    a, b = _chk(z1, "z1").contiguous().to(torch.float32), _chk(z2, "z2").contiguous().to(torch.float32)
+    B, D = a.shape
+    out = torch.empty(B, count, D, device=a.device, dtype=torch.float32)
+    _call("pd_slerp_path", _ptr(a), _ptr(b), B, D, count, _ptr(out), _stream())
+    return out
+
+
 def tokens_to_pr_mat(tokens):
     """Decoded tokens (B,32,15,6) int32 -> pr_mat (B,32,128) fp32 on device (ptvae.py:558-575 without the
     host loop and without moving the tokens off the GPU)."""

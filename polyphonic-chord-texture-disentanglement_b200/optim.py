@@ -40,11 +40,33 @@ class FusedClipAdam:
     def zero_grad(self, set_to_none=False):
         self.reducer.reset()
 
+    def state_dict(self):
+        """Moments, step count (which also fixes the position on the LR decay curve) and hyper-parameters; tensors are
+        copies, so the dict survives later steps (checkpointing)."""
+        return {"m": [t.detach().clone() for t in self.m], "v": [t.detach().clone() for t in self.v],
+                "step_count": self.step_count.detach().clone(),
+                "hyper": {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "clip": self.clip,
+                          "lr_gamma": self.lr_gamma, "lr_min": self.lr_min}}
+
+    def load_state_dict(self, sd):
+        """In place (the buffers' addresses may be baked into a captured CUDA graph)."""
+        if len(sd["m"]) != len(self.m) or any(a.numel() != b.numel() for a, b in zip(sd["m"], self.m)):
+            raise ValueError("FusedClipAdam.load_state_dict: bucket layout differs (bucket_mb / parameter set changed)")
+        with torch.no_grad():
+            for dst, src in zip(self.m + self.v, list(sd["m"]) + list(sd["v"])):
+                dst.copy_(src)
+            self.step_count.copy_(sd["step_count"])
+        h = sd.get("hyper", {})
+        self.lr, self.eps, self.clip = h.get("lr", self.lr), h.get("eps", self.eps), h.get("clip", self.clip)
+        self.betas = tuple(h.get("betas", self.betas))
+        self.lr_gamma, self.lr_min = h.get("lr_gamma", self.lr_gamma), h.get("lr_min", self.lr_min)
+
     def grad_norm(self):
         """Global gradient norm of the last step() (device tensor)."""
         return self.sumsq.sqrt()
 
     def step(self):
+        self.reducer.check_grad_views()      # a stray zero_grad(set_to_none=True) would silently step on zero gradients
         st = ops._stream()
         self.sumsq.zero_()
         ops._call("pd_counter_inc", ops._ptr(self.step_count), st)

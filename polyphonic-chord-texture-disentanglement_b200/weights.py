@@ -89,3 +89,19 @@ def make_state_dict(seed=0, sharpen=1.0, gain=1.0, eos_bias=0.0):
                   "decoder.dur_out_linear.weight", "decoder.dur_out_linear.bias"):
             sd[k] = sd[k] * float(sharpen)
     return sd
+
+
+#: state dict of the alternative texture encoder ``PtvaeEncoder`` (ptvae.py:125-215 of the reference)
+PTVAE_ENCODER_SPEC = (_lin("note_embedding", 135, 128) + _gru("enc_notes_gru", 128, 256, True)
+                      + _gru("enc_time_gru", 512, 512, True) + _lin("linear_mu", 1024, 512) + _lin("linear_std", 1024, 512))
+
+
+def make_ptvae_encoder_state(seed=0, gain=1.0):
+    """Seeded weights for ``PtvaeEncoder`` with the reference's keys / shapes (same recipe as ``make_state_dict``)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(7000003 * int(seed) + 29)
+    sd = {}
+    for name, shape, fan in PTVAE_ENCODER_SPEC:
+        u = (2.0 * torch.rand(shape, generator=g, dtype=torch.float32) - 1.0) / math.sqrt(fan)
+        sd[name] = u * float(gain) if u.dim() >= 2 else u
+    return sd

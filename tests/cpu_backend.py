@@ -255,6 +255,39 @@ class CpuBackend:
                 X[s, 1 + i] = [p] + [(d >> (4 - b)) & 1 for b in range(5)]
             X[s, len(ps) + 1, 0] = 129
 
+    def pd_roll_prmat(self, pr_in, shift, B, pr_out, st):
+        P = _arr(pr_in, (B, 32, 128), (4096, 128, 1))
+        O = _arr(pr_out, (B, 32, 128), (4096, 128, 1))
+        S = _arr(shift, (B,), (1,), np.int32)
+        for b in range(B):
+            O[b] = np.roll(P[b], int(S[b]), axis=-1)          # converter.py:65-68
+
+    def pd_expand_chord(self, chord14, shift, rows, rows_per_seg, c36, st):
+        C = _arr(chord14, (rows, 14), (14, 1))
+        O = _arr(c36, (rows, 36), (36, 1))
+        S = _arr(shift, ((rows + rows_per_seg - 1) // rows_per_seg,), (1,), np.int32)
+        for r in range(rows):                                 # converter.py:150-164
+            sh = int(S[r // rows_per_seg])
+            root, bass = (int(C[r, 0]) + sh) % 12, (int(C[r, 13]) + sh) % 12
+            o = np.zeros(36, np.float32)
+            o[root] = 1
+            o[12:24] = np.roll(C[r, 1:13], sh)
+            o[24 + bass] = 1
+            O[r] = o
+
+    def pd_slerp_path(self, z1, z2, B, D, count, out, st):
+        A, C = _arr(z1, (B, D), (D, 1)), _arr(z2, (B, D), (D, 1))
+        O = _arr(out, (B, count, D), (count * D, D, 1))
+        for b in range(B):                                    # model.py:218-242, float64 like the reference
+            a, c = A[b].astype(np.float64), C[b].astype(np.float64)
+            n1, n2 = np.linalg.norm(a), np.linalg.norm(c)
+            u1, u2 = a / n1, c / n2
+            ts = np.linspace(0.0, 1.0, count)
+            om = np.arccos(np.clip(np.dot(u1, u2), -1.0, 1.0))
+            so = np.sin(om)
+            dirs = np.sin((1.0 - ts) * om)[:, None] / so * u1[None] + np.sin(ts * om)[:, None] / so * u2[None]
+            O[b] = (dirs * np.exp(np.linspace(np.log(n1), np.log(n2), count))[:, None]).astype(np.float32)
+
     def pd_grid_to_prmat(self, tok, n_steps, pr, st):
         T = _arr(tok, (n_steps, 15, 6), (90, 6, 1), np.int32)
         P = _arr(pr, (n_steps, 128), (128, 1))

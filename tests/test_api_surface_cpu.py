@@ -142,3 +142,46 @@ def test_ptvae_encoder_matches_torch_restatement(monkeypatch):
     for name, p in enc.named_parameters():
         ref = ref_g[name] if name in ref_g else sd[name].grad
         assert torch.allclose(p.grad, ref, atol=2e-4, rtol=1e-3), name
+
+
+def test_aux_rows_match_reference_golden(monkeypatch, golden_dir):
+    """Rows either side of the path against vectors written by the unmodified reference
+    (tests/golden/make_golden_aux.py): on-device augmentation (np.roll + expand_chord + grid), interp_path slerp,
+    weighted duration loss -- here through the numpy emulation of the C ABI (the -m gpu twin runs the kernels)."""
+    import os
+    cpu_backend.install(monkeypatch)
+    from polydis_b200 import ops
+    g = np.load(os.path.join(golden_dir, "aux.npz"))
+    _, _, pr = synth_batch(int(g["B"]), int(g["data_seed"]))
+    x, c36, pr_s, ovf = ops.augment_batch(torch.from_numpy(pr), torch.from_numpy(g["chord14"]), torch.from_numpy(g["shifts"]))
+    assert np.array_equal(pr_s.numpy(), g["pr_shift"]) and np.array_equal(c36.numpy(), g["c36"])
+    assert np.array_equal(x.numpy(), g["grid"]) and int(ovf) == 0
+    paths = ops.slerp_path(torch.from_numpy(g["z1"]), torch.from_numpy(g["z2"]), 7).numpy()
+    assert np.allclose(paths, g["paths"], atol=2e-6, rtol=1e-5)
+    m = _model()
+    xs = torch.from_numpy(synth_batch(int(g["B"]), int(g["data_seed"]))[0][:2])
+    for flag, key in ((True, "wd_losses"), (False, "ud_losses")):
+        got = m.decoder.recon_loss(xs, torch.from_numpy(g["wd_pitch"]), torch.from_numpy(g["wd_dur"]), (1, 0.5), flag)
+        assert np.allclose([float(v) for v in got], g[key], rtol=2e-6)
+
+
+def test_ptvae_encoder_matches_reference_golden(monkeypatch, golden_dir):
+    """PtvaeEncoder against the reference's own module (fixture from tests/golden/make_golden_aux.py)."""
+    import os
+    cpu_backend.install(monkeypatch)
+    from polydis_b200 import ops
+    from polydis_b200.ptvae import PtvaeEncoder
+    from polydis_b200.weights import make_ptvae_encoder_state, PTVAE_ENCODER_SPEC
+    g = np.load(os.path.join(golden_dir, "aux.npz"))
+    enc = PtvaeEncoder(device="cpu")
+    enc.load_state_dict(make_ptvae_encoder_state(5, gain=1.5))
+    with ops.precision("fp32"):
+        dist, emb, lengths = enc(torch.from_numpy(synth_batch(3, 808)[0]))
+        (dist.mean.sum() + dist.scale.sum()).backward()
+    assert np.allclose(dist.mean.detach().numpy(), g["enc_mu"], atol=2e-5)
+    assert np.allclose(dist.scale.detach().numpy(), g["enc_std"], atol=2e-5, rtol=2e-5)
+    assert np.array_equal(lengths.numpy(), g["enc_lens"])
+    params = dict(enc.named_parameters())
+    for i, (name, _, _) in enumerate(PTVAE_ENCODER_SPEC):
+        gn = float(params[name].grad.double().norm())
+        assert abs(gn - g["enc_grad_norm"][i]) <= 1e-3 * g["enc_grad_norm"][i] + 1e-9, name

@@ -156,30 +156,99 @@ def test_odd_batch_sizes_match_oracle(B):
     assert (est == O.inference(sd, prs[:nd], cs[:nd])).mean() >= 0.999
 
 
-@pytest.mark.skipif(not os.environ.get("POLYDIS_TEST_EXPERIMENTAL"),
-                    reason="added after the round's GPU budget was spent; enable once it has been run")
-def test_large_batch_3xtf32_decode_matches_fp32_decode():
-    """Token parity of the LARGE-batch decode route (>= 512 segments: single-launch 3xTF32 GEMMs, operands split by the
-    gate kernel, 3-pass duration decoder) against the fp32 FFMA route of the same model, which the small-batch tests
-    pin to the reference (rows are independent)."""
-    dev = torch.device("cuda:0")
-    from polydis_b200.model import DisentangleVAE
-    from polydis_b200.synth import synth_batch
-    from polydis_b200.weights import make_state_dict
+def test_baseline_batch512_full_gradients_match_oracle():
+    """BASELINE configs[1] at its own size: teacher-forced training, batch 512 -- the routes bench.py times (persistent
+    TMA-store GEMMs, 256-wide tiles, split-K weight gradients over 245,760 rows) -- all 11 losses and all 81 full
+    gradients against the CPU oracle."""
+    dev = _dev()
+    from oracle import polydis_oracle as O
+    B = 512
+    xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 4242))
+    sd = {k: v.requires_grad_(True) for k, v in make_state_dict(31).items()}
+    torch.manual_seed(17)
+    e1, e2 = torch.randn(B, 256), torch.randn(B, 256)
+    random.seed(5)
+    ref = O.loss(sd, xs, cs, prs, O.draw_plan(1., 1., 1.), e1, e2)
+    ref[0].backward()
+    m = _model(dev, 31)
+    m.train()
+    random.seed(5)
+    got = m.loss(xs.to(dev), cs.to(dev), prs.to(dev), 1., 1., 1., eps=(e1.to(dev), e2.to(dev)))
+    got[0].backward()
+    torch.cuda.synchronize()
+    for a, b in zip(got, ref):
+        assert abs(float(a) - float(b)) <= 1e-3 * abs(float(b)) + 1e-6, (float(a), float(b))
+    worst = ("", 0.0)
+    for name, p in m.named_parameters():
+        gr, rf = p.grad.detach().cpu().double(), sd[name].grad.double()
+        err = float((gr - rf).norm() / (rf.norm() + 1e-20))
+        if err > worst[1]:
+            worst = (name, err)
+        assert err <= 1e-2, (name, err)
+    print(f"B=512 full-gradient parity: worst relative error {worst[1]:.2e} ({worst[0]})")
+
+
+def test_baseline_batch512_graphed_step_matches_oracle_losses():
+    """The CUDA-graph replay bench.py times (GraphedTrainStep, batch 512): its 11 losses against the oracle with the
+    reparameterisation noise removed (posterior std -> tiny is not available, so the check uses the KL-free pieces:
+    the graph draws its own eps).  Holds the captured path to the eager path on the same weights instead."""
+    dev = _dev()
+    from polydis_b200.graphs import GraphedTrainStep
+    B = 512
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 4243))
+    m = _model(dev, 31)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=0.0, fused=True, capturable=True)    # lr 0: weights stay put
+    g = GraphedTrainStep(m, opt, B, warmup=1).capture(x, c, pr)
+    torch.manual_seed(99)
+    lg = g(x, c, pr).clone()
+    grads_g = [p.grad.detach().clone() for p in m.parameters()]
+    torch.manual_seed(99)
+    opt.zero_grad(set_to_none=True)
+    le = m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5))
+    le[0].backward()
+    torch.cuda.synchronize()
+    le = torch.stack([v.detach() for v in le])
+    # same generator state -> same eps in replay and eager run: results are held to fp32 reassociation noise
+    assert torch.allclose(lg, le, rtol=2e-5, atol=1e-6), (lg, le)
+    for a, p in zip(grads_g, m.parameters()):
+        assert float((a - p.grad).norm()) <= 2e-4 * float(p.grad.norm()) + 1e-9
+
+
+@pytest.mark.parametrize("prec", ["tf32x3"])
+def test_large_batch_decode_matches_oracle(prec):
+    """Token parity of the LARGE-batch decode route (>= 512 segments: single-launch 3xTF32 tcgen05 GEMMs, operands
+    split by the gate kernel, 3-pass duration decoder and GRU128) against the CPU oracle's greedy decode -- 1,024
+    segments, W1-style weights so decodes vary per segment and step."""
+    dev = _dev()
+    from oracle import polydis_oracle as O
     B = 1024
-    _, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 77))
-    m = DisentangleVAE.init_model(device=dev)
-    m.load_state_dict(make_state_dict(7, gain=2.0, eos_bias=0.75))
-    m.to(dev).eval()
-    out = {}
-    for prec in ("fp32", "tf32x3"):
-        m.decode_precision = prec
-        out[prec] = m.inference(pr, c, sample=False)
-    assert (out["fp32"] == out["tf32x3"]).mean() >= 0.999
+    _, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 77))
+    sd = make_state_dict(7, gain=2.0, eos_bias=0.75)
+    ref = O.inference(sd, prs, cs)
+    m = _model(dev, 7, 2.0, 0.75)
+    m.decode_precision = prec
+    est = m.inference(prs.to(dev), cs.to(dev), sample=False)
+    match = (est == ref).mean()
+    pre = ref[..., 0] != 129
+    assert match >= 0.999, match
+    assert (est[pre] == ref[pre]).mean() >= 0.999
+    print(f"1024-segment {prec} decode vs oracle: token match {match:.6f}")
 
 
-@pytest.mark.skipif(not os.environ.get("POLYDIS_TEST_EXPERIMENTAL"),
-                    reason="opt-in batched scheduled-sampling path, pinned on the CPU emulation, not run on hardware yet")
+def test_graphed_decode_matches_eager_decode():
+    """GraphedDecode (what bench.py replays) returns the tokens of the eager public API on the same inputs."""
+    dev = _dev()
+    from polydis_b200.graphs import GraphedDecode
+    B = 640
+    _, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 78))
+    m = _model(dev, 7, 2.0, 0.75)
+    eager = m.inference(pr, c, sample=False)
+    gd = GraphedDecode(m, B).capture(pr, c)
+    tok = gd(pr, c).cpu().numpy().astype(np.int64)
+    assert (tok == eager).mean() >= 0.9999
+
+
 @pytest.mark.parametrize("tag", ["tf000", "tf555"])
 def test_batched_sampling_matches_reference_golden(golden_dir, monkeypatch, tag):
     from polydis_b200.ptvae import PtvaeDecoder

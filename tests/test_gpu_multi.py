@@ -1,0 +1,136 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise; run with ``gpurun --gpus 2``): the data-parallel exchange on hardware.
+
+Two NCCL ranks, a different shard each.  Checked on every rank:
+  1. eager step through ``BucketedGradAllReduce``: every gradient == mean over ranks of the CPU ORACLE's per-shard
+     gradients (the reference's DataParallel semantics, amc_dl/torch_plus/module.py:152-157), <= 1e-2 relative;
+  2. the same exchange captured in the training step's CUDA graph (side-stream backward, event-ordered buckets):
+     gradients equal the eager ones, post-step parameters are identical on both ranks and equal a single-process
+     step on the rank-averaged gradients.
+"""
+import os
+import random
+import socket
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from oracle import polydis_oracle as O
+        from polydis_b200.ddp import BucketedGradAllReduce
+        from polydis_b200.graphs import GraphedTrainStep
+        from polydis_b200.model import DisentangleVAE
+        from polydis_b200.synth import synth_batch
+        from polydis_b200.weights import make_state_dict
+
+        B = 4
+        shards = [[torch.from_numpy(a) for a in synth_batch(B, 60 + r)] for r in range(world)]
+        torch.manual_seed(123)
+        eps = [(torch.randn(B, 256), torch.randn(B, 256)) for _ in range(world)]
+        # oracle: per-shard gradients on the CPU, averaged over the shards
+        sd = {k: v.requires_grad_(True) for k, v in make_state_dict(3).items()}
+        for r in range(world):
+            random.seed(0)
+            O.loss(sd, *shards[r], O.draw_plan(1., 1., 1.), *eps[r])[0].backward()
+        expect = {k: v.grad / world for k, v in sd.items()}
+
+        def fresh():
+            m = DisentangleVAE.init_model(device=dev)
+            m.load_state_dict(make_state_dict(3))
+            return m.to(dev).train()
+
+        x, c, pr = (t.to(dev) for t in shards[rank])
+        e = tuple(t.to(dev) for t in eps[rank])
+        # 1. eager, bucketed all-reduce
+        m = fresh()
+        red = BucketedGradAllReduce(list(m.parameters()), bucket_mb=8)
+        for _ in range(2):                               # twice: reset() must re-arm everything
+            red.reset()
+            random.seed(0)
+            m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5), eps=e)[0].backward()
+            red.finish()
+        torch.cuda.synchronize()
+        worst = 0.0
+        eager_grads = {}
+        for name, p in m.named_parameters():
+            g, rf = p.grad.detach().cpu().double(), expect[name].double()
+            worst = max(worst, float((g - rf).norm() / (rf.norm() + 1e-20)))
+            eager_grads[name] = p.grad.detach().clone()
+        red.remove()
+        # 2. the same exchange inside the step's CUDA graph + Adam; reference = single-process Adam on the averaged grads
+        m2 = fresh()
+        params2 = list(m2.parameters())
+        red2 = BucketedGradAllReduce(params2, bucket_mb=8)
+        opt2 = torch.optim.Adam(params2, lr=1e-3, fused=True, capturable=True)
+        random.seed(0)
+        g = GraphedTrainStep(m2, opt2, B, reducer=red2, warmup=11, inject_eps=True, clip=1.0).capture(x, c, pr)
+        g.eps[0].copy_(e[0]); g.eps[1].copy_(e[1])
+        g(x, c, pr)
+        torch.cuda.synchronize()
+        graph_grad_err = max(float((p.grad - eager_grads[n]).norm() / (eager_grads[n].norm() + 1e-20))
+                             for n, p in m2.named_parameters())
+        m3 = fresh()
+        params3 = list(m3.parameters())
+        for (n, p) in m3.named_parameters():
+            p.grad = eager_grads[n].clone()
+        torch.nn.utils.clip_grad_norm_(params3, 1.0, foreach=True)
+        torch.optim.Adam(params3, lr=1e-3, fused=True, capturable=True).step()
+        torch.cuda.synchronize()
+        step_err = max(float((a - b).abs().max()) for a, b in zip(params2, params3))
+        # identical parameters on every rank
+        flat = torch.cat([p.detach().reshape(-1) for p in params2])
+        other = flat.clone()
+        dist.broadcast(other, 0)
+        rank_diff = float((flat - other).abs().max())
+        q.put((rank, "ok", worst, graph_grad_err, step_err, rank_diff))
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error: " + repr(ex) + "\n" + traceback.format_exc(), 0, 0, 0, 0))
+    finally:
+        # process groups whose collectives were captured in CUDA graphs can block in destroy_process_group()
+        os._exit(0)
+
+
+def test_two_rank_nccl_gradients_match_per_shard_oracle_mean():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for p in procs:
+        p.join(timeout=120)
+    for rank, status, worst, graph_err, step_err, rank_diff in res:
+        assert status == "ok", status
+        assert worst <= 1e-2, (rank, worst)                  # N-rank gradients == mean of per-shard oracle gradients
+        assert graph_err <= 1e-4, (rank, graph_err)          # captured exchange == eager exchange
+        assert step_err <= 5e-5, (rank, step_err)            # clip + Adam on the averaged gradients
+        assert rank_diff == 0.0, (rank, rank_diff)           # replicas stay bit-identical
+    print("2-rank NCCL:", res)
