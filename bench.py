@@ -30,7 +30,16 @@ sys.path.insert(0, ROOT)
 TRAIN_GFLOP_PER_SAMPLE = 5.45      # algorithmic minimum fwd+bwd, SURVEY.md 8(d)
 DECODE_GFLOP_PER_SEGMENT = 1.92
 METRIC = "polydis_train_samples_per_sec"
-NOTE_GEMM_DRAM_BYTES = 112.1e6     # ncu: 60.8 MB read + 51.4 MB written per note-GRU step GEMM at B=512
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")   # ncu --set full dram bytes per launch
+
+
+def _measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of ``kernel`` from the committed ncu capture of the
+    variant this bench times (profiles/r02_kernel_traffic.json, written from the .ncu-rep by tools/ncu_traffic.py)."""
+    try:
+        return json.load(open(TRAFFIC_FILE))[kernel]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def _peaks():
@@ -168,7 +177,7 @@ def run_b200(args):
         from polydis_b200.ddp import BucketedGradAllReduce
         for p in params:                                   # identical initial weights on every rank
             dist.broadcast(p.data, 0)
-        reducer = BucketedGradAllReduce(params, bucket_mb=32)
+        reducer = BucketedGradAllReduce(params, bucket_mb=8)
     fused_opt = args.fused_optim
     if fused_opt:
         from polydis_b200.optim import FusedClipAdam
@@ -236,20 +245,32 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     mark(f"timed region done: {ms_step:.2f} ms/step")
+    # BASELINE configs[3]: data-parallel training at GLOBAL batch 4096 (strong-scaling point: 4096 / N per GPU)
+    strong = None
+    if world > 1 and graphed is not None and not args.no_strong and 4096 % world == 0 and 4096 // world != B:
+        from polydis_b200.graphs import GraphedTrainStep
+        Bs = 4096 // world
+        xs_, cs_, ps_ = (torch.from_numpy(a).to(dev) for a in synth_batch(Bs, 300 + rank))
+        gs = GraphedTrainStep(model, opt, Bs, reducer=reducer, warmup=11).capture(xs_, cs_, ps_)
+        for _ in range(3):
+            gs(xs_, cs_, ps_)
+        ms_s = timed(lambda: gs(xs_, cs_, ps_), max(3, args.steps // 2))
+        strong = {"global_batch": 4096, "batch_per_gpu": Bs, "ms_per_step": ms_s, "value": 4096 / (ms_s * 1e-3),
+                  "unit": "samples/s", "what": "BASELINE configs[3]: global batch 4096 over N GPUs"}
+        del gs, xs_, cs_, ps_
+        mark(f"strong-scaling point: {ms_s:.2f} ms/step at {Bs}/GPU")
     # free-running regime (tfr = 0,0,0: what train.py's schedule yields after its first step, scheduler.py:48-49):
     # 32 x 15 sequential note steps with greedy feedback, same kernels step-wise, whole step in one CUDA graph
     ms_tfr0 = None
     if world == 1 and graphed is not None and not args.no_tfr0:
         from polydis_b200.graphs import GraphedTrainStep
-        if args.batched_sampling:       # opt-in: greedy pass + batched teacher-forced phases (ptvae.PtvaeDecoder)
-            from polydis_b200.ptvae import PtvaeDecoder
-            PtvaeDecoder.batched_sampling = True
+        from polydis_b200.ptvae import PtvaeDecoder
+        PtvaeDecoder.batched_sampling = not args.stepwise_sampling     # default: greedy pass + batched phases
         g0 = GraphedTrainStep(model, opt, B, tfr=(0., 0., 0.), warmup=1).capture(x, c, pr)
         g0(x, c, pr)
         ms_tfr0 = timed(lambda: g0(x, c, pr), 3)
         del g0
-        if args.batched_sampling:
-            PtvaeDecoder.batched_sampling = False
+        PtvaeDecoder.batched_sampling = True
         mark(f"tfr=0 step: {ms_tfr0:.1f} ms")
     # end-to-end: pinned host buffers -> device inside the timed region, loss read back
     # (graph mode: double-buffered -- every step copies one full batch from pinned host memory, the one the NEXT
@@ -282,6 +303,32 @@ def run_b200(args):
         del gd
     model.decode_precision = "tf32x3"
     ms_dec = dec_ms["tf32x3"]
+    # decode end to end (BASELINE configs[2], 65,536 segments on one GPU): 4 replays of 16,384 segments, every replay
+    # fed from its own pinned host batch (pr_mat + c, H2D inside the timed region) and its tokens brought back to the
+    # host in the compact 2-byte format (ops.pack_tokens; the reference copies int64 tokens AND the logits,
+    # ptvae.py:537-544)
+    dec_e2e = None
+    if not args.no_decode_e2e:
+        n_chunks = max(1, 65536 // Bd)
+        host = []
+        for k in range(n_chunks):
+            _, c_k, p_k = synth_batch(Bd, 7000 + 10 * rank + k)
+            host.append((torch.from_numpy(p_k).pin_memory(), torch.from_numpy(c_k).pin_memory()))
+        gd = GraphedDecode(model, Bd, pack=True).capture(pd_, cd_)
+        out_host = torch.empty((n_chunks,) + tuple(gd.packed.shape), dtype=torch.uint8).pin_memory()
+
+        def decode_all():
+            for k, (p_k, c_k) in enumerate(host):
+                gd(p_k, c_k)                                   # H2D into the static buffers + replay (+ pack)
+                out_host[k].copy_(gd.packed, non_blocking=True)
+        decode_all()
+        ms_all = timed(decode_all, 2)
+        torch.cuda.synchronize()
+        h2d_dec = sum(p_k.numel() * 4 + c_k.numel() * 4 for p_k, c_k in host)
+        dec_e2e = {"value": world * n_chunks * Bd / (ms_all * 1e-3), "unit": "segments/s", "segments_per_gpu": n_chunks * Bd,
+                   "replays": n_chunks, "ms_total": ms_all, "h2d_bytes": h2d_dec, "d2h_bytes": out_host.numel(),
+                   "how": "pinned host pr_mat + c per replay -> device, greedy decode graph, packed uint8 tokens -> pinned host"}
+        del gd, host
     # latency-bound corner (BASELINE configs[4]: a 256-bar arrangement = 128 segments over 8 GPUs = 16 per GPU)
     xs_, cs_, ps_ = (torch.from_numpy(a).to(dev) for a in synth_batch(16, 900 + rank))
     gd16 = GraphedDecode(model, 16).capture(ps_, cs_)
@@ -301,6 +348,31 @@ def run_b200(args):
         ops.gemm_nt(hA, wB, oC)
     ms_gemm = timed(lambda: ops.gemm_nt(hA, wB, oC), 20)
     gemm_tflops = 2.0 * R * 512 * 1536 / (ms_gemm * 1e-3) / 1e12
+    del hA, oC
+    # dominant kernel of the step, timed alone: the fused note-GRU step (recurrent GEMM on tcgen05 + gate math in the
+    # epilogue, all operands / results as TMA boxes).  HBM-bound: per launch it must read h_prev, gi, gi2 and write h,
+    # r|z|n, W_hn h (13 x H floats per row-step) -- 15 launches over distinct (b,t) slices, so every launch
+    # streams ~400 MB of fresh data (> 126 MB L2).
+    T_, H_ = 15, 512
+    gi_ = torch.randn(R, T_ + 1, 3 * H_, device=dev)
+    gi2_ = torch.randn(R, 3 * H_, device=dev)
+    h_ = torch.randn(R, T_ + 1, H_, device=dev) * 0.3
+    rzn_ = torch.empty(R, T_, 3 * H_, device=dev)
+    hn_ = torch.empty(R, T_, H_, device=dev)
+    wB.mul_(0.03)
+    bB = torch.randn(3 * H_, device=dev) * 0.1
+
+    def step_seq():
+        for t_ in range(T_):
+            ops._call("pd_gru_step_tma", h_[:, t_].data_ptr(), h_.stride(0), wB.data_ptr(), H_, bB.data_ptr(),
+                      gi_[:, t_].data_ptr(), gi_.stride(0), gi2_.data_ptr(), 3 * H_, h_[:, t_ + 1].data_ptr(), h_.stride(0),
+                      rzn_[:, t_].data_ptr(), rzn_.stride(0), hn_[:, t_].data_ptr(), hn_.stride(0), R, H_,
+                      torch.cuda.current_stream().cuda_stream)
+    step_seq()
+    ms_fstep = timed(step_seq, 3) / T_
+    step_bytes = R * H_ * 4 * 13 + 3 * H_ * H_ * 4          # h_prev + gi(3) + gi2(3) in, h + rzn(3) + hn out, + W_hh
+    step_gbs = step_bytes / (ms_fstep * 1e-3) / 1e9
+    del gi_, gi2_, h_, rzn_, hn_
 
     def leave():
         # a process group whose collectives were captured in CUDA graphs can block in
@@ -321,7 +393,8 @@ def run_b200(args):
     achieved = TRAIN_GFLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e3      # TFLOP/s per GPU
     out = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+           "dtype_note": "fp32 storage; GEMM operands rounded to TF32 on the tensor cores, fp32 accumulation and gate math",
            "config": {"workload": "PolyDisVAE training step (zero_grad+fwd+loss+bwd+clip_grad_norm+Adam), "
                                   "teacher-forced PianoTree decoder, batch 512 per GPU (BASELINE configs[1])",
                       "batch_per_gpu": B, "global_batch": world * B, "tfr": [1, 1, 1],
@@ -333,25 +406,30 @@ def run_b200(args):
                    "how": ("GraphedTrainStep.prefetch/step_prefetched: each step copies one full batch from pinned host "
                            "memory (the next step's, overlapped with the replay) and reads the loss back"
                            if graphed is not None else "copy, step, read the loss back")},
-           "gpu_launches": launches,
+           "gpu_launches": launches, "configs3_global_4096": strong,
            "train_free_running": None if ms_tfr0 is None else
            {"value": B / (ms_tfr0 * 1e-3), "unit": "samples/s", "ms_per_step": ms_tfr0, "tfr": [0, 0, 0], "cuda_graph": True,
-            "path": "greedy pass + batched phases" if args.batched_sampling else "step-wise"},
+            "path": "step-wise" if args.stepwise_sampling else "greedy pass + batched phases"},
            "decode": {"value": world * Bd / (ms_dec * 1e-3), "unit": "segments/s", "batch_per_gpu": Bd,
                       "ms_per_batch": ms_dec,
                       "precision": "tf32x3 (error-compensated tensor-core GEMMs; token parity with the fp32 reference)",
                       "fp32_ffma_value": world * Bd / (dec_ms["fp32"] * 1e-3),
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True,
-                      "latency_16_segments_ms": ms_dec16},
-           "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": achieved / peak_tf, "traffic": NOTE_GEMM_DRAM_BYTES, "peak_source": peak_src,
-                        "traffic_what": "dram read+write bytes per launch of the dominant GEMM from ncu --set full "
-                                        "(profiles/r01_ncu_full_kernels.md, captured with the one-shot 256-wide tile; the "
-                                        "persistent TMA-store variant timed here moves the same bytes); algorithmic 137 MB, "
-                                        "half of C stays in L2",
-                        "what": "whole step: 5.45 algorithmic GFLOP/sample x batch / step time, vs sustained bf16 peak",
-                        "dominant_kernel": {"name": "note-GRU recurrent GEMM [32B x 512].[512 x 1536]",
-                                            "ms": ms_gemm, "achieved": gemm_tflops, "frac": gemm_tflops / peak_tf}},
+                      "latency_16_segments_ms": ms_dec16, "e2e": dec_e2e},
+           "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
+                        "frac": step_gbs / peak_hbm, "traffic": _measured_traffic("gru_step_tma_kernel"),
+                        "peak_source": peak_src,
+                        "kernel": "gru_step_tma_kernel (fused note-GRU step: tcgen05 recurrent GEMM + gate math, 32B x 512)",
+                        "ms_per_launch": ms_fstep, "algorithmic_bytes_per_launch": step_bytes,
+                        "what": "dominant kernel timed alone with CUDA events (15 launches over distinct slices, 3 rounds): "
+                                "13 x H x 4 algorithmic bytes per row-step (SURVEY 8d) / launch time, vs the measured HBM copy "
+                                "bandwidth; traffic = ncu dram bytes per launch (profiles/r02_kernel_traffic.json)",
+                        "whole_step_tensor": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                                              "frac": achieved / peak_tf,
+                                              "what": "5.45 algorithmic GFLOP/sample x batch / step time vs sustained bf16 peak"},
+                        "note_gemm_alone": {"name": "note-GRU recurrent GEMM [32B x 512].[512 x 1536] (unfused route)",
+                                            "ms": ms_gemm, "achieved": gemm_tflops, "frac": gemm_tflops / peak_tf,
+                                            "traffic": _measured_traffic("gemm_tf32_persistent")}},
            "clocks": clocks}
     if world == 1 and not args.no_cpu:
         try:
@@ -378,8 +456,10 @@ def main():
     ap.add_argument("--decode-batch", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tfr0", action="store_true", help="skip the free-running (tfr=0) training measurement")
-    ap.add_argument("--batched-sampling", action="store_true",
-                    help="free-running measurement through the opt-in batched scheduled-sampling path (not yet run on hardware)")
+    ap.add_argument("--no-decode-e2e", action="store_true", help="skip the 65,536-segment end-to-end decode measurement")
+    ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] strong-scaling point under --gpus N>1")
+    ap.add_argument("--stepwise-sampling", action="store_true",
+                    help="free-running measurement through the step-wise path instead of the batched scheduled-sampling path")
     ap.add_argument("--fused-optim", action="store_true",
                     help="polydis_b200.optim.FusedClipAdam (flat buckets) instead of torch clip_grad_norm_ + fused Adam; "
                          "measured 0.9 ms/step slower at 1 GPU because backward then accumulates into the flat buckets")

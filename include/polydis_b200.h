@@ -28,7 +28,9 @@ extern "C" {
  *   C[m*ldc+n] (+)= sum_k A(m,k) B(k,n) (+ bias[n]);  A(m,k)=A[m*sam+k*sak], B(k,n)=B[k*sbk+n*sbn];
  *   one of (sam,sak) and one of (sbk,sbn) must be 1.  accumulate != 0 adds into C (L2 reductions).
  * pd_gemm_f32 : fp32 FFMA, any shape/stride.   pd_gemm_tf32: tcgen05 tensor cores (TF32 x TF32 -> fp32),
- * needs 16-byte aligned bases and row strides that are multiples of 4. */
+ * needs 16-byte aligned bases and row strides that are multiples of 4.  Large plain-store GEMMs leave through TMA bulk
+ * stores, which clip at 16-byte granularity: when N % 4 != 0 (and ldc >= N rounded up to 4) the padding columns
+ * C[m][N .. roundup4(N)) may be overwritten with zeros. */
 int pd_gemm_f32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                 const float* bias, int M, int N, int K, int accumulate, void* stream);
 int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
@@ -80,12 +82,15 @@ int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, c
 int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
                      long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                      long ldhn, const int* lengths, int t, int B, int H, void* stream);
-/* EXPERIMENTAL -- compiled and exported, not yet validated on hardware, nothing routes to it: persistent variant of the
- * fused step (4-stage ring, two TMEM accumulators, every epilogue operand / result moved as a 32x16 TMA box).  Same
- * contract without the length mask; hout must not alias hprev. */
+/* persistent variant of the fused step (two TMEM accumulators, every epilogue operand / result moved as a 32x16 TMA
+ * box, operand sets double-buffered so the next chunk's loads fly while a chunk is computed).  Same contract without the
+ * length mask; hout must not alias hprev.  Validated on B200 in round 2 (tests/test_gpu_kernels.py::test_gru_step_tma);
+ * routed to for recurrences of >= 4096 rows (the 32*B-row note GRU): 108 us vs 147 us for GEMM + gate kernel at
+ * 16384 x 512.  pd_gru_step_tma_variant(1) selects the round-1 single-buffered layout (A/B measurements). */
 int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
                     long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                     long ldhn, int B, int H, void* stream);
+int pd_gru_step_tma_variant(int variant);
 
 /* weight-resident variable-length GRU, hidden 128 (the note-summary bi-GRU, ptvae.py:446-453,:480-486): one kernel
  * runs the whole recurrence of a tile of sequences with W_hh resident in shared memory and stops at the tile's
@@ -107,6 +112,9 @@ int pd_grid_prepare(const long long* x, long n_steps, int* tok, int* lengths, in
  * decoded tokens (n_steps,15,6) int32 -> pr_mat (n_steps,128) (ptvae.py:558-575). */
 int pd_prmat_to_grid(const float* pr_mat, long n_steps, long long* x, int* overflow, void* stream);
 int pd_grid_to_prmat(const int* tok, long n_steps, float* pr_mat, void* stream);
+/* decoded tokens int32 (R,6) -> compact uint8 (R,2): [pitch 0..129, the 5 duration bits packed MSB-first]; the
+ * device->host format of a decode (2 bytes per note; est_x of ptvae.py:537-544 is rebuilt on the host). */
+int pd_pack_tokens(const int* tok, long R, unsigned char* out, void* stream);
 /* batch augmentation (dataset.py:67-120): transposition of a segment by shift[b] semitones.  pd_roll_prmat = np.roll
  * of pr_mat (B,32,128) along the pitch axis (converter.py:65-68 augment_pr; out must not alias in);
  * pd_expand_chord = converter.py:150-164 expand_chord: chord rows (rows,14) [root, 12 chroma, bass] -> (rows,36)

@@ -27,11 +27,13 @@ SIGNATURES = {
                          _I, _I, _P],
     "pd_gru_step_tf32": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_step_tma": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
+    "pd_gru_step_tma_variant": [_I],
     "pd_gru128_fwd": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P],
     "pd_gru128_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
     "pd_grid_to_prmat": [_P, _L, _P, _P],
+    "pd_pack_tokens": [_P, _L, _P, _P],
     "pd_roll_prmat": [_P, _P, _L, _P, _P],
     "pd_expand_chord": [_P, _P, _L, _I, _P, _P],
     "pd_slerp_path": [_P, _P, _I, _I, _I, _P, _P],

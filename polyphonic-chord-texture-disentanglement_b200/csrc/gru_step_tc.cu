@@ -218,7 +218,7 @@ __device__ __forceinline__ void io_write(uint8_t* buf, int lane, const float (&v
             make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-template <int STAGES>
+template <int STAGES, int NSETS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
@@ -230,13 +230,13 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_BYTES;
-    uint8_t* io = sB + STAGES * B_BYTES;                               // 4 warps x 7 buffers x 2 KB
-    uint64_t* full = (uint64_t*)(io + 4 * N_IOB * IOB);
+    uint8_t* io = sB + STAGES * B_BYTES;                               // 4 warps x NSETS sets x 7 buffers x 2 KB
+    uint64_t* full = (uint64_t*)(io + 4 * NSETS * N_IOB * IOB);
     uint64_t* empty = full + STAGES;
     uint64_t* tmem_full = empty + STAGES;                              // [2]
     uint64_t* tmem_empty = tmem_full + 2;                              // [2]
-    uint64_t* io_bar = tmem_empty + 2;                                 // [4]: epilogue operands of a warp landed
-    uint32_t* tmem_slot = (uint32_t*)(io_bar + 4);
+    uint64_t* io_bar = tmem_empty + 2;                                 // [4][NSETS]: epilogue operands of a warp's set landed
+    uint32_t* tmem_slot = (uint32_t*)(io_bar + 4 * NSETS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = (g.H + 31) / 32;
@@ -247,7 +247,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
-        for (int q = 0; q < 4; ++q) mbar_init(&io_bar[q], 1);
+        for (int q = 0; q < 4 * NSETS; ++q) mbar_init(&io_bar[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -299,13 +299,21 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else {
         const int q = warp & 3;                                        // TMEM lane quarter == rows q*32.. of the tile
-        uint8_t* bufs = io + q * (N_IOB * IOB);
-        uint64_t* lbar = &io_bar[q];
+        uint8_t* wbufs = io + q * (NSETS * N_IOB * IOB);
         const int H = g.H;
-        uint32_t lphase = 0;
-        // lane 0 of each epilogue warp is the producer of its own epilogue operands
-        auto issue_loads = [&](int m0, int u0, int c) {
-            const int col = u0 + c * 16, row = m0 + q * 32;
+        constexpr int NCH = UN / 16;                                   // 16-unit chunks per item
+        // This warp's chunk stream: chunk number k = j * NCH + c (j-th item of this CTA, chunk c).  Chunk k uses operand
+        // set k % NSETS, whose mbarrier completes once per use: parity (k / NSETS) & 1.  Lane 0 is the producer of the
+        // warp's own epilogue operands and keeps NSETS - 1 chunks of loads in flight behind the one being computed.
+        const long n_mine = (n_items > (long)blockIdx.x) ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const long n_chunks = n_mine * NCH;
+        auto issue_loads = [&](long k) {
+            const long item = blockIdx.x + (k / NCH) * (long)gridDim.x;
+            const int m0 = (int)(item / tiles_u) * BM, u0 = (int)(item % tiles_u) * UN;
+            const int col = u0 + (int)(k % NCH) * 16, row = m0 + q * 32;
+            const int set = (int)(k % NSETS);
+            uint8_t* bufs = wbufs + set * (N_IOB * IOB);
+            uint64_t* lbar = &io_bar[q * NSETS + set];
             mbar_expect_tx(lbar, (uint32_t)((g.has_gi2 ? 7 : 4) * IOB));
 #pragma unroll
             for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi, lbar, bufs + gate * IOB, gate * H + col, row);
@@ -315,24 +323,31 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             tma_load_2d(&tmHp, lbar, bufs + 6 * IOB, col, row);
         };
+        if (lane == 0) {
+            for (long k = 0; k < NSETS && k < n_chunks; ++k) issue_loads(k);
+        }
+        long k = 0;
         long j = 0;
-        if (lane == 0 && (long)blockIdx.x < n_items)
-            issue_loads((int)(blockIdx.x / tiles_u) * BM, (int)(blockIdx.x % tiles_u) * UN, 0);
         for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
             const int m0 = (int)(item / tiles_u) * BM, u0 = (int)(item % tiles_u) * UN;
             const int acc = (int)(j & 1);
             mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < UN / 16; ++c) {
+            for (int c = 0; c < NCH; ++c, ++k) {
                 const int col = u0 + c * 16, row = m0 + q * 32;
+                const int set = (int)(k % NSETS);
+                uint8_t* bufs = wbufs + set * (N_IOB * IOB);
                 float ghr[16], ghz[16], ghn[16];
                 const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN3 + c * 16;
                 tc_ld16(tbase, ghr);
                 tc_ld16(tbase + UN, ghz);
                 tc_ld16(tbase + 2 * UN, ghn);
-                mbar_wait(lbar, lphase);                               // this chunk's gi / gi2 / h_prev boxes landed
-                lphase ^= 1;
+                if (c == NCH - 1) {                                    // last TMEM read of this item: hand the accumulator back
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive1(&tmem_empty[acc]);
+                }
+                mbar_wait(&io_bar[q * NSETS + set], (uint32_t)(k / NSETS) & 1);   // this chunk's gi / gi2 / h_prev boxes landed
                 float ir[16], iz[16], in[16], hp[16];
                 io_read(bufs, lane, ir);
                 io_read(bufs + IOB, lane, iz);
@@ -378,19 +393,15 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&tmHn), "r"(smem_u32(bufs + 3 * IOB)), "r"(col), "r"(row) : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the stores have read the buffers
-                    // operands of the next chunk (of this item, or chunk 0 of this CTA's next item)
-                    if (c + 1 < UN / 16) {
-                        issue_loads(m0, u0, c + 1);
-                    } else if (item + gridDim.x < n_items) {
-                        const long nx = item + gridDim.x;
-                        issue_loads((int)(nx / tiles_u) * BM, (int)(nx % tiles_u) * UN, 0);
+                    if (k + NSETS < n_chunks) {
+                        // this set is reloaded for chunk k + NSETS once its stores have read the buffers; meanwhile the
+                        // loads of the NSETS - 1 chunks in between are already in flight
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        issue_loads(k + NSETS);
                     }
                 }
                 __syncwarp();
             }
-            tc_fence_before();
-            if (lane == 0) mbar_arrive1(&tmem_empty[acc]);
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
@@ -415,6 +426,8 @@ int make_map_io(CUtensorMap* map, const void* base, long inner, long outer, long
                      CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 700 + (int)r;
 }
+
+int g_step_variant = 0;      // tuning switch of pd_gru_step_tma (pd_gru_step_tma_variant)
 
 inline bool al16(const void* p, long ld) { return ((uintptr_t)p & 15) == 0 && (ld & 3) == 0; }
 
@@ -474,18 +487,40 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
     StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H};
-    constexpr int STAGES = 4;
-    constexpr int smem = STAGES * (BM * 128 + BN3 * 128) + 4 * N_IOB * IOB + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        attr = true;
-    }
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
-    gru_step_tma_kernel<STAGES><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn, g,
-                                                                                   tiles_m, tiles_u);
+    // variant 0 (default): 2-stage main loop, double-buffered epilogue operand sets (the loads of the next chunk are in
+    // flight while a chunk is computed and stored); variant 1: round-1 layout, 4 stages, single set
+    if (g_step_variant == 1) {
+        constexpr int STAGES = 4, NSETS = 1;
+        constexpr int smem = STAGES * (BM * 128 + BN3 * 128) + 4 * NSETS * N_IOB * IOB + 1024 + 256;
+        static bool attr = false;
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<STAGES, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            attr = true;
+        }
+        gru_step_tma_kernel<STAGES, NSETS><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn, g,
+                                                                                            tiles_m, tiles_u);
+        return pd_launch_status();
+    }
+    constexpr int STAGES = 2, NSETS = 2;
+    constexpr int smem = STAGES * (BM * 128 + BN3 * 128) + 4 * NSETS * N_IOB * IOB + 1024 + 256;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<STAGES, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    gru_step_tma_kernel<STAGES, NSETS><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn, g,
+                                                                                        tiles_m, tiles_u);
     return pd_launch_status();
+}
+
+// tuning / A-B switch for pd_gru_step_tma: 0 = double-buffered epilogue operands (default), 1 = round-1 single-set layout
+PD_API int pd_gru_step_tma_variant(int v) {
+    if (v < 0 || v > 1) return PD_BAD_ARG;
+    g_step_variant = v;
+    return 0;
 }

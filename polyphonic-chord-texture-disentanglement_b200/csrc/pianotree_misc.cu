@@ -247,6 +247,20 @@ __global__ void grid_to_prmat_kernel(const int* __restrict__ tok, long n_steps, 
     }
 }
 
+// decoded tokens int32 (R,6) [pitch 0..129, 5 duration bits] -> compact uint8 (R,2) [pitch, bits b0..b4 as 0b000b0b1b2b3b4]:
+// what leaves the device after a decode (2 bytes per note instead of the 48 of the reference's int64 est_x,
+// ptvae.py:537-544).  One thread per note; a warp reads 768 contiguous bytes and writes 64.
+__global__ void pack_tokens_kernel(const int* __restrict__ tok, long R, uint8_t* __restrict__ out) {
+    long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int* t = tok + r * TOK_W;
+    int bits = 0;
+#pragma unroll
+    for (int b = 0; b < 5; ++b) bits = (bits << 1) | (t[1 + b] & 1);
+    out[r * 2] = (uint8_t)t[0];
+    out[r * 2 + 1] = (uint8_t)bits;
+}
+
 // ---- batch augmentation on device (dataset.py:67-120): transpose a segment by `shift` semitones -----------------
 // pr_mat (B,32,128): np.roll along the pitch axis (converter.py:65-68; wraps around like np.roll).  The roll commutes
 // with piano_roll_to_target (converter.py:87-113), which works column by column, so rolling pr_mat equals rolling
@@ -426,5 +440,11 @@ PD_API int pd_slerp_path(const float* z1, const float* z2, int B, int D, int cou
     if (B <= 0 || count <= 0) return 0;
     if (D <= 0) return PD_BAD_ARG;
     slerp_path_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(z1, z2, D, count, out);
+    return pd_launch_status();
+}
+
+PD_API int pd_pack_tokens(const int* tok, long R, unsigned char* out, void* stream) {
+    if (R <= 0) return 0;
+    pack_tokens_kernel<<<pd_blocks(R, 256), 256, 0, (cudaStream_t)stream>>>(tok, R, out);
     return pd_launch_status();
 }

@@ -181,9 +181,11 @@ class GraphedDecode:
     decode -> int tokens on device (``model.swap`` / ``inference(sample=False)`` semantics, model.py:133-149).
     One segment batch = ~5,600 kernel launches captured once; replays take one launch each."""
 
-    def __init__(self, model, batch, warmup=1):
+    def __init__(self, model, batch, warmup=1, pack=False):
+        """``pack``: the graph also packs the tokens to the compact 2-byte device->host format (``self.packed``,
+        uint8 (B,32,15,2), ``ops.pack_tokens``)."""
         dev = next(model.parameters()).device
-        self.model = model
+        self.model, self.pack, self.packed = model, pack, None
         self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
         self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
         self.tokens, self.graph, self._warm = None, None, warmup
@@ -194,7 +196,10 @@ class GraphedDecode:
         m.eval()
         with torch.no_grad(), ops.precision(m.decode_precision):
             dc, dr = ops.fork_join([lambda: m.chd_encoder(self.c), lambda: m.rhy_encoder(self.pr)])
-            return m.decoder.greedy_tokens(torch.cat([dc.mean, dr.mean], -1))
+            tok = m.decoder.greedy_tokens(torch.cat([dc.mean, dr.mean], -1))
+            if self.pack:
+                self.packed = ops.pack_tokens(tok)
+            return tok
 
     def capture(self, pr_mat, c):
         self.pr.copy_(pr_mat); self.c.copy_(c)

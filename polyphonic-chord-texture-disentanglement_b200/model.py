@@ -164,7 +164,9 @@ class DisentangleVAE(PytorchModel):
             return self.decoder.greedy_tokens(torch.cat([z_chd, z_rhy], dim=-1))
 
     def inference_decode(self, z_chd, z_rhy):
-        return self.decode_tokens(z_chd, z_rhy).cpu().numpy().astype(np.int64)
+        """-> est_x (B,32,15,6) int64 ndarray (model.py:124-131).  The tokens cross PCIe as 2 bytes per note
+        (``ops.pack_tokens``) and are widened to the reference's int64 layout on the host."""
+        return ops.unpack_tokens(ops.pack_tokens(self.decode_tokens(z_chd, z_rhy)).cpu().numpy())
 
     def inference(self, pr_mat, c, sample, eps=None):
         self.eval()

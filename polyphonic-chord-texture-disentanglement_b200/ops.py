@@ -105,10 +105,12 @@ PRECISION = "tf32"
 # row-per-thread epilogue reads gi / gi2 / h_prev and writes h / r|z|n / hn as 64-byte pieces per lane.  Off until
 # the epilogue is staged through shared memory.
 FUSED_GRU_STEP = False
-# Second-generation fused step (persistent, 4-stage ring, two TMEM accumulators, all epilogue I/O as TMA boxes;
-# csrc/gru_step_tc.cu gru_step_tma_kernel).  EXPERIMENTAL: written when round 1 had no GPU time left -- it compiles and
-# has a guarded test (POLYDIS_TEST_EXPERIMENTAL=1) but has never run on hardware.  Do not enable before it passes.
-FUSED_GRU_STEP_TMA = False
+# Second-generation fused step (persistent, two TMEM accumulators, all epilogue I/O as TMA boxes, double-buffered
+# operand sets; csrc/gru_step_tc.cu gru_step_tma_kernel).  Validated on B200 in round 2: bit-level agreement with GEMM +
+# gate kernel (max |dh| 7e-7) and 108 vs 147 us on the note-GRU step (16384 x 512); equal or slower on the 512-row
+# recurrences (31.5 vs 29.5 us), hence the row threshold.
+FUSED_GRU_STEP_TMA = True
+FUSED_GRU_STEP_TMA_MIN_ROWS = 4096
 _lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
 TF32X3_MIN_ROWS = 512   # smaller 3xTF32 GEMMs are launch-latency bound: they run on the single-launch FFMA kernel
 
@@ -470,7 +472,8 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
         save["rzn"], save["hn"] = rzn, hn
     order = list(range(T - 1, -1, -1) if reverse else range(T))
     # fused step (recurrent GEMM + gate math in one tcgen05 kernel) whenever TMA can address the operands
-    fused_ok = ((FUSED_GRU_STEP or (FUSED_GRU_STEP_TMA and lengths is None)) and PRECISION == "tf32" and H % 64 == 0
+    fused_ok = ((FUSED_GRU_STEP or (FUSED_GRU_STEP_TMA and lengths is None and B >= FUSED_GRU_STEP_TMA_MIN_ROWS))
+                and PRECISION == "tf32" and H % 64 == 0
                 and w_hh.stride(1) == 1
                 and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0 and b_hh.data_ptr() % 16 == 0
                 and gi.stride(2) == 1 and gi.stride(0) % 4 == 0 and gi.stride(1) % 4 == 0 and gi.data_ptr() % 16 == 0
@@ -522,7 +525,7 @@ def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fuse
     for t in order:
         if (fused_ok and hprev is not None and hprev.stride(1) == 1 and hprev.stride(0) % 4 == 0
                 and hprev.data_ptr() % 16 == 0):
-            if FUSED_GRU_STEP_TMA and lengths is None:
+            if FUSED_GRU_STEP_TMA and lengths is None and B >= FUSED_GRU_STEP_TMA_MIN_ROWS:
                 _call("pd_gru_step_tma", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(b_hh),
                       _ptr(gi[:, t]), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
                       _ptr(h_all[:, t]), h_all.stride(0), None if rzn is None else _ptr(rzn[:, t]),
@@ -687,6 +690,26 @@ def pr_mat_to_grid(pr_mat):
     overflow = torch.zeros(1, device=pr.device, dtype=torch.int32)
     _call("pd_prmat_to_grid", _ptr(pr), B * 32, _ptr(x), _ptr(overflow), _stream())
     return x, overflow
+
+
+def pack_tokens(tokens):
+    """Decoded tokens (...,6) int32 -> compact (...,2) uint8 [pitch, 5 duration bits packed MSB-first] on the device."""
+    tok = _chk(tokens, "tokens").contiguous()
+    R = tok.numel() // 6
+    out = torch.empty(tuple(tok.shape[:-1]) + (2,), device=tok.device, dtype=torch.uint8)
+    _call("pd_pack_tokens", _ptr(tok), R, _ptr(out), _stream())
+    return out
+
+
+def unpack_tokens(packed):
+    """Host-side inverse of ``pack_tokens``: uint8 ndarray (...,2) -> int64 ndarray (...,6), the reference's est_x layout."""
+    import numpy as np
+    packed = np.asarray(packed)
+    out = np.empty(packed.shape[:-1] + (6,), dtype=np.int64)
+    out[..., 0] = packed[..., 0]
+    for b in range(5):
+        out[..., 1 + b] = (packed[..., 1] >> (4 - b)) & 1
+    return out
 
 
 def augment_batch(pr_mat, chord14, shift):

@@ -255,6 +255,12 @@ class CpuBackend:
                 X[s, 1 + i] = [p] + [(d >> (4 - b)) & 1 for b in range(5)]
             X[s, len(ps) + 1, 0] = 129
 
+    def pd_pack_tokens(self, tok, R, out, st):
+        T = _arr(tok, (R, 6), (6, 1), np.int32)
+        O = _arr(out, (R, 2), (2, 1), np.uint8)
+        O[:, 0] = T[:, 0].astype(np.uint8)
+        O[:, 1] = sum((T[:, 1 + b] & 1) << (4 - b) for b in range(5)).astype(np.uint8)
+
     def pd_roll_prmat(self, pr_in, shift, B, pr_out, st):
         P = _arr(pr_in, (B, 32, 128), (4096, 128, 1))
         O = _arr(pr_out, (B, 32, 128), (4096, 128, 1))

@@ -29,9 +29,10 @@ for (B, T, H, bc) in [(16384, 15, 512, True), (512, 32, 1024, True), (16384, 16,
         ops.gemm_nt(h_all[:, 2], w, gh, b)
         ops._gates_fwd(gi[:, 3], gi2, gh, h_all[:, 2], h_all[:, 3], rzn[:, 3], hn[:, 3], None, 3)
     line = f"B={B} H={H}: fused {t(fused):7.1f} us   gemm+gates {t(split):7.1f} us"
-    if os.environ.get("POLYDIS_TEST_EXPERIMENTAL"):
-        split(); ref = h_all[:, 3].clone(); ref_rzn = rzn[:, 3].clone()
+    split(); ref = h_all[:, 3].clone(); ref_rzn = rzn[:, 3].clone()
+    for variant in (1, 0):
+        ops._lib.lib.pd_gru_step_tma_variant(variant)
         h_all[:, 3].zero_(); fused_tma(); torch.cuda.synchronize()
         err = float((h_all[:, 3] - ref).abs().max()); err_s = float((rzn[:, 3] - ref_rzn).abs().max())
-        line += f"   fused-TMA {t(fused_tma):7.1f} us (max |dh| {err:.2e}, |d rzn| {err_s:.2e} vs gemm+gates)"
+        line += f"   fused-TMA v{variant} {t(fused_tma):7.1f} us (max |dh| {err:.2e}, |d rzn| {err_s:.2e})"
     print(line, flush=True)

@@ -1,0 +1,57 @@
+"""Round 2: launch the timed variants of the step's dominant kernels once each at the batch-512 shapes, for
+`ncu --set full --profile-from-start off` (cudaProfilerStart/Stop bracket the second repetition).
+
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r02_kernels \
+        python tools/profile_kernels_r02.py
+"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from polydis_b200 import ops
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+R, H, T = 16384, 512, 15
+h = torch.randn(R, T + 1, H, device=dev) * 0.3
+W = torch.randn(3 * H, H, device=dev) * 0.03
+b = torch.randn(3 * H, device=dev) * 0.1
+gh = torch.empty(R, 3 * H, device=dev)
+gi = torch.randn(R, T + 1, 3 * H, device=dev)
+gi2 = torch.randn(R, 3 * H, device=dev)
+rzn = torch.empty(R, T, 3 * H, device=dev)
+hn = torch.empty(R, T, H, device=dev)
+dgi = torch.empty(R, T, 3 * H, device=dev)
+dgh = torch.randn(R, T, 3 * H, device=dev)
+dh = torch.empty(R, H, device=dev)
+dz = torch.randn(R, H, device=dev)
+dm = torch.randn(R, H, device=dev)
+nz = torch.empty(R, H, device=dev)
+dout = torch.randn(R, T, H, device=dev)
+dW = torch.empty(3 * H, H, device=dev)
+Q = R * T
+h0 = torch.randn(Q, 64, device=dev)
+par = [torch.randn(192, 5, device=dev) * 0.3, torch.randn(192, device=dev) * 0.1, torch.randn(192, 64, device=dev) * 0.2,
+       torch.randn(192, device=dev) * 0.1, torch.rand(5, device=dev), torch.randn(2, 64, device=dev) * 0.3,
+       torch.randn(2, device=dev) * 0.1]
+lg = torch.empty(Q, 5, 2, device=dev); S = torch.empty(Q, 6, 72, device=dev); GX = torch.empty(Q, 6, 264, device=dev)
+dh0 = torch.empty(Q, 64, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+P = lambda t: t.data_ptr()
+for rep in range(2):
+    if rep == 1:
+        torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStart()
+    # fused note-GRU step (forward): tcgen05 recurrent GEMM + gate math, TMA epilogue I/O
+    ops._call("pd_gru_step_tma", P(h[:, 2]), h.stride(0), P(W), H, P(b), P(gi[:, 3]), gi.stride(0), P(gi2), 3 * H,
+              P(h[:, 3]), h.stride(0), P(rzn[:, 3]), rzn.stride(0), P(hn[:, 3]), hn.stride(0), R, H, st)
+    # unfused route of the same step: persistent TMA-store GEMM + gate kernel
+    ops.gemm_nt(h[:, 2], W, gh, b)
+    ops._gates_fwd(gi[:, 3], gi2, gh, h[:, 2], h[:, 3], rzn[:, 3], hn[:, 3], None, 3)
+    # backward of a note-GRU step: gate gradients, dgh . W_hh, and the sequence's split-K weight gradient
+    ops._call("pd_gru_gates_bwd", P(dz), H, P(dout[:, 3]), dout.stride(0), P(dm), H, P(rzn[:, 3]), rzn.stride(0),
+              P(hn[:, 3]), hn.stride(0), P(h[:, 2]), h.stride(0), P(dgi[:, 3]), dgi.stride(0), P(dgh[:, 3]), dgh.stride(0),
+              P(nz), H, None, 0, None, 3, R, H, st)
+    ops.gemm_nn(dgh[:, 3], W, dh)
+    ops.gemm_tn(dgh.view(R * T, 3 * H), h[:, :T].reshape(R * T, H), dW)
+    # duration decoder, TF32 warp-autonomous kernels (training mode)
+    ops._call("pd_dur_decode_fwd", P(h0), 64, Q, *[P(p) for p in par], P(lg), P(S), 1, st)
+    ops._call("pd_dur_decode_bwd", P(S), P(lg), Q, *[P(p) for p in par], P(GX), P(dh0), 64, 1, st)
+torch.cuda.synchronize(); torch.cuda.cudart().cudaProfilerStop()
