@@ -92,6 +92,27 @@ int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, 
                     long ldhn, int B, int H, void* stream);
 int pd_gru_step_tma_variant(int variant);
 
+/* Whole greedy PianoTree decode (ptvae.py:430-491 with inference=True: 32 time steps x 15 note slots x 5 duration
+ * steps, argmax feedback) of B <= 16 segments in ONE cooperative persistent launch: one CTA per SM stays resident, the
+ * dependency chain advances through grid barriers in L2, note-GRU / head / summary-GRU weights stay in shared memory.
+ * fp32 FFMA arithmetic (token parity with the fp32 reference).  h_time0 (B,1024) = z2dec_hid(z); gi_z (B,3072) =
+ * time-GRU projection of z_in incl. b_ih; weights are the state-dict tensors (wt_tok = dec_time_gru.weight_ih[:, :256]
+ * with row stride ld_wt, wn_sum / wn_tok = dec_notes_gru.weight_ih[:, :1024] / [:, 1024:] with row stride ld_wn);
+ * w_heads (194,512) = [pitch_out_linear | folded dur_hid_linear]; emb_wt (135,128) = note_embedding.weight^T;
+ * we_* / be_* = dec_notes_emb_gru forward / reverse.  tokens (32,15,B,6) int32; lens_out (32,B) int32 or NULL;
+ * ws: PD_GREEDY_SMALL_WS_FLOATS floats of scratch; bar: 2 x uint32 scratch (bar[1] != 0 afterwards = a grid barrier
+ * timed out).  PD_BAD_ARG for B > 16 or when the device cannot co-schedule one CTA per SM. */
+#define PD_GREEDY_SMALL_WS_FLOATS 310368
+int pd_greedy_decode_small(int B, const float* h_time0, const float* gi_z, const float* wt_tok, long ld_wt,
+                           const float* wt_hh, const float* bt_hh, const float* init_tok, const float* w_t2n,
+                           const float* b_t2n, const float* wn_sum, long ld_wn, const float* bn_ih, const float* wn_tok,
+                           const float* wn_hh, const float* bn_hh, const float* w_heads, const float* b_heads,
+                           const float* d_wih, const float* d_bih, const float* d_whh, const float* d_bhh,
+                           const float* d_sos, const float* d_wout, const float* d_bout, const float* emb_wt,
+                           const float* emb_b, const float* we_ih_f, const float* we_hh_f, const float* be_ih_f,
+                           const float* be_hh_f, const float* we_ih_b, const float* we_hh_b, const float* be_ih_b,
+                           const float* be_hh_b, int* tokens, int* lens_out, float* ws, unsigned* bar, void* stream);
+
 /* weight-resident variable-length GRU, hidden 128 (the note-summary bi-GRU, ptvae.py:446-453,:480-486): one kernel
  * runs the whole recurrence of a tile of sequences with W_hh resident in shared memory and stops at the tile's
  * longest sequence.  gi (R,T,384) incl. b_ih, lengths (R), h0 = 0; rows past their length carry their state.

@@ -30,6 +30,7 @@ SIGNATURES = {
     "pd_gru_step_tma_variant": [_I],
     "pd_gru128_fwd": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P],
     "pd_gru128_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P],
+    "pd_greedy_decode_small": [_I] + [_P] * 3 + [_L] + [_P] * 6 + [_L] + [_P] * 27 + [_P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],
     "pd_prmat_to_grid": [_P, _L, _P, _P, _P],
     "pd_grid_to_prmat": [_P, _L, _P, _P],
@@ -81,6 +82,7 @@ def _load():
 
 
 lib = _load()
+GREEDY_SMALL_WS_FLOATS = 310368      # PD_GREEDY_SMALL_WS_FLOATS of include/polydis_b200.h
 
 #: incremented on every kernel-launching library call (bench.py reports it as ``gpu_launches``)
 call_count = 0

@@ -189,6 +189,7 @@ class GraphedDecode:
         self.c = torch.zeros(batch, 8, 36, device=dev, dtype=torch.float32)
         self.pr = torch.zeros(batch, 32, 128, device=dev, dtype=torch.float32)
         self.tokens, self.graph, self._warm = None, None, warmup
+        self.eager, self.capture_error = False, None
 
     def _run(self):
         from . import ops
@@ -213,16 +214,24 @@ class GraphedDecode:
         from . import ops
         ops._lo_cache.clear()           # weight low parts ("tf32x3") must be (re)computed INSIDE the graph
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        try:
+            with torch.cuda.graph(self.graph):
+                self.tokens = self._run()
+        except RuntimeError as e:       # e.g. a launch type the driver cannot capture: replay eagerly instead
+            self.graph, self.eager, self.capture_error = None, True, repr(e)
+            torch.cuda.synchronize()
             self.tokens = self._run()
         ops._lo_cache.clear()
         return self
 
     def __call__(self, pr_mat, c):
         """-> (B,32,15,6) int32 tokens on device (static buffer, overwritten by the next call)."""
-        if self.graph is None:
+        if self.graph is None and not self.eager:
             self.capture(pr_mat, c)
         self.pr.copy_(pr_mat, non_blocking=True)
         self.c.copy_(c, non_blocking=True)
-        self.graph.replay()
+        if self.eager:
+            self.tokens = self._run()
+        else:
+            self.graph.replay()
         return self.tokens

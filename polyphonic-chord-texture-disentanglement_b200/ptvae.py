@@ -364,7 +364,8 @@ class PtvaeDecoder(nn.Module):
                 # free-running: the dedicated greedy schedule (fixed buffers, 7 launches per note slot); the first
                 # slot of every step is the SOS token in the data grid as well (ptvae.py:437-439)
                 lens_tb = torch.empty(T, B, device=z.device, dtype=torch.int32)
-                tokens = self._greedy_fast(z.detach(), lens_out=lens_tb)
+                greedy = self._greedy_small if B <= self.persistent_max_batch else self._greedy_fast
+                tokens = greedy(z.detach(), lens_out=lens_tb)
                 self._last_tokens = tokens
                 plen32 = lens_tb.t().reshape(-1)                                     # (R,) in (b, t) order
             else:
@@ -527,7 +528,58 @@ class PtvaeDecoder(nn.Module):
         CUDA graph (``graphs.GraphedDecode``)."""
         self._draw_plan(0., 0.)                        # consume python's random like the reference
         with torch.no_grad():
+            if z.size(0) <= self.persistent_max_batch:
+                return self._greedy_small(z).permute(2, 0, 1, 3).contiguous()
             return self._greedy_fast(z).permute(2, 0, 1, 3).contiguous()
+
+    #: Batches up to this size decode through the persistent cooperative kernel (csrc/greedy_persistent.cu: the whole
+    #: 32 x 15 x 5 loop nest in one launch per 16 segments, fp32 arithmetic) instead of ~5,400 dependent launches.
+    #: 0 disables it.
+    persistent_max_batch = 64
+
+    def _greedy_small(self, z, lens_out=None):
+        """Small-batch greedy decode: per chunk of <= 16 segments ONE persistent kernel (``pd_greedy_decode_small``).
+        Returns tokens (T, 15, B, 6) int32 like ``_greedy_fast``."""
+        B, dev = z.size(0), z.device
+        T, NS = self.num_step, self.max_simu_note
+        wt_ih, wt_hh, bt_ih, bt_hh = self.dec_time_gru.dir()
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        with ops.precision("fp32"):                    # the few per-decode projections run on the fp32 FFMA GEMM as well
+            h_time0 = self.z2dec_hid_linear(z).contiguous()
+            gi_z = ops.linear(self.z2dec_in_linear(z), wt_ih[:, 2 * self.dec_emb_hid_size:], bt_ih).contiguous()
+            w_eff, b_eff = self._dur_hid_folded()
+        w_heads = torch.cat([self.pitch_out_linear.weight, w_eff], 0).contiguous()
+        b_heads = torch.cat([self.pitch_out_linear.bias, b_eff], 0).contiguous()
+        emb_wt = ops.transpose(self.note_embedding.weight)
+        d_ih, d_hh, db_ih, db_hh = self.dec_dur_gru.dir()
+        eg = self.dec_notes_emb_gru
+        consts = [t.contiguous() for t in (
+            wt_hh, bt_hh, self.dec_init_input, self.dec_time_to_notes_hid.weight, self.dec_time_to_notes_hid.bias)]
+        tail = [t.contiguous() for t in (
+            bn_ih, wn_hh, bn_hh, w_heads, b_heads, d_ih, db_ih, d_hh, db_hh, self.dur_sos_token,
+            self.dur_out_linear.weight, self.dur_out_linear.bias, emb_wt, self.note_embedding.bias)]
+        egw = []
+        for rev in (False, True):
+            w_ih, w_hh, b_ih, b_hh = eg.dir(rev)
+            egw += [w_ih.contiguous(), w_hh.contiguous(), b_ih.contiguous(), b_hh.contiguous()]
+        wt_ih_c, wn_ih_c = wt_ih.contiguous(), wn_ih.contiguous()
+        ws = torch.empty(ops._lib.GREEDY_SMALL_WS_FLOATS, device=dev, dtype=torch.float32)
+        bar = torch.zeros(2, device=dev, dtype=torch.int32)
+        chunks = []
+        P = ops._ptr
+        for b0 in range(0, B, 16):
+            nb = min(16, B - b0)
+            tok = torch.empty(T, NS - 1, nb, 6, device=dev, dtype=torch.int32)
+            lo = torch.empty(T, nb, device=dev, dtype=torch.int32) if lens_out is not None else None
+            ops._call("pd_greedy_decode_small", nb, P(h_time0[b0:b0 + nb]), P(gi_z[b0:b0 + nb]), P(wt_ih_c), wt_ih_c.stride(0),
+                      P(consts[0]), P(consts[1]), P(consts[2]), P(consts[3]), P(consts[4]),
+                      P(wn_ih_c), wn_ih_c.stride(0), P(tail[0]), P(wn_ih_c[:, self.dec_time_hid_size:]),
+                      *[P(t) for t in tail[1:]], *[P(t) for t in egw], P(tok), P(lo), P(ws), P(bar), ops._stream())
+            if lo is not None:
+                lens_out[:, b0:b0 + nb].copy_(lo)
+            chunks.append(tok)
+        self._persistent_bar = bar                     # bar[1] != 0: a grid barrier timed out (checked by tests)
+        return chunks[0] if len(chunks) == 1 else torch.cat(chunks, 2)
 
     def _greedy_fast(self, z, lens_out=None):
         """``lens_out`` (T,B) int32, optional: receives the predicted note count of every time step."""

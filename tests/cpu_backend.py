@@ -255,6 +255,83 @@ class CpuBackend:
                 X[s, 1 + i] = [p] + [(d >> (4 - b)) & 1 for b in range(5)]
             X[s, len(ps) + 1, 0] = 129
 
+    def pd_greedy_decode_small(self, B, h_time0, gi_z, wt_tok, ld_wt, wt_hh, bt_hh, init_tok, w_t2n, b_t2n, wn_sum, ld_wn,
+                               bn_ih, wn_tok, wn_hh, bn_hh, w_heads, b_heads, d_wih, d_bih, d_whh, d_bhh, d_sos, d_wout,
+                               d_bout, emb_wt, emb_b, we_ih_f, we_hh_f, be_ih_f, be_hh_f, we_ih_b, we_hh_b, be_ih_b, be_hh_b,
+                               tokens, lens_out, ws, bar, st):
+        """numpy restatement of the persistent small-batch greedy decode (ptvae.py:430-491, inference=True)."""
+        f = np.float32
+        A = lambda ptr, shape, strides=None: _arr(ptr, shape, strides or tuple(
+            int(np.prod(shape[i + 1:])) for i in range(len(shape))))
+        h_time = A(h_time0, (B, 1024)).copy()
+        giz = A(gi_z, (B, 3072))
+        Wtt, Wth, bth = A(wt_tok, (3072, 256), (ld_wt, 1)), A(wt_hh, (3072, 1024)), A(bt_hh, (3072,))
+        Wt2n, bt2n = A(w_t2n, (512, 1024)), A(b_t2n, (512,))
+        Wns, bni = A(wn_sum, (1536, 1024), (ld_wn, 1)), A(bn_ih, (1536,))
+        Wnt, Wnh, bnh = A(wn_tok, (1536, 128), (ld_wn, 1)), A(wn_hh, (1536, 512)), A(bn_hh, (1536,))
+        Wh, bh = A(w_heads, (194, 512)), A(b_heads, (194,))
+        Dwi, Dbi, Dwh, Dbh = A(d_wih, (192, 5)), A(d_bih, (192,)), A(d_whh, (192, 64)), A(d_bhh, (192,))
+        Dsos, Dwo, Dbo = A(d_sos, (5,)), A(d_wout, (2, 64)), A(d_bout, (2,))
+        WT, eb = A(emb_wt, (135, 128)), A(emb_b, (128,))
+        eg = [(A(we_ih_f, (384, 128)), A(we_hh_f, (384, 128)), A(be_ih_f, (384,)), A(be_hh_f, (384,))),
+              (A(we_ih_b, (384, 128)), A(we_hh_b, (384, 128)), A(be_ih_b, (384,)), A(be_hh_b, (384,)))]
+        TOK = _arr(tokens, (32, 15, B, 6), (15 * B * 6, B * 6, 6, 1), np.int32)
+        LO = _arr(lens_out, (32, B), (B, 1), np.int32) if lens_out is not None else None
+
+        def cell(gi, gh, h, H):
+            r = _sig(gi[:, :H] + gh[:, :H])
+            z = _sig(gi[:, H:2 * H] + gh[:, H:2 * H])
+            n = np.tanh(gi[:, 2 * H:] + r * gh[:, 2 * H:], dtype=f)
+            return ((1 - z) * n + z * h).astype(f)
+
+        def embed(tok):                                             # tok (B,6) int
+            e = np.tile(eb, (B, 1)).astype(f)
+            for b in range(B):
+                if 0 <= tok[b, 0] < 130:
+                    e[b] += WT[tok[b, 0]]
+                for k in range(5):
+                    e[b] += f(tok[b, 1 + k]) * WT[130 + k]
+            return e
+        tok_time = np.tile(A(init_tok, (256,)), (B, 1)).astype(f)
+        sos = np.tile(np.array([128, 2, 2, 2, 2, 2]), (B, 1))
+        for t in range(32):
+            h_time = cell(tok_time @ Wtt.T + giz, h_time @ Wth.T + bth, h_time, 1024)
+            h_n = (h_time @ Wt2n.T + bt2n).astype(f)
+            gi_s = (h_time @ Wns.T + bni).astype(f)
+            pred = np.zeros((B, 16, 128), f)
+            pred[:, 0] = embed(sos)
+            lens = np.zeros(B, np.int64)
+            for n in range(1, 16):
+                h_n = cell(pred[:, n - 1] @ Wnt.T + gi_s, h_n @ Wnh.T + bnh, h_n, 512)
+                heads = (h_n @ Wh.T + bh).astype(f)
+                tk = np.zeros((B, 6), np.int64)
+                tk[:, 0] = heads[:, :130].argmax(-1)
+                hd = heads[:, 130:].copy()
+                gi_d = np.tile(Dwi @ Dsos + Dbi, (B, 1)).astype(f)
+                for k in range(5):
+                    hd = cell(gi_d, hd @ Dwh.T + Dbh, hd, 64)
+                    lg = hd @ Dwo.T + Dbo
+                    bit = (lg[:, 1] > lg[:, 0]).astype(np.int64)
+                    tk[:, 1 + k] = bit
+                    gi_d = (Dwi[:, bit].T + Dbi).astype(f)           # one-hot at index == bit value (ptvae.py:322-326)
+                TOK[t, n - 1] = tk
+                lens = np.where((lens == 0) & (tk[:, 0] == 129), n, lens)
+                pred[:, n] = embed(tk)
+            lens = np.where(lens == 0, 15, lens)
+            if LO is not None:
+                LO[t] = lens
+            if t == 31:
+                break
+            out = np.zeros((B, 256), f)
+            for d, (wi, wh, bi, bhh) in enumerate(eg):
+                for b in range(B):
+                    h = np.zeros((1, 128), f)
+                    order = range(lens[b] - 1, -1, -1) if d else range(lens[b])
+                    for k in order:
+                        h = cell((pred[b, k] @ wi.T + bi)[None], h @ wh.T + bhh, h, 128)
+                    out[b, d * 128:(d + 1) * 128] = h[0]
+            tok_time = out
+
     def pd_pack_tokens(self, tok, R, out, st):
         T = _arr(tok, (R, 6), (6, 1), np.int32)
         O = _arr(out, (R, 2), (2, 1), np.uint8)

@@ -113,8 +113,10 @@ def test_greedy_tokens_match_reference_golden(golden_dir, tag, prec):
     assert match >= 0.999, match
 
 
-@pytest.mark.parametrize("prec", ["fp32", "tf32x3"])
-def test_greedy_tokens_match_oracle_larger_batch(prec):
+@pytest.mark.parametrize("prec,persistent", [("fp32", False), ("tf32x3", False), ("tf32x3", True)])
+def test_greedy_tokens_match_oracle_larger_batch(prec, persistent):
+    """48 segments: through the step-wise schedule (7 launches per note slot) and through the persistent cooperative
+    kernel (3 launches of <= 16 segments, csrc/greedy_persistent.cu)."""
     dev = _dev()
     from oracle import polydis_oracle as O
     B = 48
@@ -123,11 +125,42 @@ def test_greedy_tokens_match_oracle_larger_batch(prec):
     ref = O.inference(sd, prs, cs)
     m = _model(dev, 5, 2.0, 0.75)
     m.decode_precision = prec
+    m.decoder.persistent_max_batch = 64 if persistent else 0
     est = m.swap(prs.to(dev), prs.to(dev), cs.to(dev), cs.to(dev), True, True)
     match = (est == ref).mean()
     pre = ref[..., 0] != 129
     assert match >= 0.999, match
     assert (est[pre] == ref[pre]).mean() >= 0.999
+    if persistent:
+        assert int(m.decoder._persistent_bar[1]) == 0          # no grid barrier timed out
+
+
+def test_persistent_decode_sixteen_segments_and_latency():
+    """BASELINE configs[4] per-GPU share (16 segments): the persistent kernel's tokens against the oracle, and its
+    latency against the step-wise schedule it replaces."""
+    dev = _dev()
+    import time
+    from oracle import polydis_oracle as O
+    B = 16
+    _, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 901))
+    sd = make_state_dict(7, gain=2.0, eos_bias=0.75)
+    ref = O.inference(sd, prs, cs)
+    m = _model(dev, 7, 2.0, 0.75)
+    pr, c = prs.to(dev), cs.to(dev)
+    times = {}
+    for persistent in (True, False):
+        m.decoder.persistent_max_batch = 64 if persistent else 0
+        est = m.inference(pr, c, sample=False)
+        assert (est == ref).mean() >= 0.999, (persistent, (est == ref).mean())
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            m.inference(pr, c, sample=False)
+        torch.cuda.synchronize()
+        times[persistent] = (time.perf_counter() - t0) / 3
+    assert int(m.decoder._persistent_bar[1]) == 0
+    print(f"16-segment decode (eager, host-timed): persistent {1e3 * times[True]:.2f} ms, step-wise {1e3 * times[False]:.2f} ms")
+    assert times[True] < times[False]
 
 
 @pytest.mark.parametrize("B", [1, 130])

@@ -30,7 +30,7 @@ for (B, T, H, bc) in [(16384, 15, 512, True), (512, 32, 1024, True), (16384, 16,
         ops._gates_fwd(gi[:, 3], gi2, gh, h_all[:, 2], h_all[:, 3], rzn[:, 3], hn[:, 3], None, 3)
     line = f"B={B} H={H}: fused {t(fused):7.1f} us   gemm+gates {t(split):7.1f} us"
     split(); ref = h_all[:, 3].clone(); ref_rzn = rzn[:, 3].clone()
-    for variant in (1, 0):
+    for variant in (1, 2, 0):
         ops._lib.lib.pd_gru_step_tma_variant(variant)
         h_all[:, 3].zero_(); fused_tma(); torch.cuda.synchronize()
         err = float((h_all[:, 3] - ref).abs().max()); err_s = float((rzn[:, 3] - ref_rzn).abs().max())
