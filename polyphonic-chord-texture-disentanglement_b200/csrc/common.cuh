@@ -16,7 +16,26 @@ static inline int pd_launch_status() {
 
 static inline unsigned pd_blocks(long n, int per) { return (unsigned)((n + per - 1) / per); }
 
-#define PD_NUM_SMS 148
+// SM count of the CURRENT device (cached per device; grids are sized from it, nothing is compiled in)
+static inline int pd_num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& c = cache[dev & 63];
+    if (c == 0 && (cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c <= 0)) c = 148;
+    return c;
+}
+#define PD_NUM_SMS pd_num_sms()
+
+// cudaFuncSetAttribute is per DEVICE: true the first time a kernel's launcher runs on the current device
+static inline bool pd_first_use_on_device(unsigned long long& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
 
 __device__ __forceinline__ float pd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 // MUFU forms for the TF32-mode recurrent kernels, which are instruction-bound on the gate math: ex2.approx +

@@ -651,12 +651,11 @@ PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_
     if (tf32 == 3 && Q < 4096) tf32 = 0;
     if (tf32) {
         if (((uintptr_t)S & 15) || ((uintptr_t)h0 & 7) || (ldh0 & 1) || ((uintptr_t)logits & 7)) return PD_BAD_ARG;
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (pd_first_use_on_device(attr)) {
             cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_fwd_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM3);
             if (e != cudaSuccess) return (int)e;
-            attr = true;
         }
         if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM3, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
         else dur_fwd_warp_kernel<1><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
@@ -674,12 +673,11 @@ PD_API int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
     constexpr int smem_ff = (3 * RT * HS + RT * GS + 3 * RT * HS) * (int)sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(dur_bwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BW_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_ff);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     if (tf32) {
         if ((((uintptr_t)S | (uintptr_t)GX) & 15) || (((uintptr_t)dlogits | (uintptr_t)dh0) & 7) || (lddh0 & 1)) return PD_BAD_ARG;

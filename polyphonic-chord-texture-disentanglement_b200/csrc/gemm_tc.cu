@@ -434,12 +434,11 @@ __global__ void zero_2d_tc_kernel(float* C, long ldc, int M, int N) {
 template <int EB, int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const TcArgs& g, dim3 grid, cudaStream_t st) {
     constexpr int smem = STAGES * (MH * BM * 128 + BN * 128) + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<EB, MH, BN, STAGES, MINB, A_MN, B_MN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     gemm_tf32_kernel<EB, MH, BN, STAGES, MINB, A_MN, B_MN><<<grid, NUM_THREADS, smem, st>>>(ta, tb, g);
     return pd_launch_status();
@@ -457,12 +456,11 @@ template <int EB, int BN, int STAGES, bool A_MN, bool B_MN>
 int launch_p(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const TcArgs& g, int tiles_m, int tiles_n,
              int split, cudaStream_t st) {
     constexpr int smem = STAGES * (BM * 128 + BN * 128) + 4 * 2 * 4096 + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32_persistent<EB, BN, STAGES, A_MN, B_MN>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     long items = (long)tiles_m * tiles_n * split;
     int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);

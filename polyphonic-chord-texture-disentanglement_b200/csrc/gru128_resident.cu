@@ -362,12 +362,11 @@ PD_API int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths
         return PD_BAD_ARG;
     FwdArgs a{gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse};
     constexpr int smem = (G3 * WS + 2 * 16 * WS) * (int)sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(gru128_fwd_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(gru128_fwd_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     long tiles = (R + 15) / 16;
     unsigned grid = (unsigned)(tiles < PD_NUM_SMS ? tiles : PD_NUM_SMS);
@@ -385,11 +384,10 @@ PD_API int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all
     if (((uintptr_t)w_hh & 15) || (ptrs & 7) || ((dr | dt | hr | ht | zr | zt | nr | nt | gr | gt | qr | qt) & 1)) return PD_BAD_ARG;
     BwdArgs a{dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T, reverse};
     constexpr int smem = (G3 * H + 16 * GS) * (int)sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(gru128_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     long tiles = (R + 15) / 16;
     unsigned grid = (unsigned)(tiles < PD_NUM_SMS ? tiles : PD_NUM_SMS);

@@ -471,11 +471,10 @@ PD_API int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, lo
     dim3 grid((B + BM - 1) / BM, H / UN);
     constexpr int STAGES = 2;
     constexpr int smem = STAGES * (BM * 128 + BN3 * 128) + 1024 + 256;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
         cudaError_t e = cudaFuncSetAttribute(gru_step_tf32_kernel<STAGES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        attr = true;
     }
     gru_step_tf32_kernel<STAGES, 2><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, g);
     return pd_launch_status();
@@ -513,11 +512,10 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
 #define PD_STEP_LAUNCH(ST, NS, OB)                                                                                          \
     {                                                                                                                       \
         constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + (OB ? 4 * N_OUTB * IOB : 0) + 1024 + 256; \
-        static bool attr = false;                                                                                           \
-        if (!attr) {                                                                                                        \
+        static unsigned long long attr = 0;                                                                                           \
+        if (pd_first_use_on_device(attr)) {                                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                                            \
-            attr = true;                                                                                                    \
         }                                                                                                                   \
         gru_step_tma_kernel<ST, NS, OB><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, \
                                                                                            thn, g, tiles_m, tiles_u);       \

@@ -371,11 +371,10 @@ PD_API int pd_note_embed_fwd(const int* tok, long R, const float* WT, const floa
 PD_API int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias,
                              void* stream) {
     if (R <= 0) return 0;
-    static bool attr_set = false;
+    static unsigned long long attr_set = 0;
     const int smem = (NOTE_SIZE + 1) * EMB * (int)sizeof(float);
-    if (!attr_set) {
+    if (pd_first_use_on_device(attr_set)) {
         cudaFuncSetAttribute(note_embed_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr_set = true;
     }
     long ctas = 3 * PD_NUM_SMS;
     long rows_per = (R + ctas - 1) / ctas;
