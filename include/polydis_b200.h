@@ -91,6 +91,14 @@ int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, 
                     long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                     long ldhn, int B, int H, void* stream);
 int pd_gru_step_tma_variant(int variant);
+/* inference form of the fused step for the error-compensated 3xTF32 path (greedy decode of >= 512 segments,
+ * ptvae.py:396-398,:461-462 at inference): a3 (B,3H) = [hi | hi | lo] split of h_prev, w3 (3H,3H) = [hi | lo | hi] split
+ * of W_hh (pd_tf32_split3 orders 0 / 1) -- the three TF32 products accumulate in TMEM; gate math with expf / tanhf; the
+ * epilogue writes the new state hout (may alias hprev) and its [hi | hi | lo] split h3out (must not alias a3).  Replaces
+ * pd_gemm_tf32 over K = 3H + pd_gru_gates_fwd_split3 (the (B,3H) h-projection never reaches HBM). */
+int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ldw3, const float* b_hh, const float* gi, long ldgi,
+                     const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho, float* h3out,
+                     long ldh3, int B, int H, void* stream);
 
 /* Whole greedy PianoTree decode (ptvae.py:430-491 with inference=True: 32 time steps x 15 note slots x 5 duration
  * steps, argmax feedback) of B <= 16 segments in ONE cooperative persistent launch: one CTA per SM stays resident, the

@@ -198,6 +198,8 @@ struct StepIo {
     const float* b_hh;
     int has_gi2, has_rzn, has_hn;
     int B, H;
+    int KA;          // columns of the A operand: H (h_prev itself) or 3H ([hi | hi | lo] split of h_prev, 3xTF32 mode)
+    int has_h3;      // also emit the [hi | hi | lo] split of the new state (operand of the next step's / the heads' GEMMs)
 };
 
 constexpr int IOB = 2048;          // one epilogue buffer: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
@@ -220,13 +222,14 @@ __device__ __forceinline__ void io_write(uint8_t* buf, int lane, const float (&v
 
 constexpr int N_OUTB = 5;          // separate result buffers (OUTB variant): h' | r | z | n | W_hn h
 
-template <int STAGES, int NSETS, bool OUTB>
+// PRECISE: expf / tanhf gate math (the fp32-faithful greedy decode) instead of the MUFU forms (training)
+template <int STAGES, int NSETS, bool OUTB, bool PRECISE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
                     const __grid_constant__ CUtensorMap tmHp, const __grid_constant__ CUtensorMap tmHo,
-                    const __grid_constant__ CUtensorMap tmRzn, const __grid_constant__ CUtensorMap tmHn, StepIo g,
-                    int tiles_m, int tiles_u) {
+                    const __grid_constant__ CUtensorMap tmRzn, const __grid_constant__ CUtensorMap tmHn,
+                    const __grid_constant__ CUtensorMap tmH3, StepIo g, int tiles_m, int tiles_u) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = BM * 128, B_BYTES = BN3 * 128;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -242,7 +245,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_slot = (uint32_t*)(io_bar + 4 * NSETS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (g.H + 31) / 32;
+    const int nkb = (g.KA + 31) / 32;
     const long n_items = (long)tiles_m * tiles_u;
 
     if (warp == 0 && lane == 0) {
@@ -377,11 +380,20 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 add16(g.b_hh + col, ghr); add16(g.b_hh + H + col, ghz); add16(g.b_hh + 2 * H + col, ghn);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float r = pd_sigmoid_fast(ir[i] + ghr[i]);
-                    const float z = pd_sigmoid_fast(iz[i] + ghz[i]);
-                    const float n = pd_tanh_fast(in[i] + r * ghn[i]);
+                    const float r = PRECISE ? pd_sigmoid(ir[i] + ghr[i]) : pd_sigmoid_fast(ir[i] + ghr[i]);
+                    const float z = PRECISE ? pd_sigmoid(iz[i] + ghz[i]) : pd_sigmoid_fast(iz[i] + ghz[i]);
+                    const float n = PRECISE ? tanhf(in[i] + r * ghn[i]) : pd_tanh_fast(in[i] + r * ghn[i]);
                     hp[i] = (1.0f - z) * n + z * hp[i];
                     ir[i] = r; iz[i] = z; in[i] = n;
+                }
+                if (g.has_h3) {                                        // ir <- hi = rn_tf32(h'), iz <- lo = h' - hi
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        uint32_t b;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(hp[i]));
+                        ir[i] = __uint_as_float(b);
+                        iz[i] = hp[i] - ir[i];
+                    }
                 }
                 uint8_t* ob = OUTB ? io_out + q * (N_OUTB * IOB) : bufs;
                 uint8_t* o_h = OUTB ? ob : bufs + 6 * IOB;
@@ -395,6 +407,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 io_write(o_h, lane, hp);
                 if (g.has_rzn) { io_write(o_r, lane, ir); io_write(o_r + IOB, lane, iz); io_write(o_r + 2 * IOB, lane, in); }
                 if (g.has_hn) io_write(o_hn, lane, ghn);
+                if (g.has_h3) { io_write(o_r, lane, ir); io_write(o_r + IOB, lane, iz); }      // (never together with rzn)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) {
@@ -409,6 +422,12 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (g.has_hn)
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                                      ::"l"(&tmHn), "r"(smem_u32(o_hn)), "r"(col), "r"(row) : "memory");
+                    if (g.has_h3) {                                    // [hi | hi | lo] at column blocks 0, H, 2H
+#pragma unroll
+                        for (int part = 0; part < 3; ++part)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                         ::"l"(&tmH3), "r"(smem_u32(o_r + (part == 2 ? IOB : 0))), "r"(part * H + col), "r"(row) : "memory");
+                    }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     if (!OUTB && k + NSETS < n_chunks) {
                         // this set is reloaded for chunk k + NSETS once its stores have read the buffers; meanwhile the
@@ -502,7 +521,9 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H};
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0};
+    const CUtensorMap th3 = tho;
+    constexpr bool kPrecise = false;
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -514,17 +535,56 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
         constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + (OB ? 4 * N_OUTB * IOB : 0) + 1024 + 256; \
         static unsigned long long attr = 0;                                                                                           \
         if (pd_first_use_on_device(attr)) {                                                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB, kPrecise>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                                            \
         }                                                                                                                   \
-        gru_step_tma_kernel<ST, NS, OB><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, \
-                                                                                           thn, g, tiles_m, tiles_u);       \
+        gru_step_tma_kernel<ST, NS, OB, kPrecise><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, \
+                                                                                           trzn, thn, th3, g, tiles_m, tiles_u); \
         return pd_launch_status();                                                                                          \
     }
     if (g_step_variant == 1) PD_STEP_LAUNCH(4, 1, false)
     if (g_step_variant == 2) PD_STEP_LAUNCH(2, 2, false)
     PD_STEP_LAUNCH(3, 1, true)
 #undef PD_STEP_LAUNCH
+}
+
+// Inference form of the fused step for the error-compensated 3xTF32 path (greedy decode at >= 512 rows): the A operand
+// is the [hi | hi | lo] split of h_prev (a3: B x 3H), W3 the [hi | lo | hi] split of W_hh (3H x 3H), so the three TF32
+// products accumulate in TMEM (fp32-class h-projection); gate math with expf / tanhf; the epilogue writes the new state
+// (hout, may alias hprev) AND its [hi | hi | lo] split (h3out: B x 3H, must not alias a3) -- the operand of the next
+// step's and the heads' GEMMs.  Replaces pd_gemm_tf32 (K = 3H) + pd_gru_gates_fwd_split3 per note slot.
+PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ldw3, const float* b_hh, const float* gi,
+                            long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
+                            float* h3out, long ldh3, int B, int H, void* stream) {
+    if (B <= 0) return 0;
+    if (H % UN != 0 || a3 == nullptr || hprev == nullptr || h3out == nullptr || h3out == a3) return PD_BAD_ARG;
+    if (!al16(a3, lda3) || !al16(w3, ldw3) || !al16(gi, ldgi) || (gi2 && !al16(gi2, ldgi2)) || !al16(hprev, ldhp) ||
+        !al16(hout, ldho) || !al16(h3out, ldh3) || ((uintptr_t)b_hh & 15) || lda3 < 4 || ldw3 < 4)
+        return PD_BAD_ARG;
+    CUtensorMap ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3;
+    int rc = make_map(&ta, a3, 4, 3L * H, B, lda3, BM, false);
+    if (!rc) rc = make_map(&tb, w3, 4, 3L * H, 3L * H, ldw3, UN, false);
+    if (!rc) rc = make_map_io(&tgi, gi, 3L * H, B, ldgi);
+    if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
+    if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
+    if (!rc) rc = make_map_io(&th3, h3out, 3L * H, B, ldh3);
+    tgi2 = tgi; trzn = tho; thn = tho;
+    if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
+    if (rc) return rc;
+    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1};
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    const long items = (long)tiles_m * tiles_u;
+    const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    constexpr int ST = 3, NS = 1;
+    constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    gru_step_tma_kernel<ST, NS, true, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn,
+                                                                                              th3, g, tiles_m, tiles_u);
+    return pd_launch_status();
 }
 
 // tuning / A-B switch for pd_gru_step_tma (see the variants above)

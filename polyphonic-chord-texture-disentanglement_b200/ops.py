@@ -419,6 +419,31 @@ def gates_fwd_split3(gi, gi2, gh, h, h3):
           gh.stride(0), _ptr(h), h.stride(0), _ptr(h), h.stride(0), None, 0, B, H, _ptr(h3), h3.stride(0), _stream())
 
 
+# Greedy decode at >= 512 rows (tf32x3): recurrent 3xTF32 GEMM + gate math + split of the new state in ONE tcgen05 kernel
+# (pd_gru_step_tma3) instead of GEMM + pd_gru_gates_fwd_split3 -- the (B,3H) h-projection never goes to HBM.
+FUSED_DECODE_STEP = True
+
+
+def gru_step_split3(a3, w3, b_hh, gi, gi2, h, h3out):
+    """In-place inference GRU step on h (B,H): a3 = [hi|hi|lo] of h (as produced by the previous step), w3 = [hi|lo|hi] of
+    W_hh (``weight_split3``); writes the new h and its split into h3out (a different buffer than a3)."""
+    B, H = h.shape
+    _call("pd_gru_step_tma3", _ptr(a3), a3.stride(0), _ptr(w3), w3.stride(0), _ptr(b_hh), _ptr(gi), gi.stride(0),
+          _ptr(gi2), 0 if gi2 is None else gi2.stride(0), _ptr(h), h.stride(0), _ptr(h), h.stride(0), _ptr(h3out),
+          h3out.stride(0), B, H, _stream())
+
+
+def weight_split3(w):
+    """[hi | lo | hi] operand of a weight matrix for the 3xTF32 GEMMs (cached within the precision scope)."""
+    return _split3(w, 1, True)
+
+
+def fused_decode_step_ok(h, w_hh):
+    return (FUSED_DECODE_STEP and PRECISION == "tf32x3" and h.dim() == 2 and h.shape[0] >= TF32X3_MIN_ROWS
+            and h.shape[1] % 64 == 0 and w_hh.shape == (3 * h.shape[1], h.shape[1]) and h.stride(1) == 1
+            and h.stride(0) % 4 == 0 and h.data_ptr() % 16 == 0)
+
+
 def split3_applies(x):
     """Would ``split3_act(x)`` return an operand (3xTF32 tensor-core GEMM path) for this tensor?"""
     return (PRECISION == "tf32x3" and x.dim() == 2 and x.shape[0] >= TF32X3_MIN_ROWS and x.stride(1) == 1 and x.shape[1] >= 8

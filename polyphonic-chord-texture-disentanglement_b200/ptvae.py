@@ -626,13 +626,26 @@ class PtvaeDecoder(nn.Module):
         x3 = ops.split3_applies(h_time)
         t3 = torch.empty(B, 3 * Ht, **f32) if x3 else None
         n3 = torch.empty(B, 3 * Hn, **f32) if x3 else None
+        # fused recurrent step (3xTF32 GEMM + gates + split of the new state in one tcgen05 kernel): the operand split is
+        # ping-ponged between two buffers (a step reads the previous split while it writes the new one)
+        fuse_t = x3 and ops.fused_decode_step_ok(h_time, wt_hh)
+        fuse_n = x3 and ops.fused_decode_step_ok(h_n, wn_hh)
+        t3b = torch.empty(B, 3 * Ht, **f32) if fuse_t else None
+        n3b = torch.empty(B, 3 * Hn, **f32) if fuse_n else None
+        wt_hh3 = ops.weight_split3(wt_hh) if fuse_t else None
+        wn_hh3 = ops.weight_split3(wn_hh) if fuse_n else None
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
-            ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh, a3=t3 if t > 0 else None)
-            if x3:
-                ops.gates_fwd_split3(gi_t, gi_z, gh_t, h_time, t3)
+            if fuse_t:
+                a_t = ops.split3_act(h_time) if t == 0 else t3
+                ops.gru_step_split3(a_t, wt_hh3, bt_hh, gi_t, gi_z, h_time, t3b)
+                t3, t3b = t3b, t3
             else:
-                ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
+                ops.gemm_nt(h_time, wt_hh, gh_t, bt_hh, a3=t3 if t > 0 else None)
+                if x3:
+                    ops.gates_fwd_split3(gi_t, gi_z, gh_t, h_time, t3)
+                else:
+                    ops._gates_fwd(gi_t, gi_z, gh_t, h_time, h_time, None, None, None, 0)
             ops.gemm_nt(h_time, self.dec_time_to_notes_hid.weight, h_n, self.dec_time_to_notes_hid.bias, a3=t3)
             ops.gemm_nt(h_time, w_sum_n, gi_s, bn_ih, a3=t3)
             ops._call("pd_note_embed_fwd", ops._ptr(sos_tok), B, ops._ptr(emb_wt), ops._ptr(emb_b), ops._ptr(pred),
@@ -641,12 +654,17 @@ class PtvaeDecoder(nn.Module):
             a_n = ops.split3_act(h_n)
             for n in range(1, NS):
                 ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
-                ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)
-                if x3:                                 # n3 serves the heads now and the recurrent GEMM of the next slot
-                    ops.gates_fwd_split3(gi_n, gi_s, gh_n, h_n, n3)
-                    a_n = n3
+                if fuse_n:
+                    ops.gru_step_split3(a_n, wn_hh3, bn_hh, gi_n, gi_s, h_n, n3b)
+                    a_n = n3b
+                    n3, n3b = n3b, n3
                 else:
-                    ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
+                    ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)
+                    if x3:                             # n3 serves the heads now and the recurrent GEMM of the next slot
+                        ops.gates_fwd_split3(gi_n, gi_s, gh_n, h_n, n3)
+                        a_n = n3
+                    else:
+                        ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
                 ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads, a3=a_n)
                 ops._call("pd_dur_decode_fwd", ops._ptr(heads[:, self.pitch_range:]), heads.stride(0), B,
                           *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, ops.dur_mode(), st())

@@ -137,6 +137,14 @@ class CpuBackend:
     def pd_gru_step_tma(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, B, H, st):
         self.pd_gru_step_tf32(hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, None, 0, B, H, st)
 
+    def pd_gru_step_tma3(self, a3, lda3, w3, ldw3, b_hh, gi, ldgi, gi2, ldgi2, hp, ldhp, ho, ldho, h3, ldh3, B, H, st):
+        A = _arr(a3, (B, 3 * H), (lda3, 1)).astype(np.float64)
+        W = _arr(w3, (3 * H, 3 * H), (ldw3, 1)).astype(np.float64)
+        gh = (A @ W.T + _arr(b_hh, (3 * H,), (1,))).astype(np.float32)     # hi.hi + hi.lo + lo.hi, fp32-class
+        self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh.ctypes.data, 3 * H, hp, ldhp, ho, ldho, None, 0, None, 0, None, 0,
+                              B, H, st)
+        self.pd_tf32_split3(ho, ldho, B, H, h3, ldh3, 0, st)
+
     def pd_gru_step_tf32(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
                          B, H, st):
         HP = _arr(hp, (B, H), (ldhp, 1))

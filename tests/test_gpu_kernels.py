@@ -637,6 +637,33 @@ def test_gru_step_tma(B, H, bcast, save):
         assert torch.allclose(g, c, atol=4e-3, rtol=0), float((g - c).abs().max())
 
 
+@pytest.mark.parametrize("B,H,bcast", [(700, 128, True), (4100, 512, True), (513, 1024, False)])
+def test_gru_step_tma3_split3_inference(B, H, bcast):
+    """Fused inference step of the 3xTF32 decode path (pd_gru_step_tma3): [hi|hi|lo] . [hi|lo|hi] on tcgen05, expf / tanhf
+    gates, in-place state update and the split of the new state -- fp32-class agreement with the fp64-accumulated
+    restatement, and an exact hi + lo == h split."""
+    _dev()
+    torch.manual_seed(6)
+    w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+    hp0 = torch.randn(B, H) * 0.5
+
+    def split3(x, order):
+        out = torch.zeros(x.shape[0], 3 * x.shape[1])
+        CPU.pd_tf32_split3(x.data_ptr(), x.shape[1], x.shape[0], x.shape[1], out.data_ptr(), 3 * x.shape[1], order, None)
+        return out
+    a3, w3 = split3(hp0, 0), split3(w, 1)
+
+    def mk():
+        h, h3 = torch.zeros(B, H), torch.zeros(B, 3 * H)       # (the model updates the state in place; covered by the
+        return ([a3, 3 * H, w3, 3 * H, b, torch.randn(B, 3 * H), 3 * H,   #  decode parity tests)
+                 torch.randn(B, 3 * H) if bcast else None, 3 * H, hp0, H, h, H, h3, 3 * H, B, H, None], [h, h3])
+    (gh_, ch_), (g3, c3) = _both("pd_gru_step_tma3", mk)
+    assert torch.allclose(gh_, ch_, atol=4e-6, rtol=0), float((gh_ - ch_).abs().max())
+    hi, lo = g3[:, :H], g3[:, 2 * H:]
+    assert torch.equal(hi, g3[:, H:2 * H]) and torch.equal(hi + lo, gh_)
+    assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros(B, H, dtype=torch.int32))
+
+
 def test_select_rows_kernels():
     """Device-flag row select (scheduled sampling with the plan as device data) and its gradient routing."""
     _dev()
