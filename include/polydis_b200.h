@@ -90,6 +90,12 @@ int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, long ldw,
 int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
                     long ldgi, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn, long ldrzn, float* hn,
                     long ldhn, int B, int H, void* stream);
+/* training form with the x-projection folded into the main loop as a second K segment (TF32, single pass): gi = W_x x is never
+ * materialised; x (B,K2) rows of the step's input (row stride ldx), w_x (3H,K2) the matching W_ih columns, gi2 (B,3H) the rest
+ * of the input projection incl. b_ih.  Teacher-forced note GRU: x = embedding of ground-truth slot n, ptvae.py:396-398. */
+int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx, const float* w_x,
+                     long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn,
+                     long ldrzn, float* hn, long ldhn, int B, int H, void* stream);
 int pd_gru_step_tma_variant(int variant);
 /* inference form of the fused step for the error-compensated 3xTF32 path (greedy decode of >= 512 segments,
  * ptvae.py:396-398,:461-462 at inference): a3 (B,3H) = [hi | hi | lo] split of h_prev, w3 (3H,3H) = [hi | lo | hi] split
@@ -99,6 +105,13 @@ int pd_gru_step_tma_variant(int variant);
 int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ldw3, const float* b_hh, const float* gi, long ldgi,
                      const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho, float* h3out,
                      long ldh3, int B, int H, void* stream);
+/* the same step with the x-projection folded in as a second K segment of the tcgen05 main loop: x3 (B,K2) = [hi | hi | lo]
+ * split of the step's input rows, wx3 (3H,K2) = [hi | lo | hi] split of the matching W_ih columns; gi2 (B,3H) carries the
+ * rest of the input projection INCLUDING b_ih.  No (B,3H) x-projection is written or read (note-GRU slot of the greedy
+ * decode: x = embedding of the previous token, ptvae.py:396-398,:421-422). */
+int pd_gru_step_tma3x(const float* a3, long lda3, const float* w3, long ldw3, const float* x3, long ldx3, const float* wx3,
+                      long ldwx3, int K2, const float* b_hh, const float* gi2, long ldgi2, const float* hprev, long ldhp,
+                      float* hout, long ldho, float* h3out, long ldh3, int B, int H, void* stream);
 
 /* Whole greedy PianoTree decode (ptvae.py:430-491 with inference=True: 32 time steps x 15 note slots x 5 duration
  * steps, argmax feedback) of B <= 16 segments in ONE cooperative persistent launch: one CTA per SM stays resident, the

@@ -28,6 +28,8 @@ SIGNATURES = {
     "pd_gru_step_tf32": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_step_tma": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
     "pd_gru_step_tma3": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
+    "pd_gru_step_tmax": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
+    "pd_gru_step_tma3x": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
     "pd_gru_step_tma_variant": [_I],
     "pd_gru128_fwd": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P],
     "pd_gru128_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P],

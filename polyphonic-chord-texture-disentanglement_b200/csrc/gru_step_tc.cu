@@ -200,6 +200,7 @@ struct StepIo {
     int B, H;
     int KA;          // columns of the A operand: H (h_prev itself) or 3H ([hi | hi | lo] split of h_prev, 3xTF32 mode)
     int has_h3;      // also emit the [hi | hi | lo] split of the new state (operand of the next step's / the heads' GEMMs)
+    int K2;          // SEG2 kernels: columns of the second A operand (the step's input x, e.g. the note embedding)
 };
 
 constexpr int IOB = 2048;          // one epilogue buffer: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
@@ -222,14 +223,20 @@ __device__ __forceinline__ void io_write(uint8_t* buf, int lane, const float (&v
 
 constexpr int N_OUTB = 5;          // separate result buffers (OUTB variant): h' | r | z | n | W_hn h
 
-// PRECISE: expf / tanhf gate math (the fp32-faithful greedy decode) instead of the MUFU forms (training)
-template <int STAGES, int NSETS, bool OUTB, bool PRECISE>
+// PRECISE: expf / tanhf gate math (the fp32-faithful greedy decode) instead of the MUFU forms (training).
+// SEG2: the x-projection of the step is computed here too instead of being read from HBM: a second K segment
+// A2 (B x K2: the step's input rows) . B2 (3H x K2: W_ih) follows the h segment through the same stage ring; its r / z
+// products accumulate onto the h-projection's r / z columns, its n product goes to a fourth 64-column block (the GRU
+// needs W_in x and W_hn h apart: n = tanh(i_n + r * h_n)).  Accumulator = 256 TMEM columns; no gi tensor exists.
+template <int STAGES, int NSETS, bool OUTB, bool PRECISE, bool SEG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
                     const __grid_constant__ CUtensorMap tmHp, const __grid_constant__ CUtensorMap tmHo,
                     const __grid_constant__ CUtensorMap tmRzn, const __grid_constant__ CUtensorMap tmHn,
-                    const __grid_constant__ CUtensorMap tmH3, StepIo g, int tiles_m, int tiles_u) {
+                    const __grid_constant__ CUtensorMap tmH3, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB2, StepIo g, int tiles_m, int tiles_u) {
+    constexpr int ACC = SEG2 ? 4 * UN : BN3;                           // TMEM columns per accumulator
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = BM * 128, B_BYTES = BN3 * 128;
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -245,7 +252,8 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_slot = (uint32_t*)(io_bar + 4 * NSETS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (g.KA + 31) / 32;
+    const int nkb1 = (g.KA + 31) / 32, nkb2 = SEG2 ? (g.K2 + 31) / 32 : 0;
+    const int nkb = nkb1 + nkb2;
     const long n_items = (long)tiles_m * tiles_u;
 
     if (warp == 0 && lane == 0) {
@@ -274,16 +282,20 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int s = (int)(cnt % STAGES), k0 = i * 32;
                     if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
                     mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                    tma_load_2d(&tmA, &full[s], sA + s * A_BYTES, k0, m0);
+                    const bool seg2 = SEG2 && i >= nkb1;
+                    const int kk = seg2 ? (i - nkb1) * 32 : k0;
+                    tma_load_2d(seg2 ? &tmA2 : &tmA, &full[s], sA + s * A_BYTES, kk, m0);
 #pragma unroll
                     for (int gate = 0; gate < 3; ++gate)      // r, z, n rows of the same 64 units
-                        tma_load_2d(&tmB, &full[s], sB + s * B_BYTES + gate * (UN * 128), k0, gate * g.H + u0);
+                        tma_load_2d(seg2 ? &tmB2 : &tmB, &full[s], sB + s * B_BYTES + gate * (UN * 128), kk, gate * g.H + u0);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN3 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc_rz = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * UN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             long cnt = 0, j = 0;
             for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
                 const int acc = (int)(j & 1);
@@ -294,10 +306,21 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&full[s], (uint32_t)(cnt / STAGES) & 1);
                     tc_fence_after();
                     const uint32_t a = smem_u32(sA + s * A_BYTES), b = smem_u32(sB + s * B_BYTES);
+                    if (SEG2 && i >= nkb1) {
+                        // x segment: r | z onto the h-projection's columns, n into its own block (columns 192..255)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_tf32(tmem_base + acc * BN3, make_desc(a + k * 32, 16, 1024, 2), make_desc(b + k * 32, 16, 1024, 2),
-                                    idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t ad = make_desc(a + k * 32, 16, 1024, 2);
+                            tc_mma_tf32(tmem_base + acc * ACC, ad, make_desc(b + k * 32, 16, 1024, 2), idesc_rz, 1u);
+                            tc_mma_tf32(tmem_base + acc * ACC + 3 * UN, ad, make_desc(b + 2 * (UN * 128) + k * 32, 16, 1024, 2),
+                                        idesc_n, (i > nkb1 || k > 0) ? 1u : 0u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_tf32(tmem_base + acc * ACC, make_desc(a + k * 32, 16, 1024, 2), make_desc(b + k * 32, 16, 1024, 2),
+                                        idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
                     tc_commit(&empty[s]);
                 }
                 tc_commit(&tmem_full[acc]);
@@ -320,9 +343,11 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int set = (int)(k % NSETS);
             uint8_t* bufs = wbufs + set * (N_IOB * IOB);
             uint64_t* lbar = &io_bar[q * NSETS + set];
-            mbar_expect_tx(lbar, (uint32_t)((g.has_gi2 ? 7 : 4) * IOB));
+            mbar_expect_tx(lbar, (uint32_t)(((g.has_gi2 ? 3 : 0) + (SEG2 ? 0 : 3) + 1) * IOB));
+            if (!SEG2) {
 #pragma unroll
-            for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi, lbar, bufs + gate * IOB, gate * H + col, row);
+                for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi, lbar, bufs + gate * IOB, gate * H + col, row);
+            }
             if (g.has_gi2) {
 #pragma unroll
                 for (int gate = 0; gate < 3; ++gate) tma_load_2d(&tmGi2, lbar, bufs + (3 + gate) * IOB, gate * H + col, row);
@@ -345,19 +370,25 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int set = (int)(k % NSETS);
                 uint8_t* bufs = wbufs + set * (N_IOB * IOB);
                 float ghr[16], ghz[16], ghn[16];
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN3 + c * 16;
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ACC + c * 16;
                 tc_ld16(tbase, ghr);
                 tc_ld16(tbase + UN, ghz);
                 tc_ld16(tbase + 2 * UN, ghn);
+                float ir[16], iz[16], in[16], hp[16];
+                if (SEG2) tc_ld16(tbase + 3 * UN, in);                 // W_in x of this chunk (r / z parts are already summed)
                 if (c == NCH - 1) {                                    // last TMEM read of this item: hand the accumulator back
                     tc_fence_before();
                     if (lane == 0) mbar_arrive1(&tmem_empty[acc]);
                 }
                 mbar_wait(&io_bar[q * NSETS + set], (uint32_t)(k / NSETS) & 1);   // this chunk's gi / gi2 / h_prev boxes landed
-                float ir[16], iz[16], in[16], hp[16];
-                io_read(bufs, lane, ir);
-                io_read(bufs + IOB, lane, iz);
-                io_read(bufs + 2 * IOB, lane, in);
+                if (SEG2) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ir[i] = iz[i] = 0.0f;
+                } else {
+                    io_read(bufs, lane, ir);
+                    io_read(bufs + IOB, lane, iz);
+                    io_read(bufs + 2 * IOB, lane, in);
+                }
                 io_read(bufs + 6 * IOB, lane, hp);
                 if (g.has_gi2) {
                     float t[16];
@@ -521,7 +552,7 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0};
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0};
     const CUtensorMap th3 = tho;
     constexpr bool kPrecise = false;
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
@@ -535,17 +566,57 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
         constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + (OB ? 4 * N_OUTB * IOB : 0) + 1024 + 256; \
         static unsigned long long attr = 0;                                                                                           \
         if (pd_first_use_on_device(attr)) {                                                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB, kPrecise>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB, kPrecise, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                                            \
         }                                                                                                                   \
-        gru_step_tma_kernel<ST, NS, OB, kPrecise><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, \
-                                                                                           trzn, thn, th3, g, tiles_m, tiles_u); \
+        gru_step_tma_kernel<ST, NS, OB, kPrecise, false><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, \
+                                                                                  tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u); \
         return pd_launch_status();                                                                                          \
     }
     if (g_step_variant == 1) PD_STEP_LAUNCH(4, 1, false)
     if (g_step_variant == 2) PD_STEP_LAUNCH(2, 2, false)
     PD_STEP_LAUNCH(3, 1, true)
 #undef PD_STEP_LAUNCH
+}
+
+// Training form with the x-projection folded in (SEG2, TF32 single pass): gi = W_x x is computed inside the kernel as a
+// second K segment (x: B x K2 rows of the step's input, w_x: 3H x K2), so the (B,T,3H) x-projection of the sequence is never
+// materialised.  gi2 (B,3H) carries the rest of the input projection incl. b_ih.  Teacher-forced note GRU (ptvae.py:396-398):
+// x = ground-truth note embedding of slot n (row stride 16*128), w_x = dec_notes_gru.weight_ih[:, 1024:].
+PD_API int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx, const float* w_x,
+                            long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn,
+                            long ldrzn, float* hn, long ldhn, int B, int H, void* stream) {
+    if (B <= 0) return 0;
+    if (H % UN != 0 || hprev == nullptr || hout == hprev || x == nullptr || gi2 == nullptr || K2 <= 0 || (K2 & 3)) return PD_BAD_ARG;
+    if (!al16(hprev, ldhp) || !al16(w_hh, ldw) || !al16(x, ldx) || !al16(w_x, ldwx) || !al16(gi2, ldgi2) || !al16(hout, ldho) ||
+        (rzn && !al16(rzn, ldrzn)) || (hn && !al16(hn, ldhn)) || ((uintptr_t)b_hh & 15) || ldhp < 4 || ldw < 4 || ldx < 4 || ldwx < 4)
+        return PD_BAD_ARG;
+    CUtensorMap ta, tb, ta2, tb2, tgi2, thp, tho, trzn, thn;
+    int rc = make_map(&ta, hprev, 4, H, B, ldhp, BM, false);
+    if (!rc) rc = make_map(&tb, w_hh, 4, H, 3L * H, ldw, UN, false);
+    if (!rc) rc = make_map(&ta2, x, 4, K2, B, ldx, BM, false);
+    if (!rc) rc = make_map(&tb2, w_x, 4, K2, 3L * H, ldwx, UN, false);
+    if (!rc) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
+    if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
+    if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
+    trzn = tho; thn = tho;
+    if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
+    if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
+    if (rc) return rc;
+    StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2};
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    const long items = (long)tiles_m * tiles_u;
+    const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    constexpr int ST = 3, NS = 1;
+    constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    gru_step_tma_kernel<ST, NS, true, false, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
+        ta, tb, tgi2, tgi2, thp, tho, trzn, thn, tho, ta2, tb2, g, tiles_m, tiles_u);
+    return pd_launch_status();
 }
 
 // Inference form of the fused step for the error-compensated 3xTF32 path (greedy decode at >= 512 rows): the A operand
@@ -557,7 +628,7 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
                             long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
                             float* h3out, long ldh3, int B, int H, void* stream) {
     if (B <= 0) return 0;
-    if (H % UN != 0 || a3 == nullptr || hprev == nullptr || h3out == nullptr || h3out == a3) return PD_BAD_ARG;
+    if (H % UN != 0 || a3 == nullptr || hprev == nullptr || h3out == nullptr || h3out == a3 || gi == nullptr) return PD_BAD_ARG;
     if (!al16(a3, lda3) || !al16(w3, ldw3) || !al16(gi, ldgi) || (gi2 && !al16(gi2, ldgi2)) || !al16(hprev, ldhp) ||
         !al16(hout, ldho) || !al16(h3out, ldh3) || ((uintptr_t)b_hh & 15) || lda3 < 4 || ldw3 < 4)
         return PD_BAD_ARG;
@@ -571,7 +642,7 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
     tgi2 = tgi; trzn = tho; thn = tho;
     if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1};
+    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1, 0};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -579,11 +650,53 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
     constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
     static unsigned long long attr = 0;
     if (pd_first_use_on_device(attr)) {
-        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    gru_step_tma_kernel<ST, NS, true, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, tho, trzn, thn,
-                                                                                              th3, g, tiles_m, tiles_u);
+    gru_step_tma_kernel<ST, NS, true, true, false><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
+        ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u);
+    return pd_launch_status();
+}
+
+// Same step with the x-projection folded in (SEG2): instead of reading gi = W_ih x + b_ih from HBM, the kernel multiplies the
+// step's input rows itself -- x3 (B, K2) = [hi | hi | lo] split of x (K2 = 3 * pad4(in_features)), wx3 (3H, K2) = [hi | lo | hi]
+// split of W_ih's columns for x -- as a second K segment of the same tcgen05 main loop.  gi2 (B,3H) must carry everything
+// else of the input projection (the sequence-constant part INCLUDING b_ih).  Note-GRU slot of the greedy decode:
+// x = embedding of the previous token, gi2 = W_ih[:, :1024] summary + b_ih.  Removes one GEMM launch and the write + read
+// of the (B,3H) x-projection per slot.
+PD_API int pd_gru_step_tma3x(const float* a3, long lda3, const float* w3, long ldw3, const float* x3, long ldx3, const float* wx3,
+                             long ldwx3, int K2, const float* b_hh, const float* gi2, long ldgi2, const float* hprev, long ldhp,
+                             float* hout, long ldho, float* h3out, long ldh3, int B, int H, void* stream) {
+    if (B <= 0) return 0;
+    if (H % UN != 0 || a3 == nullptr || x3 == nullptr || hprev == nullptr || h3out == nullptr || h3out == a3 || gi2 == nullptr ||
+        K2 <= 0 || (K2 & 3))
+        return PD_BAD_ARG;
+    if (!al16(a3, lda3) || !al16(w3, ldw3) || !al16(x3, ldx3) || !al16(wx3, ldwx3) || !al16(gi2, ldgi2) || !al16(hprev, ldhp) ||
+        !al16(hout, ldho) || !al16(h3out, ldh3) || ((uintptr_t)b_hh & 15) || lda3 < 4 || ldw3 < 4 || ldx3 < 4 || ldwx3 < 4)
+        return PD_BAD_ARG;
+    CUtensorMap ta, tb, ta2, tb2, tgi2, thp, tho, th3;
+    int rc = make_map(&ta, a3, 4, 3L * H, B, lda3, BM, false);
+    if (!rc) rc = make_map(&tb, w3, 4, 3L * H, 3L * H, ldw3, UN, false);
+    if (!rc) rc = make_map(&ta2, x3, 4, K2, B, ldx3, BM, false);
+    if (!rc) rc = make_map(&tb2, wx3, 4, K2, 3L * H, ldwx3, UN, false);
+    if (!rc) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
+    if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
+    if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
+    if (!rc) rc = make_map_io(&th3, h3out, 3L * H, B, ldh3);
+    if (rc) return rc;
+    StepIo g{b_hh, 1, 0, 0, B, H, 3 * H, 1, K2};
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    const long items = (long)tiles_m * tiles_u;
+    const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    constexpr int ST = 3, NS = 1;
+    constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    gru_step_tma_kernel<ST, NS, true, true, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
+        ta, tb, tgi2, tgi2, thp, tho, tho, tho, th3, ta2, tb2, g, tiles_m, tiles_u);
     return pd_launch_status();
 }
 

@@ -111,6 +111,19 @@ FUSED_GRU_STEP = False
 # recurrences (31.5 vs 29.5 us), hence the row threshold.
 FUSED_GRU_STEP_TMA = True
 FUSED_GRU_STEP_TMA_MIN_ROWS = 4096
+# Fold the per-step x-projection into the fused step as a second K segment (pd_gru_step_tmax): for the teacher-forced note
+# GRU the (32*B, 16, 1536) projection of the note embeddings (1.6 GB at batch 512) is then never written or read -- the
+# producing GEMM skips those columns (linear_split(skip_tail=)), each step multiplies its 128-wide embedding rows itself.
+FUSED_GRU_STEP_X = True
+
+
+def fold_x_ok(rows, H, x, w_x):
+    """Can a recurrence over ``rows`` sequences take its x-projection inside the fused step kernel?  x (rows,T,K2)
+    contiguous inputs, w_x (3H,K2) the matching W_ih columns (may be a column slice of a wider matrix)."""
+    return (FUSED_GRU_STEP_TMA and FUSED_GRU_STEP_X and PRECISION == "tf32" and torch.is_tensor(x)
+            and rows >= FUSED_GRU_STEP_TMA_MIN_ROWS and H % 64 == 0 and x.dim() == 3 and x.is_contiguous()
+            and x.shape[2] % 4 == 0 and x.data_ptr() % 16 == 0 and w_x.stride(1) == 1 and w_x.stride(0) % 4 == 0
+            and w_x.data_ptr() % 16 == 0 and w_x.shape == (3 * H, x.shape[2]))
 _lo_cache = {}          # weight low parts, keyed by (data_ptr, version): static during a decode
 TF32X3_MIN_ROWS = 512   # smaller 3xTF32 GEMMs are launch-latency bound: they run on the single-launch FFMA kernel
 
@@ -313,10 +326,16 @@ class _LinearSplit(torch.autograd.Function):
     embeddings feed both directions of the summary bi-GRU and the note GRU (ptvae.py:446-453, :396)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, sizes, bias_cols, slab):
+    def forward(ctx, x, w, b, sizes, bias_cols, slab, skip_tail=0):
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
-        gemm_nt(x2, w, y, b)
+        if skip_tail:
+            # the last head is NOT computed (its consumer multiplies x itself, ops.fold_x_ok); its columns of y stay
+            # uninitialised and only route the gradient: the backward still covers all heads
+            n = w.shape[0] - skip_tail
+            gemm_nt(x2, w[:n], y[:, :n], None if b is None else b[:n])
+        else:
+            gemm_nt(x2, w, y, b)
         ctx.save_for_backward(x2, w)
         ctx.sizes, ctx.bias_cols, ctx.slab, ctx.x_shape = sizes, bias_cols, slab, x.shape
         slab.M, slab.N, slab.dev = x2.shape[0], w.shape[0], x.device
@@ -359,18 +378,21 @@ class _LinearSplit(torch.autograd.Function):
             db = torch.zeros(w.shape[0], device=dy.device, dtype=torch.float32)
             nb = ctx.bias_cols
             colsum(dy[:, :nb], db[:nb])
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def linear_split(x, w, b, sizes, bias_cols=None):
+def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False):
     """Heads of widths ``sizes`` over the same input as one GEMM; outputs are shaped (*x.shape[:-1], n).  Only the
-    first ``bias_cols`` columns carry a trainable bias (default: all)."""
+    first ``bias_cols`` columns carry a trainable bias (default: all).  ``skip_tail``: do not compute the LAST head in the
+    forward pass (its tensor is returned uninitialised, for gradient routing only; it must carry no bias)."""
     if isinstance(sizes, int):
         sizes = (sizes, w.shape[0] - sizes)
     sizes = tuple(sizes)
     assert sum(sizes) == w.shape[0]
     slab = GradSlab()
-    outs = _LinearSplit.apply(x, w, b, sizes, w.shape[0] if bias_cols is None else bias_cols, slab)
+    nb = w.shape[0] if bias_cols is None else bias_cols
+    assert not skip_tail or nb <= w.shape[0] - sizes[-1]
+    outs = _LinearSplit.apply(x, w, b, sizes, nb, slab, sizes[-1] if skip_tail else 0)
     off = 0
     for o, n in zip(outs, sizes):
         o._pd_slab = (slab, off, n)                           # lets slab-aware consumers write their gradient in place
@@ -421,7 +443,11 @@ def gates_fwd_split3(gi, gi2, gh, h, h3):
 
 # Greedy decode at >= 512 rows (tf32x3): recurrent 3xTF32 GEMM + gate math + split of the new state in ONE tcgen05 kernel
 # (pd_gru_step_tma3) instead of GEMM + pd_gru_gates_fwd_split3 -- the (B,3H) h-projection never goes to HBM.
-FUSED_DECODE_STEP = True
+# Validated on B200 (kernel test + 1,024-segment token parity 0.9997 vs the CPU oracle) but NOT faster: with K = 3H = 1536 the
+# step is bound by L2 -> SM operand traffic (2 GB per note slot at 16,384 segments), where the 128 x 192 fused tile re-reads
+# the A operand 8x against 6x for the 256-wide GEMM tile: 213 us fused vs 138 us GEMM + 70 us gate kernel per slot
+# (profiles/r02_decode16384_launches_*.txt), 266 vs 258 ms per 16,384-segment decode.  Off by default.
+FUSED_DECODE_STEP = False
 
 
 def gru_step_split3(a3, w3, b_hh, gi, gi2, h, h3out):
@@ -431,6 +457,26 @@ def gru_step_split3(a3, w3, b_hh, gi, gi2, h, h3out):
     _call("pd_gru_step_tma3", _ptr(a3), a3.stride(0), _ptr(w3), w3.stride(0), _ptr(b_hh), _ptr(gi), gi.stride(0),
           _ptr(gi2), 0 if gi2 is None else gi2.stride(0), _ptr(h), h.stride(0), _ptr(h), h.stride(0), _ptr(h3out),
           h3out.stride(0), B, H, _stream())
+
+
+def gru_step_split3x(a3, w3, x3, wx3, b_hh, gi2, h, h3out):
+    """``gru_step_split3`` with the x-projection computed inside the kernel: x3 = [hi|hi|lo] of the step's input rows,
+    wx3 = [hi|lo|hi] of the matching W_ih columns; gi2 carries the rest of the input projection incl. b_ih."""
+    B, H = h.shape
+    _call("pd_gru_step_tma3x", _ptr(a3), a3.stride(0), _ptr(w3), w3.stride(0), _ptr(x3), x3.stride(0), _ptr(wx3),
+          wx3.stride(0), x3.shape[1], _ptr(b_hh), _ptr(gi2), gi2.stride(0), _ptr(h), h.stride(0), _ptr(h), h.stride(0),
+          _ptr(h3out), h3out.stride(0), B, H, _stream())
+
+
+def split3_into(x, out):
+    """[hi | hi | lo] split of activations x (rows, cols) into a preallocated (rows, 3*pad4(cols)) buffer."""
+    _call("pd_tf32_split3", _ptr(x), x.stride(0), x.shape[0], x.shape[1], _ptr(out), out.stride(0), 0, _stream())
+    return out
+
+
+# fold the note-embedding projection of the greedy decode into the fused step (second K segment): saves the gi GEMM launch
+# and 200 MB of x-projection traffic per note slot at 16,384 segments
+FUSED_DECODE_STEP_X = True
 
 
 def weight_split3(w):
@@ -467,9 +513,11 @@ def _resident128_ok(gi, gi2, h0, lengths, H):
             and gi.stride(1) % 2 == 0 and gi.data_ptr() % 8 == 0)
 
 
-def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None, n_steps=None):
+def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, save=None, n_steps=None, xsrc=None):
     """Run a GRU over precomputed input projections.  gi (B,T,3H) strided view, gi2 (B,3H) or None;
     ``n_steps`` (<= T) uses only the first slots of gi (the note GRU consumes 15 of the 16 embedded slots).
+    ``xsrc`` = (x (B,T,K2), w_x (3H,K2)): gi is NOT read (it may be uninitialised); every step computes W_x x[:, t] inside
+    the fused step kernel (``fold_x_ok`` must hold; gi2 carries the rest of the input projection incl. the bias).
 
     Returns h_all (B,n_steps,H).  ``save`` (dict) receives rzn / hn for the backward pass.
     """
@@ -478,6 +526,23 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
     H = H3 // 3
     dev = gi.device
     h_all = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+    if xsrc is not None:
+        x, w_x = xsrc
+        assert gi2 is not None and h0 is not None and lengths is None and fold_x_ok(B, H, x, w_x)
+        rzn = hn = None
+        if save is not None:
+            rzn = torch.empty(B, T, H3, device=dev, dtype=torch.float32)
+            hn = torch.empty(B, T, H, device=dev, dtype=torch.float32)
+            save["rzn"], save["hn"] = rzn, hn
+        hprev = h0
+        for t in (range(T - 1, -1, -1) if reverse else range(T)):
+            xt = x[:, t]
+            _call("pd_gru_step_tmax", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(xt), x.stride(0),
+                  _ptr(w_x), w_x.stride(0), x.shape[2], _ptr(b_hh), _ptr(gi2), gi2.stride(0), _ptr(h_all[:, t]),
+                  h_all.stride(0), None if rzn is None else _ptr(rzn[:, t]), 0 if rzn is None else rzn.stride(0),
+                  None if hn is None else _ptr(hn[:, t]), 0 if hn is None else hn.stride(0), B, H, _stream())
+            hprev = h_all[:, t]
+        return h_all
     if _resident128_ok(gi, gi2, h0, lengths, H):
         # weight-resident kernel: whole variable-length recurrence in one launch (csrc/gru128_resident.cu)
         rzn = hn = None
@@ -612,11 +677,11 @@ class _GruSeq(torch.autograd.Function):
     duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
 
     @staticmethod
-    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None):
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None, xsrc=None):
         _chk(gi, "gi")
         ctx.slab = slab
         save = {}
-        h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps)
+        h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps, xsrc)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
         ctx.resident = bool(save.get("resident"))
         ctx.reverse = reverse
@@ -678,16 +743,18 @@ class _GruSeq(torch.autograd.Function):
                 gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
         elif h0 is None:
             dw.zero_()
-        return dgi, dgi2, dh0, dw, db, None, None, None, None
+        return dgi, dgi2, dh0, dw, db, None, None, None, None, None
 
 
-def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None):
+def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None, xsrc=None):
     """Autograd-aware GRU over (B,T,3H) input projections; falls to the no-grad loop when nothing
-    requires grad (inference)."""
+    requires grad (inference).  ``xsrc``: see ``gru_sequence_nograd`` (gi then only routes the gradient)."""
+    if xsrc is not None:
+        xsrc = (xsrc[0].detach(), xsrc[1].detach())           # gradients flow through gi's producer (linear_split)
     if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
                                     (h0 is not None and h0.requires_grad)):
-        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]))
-    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps)
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc)
+    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps, xsrc)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -310,24 +310,29 @@ class PtvaeDecoder(nn.Module):
         eg = self.dec_notes_emb_gru
         (wf, _, bf, _), (wb, _, bb, _) = eg.dir(False), eg.dir(True)
         w_tok_n = wn_ih[:, self.dec_time_hid_size:]
+        # with the fused step kernel the note GRU multiplies its embedding rows itself (ops.fold_x_ok): the gi_tok head is
+        # then not computed here (its tensor only routes the gradient back into this projection's backward)
+        fold = ops.fold_x_ok(R, self.dec_notes_hid_size, notes, w_tok_n)
         gi_f, gi_b, gi_tok = ops.linear_split(                                            # gi_tok (R,16,1536)
             notes, torch.cat([wf, wb, w_tok_n], 0), torch.cat([bf, bb, bf.new_zeros(w_tok_n.shape[0])], 0),
-            (wf.shape[0], wb.shape[0], w_tok_n.shape[0]), bias_cols=wf.shape[0] + wb.shape[0])
+            (wf.shape[0], wb.shape[0], w_tok_n.shape[0]), bias_cols=wf.shape[0] + wb.shape[0], skip_tail=fold)
         summ = _bigru_final(eg, notes, lengths32, gi=(gi_f, gi_b)).view(B, self.num_step, -1)
-        return summ, gi_tok
+        return (summ, gi_tok, (notes, w_tok_n)) if fold else (summ, gi_tok)
 
     def _decode_teacher_forced(self, z, x, lengths32, pre=None):
         B = z.size(0)
         R = B * self.num_step
         z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
         wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
-        summ, gi_tok = pre if pre is not None else self.teacher_forced_prologue(x, lengths32)
+        pre = pre if pre is not None else self.teacher_forced_prologue(x, lengths32)
+        summ, gi_tok = pre[0], pre[1]
+        xsrc = pre[2] if len(pre) > 2 else None            # note GRU takes its x-projection inside the fused step kernel
         tok = torch.cat([self.dec_init_input.expand(B, 1, -1), summ[:, :-1]], 1)
         summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
         S = summary.reshape(R, self.dec_time_hid_size)
         h0 = self.dec_time_to_notes_hid(S)
         gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
-        h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1)  # (R,15,512)
+        h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1, xsrc=xsrc)  # (R,15,512)
         # pitch head and (folded) duration-hidden projection as one GEMM over the note states
         Q = R * (self.max_simu_note - 1)
         w_eff, b_eff = self._dur_hid_folded()
@@ -634,6 +639,9 @@ class PtvaeDecoder(nn.Module):
         n3b = torch.empty(B, 3 * Hn, **f32) if fuse_n else None
         wt_hh3 = ops.weight_split3(wt_hh) if fuse_t else None
         wn_hh3 = ops.weight_split3(wn_hh) if fuse_n else None
+        fuse_x = fuse_n and ops.FUSED_DECODE_STEP_X
+        w_tok_n3 = ops.weight_split3(w_tok_n) if fuse_x else None          # (1536, 384)
+        e3 = torch.empty(B, 3 * E, **f32) if fuse_x else None
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
             if fuse_t:
@@ -653,12 +661,18 @@ class PtvaeDecoder(nn.Module):
             lens.zero_()
             a_n = ops.split3_act(h_n)
             for n in range(1, NS):
-                ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
-                if fuse_n:
+                if fuse_x:                             # x-projection of the previous token inside the fused step
+                    ops.split3_into(pred[:, n - 1], e3)
+                    ops.gru_step_split3x(a_n, wn_hh3, e3, w_tok_n3, bn_hh, gi_s, h_n, n3b)
+                    a_n = n3b
+                    n3, n3b = n3b, n3
+                elif fuse_n:
+                    ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
                     ops.gru_step_split3(a_n, wn_hh3, bn_hh, gi_n, gi_s, h_n, n3b)
                     a_n = n3b
                     n3, n3b = n3b, n3
                 else:
+                    ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
                     ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)
                     if x3:                             # n3 serves the heads now and the recurrent GEMM of the next slot
                         ops.gates_fwd_split3(gi_n, gi_s, gh_n, h_n, n3)

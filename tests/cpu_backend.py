@@ -145,6 +145,17 @@ class CpuBackend:
                               B, H, st)
         self.pd_tf32_split3(ho, ldho, B, H, h3, ldh3, 0, st)
 
+    def pd_gru_step_tmax(self, hp, ldhp, w, ldw, x, ldx, wx, ldwx, K2, b_hh, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, B, H, st):
+        gi = (_arr(x, (B, K2), (ldx, 1)) @ _arr(wx, (3 * H, K2), (ldwx, 1)).T).astype(np.float32)
+        self.pd_gru_step_tf32(hp, ldhp, w, ldw, b_hh, gi.ctypes.data, 3 * H, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, None, 0,
+                              B, H, st)
+
+    def pd_gru_step_tma3x(self, a3, lda3, w3, ldw3, x3, ldx3, wx3, ldwx3, K2, b_hh, gi2, ldgi2, hp, ldhp, ho, ldho, h3, ldh3,
+                          B, H, st):
+        gi = (_arr(x3, (B, K2), (ldx3, 1)).astype(np.float64) @ _arr(wx3, (3 * H, K2), (ldwx3, 1)).astype(np.float64).T
+              ).astype(np.float32)
+        self.pd_gru_step_tma3(a3, lda3, w3, ldw3, b_hh, gi.ctypes.data, 3 * H, gi2, ldgi2, hp, ldhp, ho, ldho, h3, ldh3, B, H, st)
+
     def pd_gru_step_tf32(self, hp, ldhp, w, ldw, b_hh, gi, ldgi, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
                          B, H, st):
         HP = _arr(hp, (B, H), (ldhp, 1))

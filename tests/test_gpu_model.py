@@ -248,13 +248,15 @@ def test_baseline_batch512_graphed_step_matches_oracle_losses():
         assert float((a - p.grad).norm()) <= 2e-4 * float(p.grad.norm()) + 1e-9
 
 
-@pytest.mark.parametrize("prec", ["tf32x3"])
-def test_large_batch_decode_matches_oracle(prec):
+@pytest.mark.parametrize("prec,fused", [("tf32x3", False), ("tf32x3", True)])
+def test_large_batch_decode_matches_oracle(prec, fused, monkeypatch):
     """Token parity of the LARGE-batch decode route (>= 512 segments: single-launch 3xTF32 tcgen05 GEMMs, operands
     split by the gate kernel, 3-pass duration decoder and GRU128) against the CPU oracle's greedy decode -- 1,024
     segments, W1-style weights so decodes vary per segment and step."""
     dev = _dev()
     from oracle import polydis_oracle as O
+    from polydis_b200 import ops
+    monkeypatch.setattr(ops, "FUSED_DECODE_STEP", fused)     # True: recurrent GEMM + gates + split in one tcgen05 kernel
     B = 1024
     _, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 77))
     sd = make_state_dict(7, gain=2.0, eos_bias=0.75)
@@ -266,7 +268,7 @@ def test_large_batch_decode_matches_oracle(prec):
     pre = ref[..., 0] != 129
     assert match >= 0.999, match
     assert (est[pre] == ref[pre]).mean() >= 0.999
-    print(f"1024-segment {prec} decode vs oracle: token match {match:.6f}")
+    print(f"1024-segment {prec} decode (fused step {fused}) vs oracle: token match {match:.6f}")
 
 
 def test_graphed_decode_matches_eager_decode():

@@ -31,9 +31,14 @@ def test_state_dict_keys_match_reference_contract():
 
 
 @pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan",
-                                 "tf000-batched", "tf555-batched"])
+                                 "tf000-batched", "tf555-batched", "tf111-fusedstep"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
-    cpu_backend.install(monkeypatch)
+    be = cpu_backend.install(monkeypatch)
+    fused = tag.endswith("-fusedstep")
+    if fused:       # fused recurrent step kernels for every recurrence + the note GRU's x-projection folded into the step
+        from polydis_b200 import ops
+        monkeypatch.setattr(ops, "FUSED_GRU_STEP_TMA_MIN_ROWS", 1)
+        tag = tag[:-len("-fusedstep")]
     if tag.endswith("-chunked"):        # row-chunked recurrences (ops._over_row_chunks): 128-row chunks, ragged tail
         from polydis_b200 import ops
         monkeypatch.setattr(ops, "ROW_CHUNK_MIN_BYTES", 0)
@@ -58,6 +63,8 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
         out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps, plan_dev=plan)
     else:
         out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+    if fused:
+        assert be.calls.count("pd_gru_step_tmax") == 15 and be.calls.count("pd_gru_step_tma") > 40
     losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
     np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
     np.testing.assert_allclose(out[0].detach().numpy(), g["pitch"], atol=2e-5)

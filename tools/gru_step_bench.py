@@ -35,4 +35,14 @@ for (B, T, H, bc) in [(16384, 15, 512, True), (512, 32, 1024, True), (16384, 16,
         h_all[:, 3].zero_(); fused_tma(); torch.cuda.synchronize()
         err = float((h_all[:, 3] - ref).abs().max()); err_s = float((rzn[:, 3] - ref_rzn).abs().max())
         line += f"   fused-TMA v{variant} {t(fused_tma):7.1f} us (max |dh| {err:.2e}, |d rzn| {err_s:.2e})"
+    if bc and H % 64 == 0:      # x-projection folded into the step (second K segment, K2 = 128): no gi read
+        x = torch.randn(B, T + 1, 128, device=dev); wx = torch.randn(3 * H, 128, device=dev) * 0.05
+        def fused_x():
+            ops._call("pd_gru_step_tmax", h_all[:, 2].data_ptr(), T * H, w.data_ptr(), H, x[:, 3].data_ptr(), (T + 1) * 128,
+                      wx.data_ptr(), 128, 128, b.data_ptr(), gi2.data_ptr(), 3 * H, h_all[:, 3].data_ptr(), T * H,
+                      rzn[:, 3].data_ptr(), T * 3 * H, hn[:, 3].data_ptr(), T * H, B, H, st)
+        gi[:, 3] = x[:, 3] @ wx.t()
+        split(); ref = h_all[:, 3].clone()
+        h_all[:, 3].zero_(); fused_x(); torch.cuda.synchronize()
+        line += f"   fused-X {t(fused_x):7.1f} us (max |dh| {float((h_all[:, 3] - ref).abs().max()):.2e})"
     print(line, flush=True)
