@@ -350,29 +350,32 @@ def run_b200(args):
     gemm_tflops = 2.0 * R * 512 * 1536 / (ms_gemm * 1e-3) / 1e12
     del hA, oC
     # dominant kernel of the step, timed alone: the fused note-GRU step (recurrent GEMM on tcgen05 + gate math in the
-    # epilogue, all operands / results as TMA boxes).  HBM-bound: per launch it must read h_prev, gi, gi2 and write h,
-    # r|z|n, W_hn h (13 x H floats per row-step) -- 15 launches over distinct (b,t) slices, so every launch
-    # streams ~400 MB of fresh data (> 126 MB L2).
-    T_, H_ = 15, 512
-    gi_ = torch.randn(R, T_ + 1, 3 * H_, device=dev)
+    # epilogue, the step's x-projection as a second K segment, all operands / results as TMA boxes).  HBM-bound: per
+    # launch it must read h_prev, gi2 and the 128-wide embedding rows and write h, r|z|n, W_hn h -- 15 launches over
+    # distinct (b,t) slices, so every launch streams ~300 MB of fresh data (> 126 MB L2).
+    T_, H_, K2_ = 15, 512, 128
+    x_ = torch.randn(R, T_ + 1, K2_, device=dev)
     gi2_ = torch.randn(R, 3 * H_, device=dev)
     h_ = torch.randn(R, T_ + 1, H_, device=dev) * 0.3
     rzn_ = torch.empty(R, T_, 3 * H_, device=dev)
     hn_ = torch.empty(R, T_, H_, device=dev)
     wB.mul_(0.03)
+    wX = torch.randn(3 * H_, K2_, device=dev) * 0.05
     bB = torch.randn(3 * H_, device=dev) * 0.1
 
     def step_seq():
+        # exactly the call ops.gru_seq issues for the teacher-forced note GRU (x-projection folded in: no gi tensor)
         for t_ in range(T_):
-            ops._call("pd_gru_step_tma", h_[:, t_].data_ptr(), h_.stride(0), wB.data_ptr(), H_, bB.data_ptr(),
-                      gi_[:, t_].data_ptr(), gi_.stride(0), gi2_.data_ptr(), 3 * H_, h_[:, t_ + 1].data_ptr(), h_.stride(0),
-                      rzn_[:, t_].data_ptr(), rzn_.stride(0), hn_[:, t_].data_ptr(), hn_.stride(0), R, H_,
-                      torch.cuda.current_stream().cuda_stream)
+            ops._call("pd_gru_step_tmax", h_[:, t_].data_ptr(), h_.stride(0), wB.data_ptr(), H_, x_[:, t_].data_ptr(),
+                      x_.stride(0), wX.data_ptr(), K2_, K2_, bB.data_ptr(), gi2_.data_ptr(), 3 * H_,
+                      h_[:, t_ + 1].data_ptr(), h_.stride(0), rzn_[:, t_].data_ptr(), rzn_.stride(0), hn_[:, t_].data_ptr(),
+                      hn_.stride(0), R, H_, torch.cuda.current_stream().cuda_stream)
     step_seq()
     ms_fstep = timed(step_seq, 3) / T_
-    step_bytes = R * H_ * 4 * 13 + 3 * H_ * H_ * 4          # h_prev + gi(3) + gi2(3) in, h + rzn(3) + hn out, + W_hh
+    # h_prev + gi2(3) in, h + rzn(3) + hn out = 9 H floats per row-step, + the step's 128 embedding floats, + W_hh | W_x
+    step_bytes = R * (9 * H_ + K2_) * 4 + 3 * H_ * (H_ + K2_) * 4
     step_gbs = step_bytes / (ms_fstep * 1e-3) / 1e9
-    del gi_, gi2_, h_, rzn_, hn_
+    del x_, gi2_, h_, rzn_, hn_
 
     def leave():
         # a process group whose collectives were captured in CUDA graphs can block in
@@ -417,13 +420,14 @@ def run_b200(args):
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True,
                       "latency_16_segments_ms": ms_dec16, "e2e": dec_e2e},
            "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
-                        "frac": step_gbs / peak_hbm, "traffic": _measured_traffic("gru_step_tma_kernel"),
+                        "frac": step_gbs / peak_hbm, "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1>"),
                         "peak_source": peak_src,
-                        "kernel": "gru_step_tma_kernel (fused note-GRU step: tcgen05 recurrent GEMM + gate math, 32B x 512)",
+                        "kernel": "gru_step_tma_kernel<SEG2> via pd_gru_step_tmax (fused note-GRU step: tcgen05 recurrent GEMM + folded x-projection + gate math, 32B x 512)",
                         "ms_per_launch": ms_fstep, "algorithmic_bytes_per_launch": step_bytes,
                         "what": "dominant kernel timed alone with CUDA events (15 launches over distinct slices, 3 rounds): "
-                                "13 x H x 4 algorithmic bytes per row-step (SURVEY 8d) / launch time, vs the measured HBM copy "
-                                "bandwidth; traffic = ncu dram bytes per launch (profiles/r02_kernel_traffic.json)",
+                                "(9 x H + 128) x 4 algorithmic bytes per row-step (h_prev, gi2 in; h, r|z|n, W_hn.h out; x rows) "
+                                "/ launch time, vs the measured HBM copy bandwidth; traffic = ncu dram bytes per launch of the "
+                                "same variant (profiles/r02_kernel_traffic.json)",
                         "whole_step_tensor": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                                               "frac": achieved / peak_tf,
                                               "what": "5.45 algorithmic GFLOP/sample x batch / step time vs sustained bf16 peak"},

@@ -23,13 +23,22 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _cuda_like(a):
+    """GPU copy of ``a`` that keeps its strides: strided views (a step slice of a (B,T,K) buffer, a column block of a wider
+    weight) are rebuilt over a copy of their base -- ``.cuda()`` alone would compact them while the test passes the
+    original row strides to the kernel."""
+    if a.is_contiguous() or a._base is None or not a._base.is_contiguous():
+        return a.cuda()
+    return a._base.cuda().as_strided(a.shape, a.stride(), a.storage_offset() - a._base.storage_offset())
+
+
 def _both(name, make_args):
     """make_args(device) -> (args list with tensors, outputs list of tensors).  Runs the CUDA entry on
     GPU tensors and the numpy emulation on CPU copies; returns [(gpu_out, cpu_out)]."""
     from polydis_b200 import _lib
     torch.manual_seed(0)
     args, outs = make_args()
-    gargs = [a.cuda() if torch.is_tensor(a) else a for a in args]
+    gargs = [_cuda_like(a) if torch.is_tensor(a) else a for a in args]
     gouts = [gargs[next(i for i, a in enumerate(args) if a is o)] for o in outs]
     st = torch.cuda.current_stream().cuda_stream
     _lib.call(name, *[_p(a) if torch.is_tensor(a) else a for a in gargs[:-1]], st)

@@ -39,11 +39,13 @@ for r in rows[2:]:
          "tensor": val(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
          or val(r, "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active"),
          "issue": val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"), "regs": val(r, "launch__registers_per_thread")}
-    a = agg.setdefault(short, {"n": 0, "dur": 0.0, "rd": 0.0, "wr": 0.0, "full": full})
-    a["n"] += 1
-    a["dur"] += d["dur"] or 0.0
-    a["rd"] += d["rd"] or 0.0
-    a["wr"] += d["wr"] or 0.0
+    templ = full.split("::")[-1].strip()                 # name with its template arguments: one entry per variant
+    for key in {short, templ}:
+        a = agg.setdefault(key, {"n": 0, "dur": 0.0, "rd": 0.0, "wr": 0.0, "full": full})
+        a["n"] += 1
+        a["dur"] += d["dur"] or 0.0
+        a["rd"] += d["rd"] or 0.0
+        a["wr"] += d["wr"] or 0.0
     f = lambda v, p=1: "-" if v is None else f"{v:.{p}f}"
     print(f"| `{full[:70]}` | 1 | {f(d['dur'])} | {f((d['rd'] or 0) / 1e6)} | {f((d['wr'] or 0) / 1e6)} | {f(d['dram'])} | "
           f"{f(d['tensor'])} | {f(d['issue'])} | {f(d['regs'], 0)} |")

@@ -19,6 +19,8 @@ gi = torch.randn(R, T + 1, 3 * H, device=dev)
 gi2 = torch.randn(R, 3 * H, device=dev)
 rzn = torch.empty(R, T, 3 * H, device=dev)
 hn = torch.empty(R, T, H, device=dev)
+xe = torch.randn(R, T + 1, 128, device=dev)
+Wx = torch.randn(3 * H, 128, device=dev) * 0.05
 dgi = torch.empty(R, T, 3 * H, device=dev)
 dgh = torch.randn(R, T, 3 * H, device=dev)
 dh = torch.empty(R, H, device=dev)
@@ -27,6 +29,16 @@ dm = torch.randn(R, H, device=dev)
 nz = torch.empty(R, H, device=dev)
 dout = torch.randn(R, T, H, device=dev)
 dW = torch.empty(3 * H, H, device=dev)
+Bs, Hs = 512, 1024
+hs = torch.randn(Bs, 33, Hs, device=dev) * 0.3
+Ws = torch.randn(3 * Hs, Hs, device=dev) * 0.03
+bs = torch.randn(3 * Hs, device=dev) * 0.1
+ghs = torch.empty(Bs, 3 * Hs, device=dev)
+gis = torch.randn(Bs, 33, 3 * Hs, device=dev)
+rzns = torch.empty(Bs, 32, 3 * Hs, device=dev)
+hns = torch.empty(Bs, 32, Hs, device=dev)
+dghs = torch.randn(Bs, 3 * Hs, device=dev)
+dhs = torch.empty(Bs, Hs, device=dev)
 Q = R * T
 h0 = torch.randn(Q, 64, device=dev)
 par = [torch.randn(192, 5, device=dev) * 0.3, torch.randn(192, device=dev) * 0.1, torch.randn(192, 64, device=dev) * 0.2,
@@ -42,6 +54,9 @@ for rep in range(2):
     # fused note-GRU step (forward): tcgen05 recurrent GEMM + gate math, TMA epilogue I/O
     ops._call("pd_gru_step_tma", P(h[:, 2]), h.stride(0), P(W), H, P(b), P(gi[:, 3]), gi.stride(0), P(gi2), 3 * H,
               P(h[:, 3]), h.stride(0), P(rzn[:, 3]), rzn.stride(0), P(hn[:, 3]), hn.stride(0), R, H, st)
+    # the variant the training step runs: x-projection folded in as a second K segment (no gi tensor)
+    ops._call("pd_gru_step_tmax", P(h[:, 2]), h.stride(0), P(W), H, P(xe[:, 3]), xe.stride(0), P(Wx), 128, 128, P(b), P(gi2), 3 * H,
+              P(h[:, 3]), h.stride(0), P(rzn[:, 3]), rzn.stride(0), P(hn[:, 3]), hn.stride(0), R, H, st)
     # unfused route of the same step: persistent TMA-store GEMM + gate kernel
     ops.gemm_nt(h[:, 2], W, gh, b)
     ops._gates_fwd(gi[:, 3], gi2, gh, h[:, 2], h[:, 3], rzn[:, 3], hn[:, 3], None, 3)
@@ -51,6 +66,10 @@ for rep in range(2):
               P(nz), H, None, 0, None, 3, R, H, st)
     ops.gemm_nn(dgh[:, 3], W, dh)
     ops.gemm_tn(dgh.view(R * T, 3 * H), h[:, :T].reshape(R * T, H), dW)
+    # one step of a batch-sized (512-row) recurrence, H = 1024: forward GEMM + gates, backward gates + split-K dh GEMM
+    ops.gemm_nt(hs[:, 2], Ws, ghs, bs)
+    ops._gates_fwd(gis[:, 3], None, ghs, hs[:, 2], hs[:, 3], rzns[:, 3], hns[:, 3], None, 3)
+    ops.gemm_nn(dghs, Ws, dhs)
     # duration decoder, TF32 warp-autonomous kernels (training mode)
     ops._call("pd_dur_decode_fwd", P(h0), 64, Q, *[P(p) for p in par], P(lg), P(S), 1, st)
     ops._call("pd_dur_decode_bwd", P(S), P(lg), Q, *[P(p) for p in par], P(GX), P(dh0), 64, 1, st)
