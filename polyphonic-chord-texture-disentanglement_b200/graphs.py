@@ -118,7 +118,7 @@ class GraphedTrainStep:
         if self.device_plan:
             self._upload_plan()
         snap = self._snapshot() if self.restore_after_capture else None
-        s = torch.cuda.Stream()
+        s = torch.cuda.Stream(priority=-1)      # the step's chain outranks its deferred weight-gradient jobs (ops.defer)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(self._warm):

@@ -106,6 +106,10 @@ class DisentangleVAE(PytorchModel):
     def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None, plan_dev=None):
         """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
         recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
+        # the parameters' gradient-accumulation nodes go to the weight-gradient stream (ops.defer: weight gradients are
+        # computed off backward's critical chain)
+        ops.pin_leaf_streams(self.parameters())
+
         # independent branches go to side streams (ops.fork_join); python-side order is the reference's
         def embed():
             embedded_x, lengths = self.decoder.emb_x(x)

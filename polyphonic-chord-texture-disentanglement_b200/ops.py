@@ -75,7 +75,7 @@ def fork_join(fns):
     cur = torch.cuda.current_stream()
     n_side = len(fns) - 1
     while len(_stream_pool) < _stream_depth + n_side:
-        _stream_pool.append(torch.cuda.Stream())
+        _stream_pool.append(torch.cuda.Stream(priority=-1))     # chain streams outrank the weight-gradient stream
     side = _stream_pool[_stream_depth:_stream_depth + n_side]
     _stream_depth += n_side
     try:
@@ -90,6 +90,161 @@ def fork_join(fns):
     finally:
         _stream_depth -= n_side
     return outs
+
+
+# ------------------------------------------------------------------------------------------------
+# Deferred weight gradients.  Backward's critical path is the chain of INPUT gradients (gate gradients -> dgh.W_hh ->
+# next step ...); the weight / bias gradients (split-K GEMMs over all rows of a sequence, column sums, the embedding and
+# conv scatter kernels: ~4 ms of a 15 ms step at batch 512) feed nothing but the optimizer.  Issued in line they sit
+# between the latency-bound 512-row recurrences of the time GRU and the encoders, which leave most SMs idle.  Here they
+# leave the chain: every op that owns such work tags its parameters with ``defer`` right before use; the tag is an
+# identity autograd node created under the weight-gradient stream, so autograd replays it (and everything between it
+# and the leaf: slices, concatenations, the duration-head fold, AccumulateGrad) on that stream.  The op's backward only
+# allocates the gradient buffers and hands the tag a job; the tag's backward launches the job on the weight-gradient
+# stream (the engine has made that stream wait for the op's backward).  In a captured step the jobs become parallel
+# branches of the graph that join before the clip.  Results are the in-line ones (same kernels, same operands).
+DEFER_WGRAD = True
+BG_GEMM_CFG = 0        # launch configuration of GEMMs issued on the weight-gradient stream (0: the usual heuristic)
+DBG_WS_OFF = DBG_PIN_OFF = DBG_INLINE = False
+DBG_WS_SKIP = set()
+_wg_stream = None
+_leaf_pins = []
+_warn_off = False
+_ws_active = []
+
+
+def wgrad_stream():
+    """The low-priority side stream of the deferred weight-gradient jobs (None without CUDA)."""
+    global _wg_stream
+    if _wg_stream is None and torch.cuda.is_available():
+        _wg_stream = torch.cuda.Stream()
+    return _wg_stream
+
+
+def _on_wgrad_stream():
+    return _wg_stream is not None and torch.cuda.current_stream() == _wg_stream
+
+
+class weight_space:
+    """``with ops.weight_space(): w = ...``: build weight-space tensors (column slices, concatenated heads, folded
+    products of parameters) on the weight-gradient stream, so their autograd nodes -- which in backward consume deferred
+    weight gradients -- run there too instead of making the chain's stream wait.  Joins both ways, so the block is an
+    ordinary fork-join for the forward pass.  Mark the results with ``wmark`` to make them deferrable."""
+
+    def __init__(self, site=""):
+        self.site = site
+
+    def __enter__(self):
+        self.on = (DEFER_WGRAD and not DBG_WS_OFF and self.site not in DBG_WS_SKIP and torch.cuda.is_available() and torch.is_grad_enabled() and not _on_wgrad_stream())
+        if self.on:
+            self.cur = torch.cuda.current_stream()
+            s = wgrad_stream()
+            s.wait_stream(self.cur)
+            self.ctx = torch.cuda.stream(s)
+            self.ctx.__enter__()
+            _ws_active.append(self)
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _ws_active.pop()
+            self.ctx.__exit__(*exc)
+            self.cur.wait_stream(wgrad_stream())
+        return False
+
+
+def wmark(*ts):
+    """Declare tensors built inside ``weight_space`` deferrable (their producers live on the weight-gradient stream)."""
+    for t in ts:
+        if torch.is_tensor(t):
+            t._pd_wspace = True
+            if _ws_active and t.is_cuda:
+                # allocated on the weight-gradient stream, consumed by the caller's: without this the allocator may hand
+                # the block to the next weight-space tensor as soon as python drops the reference (e.g. a merged bias
+                # that no backward saves), while the consuming GEMM is still queued on the other stream
+                t.record_stream(_ws_active[-1].cur)
+    return ts[0] if len(ts) == 1 else ts
+
+
+def pin_leaf_streams(params):
+    """Create the parameters' AccumulateGrad nodes under the weight-gradient stream (a node runs on the stream that was
+    current when it was created; they are created on a parameter's first use and die with the graph).  Without this
+    the engine makes the stream of a parameter's first forward use -- the chain's -- wait for the deferred job."""
+    global _leaf_pins
+    _leaf_pins = []
+    s = wgrad_stream()
+    if not (DEFER_WGRAD and s is not None and torch.is_grad_enabled()) or _on_wgrad_stream() or DBG_PIN_OFF:
+        return
+    global _warn_off
+    if not _warn_off:       # the stream mismatch between a gradient's producer and AccumulateGrad is the point here
+        _warn_off = True
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    with torch.cuda.stream(s):
+        _leaf_pins = [p.view_as(p) for p in params if p.requires_grad and p.is_cuda]
+
+
+class _WGradJob:
+    __slots__ = ("job",)
+
+    def __init__(self):
+        self.job = None
+
+    def set(self, job, keep=()):
+        """``job()`` launches the weight-gradient kernels (it runs under the weight-gradient stream); ``keep``: device
+        buffers it reads that the calling backward may release before the job has executed."""
+        s = _wg_stream
+        if s is not None:
+            for t in keep:
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(s)
+        self.job = job
+        if DBG_INLINE:
+            self.job = None
+            job()
+
+
+class _DeferTag(torch.autograd.Function):
+    """Identity on parameters; its backward runs the consumer's weight-gradient job (see ``defer``)."""
+
+    @staticmethod
+    def forward(ctx, wg, *ws):
+        ctx.wg = wg
+        return tuple(w.view_as(w) for w in ws)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        job, ctx.wg.job = ctx.wg.job, None
+        if job is not None:
+            job()
+        return (None,) + tuple(gs)
+
+
+def _deferrable(w):
+    return w.is_leaf or getattr(w, "_pd_wspace", False)
+
+
+def defer(*ws):
+    """Tag the parameters of ONE op call for a deferred weight-gradient job.  Returns ``(*tagged, wg)``; ``wg`` is None
+    (and ``ws`` come back untouched) when deferral does not apply -- then the op computes its weight gradients in line.
+    With a job handle the op's backward must return freshly allocated, UNWRITTEN gradient buffers for these parameters
+    and register the job that fills them (``wg.set``)."""
+    if not (DEFER_WGRAD and torch.is_grad_enabled()) or _on_wgrad_stream():
+        return ws + (None,)
+    idx = [i for i, w in enumerate(ws) if torch.is_tensor(w) and w.requires_grad]
+    if not idx or not all(_deferrable(ws[i]) for i in idx):
+        return ws + (None,)
+    wg = _WGradJob()
+    s = wgrad_stream() if ws[idx[0]].is_cuda else None
+    if s is not None:
+        with torch.cuda.stream(s):
+            tagged = _DeferTag.apply(wg, *[ws[i] for i in idx])
+    else:
+        tagged = _DeferTag.apply(wg, *[ws[i] for i in idx])
+    out = list(ws)
+    for i, t in zip(idx, tagged):
+        out[i] = t
+    return tuple(out) + (wg,)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -181,6 +336,11 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None):
         return out
     if tc_ok and PRECISION == "tf32":
         name = "pd_gemm_tf32"
+        if BG_GEMM_CFG and _on_wgrad_stream():
+            # deferred weight-gradient GEMM: the "background" launch shape (see csrc/gemm_tc.cu launch())
+            _call("pd_gemm_tf32_cfg", _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
+                  int(accumulate), int(BG_GEMM_CFG), _stream())
+            return out
     _call(name, _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
           int(accumulate), _stream())
     return out
@@ -243,11 +403,12 @@ class _Linear(torch.autograd.Function):
     """y = x W^T + b on 2-D x with strided rows (nn.Linear; K7 of SURVEY.md 2.2)."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, wg=None):
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
         K = x2.shape[1]
         ctx.k = K
+        ctx.wg = wg
         if PRECISION == "tf32" and K % 4 and K >= 64 and x2.shape[0] >= 256:
             # an input width TMA cannot address (row pitch not a multiple of 16 bytes: fc1 of the texture encoder,
             # 290 -> 1000) would send all three GEMMs of the layer to the FFMA kernel; zero-padded copies of the two
@@ -279,19 +440,49 @@ class _Linear(torch.autograd.Function):
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
             gemm_nn(dy2, w, dx)
             dx = dx[:, :ctx.k].reshape(ctx.x_shape)           # (drops the zero-padding columns, if any)
+        k = ctx.k
+        if ctx.wg is not None:
+            # weight / bias gradients leave the chain: buffers now, kernels on the weight-gradient stream (ops.defer)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty(w.shape[0], k, device=dy.device, dtype=torch.float32)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
+
+            def job():
+                if dw is not None:
+                    if k != w.shape[1]:
+                        tmp = torch.empty(w.shape, device=dw.device, dtype=torch.float32)
+                        gemm_tn(dy2, x2, tmp)
+                        dw.copy_(tmp[:, :k])
+                    else:
+                        gemm_tn(dy2, x2, dw)
+                if db is not None:
+                    colsum(dy2, db)
+            ctx.wg.set(job, keep=(dy2, x2))
+            return dx, dw, db, None
         if ctx.needs_input_grad[1]:
             dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
             gemm_tn(dy2, x2, dw)
-            if ctx.k != w.shape[1]:
-                dw = dw[:, :ctx.k].contiguous()
+            if k != w.shape[1]:
+                dw = dw[:, :k].contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
             colsum(dy2, db)
-        return dx, dw, db
+        return dx, dw, db, None
+
+
+DEFER_MIN_ROWS = 256       # smaller layers keep their weight gradients in line (a tag node costs more than it hides)
+
+
+def _n_rows(x):
+    return x.numel() // max(1, x.shape[-1])
 
 
 def linear(x, w, b=None):
-    return _Linear.apply(x, w, b)
+    wg = None
+    if _n_rows(x) >= DEFER_MIN_ROWS:
+        w, b, wg = defer(w, b)
+    return _Linear.apply(x, w, b, wg)
 
 
 class GradSlab:
@@ -326,7 +517,8 @@ class _LinearSplit(torch.autograd.Function):
     embeddings feed both directions of the summary bi-GRU and the note GRU (ptvae.py:446-453, :396)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, sizes, bias_cols, slab, skip_tail=0):
+    def forward(ctx, x, w, b, sizes, bias_cols, slab, skip_tail=0, wg=None):
+        ctx.wg = wg
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
         if skip_tail:
@@ -371,14 +563,28 @@ class _LinearSplit(torch.autograd.Function):
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
             gemm_nn(dy, w, dx)
             dx = dx.view(ctx.x_shape)
+        nb = ctx.bias_cols
+        if ctx.wg is not None:
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
+            if ctx.needs_input_grad[2]:
+                db = torch.empty(w.shape[0], device=dy.device, dtype=torch.float32)
+
+            def job():
+                if dw is not None:
+                    gemm_tn(dy, x2, dw)
+                if db is not None:
+                    db.zero_()
+                    colsum(dy[:, :nb], db[:nb])
+            ctx.wg.set(job, keep=(dy, x2))
+            return dx, dw, db, None, None, None, None, None
         if ctx.needs_input_grad[1]:
             dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
             gemm_tn(dy, x2, dw)
         if ctx.needs_input_grad[2]:
             db = torch.zeros(w.shape[0], device=dy.device, dtype=torch.float32)
-            nb = ctx.bias_cols
             colsum(dy[:, :nb], db[:nb])
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False):
@@ -392,7 +598,10 @@ def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False):
     slab = GradSlab()
     nb = w.shape[0] if bias_cols is None else bias_cols
     assert not skip_tail or nb <= w.shape[0] - sizes[-1]
-    outs = _LinearSplit.apply(x, w, b, sizes, nb, slab, sizes[-1] if skip_tail else 0)
+    wg = None
+    if _n_rows(x) >= DEFER_MIN_ROWS:
+        w, b, wg = defer(w, b)
+    outs = _LinearSplit.apply(x, w, b, sizes, nb, slab, sizes[-1] if skip_tail else 0, wg)
     off = 0
     for o, n in zip(outs, sizes):
         o._pd_slab = (slab, off, n)                           # lets slab-aware consumers write their gradient in place
@@ -677,9 +886,10 @@ class _GruSeq(torch.autograd.Function):
     duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
 
     @staticmethod
-    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None, xsrc=None):
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None, xsrc=None, wg=None):
         _chk(gi, "gi")
         ctx.slab = slab
+        ctx.wg = wg
         save = {}
         h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps, xsrc)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
@@ -719,31 +929,40 @@ class _GruSeq(torch.autograd.Function):
             _over_row_chunks(B, 3 * H, run)
         dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)
-        if ctx.has_gi2:
+        has_gi2 = ctx.has_gi2
+        if has_gi2:
             # one pass over dgi instead of a read-modify-write of (B,3H) in every step's gate kernel; the r and z
             # thirds of db_hh equal those of sum(dgi) (dgh differs from dgi only in the n gate)
             dgi2 = sum_steps(dgi, T)
-            colsum(dgi2[:, :2 * H], db[:2 * H])
-            colsum(dgh_flat[:, 2 * H:], db[2 * H:])
-        else:
-            colsum(dgh_flat, db)
-        # dW_hh = sum_{b,t} dgh[b,t]^T h_prev[b,t] as ONE split-K GEMM over all (b,t) rows: h_prev of row r is
-        # row r-1 (r+1 when reversed) of the flattened state buffer, except at each sequence's first step,
-        # whose h_prev is h0 -- those rows are handled by a small GEMM and then zeroed in dgh.
+            colsum(dgi2[:, :2 * H], db[:2 * H])        # (in line: dgi2 goes back to the engine, which may add into it)
         dw = torch.empty(w_hh.shape, device=dev, dtype=torch.float32)
         first = order[0]
-        if h0 is not None:
-            gemm_tn(dgh[:, first], h0, dw)
-        if T > 1:
-            dgh[:, first].zero_()
-            h_flat = h_all.view(B * T, H)
-            if ctx.reverse:
-                gemm_tn(dgh_flat[:-1], h_flat[1:], dw, accumulate=h0 is not None)
+        reverse = ctx.reverse
+
+        def wgrads():
+            if has_gi2:
+                colsum(dgh_flat[:, 2 * H:], db[2 * H:])
             else:
-                gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
-        elif h0 is None:
-            dw.zero_()
-        return dgi, dgi2, dh0, dw, db, None, None, None, None, None
+                colsum(dgh_flat, db)
+            # dW_hh = sum_{b,t} dgh[b,t]^T h_prev[b,t] as ONE split-K GEMM over all (b,t) rows: h_prev of row r is
+            # row r-1 (r+1 when reversed) of the flattened state buffer, except at each sequence's first step,
+            # whose h_prev is h0 -- those rows are handled by a small GEMM and then zeroed in dgh.
+            if h0 is not None:
+                gemm_tn(dgh[:, first], h0, dw)
+            if T > 1:
+                dgh[:, first].zero_()
+                h_flat = h_all.view(B * T, H)
+                if reverse:
+                    gemm_tn(dgh_flat[:-1], h_flat[1:], dw, accumulate=h0 is not None)
+                else:
+                    gemm_tn(dgh_flat[1:], h_flat[:-1], dw, accumulate=h0 is not None)
+            elif h0 is None:
+                dw.zero_()
+        if ctx.wg is not None:
+            ctx.wg.set(wgrads, keep=(dgh, h_all, h0))     # off the chain: on the weight-gradient stream (ops.defer)
+        else:
+            wgrads()
+        return dgi, dgi2, dh0, dw, db, None, None, None, None, None, None
 
 
 def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None, xsrc=None):
@@ -753,7 +972,10 @@ def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=N
         xsrc = (xsrc[0].detach(), xsrc[1].detach())           # gradients flow through gi's producer (linear_split)
     if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
                                     (h0 is not None and h0.requires_grad)):
-        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc)
+        wg = None
+        if gi.shape[0] * gi.shape[1] >= DEFER_MIN_ROWS:
+            w_hh, b_hh, wg = defer(w_hh, b_hh)
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc, wg)
     return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps, xsrc)
 
 
@@ -847,33 +1069,45 @@ class _NoteEmbed(torch.autograd.Function):
     """note_embedding(multi-hot) as a 6-row gather-add (ptvae.py:299-313,:333); tok int32 (R,6)."""
 
     @staticmethod
-    def forward(ctx, tok, w, b, out=None):
+    def forward(ctx, tok, w, b, out=None, wg=None):
         R = tok.shape[0]
         wt = transpose(w)                                  # (135,128): rows contiguous per pitch
         if out is None:
             out = torch.empty(R, 128, device=w.device, dtype=torch.float32)
         _call("pd_note_embed_fwd", _ptr(tok), R, _ptr(wt), _ptr(b), _ptr(out), out.stride(0), _stream())
         ctx.save_for_backward(tok)
+        ctx.wg = wg
         return out
 
     @staticmethod
     def backward(ctx, g):
         (tok,) = ctx.saved_tensors
         g2, _ = _rows(g)
-        dwt = torch.zeros(135, 128, device=g.device, dtype=torch.float32)
-        db = torch.zeros(128, device=g.device, dtype=torch.float32)
-        _call("pd_note_embed_bwd", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db),
-              _stream())
-        return None, transpose(dwt), db, None
+        dw = torch.empty(128, 135, device=g.device, dtype=torch.float32)
+        db = torch.empty(128, device=g.device, dtype=torch.float32)
+
+        def wgrads():                                      # the whole backward is parameter gradients (tokens are ints)
+            dwt = torch.zeros(135, 128, device=dw.device, dtype=torch.float32)
+            db.zero_()
+            _call("pd_note_embed_bwd", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db), _stream())
+            _call("pd_transpose_f32", _ptr(dwt), 135, 128, _ptr(dw), _stream())
+        if ctx.wg is not None:
+            ctx.wg.set(wgrads, keep=(g2, tok))
+        else:
+            wgrads()
+        return None, dw, db, None, None
 
 
 def note_embed(tok, w, b):
-    return _NoteEmbed.apply(tok, w, b)
+    wg = None
+    if torch.is_grad_enabled() and tok.shape[0] >= DEFER_MIN_ROWS:
+        w, b, wg = defer(w, b)
+    return _NoteEmbed.apply(tok, w, b, None, wg)
 
 
 class _TextureFrontend(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pr_mat, w, b):
+    def forward(ctx, pr_mat, w, b, wg=None):
         _chk(pr_mat, "pr_mat")
         pr = pr_mat.contiguous()
         B, C = pr.shape[0], w.shape[0]
@@ -881,21 +1115,33 @@ class _TextureFrontend(torch.autograd.Function):
         wc = w.contiguous()
         _call("pd_texture_frontend_fwd", _ptr(pr), _ptr(wc), _ptr(b), B, C, _ptr(out), _stream())
         ctx.save_for_backward(pr, wc, b)
+        ctx.wg = wg
         return out
 
     @staticmethod
     def backward(ctx, g):
         pr, w, b = ctx.saved_tensors
         g = g.contiguous()
-        dw = torch.zeros_like(w)
-        db = torch.zeros_like(b)
-        _call("pd_texture_frontend_bwd", _ptr(pr), _ptr(w), _ptr(b), pr.shape[0], w.shape[0], _ptr(g),
-              _ptr(dw), _ptr(db), _stream())
-        return None, dw, db
+        dw = torch.empty_like(w)
+        db = torch.empty_like(b)
+
+        def wgrads():                                      # (the piano-roll input needs no gradient)
+            dw.zero_()
+            db.zero_()
+            _call("pd_texture_frontend_bwd", _ptr(pr), _ptr(w), _ptr(b), pr.shape[0], w.shape[0], _ptr(g),
+                  _ptr(dw), _ptr(db), _stream())
+        if ctx.wg is not None:
+            ctx.wg.set(wgrads, keep=(g, pr))
+        else:
+            wgrads()
+        return None, dw, db, None
 
 
 def texture_frontend(pr_mat, w, b):
-    return _TextureFrontend.apply(pr_mat, w, b)
+    wg = None
+    if torch.is_grad_enabled() and pr_mat.shape[0] * 32 >= DEFER_MIN_ROWS:
+        w, b, wg = defer(w, b)
+    return _TextureFrontend.apply(pr_mat, w, b, wg)
 
 
 class _MaskedCE(torch.autograd.Function):
@@ -1050,9 +1296,10 @@ class _DurDecode(torch.autograd.Function):
     (GX^T . S) that produces every parameter gradient (layout in csrc/dur_decoder.cu)."""
 
     @staticmethod
-    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab=None):
+    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab=None, wg=None):
         h2, _ = _rows(_chk(h0, "dur h0"))
         ctx.slab = slab
+        ctx.wg = wg
         Q = h2.shape[0]
         dev = h2.device
         logits = torch.empty(Q, 5, 2, device=dev, dtype=torch.float32)
@@ -1080,6 +1327,20 @@ class _DurDecode(torch.autograd.Function):
         _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
                                                                                  b_out)],
               _ptr(GX), _ptr(dh0), dh0.stride(0), ctx.tf32, _stream())
+        if ctx.wg is not None:
+            # every parameter gradient comes from the GX^T . S GEMM: buffers now, the GEMM and its unpacking on the
+            # weight-gradient stream (ops.defer)
+            outs = [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)]
+
+            def job():
+                G = torch.empty(264, 72, device=dev, dtype=torch.float32)
+                gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
+                gi_rows = torch.cat([G[0:128], G[192:256]], 0)
+                for o, v in zip(outs, (gi_rows[:, 64:69], gi_rows[:, 69], G[0:192, 0:64], G[0:192, 69],
+                                       w_ih.t() @ gi_rows[:, 70], G[256:258, 0:64], G[256:258, 69])):
+                    o.copy_(v)
+            ctx.wg.set(job, keep=(GX, S))
+            return (dh0.view(ctx.h_shape), *outs, None, None)
         G = torch.empty(264, 72, device=dev, dtype=torch.float32)
         gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
         gi_rows = torch.cat([G[0:128], G[192:256]], 0)            # [dr | dz | dn] x S columns
@@ -1088,7 +1349,7 @@ class _DurDecode(torch.autograd.Function):
         dsos = w_ih.t() @ gi_rows[:, 70]                           # (5,) from the step-0 input-gate grads
         dw_out, db_out = G[256:258, 0:64], G[256:258, 69]
         return (dh0.view(ctx.h_shape), dw_ih.contiguous(), db_ih.contiguous(), dw_hh.contiguous(),
-                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None)
+                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None, None)
 
 
 def dur_mode():
@@ -1097,7 +1358,11 @@ def dur_mode():
 
 
 def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
-    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, _slab_of(h0, 64) if h0.dim() == 2 else None)
+    slab = _slab_of(h0, 64) if h0.dim() == 2 else None            # (before tagging: tags are new tensor objects)
+    wg = None
+    if torch.is_grad_enabled() and _n_rows(h0) >= DEFER_MIN_ROWS:
+        w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, wg = defer(w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)
+    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab, wg)
 
 
 class _SelectRows(torch.autograd.Function):

@@ -176,8 +176,10 @@ class RnnDecoder(nn.Module):
         if inference:
             tfr = 0.
         w_ih, w_hh, b_ih, b_hh = self.gru.dir()
+        with ops.weight_space("chd_in"):               # weight-space views / merged heads live on the weight-gradient stream
+            w_ih_z, w_ih_tok = ops.wmark(w_ih[:, self.input_dim:], w_ih[:, :self.input_dim])
         h = self.z2dec_hid(z_chd)
-        gi_z = ops.linear(self.z2dec_in(z_chd), w_ih[:, self.input_dim:], b_ih)   # constant over steps
+        gi_z = ops.linear(self.z2dec_in(z_chd), w_ih_z, b_ih)   # constant over steps
         n = int(self.num_step / 4)
         if plan_dev is not None:
             plan = None
@@ -187,15 +189,17 @@ class RnnDecoder(nn.Module):
             # every fed-back token is the ground truth: the 8 steps are one GRU sequence over known inputs and the
             # three heads one GEMM over all states (the reference's per-step loop, batched)
             toks = torch.cat([self.init_input.expand(bs, 1, self.input_dim), c[:, :n - 1]], 1).contiguous()
-            hs = ops.gru_sequence(ops.linear(toks, w_ih[:, :self.input_dim], None), gi_z, h, w_hh, b_hh)
-            r, ch, b = ops.linear_split(
-                hs, torch.cat([self.root_out.weight, self.chroma_out.weight, self.bass_out.weight], 0),
-                torch.cat([self.root_out.bias, self.chroma_out.bias, self.bass_out.bias], 0), (12, 24, 12))
+            hs = ops.gru_sequence(ops.linear(toks, w_ih_tok, None), gi_z, h, w_hh, b_hh)
+            with ops.weight_space("chd_heads"):
+                w_heads, b_heads = ops.wmark(
+                    torch.cat([self.root_out.weight, self.chroma_out.weight, self.bass_out.weight], 0),
+                    torch.cat([self.root_out.bias, self.chroma_out.bias, self.bass_out.bias], 0))
+            r, ch, b = ops.linear_split(hs, w_heads, b_heads, (12, 24, 12))
             return r, ch.view(bs, n, 12, 2), b
         tok = self.init_input.expand(bs, self.input_dim)
         roots, chromas, basses = [], [], []
         for t in range(n):
-            gi = ops.linear(tok, w_ih[:, :self.input_dim], None)
+            gi = ops.linear(tok, w_ih_tok, None)
             h = ops.gru_sequence(gi.view(bs, 1, -1), gi_z, h, w_hh, b_hh)[:, 0]
             r, ch, b = self.root_out(h), self.chroma_out(h).view(bs, 12, 2), self.bass_out(h)
             roots.append(r.unsqueeze(1))
@@ -292,9 +296,11 @@ class PtvaeDecoder(nn.Module):
     # -- teacher-forced (tfr1 = tfr2 = 1 decisions): batched phases -------------------------------
     def _time_inputs(self, z):
         w_ih, w_hh, b_ih, b_hh = self.dec_time_gru.dir()
+        with ops.weight_space("time_in"):
+            w_z, w_tok = ops.wmark(w_ih[:, 2 * self.dec_emb_hid_size:], w_ih[:, :2 * self.dec_emb_hid_size])
         z_hid = self.z2dec_hid_linear(z)
-        gi_z = ops.linear(self.z2dec_in_linear(z), w_ih[:, 2 * self.dec_emb_hid_size:], b_ih)
-        return z_hid, gi_z, w_ih[:, :2 * self.dec_emb_hid_size], w_hh, b_hh
+        gi_z = ops.linear(self.z2dec_in_linear(z), w_z, b_ih)
+        return z_hid, gi_z, w_tok, w_hh, b_hh
 
     def teacher_forced_prologue(self, x, lengths):
         """The part of the teacher-forced decoder that does not depend on z: x-projections of the ground-truth note
@@ -309,12 +315,14 @@ class PtvaeDecoder(nn.Module):
         # one GEMM, one input gradient (ops.linear_split)
         eg = self.dec_notes_emb_gru
         (wf, _, bf, _), (wb, _, bb, _) = eg.dir(False), eg.dir(True)
-        w_tok_n = wn_ih[:, self.dec_time_hid_size:]
+        with ops.weight_space("prologue"):
+            w_tok_n = wn_ih[:, self.dec_time_hid_size:]
+            w_cat, b_cat = ops.wmark(torch.cat([wf, wb, w_tok_n], 0), torch.cat([bf, bb, bf.new_zeros(w_tok_n.shape[0])], 0))
         # with the fused step kernel the note GRU multiplies its embedding rows itself (ops.fold_x_ok): the gi_tok head is
         # then not computed here (its tensor only routes the gradient back into this projection's backward)
         fold = ops.fold_x_ok(R, self.dec_notes_hid_size, notes, w_tok_n)
         gi_f, gi_b, gi_tok = ops.linear_split(                                            # gi_tok (R,16,1536)
-            notes, torch.cat([wf, wb, w_tok_n], 0), torch.cat([bf, bb, bf.new_zeros(w_tok_n.shape[0])], 0),
+            notes, w_cat, b_cat,
             (wf.shape[0], wb.shape[0], w_tok_n.shape[0]), bias_cols=wf.shape[0] + wb.shape[0], skip_tail=fold)
         summ = _bigru_final(eg, notes, lengths32, gi=(gi_f, gi_b)).view(B, self.num_step, -1)
         return (summ, gi_tok, (notes, w_tok_n)) if fold else (summ, gi_tok)
@@ -331,13 +339,16 @@ class PtvaeDecoder(nn.Module):
         summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
         S = summary.reshape(R, self.dec_time_hid_size)
         h0 = self.dec_time_to_notes_hid(S)
-        gi_s = ops.linear(S, wn_ih[:, :self.dec_time_hid_size], bn_ih)
+        with ops.weight_space("tf_heads"):
+            wn_s = ops.wmark(wn_ih[:, :self.dec_time_hid_size])
+            w_eff, b_eff = self._dur_hid_folded()
+            w_ph, b_ph = ops.wmark(torch.cat([self.pitch_out_linear.weight, w_eff], 0),
+                                   torch.cat([self.pitch_out_linear.bias, b_eff], 0))
+        gi_s = ops.linear(S, wn_s, bn_ih)
         h = ops.gru_sequence(gi_tok, gi_s, h0, wn_hh, bn_hh, n_steps=self.max_simu_note - 1, xsrc=xsrc)  # (R,15,512)
         # pitch head and (folded) duration-hidden projection as one GEMM over the note states
         Q = R * (self.max_simu_note - 1)
-        w_eff, b_eff = self._dur_hid_folded()
-        pitch, dh = ops.linear_split(h.reshape(Q, -1), torch.cat([self.pitch_out_linear.weight, w_eff], 0),
-                                     torch.cat([self.pitch_out_linear.bias, b_eff], 0), self.pitch_range)
+        pitch, dh = ops.linear_split(h.reshape(Q, -1), w_ph, b_ph, self.pitch_range)
         w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
         dur = ops.dur_decode(dh, w_ih, b_ih, w_hh, b_hh, self.dur_sos_token, self.dur_out_linear.weight,
                              self.dur_out_linear.bias)
@@ -397,7 +408,9 @@ class PtvaeDecoder(nn.Module):
         else:
             summ = summ_pred
         wn_ih = self.dec_notes_gru.dir()[0]
-        gi_tok = ops.linear(mix_emb, wn_ih[:, self.dec_time_hid_size:], None)
+        with ops.weight_space("sampled"):
+            w_tok_n = ops.wmark(wn_ih[:, self.dec_time_hid_size:])
+        gi_tok = ops.linear(mix_emb, w_tok_n, None)
         return self._decode_teacher_forced(z, None, None, pre=(summ, gi_tok))
 
     # -- general step-wise path (scheduled sampling / inference) ----------------------------------

@@ -31,9 +31,17 @@ def test_state_dict_keys_match_reference_contract():
 
 
 @pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan",
-                                 "tf000-batched", "tf555-batched", "tf111-fusedstep"])
+                                 "tf000-batched", "tf555-batched", "tf111-fusedstep", "tf111-deferall", "tf555-deferall",
+                                 "tf111-nodefer"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     be = cpu_backend.install(monkeypatch)
+    if tag.endswith("-deferall") or tag.endswith("-nodefer"):
+        # weight gradients as deferred jobs behind tag nodes (ops.defer) at EVERY site incl. the batch-sized layers, or
+        # nowhere (the in-line computation): same gradients either way
+        from polydis_b200 import ops
+        monkeypatch.setattr(ops, "DEFER_MIN_ROWS", 1)
+        monkeypatch.setattr(ops, "DEFER_WGRAD", tag.endswith("-deferall"))
+        tag = tag[:tag.rindex("-")]
     fused = tag.endswith("-fusedstep")
     if fused:       # fused recurrent step kernels for every recurrence + the note GRU's x-projection folded into the step
         from polydis_b200 import ops
