@@ -235,6 +235,50 @@ int pd_counter_inc(int* counter, void* stream);
 int pd_adam_clip_step(float* p, const float* g, float* m, float* v, long n, const float* sumsq, const int* step,
                       float lr0, float gamma, float lr_min, float b1, float b2, float eps, float clip, void* stream);
 
+/* ---- packed note level of the teacher-forced PianoTree decoder in loss mode (csrc/packed.cu, ops.py "packed notes").
+ * Replaces, for training, the dense 15-slot note loop of ptvae.py:370-428 and its heads / duration decoder (:336-368):
+ * the reference computes every slot of every (segment, time step) row and lets the loss ignore the PAD targets
+ * (ptvae.py:498-511); here rows are sorted by token count (as pack_padded_sequence does for the summary GRU,
+ * ptvae.py:446-453), note-level buffers are slot-major (slot n, sorted row r), and a DEVICE table says how many rows of
+ * each slot are live.  Kernels are launched for the full extent and skip dead tiles, so one CUDA graph serves every batch.
+ * table (64 int32): [0,17) c[t] = rows with more than t tokens; [17,34) cp[t] = min(R, c[t] rounded up to 128);
+ * [34,51) 6*cp[t].  A live-row predicate is (cp pointer, slot_rows): row q of a slot-major buffer is live iff
+ * q % slot_rows < cp[q / slot_rows]. */
+int pd_pack_order(const int* lengths, int R, int* perm, int* inv, int* table, void* stream);
+int pd_pack_grid(const int* tok, const int* lengths, const int* perm, int R, int* tok_s, int* pitch_tgt_s, int* dur_tgt_s,
+                 int* lengths_s, void* stream);
+/* dst (R,C) = src[idx] */
+int pd_gather_rows_f32(const float* src, long lds, const int* idx, long R, int C, float* dst, long ldd, void* stream);
+/* out (R,C) = sum over slots t < T with r < cp[t] of X (T,R,C) */
+int pd_sum_slots_rows_f32(const float* X, long ldt, long ldr, int T, const int* cp, float* out, long ldo, long R, int C,
+                          void* stream);
+/* column sums over the live rows */
+int pd_colsum_rows_f32(const float* X, long ldx, long M, int N, float* out, int accumulate, const int* cp, int slot_rows,
+                       void* stream);
+/* pd_gemm_tf32 with a live-row predicate: pred 1 = on the rows of A / C (dead 128-row tiles are neither loaded, multiplied
+ * nor stored), pred 2 = on the contraction index (weight gradients: only live 32-row k-blocks are accumulated) */
+int pd_gemm_tf32_rows(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                      const float* bias, int M, int N, int K, int accumulate, int pred, const int* cp, int slot_rows,
+                      void* stream);
+/* pd_gru_step_tmax / pd_gru_gates_bwd over the first *nrows rows (a device count) */
+int pd_gru_step_tmax_rows(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx,
+                          const float* w_x, long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout,
+                          long ldho, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H, const int* nrows,
+                          void* stream);
+int pd_gru_gates_bwd_rows(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                          const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp,
+                          float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, int B, int H,
+                          const int* nrows, void* stream);
+/* duration decoder / embedding gradient with the live-row predicate (TF32 training mode) */
+int pd_dur_decode_fwd_rows(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih, const float* w_hh,
+                           const float* b_hh, const float* sos, const float* w_out, const float* b_out, float* logits,
+                           float* S, const int* cp, int slot_rows, void* stream);
+int pd_dur_decode_bwd_rows(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+                           const float* w_hh, const float* b_hh, const float* sos, const float* w_out, const float* b_out,
+                           float* GX, float* dh0, long lddh0, const int* cp, int slot_rows, void* stream);
+int pd_note_embed_bwd_rows(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, const int* cp,
+                           int slot_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,18 @@ SIGNATURES = {
     "pd_sumsq_f32": [_P, _L, _P, _P],
     "pd_counter_inc": [_P, _P],
     "pd_adam_clip_step": [_P, _P, _P, _P, _L, _P, _P, _F, _F, _F, _F, _F, _F, _F, _P],
+    # packed note level (length-sorted rows, slot-major buffers, device live-row table)
+    "pd_pack_order": [_P, _I, _P, _P, _P, _P],
+    "pd_pack_grid": [_P, _P, _P, _I, _P, _P, _P, _P, _P],
+    "pd_gather_rows_f32": [_P, _L, _P, _L, _I, _P, _L, _P],
+    "pd_sum_slots_rows_f32": [_P, _L, _L, _I, _P, _P, _L, _L, _I, _P],
+    "pd_colsum_rows_f32": [_P, _L, _L, _I, _P, _I, _P, _I, _P],
+    "pd_gemm_tf32_rows": [_P, _L, _L, _P, _L, _L, _P, _L, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "pd_gru_step_tmax_rows": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P, _P],
+    "pd_gru_gates_bwd_rows": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P, _P],
+    "pd_dur_decode_fwd_rows": [_P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "pd_dur_decode_bwd_rows": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _I, _P],
+    "pd_note_embed_bwd_rows": [_P, _L, _P, _L, _P, _P, _P, _I, _P],
 }
 
 LIB_PATH = _build.LIB_PATH

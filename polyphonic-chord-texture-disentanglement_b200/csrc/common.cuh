@@ -37,6 +37,62 @@ static inline bool pd_first_use_on_device(unsigned long long& mask) {
     return true;
 }
 
+// Row predicate of the packed note level (length-sorted rows, slot-major buffers; ops.py "packed notes"): row q of a
+// (n_slots * slot_rows)-row buffer belongs to slot q / slot_rows and is LIVE iff q % slot_rows < cp[slot].  cp is DEVICE
+// data (it depends on the batch's note counts), so one captured CUDA graph serves every batch: kernels are launched
+// for the full extent and skip dead tiles.  cp == nullptr: everything is live.
+struct PdRows {
+    const int* cp;
+    int slot_rows, n_slots;
+};
+// any live row in [q0, q0 + n)?
+__device__ __forceinline__ bool pd_rows_live(const PdRows& p, long q0, int n) {
+    if (p.cp == nullptr) return true;
+    const long q1 = q0 + n;
+    int s = (int)(q0 / p.slot_rows);
+    long base = (long)s * p.slot_rows;
+    while (base < q1 && s < p.n_slots) {
+        const long lo = (q0 > base ? q0 : base) - base;
+        if (lo < p.cp[s]) return true;
+        ++s;
+        base += p.slot_rows;
+    }
+    return false;
+}
+// Live k-blocks (BK consecutive rows, slot_rows % BK == 0) of a slot-major K range, enumerated in order: the split-K
+// weight-gradient GEMMs iterate these instead of [0, K / BK).
+struct PdLiveBlocks {
+    const int* cp;
+    int slot_rows, n_slots, bk, s, j, ls;
+    __device__ __forceinline__ int live_of(int slot) const {
+        const int c = cp[slot] < slot_rows ? cp[slot] : slot_rows;
+        return c <= 0 ? 0 : (c + bk - 1) / bk;
+    }
+    __device__ __forceinline__ int total() const {
+        int t = 0;
+        for (int i = 0; i < n_slots; ++i) t += live_of(i);
+        return t;
+    }
+    __device__ __forceinline__ void seek(int a) {       // position at live block number a (a < total())
+        s = 0;
+        ls = 0;
+        while (s < n_slots) {
+            ls = live_of(s);
+            if (a < ls) break;
+            a -= ls;
+            ++s;
+        }
+        j = a;
+    }
+    __device__ __forceinline__ int row0() const { return s * slot_rows + j * bk; }
+    __device__ __forceinline__ void next() {
+        if (++j >= ls) {
+            j = 0;
+            do { ++s; } while (s < n_slots && (ls = live_of(s)) == 0);
+        }
+    }
+};
+
 __device__ __forceinline__ float pd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 // MUFU forms for the TF32-mode recurrent kernels, which are instruction-bound on the gate math: ex2.approx +
 // rcp.approx, absolute error ~1e-6 (three orders below the TF32 operand rounding of the matvec next to them);

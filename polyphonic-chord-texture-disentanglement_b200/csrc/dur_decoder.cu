@@ -416,7 +416,7 @@ template <int PASSES> __device__ __forceinline__ float gate_tanh(float x) { retu
 template <int PASSES>
 __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const float* __restrict__ h0, long ldh0, long Q,
                                                                          DurParams p, float* __restrict__ logits,
-                                                                         float* __restrict__ S) {
+                                                                         float* __restrict__ S, PdRows live) {
     extern __shared__ __align__(16) float dyn_smem[];
     WarpShared* sh = reinterpret_cast<WarpShared*>(dyn_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
@@ -432,6 +432,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
     for (long t16 = blockIdx.x + (long)gridDim.x * warp; t16 < n16; t16 += (long)gridDim.x * FW_WARPS) {   // tiles spread over CTAs first
         const long q0 = t16 * WM;
         const int rows = (int)min((long)WM, Q - q0);
+        if (!pd_rows_live(live, q0, WM)) continue;         // packed note level: dead notes are neither read nor written
         __syncwarp();
         warp_load_rows(h0 + q0 * ldh0, ldh0, rows, hw, lane, al16);
         if (lane < WM) tokw[lane] = 0;
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
 __global__ void __launch_bounds__(BW_WARPS * 32, 1) dur_bwd_warp_kernel(const float* __restrict__ S,
                                                                          const float* __restrict__ dlog, long Q, DurParams p,
                                                                          float* __restrict__ GX, float* __restrict__ dh0,
-                                                                         long lddh0) {
+                                                                         long lddh0, PdRows live) {
     extern __shared__ __align__(16) float dyn_smem[];
     WarpShared* sh = reinterpret_cast<WarpShared*>(dyn_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, 1) dur_bwd_warp_kernel(const fl
     for (long t16 = blockIdx.x + (long)gridDim.x * warp; t16 < n16; t16 += (long)gridDim.x * BW_WARPS) {
         const long q0 = t16 * WM;
         const int rows = (int)min((long)WM, Q - q0);
+        if (!pd_rows_live(live, q0, WM)) continue;
         float dh[8][4];                                    // grad wrt the step's output state, accumulator layout
 #pragma unroll
         for (int j = 0; j < 8; ++j) dh[j][0] = dh[j][1] = dh[j][2] = dh[j][3] = 0.0f;
@@ -640,10 +642,11 @@ unsigned warp_grid(long Q) {
 // logits (Q,5,2) <- 5-step greedy-feedback duration GRU from h0 (Q,64; row stride ldh0).  S (Q,6,72) may be
 // NULL (inference).  tf32: 0 = fp32 FFMA kernels, 1 = TF32 tensor-core matvecs, 3 = error-compensated 3xTF32 matvecs with
 // expf / tanhf gates (fp32-class, forward only).  Nonzero: S must be 16-byte and h0 8-byte aligned, ldh0 even.
-PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
-                             const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
-                             const float* b_out, float* logits, float* S, int tf32, void* stream) {
+static int dur_fwd_impl(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
+                        const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                        const float* b_out, float* logits, float* S, int tf32, PdRows live, void* stream) {
     if (Q <= 0) return 0;
+    if (live.cp != nullptr && tf32 != 1) return PD_BAD_ARG;      // the live-row table is a training-mode feature
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
     // small fp32-class calls (step-wise decode of a few segments) are latency bound: one warp per 16 notes doing
@@ -657,19 +660,36 @@ PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_
             if (e == cudaSuccess) e = cudaFuncSetAttribute(dur_fwd_warp_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM3);
             if (e != cudaSuccess) return (int)e;
         }
-        if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM3, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
-        else dur_fwd_warp_kernel<1><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
+        if (tf32 == 3) dur_fwd_warp_kernel<3><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM3, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S, live);
+        else dur_fwd_warp_kernel<1><<<warp_grid(Q), FW_WARPS * 32, FW_SMEM, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S, live);
     } else {
         dur_fwd_kernel<<<dur_grid(Q), NTHR, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits, S);
     }
     return pd_launch_status();
 }
 
-// GX (Q,6,264) and dh0 (Q,64) <- S, dlogits (Q,5,2).  Parameter gradients = GX^T . S (one GEMM by the caller).
-PD_API int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+PD_API int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
                              const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
-                             const float* b_out, float* GX, float* dh0, long lddh0, int tf32, void* stream) {
+                             const float* b_out, float* logits, float* S, int tf32, void* stream) {
+    return dur_fwd_impl(h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, tf32, PdRows{nullptr, 0, 0}, stream);
+}
+
+// Packed note level: notes are slot-major rows (Q = n_slots * slot_rows) with a DEVICE live-row table cp (common.cuh
+// PdRows); 16-note tiles without a live note are skipped (their logits / S rows are not written).  TF32 mode only.
+PD_API int pd_dur_decode_fwd_rows(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
+                                  const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                                  const float* b_out, float* logits, float* S, const int* cp, int slot_rows, void* stream) {
+    if (cp == nullptr || slot_rows <= 0) return PD_BAD_ARG;
+    return dur_fwd_impl(h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, 1,
+                        PdRows{cp, slot_rows, (int)((Q + slot_rows - 1) / slot_rows)}, stream);
+}
+
+// GX (Q,6,264) and dh0 (Q,64) <- S, dlogits (Q,5,2).  Parameter gradients = GX^T . S (one GEMM by the caller).
+static int dur_bwd_impl(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+                        const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                        const float* b_out, float* GX, float* dh0, long lddh0, int tf32, PdRows live, void* stream) {
     if (Q <= 0) return 0;
+    if (live.cp != nullptr && tf32 != 1) return PD_BAD_ARG;
     if (((uintptr_t)w_hh & 15)) return PD_BAD_ARG;
     DurParams p{w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out};
     constexpr int smem_ff = (3 * RT * HS + RT * GS + 3 * RT * HS) * (int)sizeof(float);
@@ -681,9 +701,25 @@ PD_API int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const
     }
     if (tf32) {
         if ((((uintptr_t)S | (uintptr_t)GX) & 15) || (((uintptr_t)dlogits | (uintptr_t)dh0) & 7) || (lddh0 & 1)) return PD_BAD_ARG;
-        dur_bwd_warp_kernel<<<warp_grid(Q), BW_WARPS * 32, BW_SMEM, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
+        dur_bwd_warp_kernel<<<warp_grid(Q), BW_WARPS * 32, BW_SMEM, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0, live);
     } else {
         dur_bwd_kernel<<<dur_grid(Q), NTHR, smem_ff, (cudaStream_t)stream>>>(S, dlogits, Q, p, GX, dh0, lddh0);
     }
     return pd_launch_status();
+}
+
+PD_API int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+                             const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                             const float* b_out, float* GX, float* dh0, long lddh0, int tf32, void* stream) {
+    return dur_bwd_impl(S, dlogits, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, tf32, PdRows{nullptr, 0, 0}, stream);
+}
+
+// Packed note level (see pd_dur_decode_fwd_rows): GX / dh0 rows of dead 16-note tiles are not written.
+PD_API int pd_dur_decode_bwd_rows(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
+                                  const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
+                                  const float* b_out, float* GX, float* dh0, long lddh0, const int* cp, int slot_rows,
+                                  void* stream) {
+    if (cp == nullptr || slot_rows <= 0) return PD_BAD_ARG;
+    return dur_bwd_impl(S, dlogits, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, 1,
+                        PdRows{cp, slot_rows, (int)((Q + slot_rows - 1) / slot_rows)}, stream);
 }

@@ -27,6 +27,8 @@ struct TcArgs {
     int atomic;         // accumulate into C (C += result, or split-K partial sums): red.global.add epilogue
     int dbg;            // tuning only: 1 = skip the epilogue stores, 2 = skip the MMAs, 3 = both
     int tma_store;      // persistent kernel: write C tiles with TMA bulk stores (plain stores, aligned C)
+    PdRows rows;        // packed note level: live-row predicate (common.cuh) ...
+    int pred;           // ... 0 = none, 1 = on the rows of A / C (dead M tiles are skipped), 2 = on K (dead k-blocks are skipped)
 };
 
 // MH = number of 128-row halves per CTA tile (1 or 2).  The per-step GEMMs of this path are L2->SM bandwidth
@@ -48,9 +50,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * (MH * BM), n0 = blockIdx.y * BN;
+    if (g.pred == 1 && !pd_rows_live(g.rows, m0, MH * BM)) return;      // dead row tile of the packed note level
     const int kb_total = (g.K + BKE - 1) / BKE;
-    const int kb_beg = blockIdx.z * g.kb_per_split;
-    const int kb_end = min(kb_total, kb_beg + g.kb_per_split);
+    int kb_beg = blockIdx.z * g.kb_per_split;
+    int kb_end = min(kb_total, kb_beg + g.kb_per_split);
+    PdLiveBlocks lb{g.rows.cp, g.rows.slot_rows, g.rows.n_slots, BKE, 0, 0, 0};
+    if (g.pred == 2) {
+        // K runs over slot-major rows: this CTA takes an equal share of the LIVE k-blocks (kb_* count live blocks)
+        const int total = lb.total();
+        const int per = (total + (int)gridDim.z - 1) / (int)gridDim.z;
+        kb_beg = min(total, (int)blockIdx.z * per);
+        kb_end = min(total, kb_beg + per);
+    }
     const int nkb = kb_end - kb_beg;
 
     if (warp == 0 && lane == 0) {
@@ -71,8 +82,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
+            if (g.pred == 2 && nkb > 0) lb.seek(kb_beg);
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % STAGES, k0 = (kb_beg + i) * BKE;
+                const int s = i % STAGES;
+                int k0 = (kb_beg + i) * BKE;
+                if (g.pred == 2) { k0 = lb.row0(); lb.next(); }
                 if (i >= STAGES) mbar_wait(&empty[s], ((i / STAGES) - 1) & 1);
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                 uint8_t* a = sA + s * A_BYTES;
@@ -266,6 +280,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
             for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int m0, n0, kb_beg, nkb, z;
                 decode(item, m0, n0, kb_beg, nkb, z);
+                if (g.pred == 1 && !pd_rows_live(g.rows, m0, BM)) continue;     // dead row tile (all three roles skip it)
                 for (int i = 0; i < nkb; ++i, ++cnt) {
                     const int s = (int)(cnt % STAGES), k0 = (kb_beg + i) * BKE;
                     if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
@@ -292,9 +307,10 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
             const uint32_t idesc = (1u << 4) | (Elem<EB>::FMT << 7) | (Elem<EB>::FMT << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             long cnt = 0, j = 0;
-            for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+            for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 int m0, n0, kb_beg, nkb, z;
                 decode(item, m0, n0, kb_beg, nkb, z);
+                if (g.pred == 1 && !pd_rows_live(g.rows, m0, BM)) continue;
                 const int acc = (int)(j & 1);
                 if (j >= 2) mbar_wait(&tmem_empty[acc], (uint32_t)((j >> 1) - 1) & 1);   // epilogue drained it
                 tc_fence_after();
@@ -314,6 +330,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     tc_commit(&empty[s]);
                 }
                 tc_commit(&tmem_full[acc]);
+                ++j;
             }
         }
     } else {
@@ -324,9 +341,10 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int sub_r = lane >> 3, colq = (lane & 7) * 4;
         long j = 0;
         int n_st = 0;                                     // bulk stores issued by this warp
-        for (long item = blockIdx.x; item < n_items; item += gridDim.x, ++j) {
+        for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
             int m0, n0, kb_beg, nkb, z;
             decode(item, m0, n0, kb_beg, nkb, z);
+            if (g.pred == 1 && !pd_rows_live(g.rows, m0, BM)) continue;
             const int acc = (int)(j & 1);
             mbar_wait(&tmem_full[acc], (uint32_t)(j >> 1) & 1);
             tc_fence_after();
@@ -363,6 +381,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 }
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                ++j;
                 continue;
             }
 #pragma unroll 1
@@ -415,6 +434,7 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
             // this warp's TMEM reads of accumulator `acc` are complete: hand it back to the MMA warp
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            ++j;
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // all bulk stores of this warp landed
     }
@@ -426,9 +446,14 @@ gemm_tf32_persistent(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-__global__ void zero_2d_tc_kernel(float* C, long ldc, int M, int N) {
+// zero-fill of a split-K output; with a live-row predicate only the row tiles the GEMM will write (dead rows keep their
+// contents, as in the unsplit launch)
+__global__ void zero_2d_tc_kernel(float* C, long ldc, int M, int N, PdRows rows, int tile_rows) {
     long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (long)M * N) C[(i / N) * ldc + (i % N)] = 0.0f;
+    if (i >= (long)M * N) return;
+    const long m = i / N;
+    if (rows.cp != nullptr && !pd_rows_live(rows, m / tile_rows * tile_rows, tile_rows)) return;
+    C[m * ldc + (i % N)] = 0.0f;
 }
 
 template <int EB, int MH, int BN, int STAGES, int MINB, bool A_MN, bool B_MN>
@@ -513,7 +538,8 @@ int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUten
 // EB = 4: A, B fp32 (TF32 multiply).  EB = 2: A, B bf16.  Strides in elements; C / bias fp32.
 template <int EB>
 int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, long sbn, float* C, long ldc,
-                 const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st) {
+                 const float* bias, int M, int N, int K, int accumulate, int cfg, cudaStream_t st, int pred = 0,
+                 const int* cp = nullptr, int slot_rows = 0) {
     constexpr int BKE = 128 / EB, ALIGN = 16 / EB;       // k-block elements; stride alignment in elements
     const int dbg = cfg / 1000000;
     cfg %= 1000000;
@@ -523,6 +549,7 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     const long lda = a_mn ? sak : sam, ldb = b_mn ? sbk : sbn;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda % ALIGN) || (ldb % ALIGN) || lda < ALIGN || ldb < ALIGN)
         return PD_BAD_ARG;
+    if (pred && (cp == nullptr || slot_rows <= 0 || (pred == 2 && slot_rows % BKE))) return PD_BAD_ARG;
     if (cfg == 0) {
         // measured on B200 (tools/gemm_tune.py, tools/gemm_dissect.py)
         const int tiles_m = (M + BM - 1) / BM;
@@ -535,6 +562,7 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
         else if (t256 >= PD_NUM_SMS) cfg = 25622;                    // 2 CTAs/SM
         else if (t128 >= PD_NUM_SMS) cfg = 12823;
         else cfg = 6441;                                             // small per-step recurrent GEMMs
+        if (pred == 2 && cfg >= 900000) cfg = 12823;                 // live-k-block iteration lives in the one-shot kernel
     }
     const int mh = (cfg >= 100000 && cfg < 900000) ? 2 : 1;
     const int bn = (cfg % 100000) / 100;
@@ -556,7 +584,8 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     }
     int kb_per = (kb + split - 1) / split;
     split = (kb + kb_per - 1) / kb_per;
-    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate) ? 1 : 0, dbg, 0};
+    TcArgs g{C, ldc, bias, M, N, K, kb_per, (split > 1 || accumulate || pred == 2) ? 1 : 0, dbg, 0,
+             PdRows{cp, slot_rows, pred ? (int)(((pred == 1 ? (long)M : (long)K) + slot_rows - 1) / slot_rows) : 0}, pred};
     CUtensorMap ta, tb;
     int rc;
     // K-major: [rows][K] -> dims {K, rows}, box {128 B, BM|bn rows}.  MN-major: [K][rows] -> dims {rows, K},
@@ -565,9 +594,10 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
     if (rc) return rc;
     rc = b_mn ? make_map(&tb, B, EB, N, K, ldb, BKE, true) : make_map(&tb, B, EB, K, N, ldb, bn, false);
     if (rc) return rc;
-    if (split > 1 && !accumulate) {
-        if (ldc == N) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);      // dense C: a memset node
-        else zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N);
+    if ((split > 1 || pred == 2) && !accumulate) {
+        if (ldc == N && pred != 1) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st);      // dense C: a memset node
+        else zero_2d_tc_kernel<<<pd_blocks((long)M * N, 256), 256, 0, st>>>(C, ldc, M, N, pred == 1 ? g.rows : PdRows{nullptr, 0, 0},
+                                                                            mh * BM);
     }
     if (cfg == 925641 || (cfg == 912861 && EB == 4)) {
         // C tiles leave through TMA bulk stores when they are plain stores into a 16-byte aligned matrix
@@ -612,6 +642,17 @@ PD_API int pd_gemm_tf32(const float* A, long sam, long sak, const float* B, long
 }
 
 // Tuning variant: cfg = BN*100 + stages*10 + CTAs/SM (one of the instantiated configurations), 0 = heuristic.
+// Packed note level (ops.py): the same GEMM over slot-major row buffers with a DEVICE-side live-row table (common.cuh
+// PdRows).  pred = 1: the rows of A and C are slot-major rows -- dead 128-row tiles are neither loaded, multiplied nor
+// stored (their C rows keep whatever they held).  pred = 2: K runs over slot-major rows (weight gradients) -- only live
+// 32-row k-blocks are accumulated, shared evenly between the split-K CTAs; slot_rows % 32 == 0.  cp: n_slots ints.
+PD_API int pd_gemm_tf32_rows(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
+                             const float* bias, int M, int N, int K, int accumulate, int pred, const int* cp, int slot_rows,
+                             void* stream) {
+    return gemm_tc_impl<4>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream, pred, cp,
+                           slot_rows);
+}
+
 PD_API int pd_gemm_tf32_cfg(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,
                             const float* bias, int M, int N, int K, int accumulate, int cfg, void* stream) {
     return gemm_tc_impl<4>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, cfg, (cudaStream_t)stream);

@@ -97,6 +97,7 @@ struct GateBwd {
     float* dgi2; long lddgi2;          // optional: accumulate dgi over the sequence (broadcast term)
     const int* lengths; int t;
     int B, H;
+    const int* nrows;                  // packed note level: DEVICE count of live rows (a prefix); nullptr = all B
 };
 
 __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
     long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)a.B * hq) return;
     const int b = (int)(idx / hq), j = (int)(idx % hq) * 4;
+    if (a.nrows != nullptr && b >= *a.nrows) return;
     float4 d = a.dh ? *reinterpret_cast<const float4*>(a.dh + (long)b * a.lddh + j) : make_float4(0, 0, 0, 0);
     if (a.dh2) {
         float4 e = *reinterpret_cast<const float4*>(a.dh2 + (long)b * a.lddh2 + j);
@@ -190,10 +192,10 @@ PD_API int pd_gru_gates_fwd_split3(const float* gi, long ldgi, const float* gi2,
                             h3, ldh3, stream);
 }
 
-PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,
+static int gates_bwd_launch(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,
                             long lddh3, const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
                             long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
-                            long lddgi2, const int* lengths, int t, int B, int H, void* stream) {
+                            long lddgi2, const int* lengths, int t, int B, int H, const int* nrows, void* stream) {
     if (B <= 0) return 0;
     if ((H & 3) || (dh && !al4(dh, lddh)) || (dh2 && !al4(dh2, lddh2)) || (dh3 && !al4(dh3, lddh3)) ||
         !al4(rzn, ldrzn) || !al4(hn, ldhn) ||
@@ -201,8 +203,26 @@ PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long l
         (dgi2 && !al4(dgi2, lddgi2)))
         return PD_BAD_ARG;
     GateBwd a{dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh,
-              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H};
+              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H, nrows};
     long n = (long)B * (H >> 2);
     gru_gates_bwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return pd_launch_status();
+}
+
+PD_API int pd_gru_gates_bwd(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,
+                            long lddh3, const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
+                            long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
+                            long lddgi2, const int* lengths, int t, int B, int H, void* stream) {
+    return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
+                            lddhp, dgi2, lddgi2, lengths, t, B, H, nullptr, stream);
+}
+
+// Packed note level: gate gradients of the first *nrows rows only (DEVICE count; the other rows are left untouched)
+PD_API int pd_gru_gates_bwd_rows(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                                 const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp,
+                                 float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, int B, int H,
+                                 const int* nrows, void* stream) {
+    if (nrows == nullptr) return PD_BAD_ARG;
+    return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
+                            lddhp, nullptr, 0, nullptr, 0, B, H, nrows, stream);
 }

@@ -201,6 +201,8 @@ struct StepIo {
     int KA;          // columns of the A operand: H (h_prev itself) or 3H ([hi | hi | lo] split of h_prev, 3xTF32 mode)
     int has_h3;      // also emit the [hi | hi | lo] split of the new state (operand of the next step's / the heads' GEMMs)
     int K2;          // SEG2 kernels: columns of the second A operand (the step's input x, e.g. the note embedding)
+    const int* nrows;   // packed note level: DEVICE count of live rows of this step (rows are length-sorted, so they are a
+                        // prefix; nullptr = all B).  Whole 128-row tiles up to the count are processed, the rest untouched.
 };
 
 constexpr int IOB = 2048;          // one epilogue buffer: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
@@ -254,6 +256,10 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb1 = (g.KA + 31) / 32, nkb2 = SEG2 ? (g.K2 + 31) / 32 : 0;
     const int nkb = nkb1 + nkb2;
+    if (g.nrows != nullptr) {
+        const int live = min(g.B, *g.nrows);
+        tiles_m = (live + BM - 1) / BM;
+    }
     const long n_items = (long)tiles_m * tiles_u;
 
     if (warp == 0 && lane == 0) {
@@ -552,7 +558,7 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0};
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr};
     const CUtensorMap th3 = tho;
     constexpr bool kPrecise = false;
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
@@ -583,9 +589,9 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
 // second K segment (x: B x K2 rows of the step's input, w_x: 3H x K2), so the (B,T,3H) x-projection of the sequence is never
 // materialised.  gi2 (B,3H) carries the rest of the input projection incl. b_ih.  Teacher-forced note GRU (ptvae.py:396-398):
 // x = ground-truth note embedding of slot n (row stride 16*128), w_x = dec_notes_gru.weight_ih[:, 1024:].
-PD_API int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx, const float* w_x,
-                            long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn,
-                            long ldrzn, float* hn, long ldhn, int B, int H, void* stream) {
+static int gru_step_tmax_impl(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx, const float* w_x,
+                              long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn,
+                              long ldrzn, float* hn, long ldhn, int B, int H, const int* nrows, void* stream) {
     if (B <= 0) return 0;
     if (H % UN != 0 || hprev == nullptr || hout == hprev || x == nullptr || gi2 == nullptr || K2 <= 0 || (K2 & 3)) return PD_BAD_ARG;
     if (!al16(hprev, ldhp) || !al16(w_hh, ldw) || !al16(x, ldx) || !al16(w_x, ldwx) || !al16(gi2, ldgi2) || !al16(hout, ldho) ||
@@ -603,7 +609,7 @@ PD_API int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, lo
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2};
+    StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2, nrows};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -617,6 +623,24 @@ PD_API int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, lo
     gru_step_tma_kernel<ST, NS, true, false, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
         ta, tb, tgi2, tgi2, thp, tho, trzn, thn, tho, ta2, tb2, g, tiles_m, tiles_u);
     return pd_launch_status();
+}
+
+PD_API int pd_gru_step_tmax(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx, const float* w_x,
+                            long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout, long ldho, float* rzn,
+                            long ldrzn, float* hn, long ldhn, int B, int H, void* stream) {
+    return gru_step_tmax_impl(hprev, ldhp, w_hh, ldw, x, ldx, w_x, ldwx, K2, b_hh, gi2, ldgi2, hout, ldho, rzn, ldrzn, hn, ldhn, B, H,
+                              nullptr, stream);
+}
+
+// Packed note level: the same step over the first *nrows rows only (a DEVICE count; rows are sorted by note count, so the
+// live rows of note slot n are a prefix).  Rows beyond the last touched 128-row tile are neither read nor written.
+PD_API int pd_gru_step_tmax_rows(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* x, long ldx,
+                                 const float* w_x, long ldwx, int K2, const float* b_hh, const float* gi2, long ldgi2, float* hout,
+                                 long ldho, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H, const int* nrows,
+                                 void* stream) {
+    if (nrows == nullptr) return PD_BAD_ARG;
+    return gru_step_tmax_impl(hprev, ldhp, w_hh, ldw, x, ldx, w_x, ldwx, K2, b_hh, gi2, ldgi2, hout, ldho, rzn, ldrzn, hn, ldhn, B, H,
+                              nrows, stream);
 }
 
 // Inference form of the fused step for the error-compensated 3xTF32 path (greedy decode at >= 512 rows): the A operand
@@ -642,7 +666,7 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
     tgi2 = tgi; trzn = tho; thn = tho;
     if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1, 0};
+    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1, 0, nullptr};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -684,7 +708,7 @@ PD_API int pd_gru_step_tma3x(const float* a3, long lda3, const float* w3, long l
     if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
     if (!rc) rc = make_map_io(&th3, h3out, 3L * H, B, ldh3);
     if (rc) return rc;
-    StepIo g{b_hh, 1, 0, 0, B, H, 3 * H, 1, K2};
+    StepIo g{b_hh, 1, 0, 0, B, H, 3 * H, 1, K2, nullptr};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);

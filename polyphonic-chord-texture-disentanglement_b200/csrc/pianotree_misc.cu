@@ -65,12 +65,24 @@ __global__ void __launch_bounds__(256) note_embed_fwd_kernel(const int* __restri
 // atomics), rows are streamed coalesced, one global atomicAdd per accumulator cell per CTA.
 __global__ void __launch_bounds__(EMB) note_embed_bwd_kernel(const int* __restrict__ tok, long R,
                                                              const float* __restrict__ g, long ldg, float* dWT,
-                                                             float* dbias, long rows_per_cta) {
+                                                             float* dbias, long rows_per_cta, PdRows live) {
     extern __shared__ float acc[];   // (NOTE_SIZE + 1) * EMB
     const int j = threadIdx.x;
     for (int i = 0; i <= NOTE_SIZE; ++i) acc[i * EMB + j] = 0.0f;
+    // packed note level: rows are slot-major and only a prefix of each slot is live (dead rows carry no gradient and may
+    // hold anything): the CTAs share the LIVE rows evenly and walk them in order
+    PdLiveBlocks lb{live.cp, live.slot_rows, live.n_slots, 1, 0, 0, 0};
     long r0 = (long)blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
-    for (long r = r0; r < r1; ++r) {
+    if (live.cp) {
+        const long total = lb.total();
+        const long per = (total + gridDim.x - 1) / gridDim.x;
+        r0 = min(total, (long)blockIdx.x * per);
+        r1 = min(total, r0 + per);
+        if (r0 < r1) lb.seek((int)r0);
+    }
+    for (long i = r0; i < r1; ++i) {
+        long r = i;
+        if (live.cp) { r = lb.row0(); lb.next(); }
         const int* t = tok + r * TOK_W;
         float v = g[r * ldg + j];
         int p = t[0];
@@ -368,8 +380,8 @@ PD_API int pd_note_embed_fwd(const int* tok, long R, const float* WT, const floa
     return pd_launch_status();
 }
 
-PD_API int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias,
-                             void* stream) {
+static int note_embed_bwd_impl(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, PdRows live,
+                               void* stream) {
     if (R <= 0) return 0;
     static unsigned long long attr_set = 0;
     const int smem = (NOTE_SIZE + 1) * EMB * (int)sizeof(float);
@@ -380,8 +392,21 @@ PD_API int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, f
     long rows_per = (R + ctas - 1) / ctas;
     if (rows_per < 64) rows_per = 64;
     ctas = (R + rows_per - 1) / rows_per;
-    note_embed_bwd_kernel<<<(unsigned)ctas, EMB, smem, (cudaStream_t)stream>>>(tok, R, g, ldg, dWT, dbias, rows_per);
+    note_embed_bwd_kernel<<<(unsigned)ctas, EMB, smem, (cudaStream_t)stream>>>(tok, R, g, ldg, dWT, dbias, rows_per, live);
     return pd_launch_status();
+}
+
+PD_API int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias,
+                             void* stream) {
+    return note_embed_bwd_impl(tok, R, g, ldg, dWT, dbias, PdRows{nullptr, 0, 0}, stream);
+}
+
+// Packed note level: tok / g rows are slot-major (R = n_slots * slot_rows); only rows r % slot_rows < cp[r / slot_rows]
+// contribute (common.cuh PdRows)
+PD_API int pd_note_embed_bwd_rows(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, const int* cp,
+                                  int slot_rows, void* stream) {
+    if (cp == nullptr || slot_rows <= 0) return PD_BAD_ARG;
+    return note_embed_bwd_impl(tok, R, g, ldg, dWT, dbias, PdRows{cp, slot_rows, (int)((R + slot_rows - 1) / slot_rows)}, stream);
 }
 
 PD_API int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok,

@@ -103,7 +103,7 @@ class DisentangleVAE(PytorchModel):
         assert len(flat) == self.N_PLAN
         return flat
 
-    def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None, plan_dev=None):
+    def run(self, x, c, pr_mat, tfr1, tfr2, tfr3, confuse=True, eps=None, plan_dev=None, _packed=False):
         """-> pitch_outs (B,32,15,130), dur_outs (B,32,15,5,2), dist_chd, dist_rhy, recon_root (B,8,12),
         recon_chroma (B,8,12,2), recon_bass (B,8,12).                              model.py:42-55"""
         # the parameters' gradient-accumulation nodes go to the weight-gradient stream (ops.defer: weight gradients are
@@ -111,7 +111,15 @@ class DisentangleVAE(PytorchModel):
         ops.pin_leaf_streams(self.parameters())
 
         # independent branches go to side streams (ops.fork_join); python-side order is the reference's
+        # loss mode with full teacher forcing: the note level runs packed (ptvae.PtvaeDecoder.packed_prologue) -- the logits
+        # of PAD-target positions, which the loss ignores, are not computed; ``_packed`` is only set by ``loss()``
+        packed = (_packed and tfr1 >= 1. and tfr2 >= 1. and plan_dev is None
+                  and ops.packed_ok(x.size(0) * self.decoder.num_step, self.decoder.dec_notes_hid_size,
+                                    self.decoder.note_emb_size))
+
         def embed():
+            if packed:
+                return None, None, self.decoder.packed_prologue(x)
             embedded_x, lengths = self.decoder.emb_x(x)
             # with full teacher forcing (every draw < 1) the decoder's z-independent prologue runs here, beside the
             # encoders, instead of after them
@@ -123,7 +131,10 @@ class DisentangleVAE(PytorchModel):
         z_chd = _sample(dist_chd, True, None if eps is None else eps[0])
         z_rhy = _sample(dist_rhy, True, None if eps is None else eps[1])
         dec_z = torch.cat([z_chd, z_rhy], dim=-1)
+        if packed:
+            self.decoder._draw_plan(tfr1, tfr2)                # consume python's random like the dense path
         (pitch_outs, dur_outs), (recon_root, recon_chroma, recon_bass) = ops.fork_join([
+            (lambda: self.decoder.decode_packed(dec_z, *pre)) if packed else
             lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2, pre=pre,
                                  plan_dev=None if plan_dev is None else plan_dev[:479]),
             lambda: self.chd_decoder(z_chd, False, tfr3, c, plan_dev=None if plan_dev is None else plan_dev[479:])])
@@ -151,7 +162,7 @@ class DisentangleVAE(PytorchModel):
         return kl_chd + kl_rhy, kl_chd, kl_rhy
 
     def loss(self, x, c, pr_mat, tfr1=0., tfr2=0., tfr3=0., beta=0.1, weights=(1, 0.5), eps=None, plan_dev=None):
-        outputs = self.run(x, c, pr_mat, tfr1, tfr2, tfr3, eps=eps, plan_dev=plan_dev)
+        outputs = self.run(x, c, pr_mat, tfr1, tfr2, tfr3, eps=eps, plan_dev=plan_dev, _packed=True)
         return self.loss_function(x, c, *outputs, beta, weights)
 
     # -- inference ---------------------------------------------------------------------------------

@@ -317,7 +317,14 @@ def _split3(t, order, cache):
     return out
 
 
-def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None):
+def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None, rows=None, pred=0):
+    if rows is not None:
+        # packed note level: slot-major rows with a device live-row table (rows = (cp int32 tensor, slot_rows)); pred 1 =
+        # the rows of a / out, 2 = the contraction index.  Tensor-core kernel only (the packed path is TF32 training).
+        cp, slot_rows = rows
+        _call("pd_gemm_tf32_rows", _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
+              int(accumulate), pred, _ptr(cp), slot_rows, _stream())
+        return out
     name = "pd_gemm_f32"
     tc_ok = False
     if PRECISION != "fp32" and K >= 8 and N >= 16:
@@ -352,33 +359,38 @@ def split3_act(x):
     return _split3(x, 0, False) if split3_applies(x) else None
 
 
-def gemm_nt(x, w, out, bias=None, accumulate=False, a3=None):
-    """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias).  a3: ``split3_act(x)`` computed by the caller (optional)."""
+def gemm_nt(x, w, out, bias=None, accumulate=False, a3=None, rows=None):
+    """out (M,N) (+)= x (M,K) @ w (N,K)^T (+ bias).  a3: ``split3_act(x)`` computed by the caller (optional).
+    ``rows`` = (cp, slot_rows): x / out rows are slot-major rows of the packed note level; dead row tiles are skipped."""
     M, K = x.shape
     N = w.shape[0]
     assert w.shape[1] == K and out.shape == (M, N) and x.stride(1) == 1 and out.stride(1) == 1
     assert w.stride(1) == 1 or K == 1
-    return _gemm(x, x.stride(0), 1, w, 1, w.stride(0), out, bias, M, N, K, accumulate, a3)
+    return _gemm(x, x.stride(0), 1, w, 1, w.stride(0), out, bias, M, N, K, accumulate, a3, rows, 1)
 
 
-def gemm_nn(x, w, out, accumulate=False):
-    """out (M,N) (+)= x (M,K) @ w (K,N)."""
+def gemm_nn(x, w, out, accumulate=False, rows=None):
+    """out (M,N) (+)= x (M,K) @ w (K,N).  ``rows``: see gemm_nt."""
     M, K = x.shape
     N = w.shape[1]
     assert w.shape[0] == K and out.shape == (M, N) and x.stride(1) == 1 and w.stride(1) == 1
-    return _gemm(x, x.stride(0), 1, w, w.stride(0), 1, out, None, M, N, K, accumulate)
+    return _gemm(x, x.stride(0), 1, w, w.stride(0), 1, out, None, M, N, K, accumulate, None, rows, 1)
 
 
-def gemm_tn(a, b, out, accumulate=False):
-    """out (M,N) (+)= a (R,M)^T @ b (R,N)."""
+def gemm_tn(a, b, out, accumulate=False, rows=None):
+    """out (M,N) (+)= a (R,M)^T @ b (R,N).  ``rows`` = (cp, slot_rows): the R rows are slot-major rows of the packed note
+    level; only live 32-row blocks are accumulated."""
     R, M = a.shape
     N = b.shape[1]
     assert b.shape[0] == R and out.shape == (M, N) and a.stride(1) == 1 and b.stride(1) == 1
-    return _gemm(a, 1, a.stride(0), b, b.stride(0), 1, out, None, M, N, R, accumulate)
+    return _gemm(a, 1, a.stride(0), b, b.stride(0), 1, out, None, M, N, R, accumulate, None, rows, 2)
 
 
-def colsum(x, out, accumulate=False):
+def colsum(x, out, accumulate=False, rows=None):
     M, N = x.shape
+    if rows is not None:
+        _call("pd_colsum_rows_f32", _ptr(x), x.stride(0), M, N, _ptr(out), int(accumulate), _ptr(rows[0]), rows[1], _stream())
+        return out
     _call("pd_colsum_f32", _ptr(x), x.stride(0), M, N, _ptr(out), int(accumulate), _stream())
     return out
 
@@ -499,9 +511,13 @@ class GradSlab:
             self.buf = _empty_rows(self.M, self.N, self.dev)
         return self.buf
 
-    def block(self, off, n, lead):
-        """Column block [off, off+n) viewed as (*lead, n) (rows = prod(lead))."""
+    def block(self, off, n, lead, slot_major=False):
+        """Column block [off, off+n) viewed as (*lead, n) (rows = prod(lead)).  ``slot_major``: lead = (B, T) over rows
+        stored (t, b)-major (the packed note level): the view is (B, T, n) with strides (ld, B*ld, 1)."""
         part = self.get()[:, off:off + n]
+        if slot_major:
+            B, T = lead
+            return part.as_strided((B, T, n), (part.stride(0), B * part.stride(0), 1))
         strides, acc = [], part.stride(0)
         for d in reversed(lead):
             strides.append(acc)
@@ -517,11 +533,15 @@ class _LinearSplit(torch.autograd.Function):
     embeddings feed both directions of the summary bi-GRU and the note GRU (ptvae.py:446-453, :396)."""
 
     @staticmethod
-    def forward(ctx, x, w, b, sizes, bias_cols, slab, skip_tail=0, wg=None):
+    def forward(ctx, x, w, b, sizes, bias_cols, slab, skip_tail=0, wg=None, rows=None):
         ctx.wg = wg
+        ctx.rows = rows         # packed note level: x rows are slot-major with a device live-row table (dead rows: no work)
         x2, _ = _rows(_chk(x, "x"))
         y = _empty_rows(x2.shape[0], w.shape[0], x.device)
-        if skip_tail:
+        if rows is not None:
+            assert not skip_tail
+            gemm_nt(x2, w, y, b, rows=rows)
+        elif skip_tail:
             # the last head is NOT computed (its consumer multiplies x itself, ops.fold_x_ok); its columns of y stay
             # uninitialised and only route the gradient: the backward still covers all heads
             n = w.shape[0] - skip_tail
@@ -559,9 +579,10 @@ class _LinearSplit(torch.autograd.Function):
             elif not (d.data_ptr() == part.data_ptr() and d.stride(-1) == 1 and d.stride(-2) == part.stride(0)):
                 part.copy_(d.reshape(part.shape))             # a consumer that did not write into the slab
         dx = dw = db = None
+        rows = ctx.rows
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x2.shape, device=dy.device, dtype=torch.float32)
-            gemm_nn(dy, w, dx)
+            gemm_nn(dy, w, dx, rows=rows)                       # (packed: dead rows of dx stay unwritten)
             dx = dx.view(ctx.x_shape)
         nb = ctx.bias_cols
         if ctx.wg is not None:
@@ -572,22 +593,22 @@ class _LinearSplit(torch.autograd.Function):
 
             def job():
                 if dw is not None:
-                    gemm_tn(dy, x2, dw)
+                    gemm_tn(dy, x2, dw, rows=rows)
                 if db is not None:
                     db.zero_()
-                    colsum(dy[:, :nb], db[:nb])
+                    colsum(dy[:, :nb], db[:nb], rows=rows)
             ctx.wg.set(job, keep=(dy, x2))
-            return dx, dw, db, None, None, None, None, None
+            return dx, dw, db, None, None, None, None, None, None
         if ctx.needs_input_grad[1]:
             dw = torch.empty(w.shape, device=dy.device, dtype=torch.float32)
-            gemm_tn(dy, x2, dw)
+            gemm_tn(dy, x2, dw, rows=rows)
         if ctx.needs_input_grad[2]:
             db = torch.zeros(w.shape[0], device=dy.device, dtype=torch.float32)
-            colsum(dy[:, :nb], db[:nb])
-        return dx, dw, db, None, None, None, None, None
+            colsum(dy[:, :nb], db[:nb], rows=rows)
+        return dx, dw, db, None, None, None, None, None, None
 
 
-def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False):
+def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False, rows=None):
     """Heads of widths ``sizes`` over the same input as one GEMM; outputs are shaped (*x.shape[:-1], n).  Only the
     first ``bias_cols`` columns carry a trainable bias (default: all).  ``skip_tail``: do not compute the LAST head in the
     forward pass (its tensor is returned uninitialised, for gradient routing only; it must carry no bias)."""
@@ -601,7 +622,7 @@ def linear_split(x, w, b, sizes, bias_cols=None, skip_tail=False):
     wg = None
     if _n_rows(x) >= DEFER_MIN_ROWS:
         w, b, wg = defer(w, b)
-    outs = _LinearSplit.apply(x, w, b, sizes, nb, slab, sizes[-1] if skip_tail else 0, wg)
+    outs = _LinearSplit.apply(x, w, b, sizes, nb, slab, sizes[-1] if skip_tail else 0, wg, rows)
     off = 0
     for o, n in zip(outs, sizes):
         o._pd_slab = (slab, off, n)                           # lets slab-aware consumers write their gradient in place
@@ -713,11 +734,29 @@ def split3_applies(x):
 # decode) and the 3-pass tf32x3 decode win 6-12 %.  Hence the row limit in TF32 mode.
 RESIDENT_GRU128 = True
 RESIDENT_GRU128_MAX_ROWS_TF32 = 4096
+# Length-SORTED rows (the packed note level): the 16 sequences of a CTA then have (nearly) the same length, the kernel's
+# loop stops at the tile's longest sequence, so its work is sum(lengths) instead of ~rows x max -- it then wins at any size
+RESIDENT_GRU128_SORTED = True
+_rows_sorted = False
+
+
+class rows_sorted:
+    """``with ops.rows_sorted():`` the sequences handed to ``gru_sequence`` inside are sorted by length."""
+
+    def __enter__(self):
+        global _rows_sorted
+        self.prev, _rows_sorted = _rows_sorted, True
+
+    def __exit__(self, *exc):
+        global _rows_sorted
+        _rows_sorted = self.prev
+        return False
 
 
 def _resident128_ok(gi, gi2, h0, lengths, H):
     return (RESIDENT_GRU128 and H == 128 and lengths is not None and h0 is None and gi2 is None
-            and (PRECISION == "tf32x3" or (PRECISION == "tf32" and gi.shape[0] <= RESIDENT_GRU128_MAX_ROWS_TF32))
+            and (PRECISION == "tf32x3" or (PRECISION == "tf32" and (gi.shape[0] <= RESIDENT_GRU128_MAX_ROWS_TF32
+                                                                     or (_rows_sorted and RESIDENT_GRU128_SORTED))))
             and gi.stride(2) == 1 and gi.stride(0) % 2 == 0
             and gi.stride(1) % 2 == 0 and gi.data_ptr() % 8 == 0)
 
@@ -907,7 +946,7 @@ class _GruSeq(torch.autograd.Function):
         if not dout.is_contiguous():
             dout = dout.contiguous()
         if ctx.slab is not None:       # gi is a head of a linear_split: its gradient goes straight into that op's slab
-            dgi = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (B, ctx.t_full))
+            dgi = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (B, ctx.t_full), slot_major=len(ctx.slab) > 3)
         else:
             dgi = torch.empty(B, ctx.t_full, 3 * H, device=dev, dtype=torch.float32)
         if ctx.t_full > T:
@@ -977,6 +1016,161 @@ def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=N
             w_hh, b_hh, wg = defer(w_hh, b_hh)
         return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc, wg)
     return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps, xsrc)
+
+
+# ------------------------------------------------------------------------------------------------
+# Packed note level (csrc/packed.cu).  In loss mode 3/4 of the teacher-forced note-level work of the reference is dead: a
+# (segment, time step) row with k notes has k + 1 target tokens, the loss ignores the other slots of the 15 and no
+# gradient leaves them.  The rows are therefore sorted by token count and every note-level buffer is slot-major, so the
+# live rows of a slot are a prefix whose length is DEVICE data (``table``): kernels are launched for the full extent -- the
+# step stays one CUDA graph for every batch -- and skip dead tiles.  Results on live positions are those of the full
+# computation; dead positions are never written and never read.
+PACKED_NOTES = True
+PACK_NB = 17           # entries per block of the pack table: c[t] | cp[t] | 6 cp[t], t = 0..16 (csrc/packed.cu)
+
+
+class Packed:
+    """Row order of one batch: ``perm`` (sorted position -> row), ``inv``, the live-row ``table``, and the slot-major
+    tokens / targets of the sorted rows."""
+
+    def __init__(self, tok, lengths32):
+        R = lengths32.numel()
+        dev = tok.device
+        self.R = R
+        self.perm = torch.empty(R, device=dev, dtype=torch.int32)
+        self.inv = torch.empty(R, device=dev, dtype=torch.int32)
+        self.table = torch.zeros(64, device=dev, dtype=torch.int32)
+        _call("pd_pack_order", _ptr(lengths32), R, _ptr(self.perm), _ptr(self.inv), _ptr(self.table), _stream())
+        self.tok = torch.empty(16 * R, 6, device=dev, dtype=torch.int32)          # (16, R, 6)
+        self.pitch_tgt = torch.empty(15 * R, device=dev, dtype=torch.int32)       # (15, R)
+        self.dur_tgt = torch.empty(15 * R * 5, device=dev, dtype=torch.int32)     # (15, R, 5)
+        self.lengths = torch.empty(R, device=dev, dtype=torch.int32)              # of the sorted rows (descending)
+        _call("pd_pack_grid", _ptr(tok), _ptr(lengths32), _ptr(self.perm), R, _ptr(self.tok), _ptr(self.pitch_tgt),
+              _ptr(self.dur_tgt), _ptr(self.lengths), _stream())
+
+    def rows(self, t0):
+        """Live-row predicate (cp tensor, slot_rows) of slot-major buffers whose slot 0 needs tokens beyond position ``t0``:
+        0 for the embedded tokens (slot n is live for rows with more than n tokens), 1 for the note-GRU states / logits
+        (slot n predicts token n + 1)."""
+        return (self.table[PACK_NB + t0:], self.R)
+
+
+class _GatherRows(torch.autograd.Function):
+    """y = x[idx] for a PERMUTATION idx of the rows (inverse ``inv``): backward is the inverse gather."""
+
+    @staticmethod
+    def forward(ctx, x, idx, inv):
+        x2, _ = _rows(_chk(x, "x"))
+        y = torch.empty(x2.shape[0], x2.shape[1], device=x.device, dtype=torch.float32)
+        _call("pd_gather_rows_f32", _ptr(x2), x2.stride(0), _ptr(idx), x2.shape[0], x2.shape[1], _ptr(y), y.stride(0), _stream())
+        ctx.save_for_backward(inv)
+        ctx.x_shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (inv,) = ctx.saved_tensors
+        g2, _ = _rows(g)
+        d = torch.empty(g2.shape[0], g2.shape[1], device=g.device, dtype=torch.float32)
+        _call("pd_gather_rows_f32", _ptr(g2), g2.stride(0), _ptr(inv), g2.shape[0], g2.shape[1], _ptr(d), d.stride(0), _stream())
+        return d.view(ctx.x_shape), None, None
+
+
+def gather_rows(x, idx, inv):
+    return _GatherRows.apply(x, idx, inv)
+
+
+class _NoteGruPacked(torch.autograd.Function):
+    """Teacher-forced note GRU (ptvae.py:396-398 for all 15 slots) over length-sorted rows, slot-major.
+    emb (16,R,K2) embedded ground-truth tokens, w_x (3H,K2) their W_ih columns, gi_s (R,3H) the step-constant rest of the
+    input projection incl. b_ih, h0 (R,H).  Returns the states (15,R,H); slot n is computed for the first table[cp][n+1]
+    rows only (fused step kernel with the x-projection as a second K segment), the rest of the buffer is never written."""
+
+    @staticmethod
+    def forward(ctx, emb, w_x, gi_s, h0, w_hh, b_hh, table, wg):
+        T, R, H = emb.shape[0] - 1, emb.shape[1], h0.shape[1]
+        dev = emb.device
+        h_all = torch.empty(T, R, H, device=dev, dtype=torch.float32)
+        rzn = torch.empty(T, R, 3 * H, device=dev, dtype=torch.float32)
+        hn = torch.empty(T, R, H, device=dev, dtype=torch.float32)
+        hprev = h0
+        for n in range(T):
+            _call("pd_gru_step_tmax_rows", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(emb[n]), emb.stride(1),
+                  _ptr(w_x), w_x.stride(0), emb.shape[2], _ptr(b_hh), _ptr(gi_s), gi_s.stride(0), _ptr(h_all[n]), H,
+                  _ptr(rzn[n]), 3 * H, _ptr(hn[n]), H, R, H, _ptr(table[PACK_NB + n + 1:]), _stream())
+            hprev = h_all[n]
+        ctx.save_for_backward(emb, w_x, h0, w_hh, rzn, hn, h_all, table)
+        ctx.wg = wg
+        return h_all
+
+    @staticmethod
+    def backward(ctx, dout):
+        emb, w_x, h0, w_hh, rzn, hn, h_all, table = ctx.saved_tensors
+        T, R, H = h_all.shape
+        K2 = emb.shape[2]
+        dev = dout.device
+        if not dout.is_contiguous():
+            dout = dout.contiguous()
+        st = _stream()
+        # recurrent gradient carriers (dh*z of the later step, dgh.W_hh of the later step), ping-pong.  Zero-filled ONCE:
+        # a row enters the live prefix at its last token and has no later step, so it must read zeros there
+        bufs = torch.zeros(4, R, H, device=dev, dtype=torch.float32)
+        dz_a, dz_b, dm_a, dm_b = bufs[0], bufs[1], bufs[2], bufs[3]
+        dgi = torch.empty(T, R, 3 * H, device=dev, dtype=torch.float32)
+        dgh = torch.empty(T, R, 3 * H, device=dev, dtype=torch.float32)
+        dz = dm = None
+        for n in range(T - 1, -1, -1):
+            hprev = h_all[n - 1] if n > 0 else h0
+            nz = dz_b if dz is dz_a else dz_a
+            nm = dm_b if dm is dm_a else dm_a
+            cp_n = table[PACK_NB + n + 1:]
+            _call("pd_gru_gates_bwd_rows", _ptr(dz), 0 if dz is None else H, _ptr(dout[n]), H, _ptr(dm), 0 if dm is None else H,
+                  _ptr(rzn[n]), 3 * H, _ptr(hn[n]), H, _ptr(hprev), hprev.stride(0), _ptr(dgi[n]), 3 * H, _ptr(dgh[n]), 3 * H,
+                  _ptr(nz), H, R, H, _ptr(cp_n), st)
+            gemm_nn(dgh[n], w_hh, nm, rows=(cp_n, R))                 # dgh W_hh for the live row tiles
+            dz, dm = nz, nm
+        dh0 = torch.empty(R, H, device=dev, dtype=torch.float32)
+        _call("pd_add_f32", _ptr(dz), _ptr(dm), dz.numel(), _ptr(dh0), st)
+        rows1 = (table[PACK_NB + 1:], R)
+        # gradient of the step-constant projection: the live slots of every row, one pass
+        dgi2 = torch.empty(R, 3 * H, device=dev, dtype=torch.float32)
+        _call("pd_sum_slots_rows_f32", _ptr(dgi), R * 3 * H, 3 * H, T, _ptr(rows1[0]), _ptr(dgi2), 3 * H, R, 3 * H, st)
+        db = torch.empty(3 * H, device=dev, dtype=torch.float32)
+        colsum(dgi2[:, :2 * H], db[:2 * H])       # r / z thirds of db_hh = those of sum(dgi); in line (dgi2 goes to the engine)
+        # input gradient of the embedded tokens: zero where no live step consumed them (slot 15 is never an input)
+        demb = torch.zeros(T + 1, R, K2, device=dev, dtype=torch.float32)
+        dgi_flat, dgh_flat = dgi.view(T * R, 3 * H), dgh.view(T * R, 3 * H)
+        gemm_nn(dgi_flat, w_x, demb[:T].view(T * R, K2), rows=rows1)
+        dwx = torch.empty(w_x.shape, device=dev, dtype=torch.float32)
+        dw = torch.empty(w_hh.shape, device=dev, dtype=torch.float32)
+
+        def wgrads():
+            colsum(dgh_flat[:, 2 * H:], db[2 * H:], rows=rows1)
+            gemm_tn(dgi_flat, emb[:T].view(T * R, K2), dwx, rows=rows1)
+            # dW_hh: h_prev of (slot n, row r) is (slot n - 1, row r) -- R rows earlier in the slot-major buffer -- and h0
+            # for slot 0
+            gemm_tn(dgh[0], h0, dw, rows=rows1)
+            if T > 1:
+                gemm_tn(dgh_flat[R:], h_all.view(T * R, H)[:-R], dw, accumulate=True, rows=(table[PACK_NB + 2:], R))
+        if ctx.wg is not None:
+            ctx.wg.set(wgrads, keep=(dgi, dgh, emb, h_all, h0))
+        else:
+            wgrads()
+        return demb, dwx, dgi2, dh0, dw, db, None, None
+
+
+def note_gru_packed(emb, w_x, gi_s, h0, w_hh, b_hh, table):
+    """See ``_NoteGruPacked``.  emb (16,R,K2) contiguous; requires the tensor-core (tf32) precision mode."""
+    wg = None
+    w_x, w_hh, b_hh, wg = defer(w_x, w_hh, b_hh)
+    return _NoteGruPacked.apply(emb, w_x, gi_s, h0, w_hh, b_hh, table, wg)
+
+
+def packed_ok(R, H, K2):
+    """Can a batch of R (segment, time step) rows take the packed note level?  (TF32 tensor-core mode; TMA-addressable
+    shapes; 32-row groups must not straddle slots.)"""
+    return (PACKED_NOTES and PRECISION == "tf32" and FUSED_GRU_STEP_TMA and R % 32 == 0 and H % 64 == 0 and K2 % 4 == 0
+            and torch.is_grad_enabled())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1069,7 +1263,8 @@ class _NoteEmbed(torch.autograd.Function):
     """note_embedding(multi-hot) as a 6-row gather-add (ptvae.py:299-313,:333); tok int32 (R,6)."""
 
     @staticmethod
-    def forward(ctx, tok, w, b, out=None, wg=None):
+    def forward(ctx, tok, w, b, out=None, wg=None, rows=None):
+        ctx.rows = rows          # packed note level: tok rows are slot-major; only live rows send gradient to the table
         R = tok.shape[0]
         wt = transpose(w)                                  # (135,128): rows contiguous per pitch
         if out is None:
@@ -1086,23 +1281,29 @@ class _NoteEmbed(torch.autograd.Function):
         dw = torch.empty(128, 135, device=g.device, dtype=torch.float32)
         db = torch.empty(128, device=g.device, dtype=torch.float32)
 
+        rows = ctx.rows
+
         def wgrads():                                      # the whole backward is parameter gradients (tokens are ints)
             dwt = torch.zeros(135, 128, device=dw.device, dtype=torch.float32)
             db.zero_()
-            _call("pd_note_embed_bwd", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db), _stream())
+            if rows is not None:
+                _call("pd_note_embed_bwd_rows", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db),
+                      _ptr(rows[0]), rows[1], _stream())
+            else:
+                _call("pd_note_embed_bwd", _ptr(tok), tok.shape[0], _ptr(g2), g2.stride(0), _ptr(dwt), _ptr(db), _stream())
             _call("pd_transpose_f32", _ptr(dwt), 135, 128, _ptr(dw), _stream())
         if ctx.wg is not None:
             ctx.wg.set(wgrads, keep=(g2, tok))
         else:
             wgrads()
-        return None, dw, db, None, None
+        return None, dw, db, None, None, None
 
 
-def note_embed(tok, w, b):
+def note_embed(tok, w, b, rows=None):
     wg = None
     if torch.is_grad_enabled() and tok.shape[0] >= DEFER_MIN_ROWS:
         w, b, wg = defer(w, b)
-    return _NoteEmbed.apply(tok, w, b, None, wg)
+    return _NoteEmbed.apply(tok, w, b, None, wg, rows)
 
 
 class _TextureFrontend(torch.autograd.Function):
@@ -1183,6 +1384,16 @@ class _MaskedCE(torch.autograd.Function):
 def _slab_of(t, width):
     slab = getattr(t, "_pd_slab", None)
     return slab if slab is not None and slab[2] == width else None
+
+
+def slot_major_seq(g, T, R):
+    """A head of a ``linear_split`` over slot-major rows (T*R, n) as the (R, T, n) sequence view the GRU ops take; the
+    gradient-slab tag follows (the recurrence's backward then writes its input gradient in place, slot-major)."""
+    v = g.view(T, R, -1).permute(1, 0, 2)
+    tag = getattr(g, "_pd_slab", None)
+    if tag is not None:
+        v._pd_slab = tag + ("slot_major",)
+    return v
 
 
 def keep_slab(new, old):
@@ -1296,10 +1507,11 @@ class _DurDecode(torch.autograd.Function):
     (GX^T . S) that produces every parameter gradient (layout in csrc/dur_decoder.cu)."""
 
     @staticmethod
-    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab=None, wg=None):
+    def forward(ctx, h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab=None, wg=None, rows=None):
         h2, _ = _rows(_chk(h0, "dur h0"))
         ctx.slab = slab
         ctx.wg = wg
+        ctx.rows = rows          # packed note level: notes are slot-major rows; dead 16-note tiles are skipped
         Q = h2.shape[0]
         dev = h2.device
         logits = torch.empty(Q, 5, 2, device=dev, dtype=torch.float32)
@@ -1307,8 +1519,13 @@ class _DurDecode(torch.autograd.Function):
         S = torch.empty(Q, 6, 72, device=dev, dtype=torch.float32) if need else None
         params = [t.contiguous() for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)]
         ctx.tf32 = dur_mode()
-        _call("pd_dur_decode_fwd", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
-              ctx.tf32, _stream())
+        if rows is not None:
+            assert ctx.tf32 == 1
+            _call("pd_dur_decode_fwd_rows", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
+                  _ptr(rows[0]), rows[1], _stream())
+        else:
+            _call("pd_dur_decode_fwd", _ptr(h2), h2.stride(0), Q, *[_ptr(t) for t in params], _ptr(logits), _ptr(S),
+                  ctx.tf32, _stream())
         ctx.save_for_backward(S, *params)
         ctx.h_shape = h0.shape
         return logits
@@ -1324,9 +1541,17 @@ class _DurDecode(torch.autograd.Function):
             dh0 = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (Q,))
         else:
             dh0 = torch.empty(Q, 64, device=dev, dtype=torch.float32)
-        _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
-                                                                                 b_out)],
-              _ptr(GX), _ptr(dh0), dh0.stride(0), ctx.tf32, _stream())
+        rows = ctx.rows
+        # rows of the GX^T . S contraction: 6 per note, so the live-row table in units of 6 (third block of the pack table)
+        rows6 = None if rows is None else (rows[0][PACK_NB:], 6 * rows[1])
+        if rows is not None:
+            _call("pd_dur_decode_bwd_rows", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
+                                                                                          b_out)],
+                  _ptr(GX), _ptr(dh0), dh0.stride(0), _ptr(rows[0]), rows[1], _stream())
+        else:
+            _call("pd_dur_decode_bwd", _ptr(S), _ptr(dlogits), Q, *[_ptr(t) for t in (w_ih, b_ih, w_hh, b_hh, sos, w_out,
+                                                                                     b_out)],
+                  _ptr(GX), _ptr(dh0), dh0.stride(0), ctx.tf32, _stream())
         if ctx.wg is not None:
             # every parameter gradient comes from the GX^T . S GEMM: buffers now, the GEMM and its unpacking on the
             # weight-gradient stream (ops.defer)
@@ -1334,22 +1559,22 @@ class _DurDecode(torch.autograd.Function):
 
             def job():
                 G = torch.empty(264, 72, device=dev, dtype=torch.float32)
-                gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
+                gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G, rows=rows6)
                 gi_rows = torch.cat([G[0:128], G[192:256]], 0)
                 for o, v in zip(outs, (gi_rows[:, 64:69], gi_rows[:, 69], G[0:192, 0:64], G[0:192, 69],
                                        w_ih.t() @ gi_rows[:, 70], G[256:258, 0:64], G[256:258, 69])):
                     o.copy_(v)
             ctx.wg.set(job, keep=(GX, S))
-            return (dh0.view(ctx.h_shape), *outs, None, None)
+            return (dh0.view(ctx.h_shape), *outs, None, None, None)
         G = torch.empty(264, 72, device=dev, dtype=torch.float32)
-        gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G)
+        gemm_tn(GX.view(Q * 6, 264), S.view(Q * 6, 72), G, rows=rows6)
         gi_rows = torch.cat([G[0:128], G[192:256]], 0)            # [dr | dz | dn] x S columns
         dw_hh, db_hh = G[0:192, 0:64], G[0:192, 69]
         dw_ih, db_ih = gi_rows[:, 64:69], gi_rows[:, 69]
         dsos = w_ih.t() @ gi_rows[:, 70]                           # (5,) from the step-0 input-gate grads
         dw_out, db_out = G[256:258, 0:64], G[256:258, 69]
         return (dh0.view(ctx.h_shape), dw_ih.contiguous(), db_ih.contiguous(), dw_hh.contiguous(),
-                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None, None)
+                db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None, None, None)
 
 
 def dur_mode():
@@ -1357,12 +1582,12 @@ def dur_mode():
     return {"fp32": 0, "tf32": 1, "tf32x3": 3}[PRECISION]
 
 
-def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out):
+def dur_decode(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, rows=None):
     slab = _slab_of(h0, 64) if h0.dim() == 2 else None            # (before tagging: tags are new tensor objects)
     wg = None
     if torch.is_grad_enabled() and _n_rows(h0) >= DEFER_MIN_ROWS:
         w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, wg = defer(w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out)
-    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab, wg)
+    return _DurDecode.apply(h0, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, slab, wg, rows)
 
 
 class _SelectRows(torch.autograd.Function):

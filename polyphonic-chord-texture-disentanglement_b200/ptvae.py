@@ -355,6 +355,61 @@ class PtvaeDecoder(nn.Module):
         return ops.keep_slab(pitch.view(B, self.num_step, self.max_simu_note - 1, self.pitch_range), pitch), \
             dur.view(B, self.num_step, self.max_simu_note - 1, self.dur_width, 2)
 
+    # -- teacher-forced, loss mode: packed note level ---------------------------------------------
+    #: In loss mode (``DisentangleVAE.loss`` / ``forward('train')``) only the losses leave the model, and the loss ignores
+    #: every note slot whose target is PAD (ptvae.py:498-511): a (segment, step) row with k notes has k + 1 live slots of 15.
+    #: The packed path sorts the rows by token count, keeps every note-level buffer slot-major and lets the kernels skip
+    #: the dead rows of each slot (``ops.Packed``, csrc/packed.cu) -- the live positions get exactly the values of the
+    #: dense computation, so losses and all 81 gradients are unchanged.  ``run()`` (which returns the logits of every
+    #: position) keeps the dense path.
+    def packed_prologue(self, x):
+        """Grid -> (Packed order, embedded tokens (16,R,128) slot-major in sorted row order, note summaries (B,32,256))."""
+        B = x.size(0)
+        R = B * self.num_step
+        tok, lengths32, _, _ = ops.grid_prepare(x)
+        pk = ops.Packed(tok, lengths32)
+        emb = ops.note_embed(pk.tok, self.note_embedding.weight, self.note_embedding.bias, rows=pk.rows(0))
+        emb = emb.view(self.max_simu_note, R, self.note_emb_size)
+        eg = self.dec_notes_emb_gru
+        (wf, _, bf, _), (wb, _, bb, _) = eg.dir(False), eg.dir(True)
+        with ops.weight_space("prologue"):
+            w_cat, b_cat = ops.wmark(torch.cat([wf, wb], 0), torch.cat([bf, bb], 0))
+        gi_f, gi_b = ops.linear_split(emb.view(self.max_simu_note * R, -1), w_cat, b_cat, (wf.shape[0], wb.shape[0]))
+        as_seq = lambda g: ops.slot_major_seq(g, self.max_simu_note, R)            # (R,16,384) view of the slot-major rows
+        with ops.rows_sorted():
+            summ_s = _bigru_final(eg, None, pk.lengths, gi=(as_seq(gi_f), as_seq(gi_b)))           # sorted order
+        summ = ops.gather_rows(summ_s, pk.inv, pk.perm).view(B, self.num_step, -1)                  # back to (b,t) order
+        return pk, emb, summ
+
+    def decode_packed(self, z, pk, emb, summ):
+        """Teacher-forced decode over the packed note level -> pitch logits (15,R,130), duration logits (15,R,5,2) in
+        sorted-row, slot-major order (dead positions unwritten), tagged with the order for ``recon_loss``."""
+        B, R = z.size(0), pk.R
+        NS = self.max_simu_note
+        z_hid, gi_z, w_tok, w_hh, b_hh = self._time_inputs(z)
+        wn_ih, wn_hh, bn_ih, bn_hh = self.dec_notes_gru.dir()
+        tok = torch.cat([self.dec_init_input.expand(B, 1, -1), summ[:, :-1]], 1)
+        summary = ops.gru_sequence(ops.linear(tok, w_tok, None), gi_z, z_hid, w_hh, b_hh)    # (B,32,1024)
+        S = ops.gather_rows(summary.reshape(R, self.dec_time_hid_size), pk.perm, pk.inv)      # sorted row order
+        h0 = self.dec_time_to_notes_hid(S)
+        with ops.weight_space("tf_heads"):
+            wn_s, w_tok_n = ops.wmark(wn_ih[:, :self.dec_time_hid_size], wn_ih[:, self.dec_time_hid_size:])
+            w_eff, b_eff = self._dur_hid_folded()
+            w_ph, b_ph = ops.wmark(torch.cat([self.pitch_out_linear.weight, w_eff], 0),
+                                   torch.cat([self.pitch_out_linear.bias, b_eff], 0))
+        gi_s = ops.linear(S, wn_s, bn_ih)
+        h = ops.note_gru_packed(emb, w_tok_n, gi_s, h0, wn_hh, bn_hh, pk.table)               # (15,R,512)
+        rows1 = pk.rows(1)
+        Q = (NS - 1) * R
+        pitch, dh = ops.linear_split(h.view(Q, -1), w_ph, b_ph, self.pitch_range, rows=rows1)
+        w_ih, w_hh, b_ih, b_hh = self.dec_dur_gru.dir()
+        dur = ops.dur_decode(dh, w_ih, b_ih, w_hh, b_hh, self.dur_sos_token, self.dur_out_linear.weight,
+                             self.dur_out_linear.bias, rows=rows1)
+        pitch_out = ops.keep_slab(pitch.view(NS - 1, R, self.pitch_range), pitch)
+        dur_out = dur.view(NS - 1, R, self.dur_width, 2)
+        pitch_out._pd_packed = dur_out._pd_packed = pk
+        return pitch_out, dur_out
+
     # -- scheduled sampling / free-running training, batched (opt-in) ------------------------------
     #: Greedy feedback carries no gradient (argmax), so a training forward with 0 <= tfr < 1 is exactly the
     #: teacher-forced computation evaluated on MIXED inputs: note slot n is fed the ground-truth or the predicted
@@ -730,7 +785,11 @@ class PtvaeDecoder(nn.Module):
     # -- losses / output formatting ---------------------------------------------------------------
     def recon_loss(self, x, recon_pitch, recon_dur, weights=(1, 0.5), weighted_dur=False):
         """Pitch CE (ignore PAD 130) + duration CE (ignore 2).                    ptvae.py:498-529"""
-        _, _, pitch_tgt, dur_tgt = ops.grid_prepare(x)
+        pk = getattr(recon_pitch, "_pd_packed", None)
+        if pk is not None:          # logits of the packed note level: targets in the same (slot, sorted row) order
+            pitch_tgt, dur_tgt = pk.pitch_tgt, pk.dur_tgt
+        else:
+            _, _, pitch_tgt, dur_tgt = ops.grid_prepare(x)
         pitch_loss = ops.masked_ce(ops.keep_slab(recon_pitch.reshape(-1, recon_pitch.size(-1)), recon_pitch), pitch_tgt,
                                    self.pitch_pad)
         if not weighted_dur:

@@ -247,6 +247,120 @@ class CpuBackend:
             G2 = _arr(dgi2, (B, 3 * H), (lddgi2, 1))
             G2[...] = G2 + G
 
+    # ---- packed note level (csrc/packed.cu and the *_rows entry points) ----
+    # The emulations write exactly the rows the kernels write and leave the others untouched; the packed-path tests fill
+    # every ``torch.empty`` buffer with NaN (``poison_empty``), so host logic that lets a dead row leak into a result fails.
+    @staticmethod
+    def _live(cp, slot_rows, n_rows, gran):
+        """-> (processed, live) bool masks over n_rows slot-major rows: a row is processed iff its ``gran``-row block holds
+        a live row (r % slot_rows < cp[r // slot_rows])."""
+        n_slots = (n_rows + slot_rows - 1) // slot_rows
+        CP = _arr(cp, (n_slots,), (1,), np.int32)
+        q = np.arange(n_rows)
+        live = (q % slot_rows) < CP[q // slot_rows]
+        blk = np.zeros((n_rows + gran - 1) // gran, bool)
+        np.logical_or.at(blk, q // gran, live)
+        return blk[q // gran], live
+
+    def pd_pack_order(self, lengths, R, perm, inv, table, st):
+        L = np.clip(_arr(lengths, (R,), (1,), np.int32), 0, 16)
+        order = np.argsort(-L, kind="stable").astype(np.int32)
+        _arr(perm, (R,), (1,), np.int32)[...] = order
+        iv = np.empty(R, np.int32)
+        iv[order] = np.arange(R, dtype=np.int32)
+        _arr(inv, (R,), (1,), np.int32)[...] = iv
+        T = _arr(table, (64,), (1,), np.int32)
+        for t in range(17):
+            c = int((L > t).sum())
+            cp = min(R, (c + 127) // 128 * 128)
+            T[t], T[17 + t], T[34 + t] = c, cp, 6 * cp
+
+    def pd_pack_grid(self, tok, lengths, perm, R, tok_s, pt_s, dt_s, len_s, st):
+        T = _arr(tok, (R, 16, 6), (96, 6, 1), np.int32)
+        P = _arr(perm, (R,), (1,), np.int32)
+        S = T[P].transpose(1, 0, 2)                          # (16, R, 6)
+        _arr(tok_s, (16, R, 6), (R * 6, 6, 1), np.int32)[...] = S
+        _arr(pt_s, (15, R), (R, 1), np.int32)[...] = S[1:, :, 0]
+        _arr(dt_s, (15, R, 5), (R * 5, 5, 1), np.int32)[...] = S[1:, :, 1:]
+        _arr(len_s, (R,), (1,), np.int32)[...] = _arr(lengths, (R,), (1,), np.int32)[P]
+
+    def pd_gather_rows_f32(self, src, lds, idx, R, C, dst, ldd, st):
+        I = _arr(idx, (R,), (1,), np.int32)
+        _arr(dst, (R, C), (ldd, 1))[...] = _arr(src, (R, C), (lds, 1))[I]
+
+    def pd_sum_slots_rows_f32(self, X, ldt, ldr, T, cp, out, ldo, R, C, st):
+        x = _arr(X, (T, R, C), (ldt, ldr, 1))
+        CP = _arr(cp, (T,), (1,), np.int32)
+        m = (np.arange(R)[None, :] < CP[:, None])[:, :, None]
+        _arr(out, (R, C), (ldo, 1))[...] = np.where(m, x, 0).sum(0, dtype=np.float32)
+
+    def pd_colsum_rows_f32(self, X, ldx, M, N, out, acc, cp, slot_rows, st):
+        o = _arr(out, (N,), (1,))
+        proc, _ = self._live(cp, slot_rows, M, 32)
+        s = _arr(X, (M, N), (ldx, 1))[proc].sum(0, dtype=np.float32)
+        o[...] = o + s if acc else s
+
+    def pd_gemm_tf32_rows(self, A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, acc, pred, cp, slot_rows, st):
+        a = _arr(A, (M, K), (sam, sak))
+        b = _arr(B, (K, N), (sbk, sbn))
+        c = _arr(C, (M, N), (ldc, 1))
+        with np.errstate(all="ignore"):
+            if pred == 1:
+                proc, _ = self._live(cp, slot_rows, M, 128)
+                r = (a[proc] @ b).astype(np.float32)
+                if bias is not None:
+                    r = r + _arr(bias, (N,), (1,))
+                c[proc] = c[proc] + r if acc else r
+            else:
+                proc, _ = self._live(cp, slot_rows, K, 32)
+                r = (a[:, proc] @ b[proc]).astype(np.float32)
+                c[...] = c + r if acc else r
+
+    def pd_gru_step_tmax_rows(self, hp, ldhp, w, ldw, x, ldx, wx, ldwx, K2, b_hh, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn,
+                              B, H, nrows, st):
+        live = min(B, int(_arr(nrows, (1,), (1,), np.int32)[0]))
+        P = min(B, (live + 127) // 128 * 128)
+        with np.errstate(all="ignore"):
+            if P > 0:
+                self.pd_gru_step_tmax(hp, ldhp, w, ldw, x, ldx, wx, ldwx, K2, b_hh, gi2, ldgi2, ho, ldho, rzn, ldrzn, hn, ldhn, P, H, st)
+
+    def pd_gru_gates_bwd_rows(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                              dhp, lddhp, B, H, nrows, st):
+        P = min(B, int(_arr(nrows, (1,), (1,), np.int32)[0]))
+        if P > 0:
+            self.pd_gru_gates_bwd(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                                  dhp, lddhp, None, 0, None, 0, P, H, st)
+
+    def pd_dur_decode_fwd_rows(self, h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, cp, slot_rows, st):
+        proc, _ = self._live(cp, slot_rows, Q, 16)
+        L = _arr(logits, (Q, 5, 2), (10, 2, 1))
+        Sb = _arr(S, (Q, 6, 72), (432, 72, 1)) if S is not None else None
+        keep = (L[~proc].copy(), None if Sb is None else Sb[~proc].copy())
+        with np.errstate(all="ignore"):
+            self.pd_dur_decode_fwd(h0, ldh0, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, logits, S, 1, st)
+        L[~proc] = keep[0]                                   # dead 16-note tiles are not written
+        if Sb is not None:
+            Sb[~proc] = keep[1]
+
+    def pd_dur_decode_bwd_rows(self, S, dlog, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, cp, slot_rows, st):
+        proc, _ = self._live(cp, slot_rows, Q, 16)
+        G, D = _arr(GX, (Q, 6, 264), (6 * 264, 264, 1)), _arr(dh0, (Q, 64), (lddh0, 1))
+        keep = (G[~proc].copy(), D[~proc].copy())
+        with np.errstate(all="ignore"):
+            self.pd_dur_decode_bwd(S, dlog, Q, w_ih, b_ih, w_hh, b_hh, sos, w_out, b_out, GX, dh0, lddh0, 1, st)
+        G[~proc], D[~proc] = keep
+
+    def pd_note_embed_bwd_rows(self, tok, R, g, ldg, dWT, db, cp, slot_rows, st):
+        _, live = self._live(cp, slot_rows, R, 1)
+        T = _arr(tok, (R, 6), (6, 1), np.int32)[live]
+        G = _arr(g, (R, 128), (ldg, 1))[live]
+        W = _arr(dWT, (135, 128), (128, 1))
+        p = T[:, 0]
+        ok = (p >= 0) & (p < 130)
+        np.add.at(W, p[ok], G[ok])
+        W[130:] += T[:, 1:].astype(np.float32).T @ G
+        _arr(db, (128,), (1,))[...] += G.sum(0)
+
     # ---- pianotree misc ----
     def pd_grid_prepare(self, x, steps, tok, lengths, pt, dt, st):
         X = _arr(x, (steps, 16, 6), (96, 6, 1), np.int64)
@@ -642,6 +756,20 @@ class CpuBackend:
         M[...] = b1 * M + (1 - b1) * gi
         V[...] = b2 * V + (1 - b2) * gi * gi
         P[...] -= (lr / (1 - b1 ** t)) * M / (np.sqrt(V) / np.sqrt(1 - b2 ** t) + eps)
+
+
+def poison_empty(monkeypatch):
+    """Fill every floating-point ``torch.empty`` with NaN for the duration of a test: reads of rows that a kernel
+    legitimately leaves unwritten (dead rows of the packed note level) then poison whatever they leak into."""
+    import torch
+    real = torch.empty
+
+    def empty(*a, **k):
+        t = real(*a, **k)
+        if t.is_floating_point():
+            t.fill_(float("nan"))
+        return t
+    monkeypatch.setattr(torch, "empty", empty)
 
 
 def install(monkeypatch):

@@ -72,6 +72,45 @@ def test_training_matches_reference_golden(golden_dir, tag, prec):
         assert err <= 1e-2, (name, err)
 
 
+def test_packed_loss_mode_matches_reference_golden(golden_dir):
+    """Loss mode (``model('train', ...)``) runs the teacher-forced note level packed: rows sorted by token count, slot-major
+    buffers, dead note slots skipped.  The 11 losses and the gradient probes of all 81 parameters must still be the
+    reference's (fixture written by the unmodified reference at tfr = 1/1/1; 192 rows, so slots are not tile-aligned)."""
+    dev = _dev()
+    from polydis_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "train_tf111.npz"))
+    B = int(g["B"])
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, int(g["data_seed"])))
+    m = _model(dev, int(g["w_seed"]), float(g["gain"]), float(g["eos_bias"]))
+    m.train()
+    random.seed(int(g["rng_seed"]))
+    eps = (torch.from_numpy(g["eps_chd"]).to(dev), torch.from_numpy(g["eps_rhy"]).to(dev))
+    calls = []
+    real = _lib.call
+
+    def spy(name, *a):
+        calls.append(name)
+        return real(name, *a)
+    from polydis_b200 import ops
+    ops._call, keep = spy, ops._call
+    try:
+        losses = m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5), eps=eps)
+        losses[0].backward()
+    finally:
+        ops._call = keep
+    torch.cuda.synchronize()
+    assert calls.count("pd_gru_step_tmax_rows") == 15 and "pd_dur_decode_fwd_rows" in calls
+    np.testing.assert_allclose(np.array([float(v.detach()) for v in losses]), g["losses"], rtol=1e-3, atol=1e-6)
+    params = dict(m.named_parameters())
+    for i, (name, _, _) in enumerate(STATE_DICT_SPEC):
+        gr = params[name].grad.reshape(-1).double().cpu()
+        assert bool(torch.isfinite(gr).all()), name
+        assert abs(float(gr.norm()) - g["grad_norm"][i]) <= 1e-2 * g["grad_norm"][i] + 1e-9, name
+        probe = gr[torch.from_numpy(probe_indices(name, gr.numel()))].numpy()
+        err = np.linalg.norm(probe - g["grad_probe"][i]) / (np.linalg.norm(g["grad_probe"][i]) + 1e-12)
+        assert err <= 1e-2, (name, err)
+
+
 @pytest.mark.parametrize("tfr", [(1.0, 1.0, 1.0), (0.5, 0.5, 0.5)])
 def test_training_matches_oracle_full_gradients(tfr):
     dev = _dev()
@@ -189,36 +228,56 @@ def test_odd_batch_sizes_match_oracle(B):
     assert (est == O.inference(sd, prs[:nd], cs[:nd])).mean() >= 0.999
 
 
-def test_baseline_batch512_full_gradients_match_oracle():
+_ORACLE_512 = {}
+
+
+def _oracle_batch512():
+    """CPU oracle at BASELINE's batch 512 (about half a minute): computed once for the parametrised checks below."""
+    if not _ORACLE_512:
+        from oracle import polydis_oracle as O
+        B = 512
+        xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 4242))
+        sd = {k: v.requires_grad_(True) for k, v in make_state_dict(31).items()}
+        torch.manual_seed(17)
+        e1, e2 = torch.randn(B, 256), torch.randn(B, 256)
+        random.seed(5)
+        ref = O.loss(sd, xs, cs, prs, O.draw_plan(1., 1., 1.), e1, e2)
+        ref[0].backward()
+        _ORACLE_512.update(inputs=(xs, cs, prs), eps=(e1, e2), losses=[float(v) for v in ref],
+                           grads={k: v.grad.double() for k, v in sd.items()})
+    return _ORACLE_512
+
+
+@pytest.mark.parametrize("packed", [True, False])
+def test_baseline_batch512_full_gradients_match_oracle(packed, monkeypatch):
     """BASELINE configs[1] at its own size: teacher-forced training, batch 512 -- the routes bench.py times (persistent
-    TMA-store GEMMs, 256-wide tiles, split-K weight gradients over 245,760 rows) -- all 11 losses and all 81 full
-    gradients against the CPU oracle."""
+    TMA-store GEMMs, 256-wide tiles, split-K weight gradients over the note rows) -- all 11 losses and all 81 full
+    gradients against the CPU oracle.  ``packed``: loss mode through the packed note level (length-sorted rows, dead note
+    slots skipped; what bench.py times) and through the dense path."""
     dev = _dev()
-    from oracle import polydis_oracle as O
-    B = 512
-    xs, cs, prs = (torch.from_numpy(a) for a in synth_batch(B, 4242))
-    sd = {k: v.requires_grad_(True) for k, v in make_state_dict(31).items()}
-    torch.manual_seed(17)
-    e1, e2 = torch.randn(B, 256), torch.randn(B, 256)
-    random.seed(5)
-    ref = O.loss(sd, xs, cs, prs, O.draw_plan(1., 1., 1.), e1, e2)
-    ref[0].backward()
+    from polydis_b200 import ops
+    monkeypatch.setattr(ops, "PACKED_NOTES", packed)
+    o = _oracle_batch512()
+    xs, cs, prs = o["inputs"]
+    e1, e2 = o["eps"]
     m = _model(dev, 31)
     m.train()
     random.seed(5)
+    c0 = ops._lib.call_count
     got = m.loss(xs.to(dev), cs.to(dev), prs.to(dev), 1., 1., 1., eps=(e1.to(dev), e2.to(dev)))
     got[0].backward()
     torch.cuda.synchronize()
-    for a, b in zip(got, ref):
-        assert abs(float(a) - float(b)) <= 1e-3 * abs(float(b)) + 1e-6, (float(a), float(b))
+    for a, b in zip(got, o["losses"]):
+        assert abs(float(a) - b) <= 1e-3 * abs(b) + 1e-6, (float(a), b)
     worst = ("", 0.0)
     for name, p in m.named_parameters():
-        gr, rf = p.grad.detach().cpu().double(), sd[name].grad.double()
+        gr, rf = p.grad.detach().cpu().double(), o["grads"][name]
         err = float((gr - rf).norm() / (rf.norm() + 1e-20))
         if err > worst[1]:
             worst = (name, err)
         assert err <= 1e-2, (name, err)
-    print(f"B=512 full-gradient parity: worst relative error {worst[1]:.2e} ({worst[0]})")
+    print(f"B=512 full-gradient parity (packed={packed}, {ops._lib.call_count - c0} library calls): worst relative error "
+          f"{worst[1]:.2e} ({worst[0]})")
 
 
 def test_baseline_batch512_graphed_step_matches_oracle_losses():

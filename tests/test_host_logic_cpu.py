@@ -32,7 +32,7 @@ def test_state_dict_keys_match_reference_contract():
 
 @pytest.mark.parametrize("tag", ["tf111", "tf000", "tf555", "tf111-chunked", "tf555-devplan", "tf111-devplan",
                                  "tf000-batched", "tf555-batched", "tf111-fusedstep", "tf111-deferall", "tf555-deferall",
-                                 "tf111-nodefer"])
+                                 "tf111-nodefer", "tf111-packed", "tf111-packed-nodefer"])
 def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     be = cpu_backend.install(monkeypatch)
     if tag.endswith("-deferall") or tag.endswith("-nodefer"):
@@ -42,6 +42,15 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
         monkeypatch.setattr(ops, "DEFER_MIN_ROWS", 1)
         monkeypatch.setattr(ops, "DEFER_WGRAD", tag.endswith("-deferall"))
         tag = tag[:tag.rindex("-")]
+    packed = "-packed" in tag
+    if packed:
+        # loss mode through the packed note level (sorted rows, slot-major buffers, dead rows skipped AND poisoned by the
+        # emulation): same losses and gradients as the dense path; no logits leave the model in this mode
+        from polydis_b200 import ops
+        if tag.endswith("-nodefer"):
+            monkeypatch.setattr(ops, "DEFER_WGRAD", False)
+        cpu_backend.poison_empty(monkeypatch)
+        tag = tag[:tag.index("-packed")]
     fused = tag.endswith("-fusedstep")
     if fused:       # fused recurrent step kernels for every recurrence + the note GRU's x-projection folded into the step
         from polydis_b200 import ops
@@ -66,19 +75,25 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     m.train()
     random.seed(int(g["rng_seed"]))
     eps = (torch.from_numpy(g["eps_chd"]), torch.from_numpy(g["eps_rhy"]))
-    if devplan:     # teacher-forcing decisions as device data (one CUDA graph for every ratio): same draws, same result
-        plan = torch.tensor(m.draw_plan(*[float(v) for v in g["tfr"]]), dtype=torch.int32)
-        out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps, plan_dev=plan)
+    if packed:
+        t1, t2, t3 = [float(v) for v in g["tfr"]]
+        losses = m('train', x, c, pr, tfr1=t1, tfr2=t2, tfr3=t3, beta=0.1, weights=(1, 0.5), eps=eps)
+        assert be.calls.count("pd_gru_step_tmax_rows") == 15 and be.calls.count("pd_pack_order") == 1
+        np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
     else:
-        out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
-    if fused:
-        assert be.calls.count("pd_gru_step_tmax") == 15 and be.calls.count("pd_gru_step_tma") > 40
-    losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
-    np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
-    np.testing.assert_allclose(out[0].detach().numpy(), g["pitch"], atol=2e-5)
-    np.testing.assert_allclose(out[1].detach().numpy(), g["dur"], atol=2e-5)
-    np.testing.assert_allclose(out[3].scale.detach().numpy(), g["std_rhy"], atol=2e-5)
-    np.testing.assert_allclose(out[5].detach().numpy(), g["chroma"], atol=2e-5)
+        if devplan:     # teacher-forcing decisions as device data (one CUDA graph for every ratio): same draws, same result
+            plan = torch.tensor(m.draw_plan(*[float(v) for v in g["tfr"]]), dtype=torch.int32)
+            out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps, plan_dev=plan)
+        else:
+            out = m.run(x, c, pr, *[float(v) for v in g["tfr"]], eps=eps)
+        if fused:
+            assert be.calls.count("pd_gru_step_tmax") == 15 and be.calls.count("pd_gru_step_tma") > 40
+        losses = m.loss_function(x, c, *out, 0.1, (1, 0.5))
+        np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(out[0].detach().numpy(), g["pitch"], atol=2e-5)
+        np.testing.assert_allclose(out[1].detach().numpy(), g["dur"], atol=2e-5)
+        np.testing.assert_allclose(out[3].scale.detach().numpy(), g["std_rhy"], atol=2e-5)
+        np.testing.assert_allclose(out[5].detach().numpy(), g["chroma"], atol=2e-5)
     losses[0].backward()
     params = dict(m.named_parameters())
     for i, (name, _, _) in enumerate(STATE_DICT_SPEC):
