@@ -279,6 +279,15 @@ int pd_dur_decode_bwd_rows(const float* S, const float* dlogits, long Q, const f
 int pd_note_embed_bwd_rows(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, const int* cp,
                            int slot_rows, void* stream);
 
+/* pd_gru_gates_bwd that also clears zero_out (B,H): the accumulator of the split-K dgh.W_hh GEMM that follows, which then
+ * runs with accumulate = 1 and no zero-fill node of its own.  pd_gemm_tf32_splits: the number of K splits pd_gemm_tf32
+ * uses for a problem (returns the count, not a status). */
+int pd_gru_gates_bwd_z(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                       const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
+                       long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, const int* lengths, int t, int B, int H,
+                       float* zero_out, long ldzo, void* stream);
+int pd_gemm_tf32_splits(int M, int N, int K);
+
 #ifdef __cplusplus
 }
 #endif

@@ -515,6 +515,7 @@ int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUten
         case 25622: return launch_l<EB, 1, 256, 2, 2>(a_mn, b_mn, ta, tb, g, grid, st);
         case 12823: return launch_l<EB, 1, 128, 2, 3>(a_mn, b_mn, ta, tb, g, grid, st);
         case 6441: return launch_l<EB, 1, 64, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
+        case 6433: return launch_l<EB, 1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
         default: break;
     }
     if (EB == 4) {          // tuning-only configurations exist for the fp32/TF32 operand type
@@ -522,7 +523,6 @@ int launch_cfg(int cfg, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUten
             case 25641: return launch_l<4, 1, 256, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
             case 12841: return launch_l<4, 1, 128, 4, 1>(a_mn, b_mn, ta, tb, g, grid, st);
             case 12832: return launch_l<4, 1, 128, 3, 2>(a_mn, b_mn, ta, tb, g, grid, st);
-            case 6433: return launch_l<4, 1, 64, 3, 3>(a_mn, b_mn, ta, tb, g, grid, st);
             case 6442: return launch_l<4, 1, 64, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
             case 6462: return launch_l<4, 1, 64, 6, 2>(a_mn, b_mn, ta, tb, g, grid, st);
             case 12842: return launch_l<4, 1, 128, 4, 2>(a_mn, b_mn, ta, tb, g, grid, st);
@@ -561,7 +561,7 @@ int gemm_tc_impl(const void* A, long sam, long sak, const void* B, long sbk, lon
         else if (t256 >= 2L * PD_NUM_SMS && kb0 >= 4) cfg = 925641;  // persistent, epilogue overlapped
         else if (t256 >= PD_NUM_SMS) cfg = 25622;                    // 2 CTAs/SM
         else if (t128 >= PD_NUM_SMS) cfg = 12823;
-        else cfg = 6441;                                             // small per-step recurrent GEMMs
+        else cfg = 6433;     // small per-step recurrent GEMMs (3 stages, 3 CTAs/SM: batch-512 step 9.59 -> 9.39 ms vs 6441)
         if (pred == 2 && cfg >= 900000) cfg = 12823;                 // live-k-block iteration lives in the one-shot kernel
     }
     const int mh = (cfg >= 100000 && cfg < 900000) ? 2 : 1;
@@ -651,6 +651,31 @@ PD_API int pd_gemm_tf32_rows(const float* A, long sam, long sak, const float* B,
                              void* stream) {
     return gemm_tc_impl<4>(A, sam, sak, B, sbk, sbn, C, ldc, bias, M, N, K, accumulate, 0, (cudaStream_t)stream, pred, cp,
                            slot_rows);
+}
+
+// How many K splits pd_gemm_tf32 uses for this problem (1 = plain stores; > 1 = zero-fill + red.global.add epilogue):
+// lets a caller that can clear C elsewhere pass accumulate = 1 and save the zero-fill node.
+PD_API int pd_gemm_tf32_splits(int M, int N, int K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 1;
+    const int tiles_m = (M + BM - 1) / BM, kb0 = (K + 31) / 32;
+    const long t256 = (long)tiles_m * ((N + 255) / 256), t128 = (long)tiles_m * ((N + 127) / 128);
+    int bn;
+    if (N <= 64) bn = 64;
+    else if (N <= 128) bn = 128;
+    else if ((long)kb0 * 32 >= 32768 && t256 < PD_NUM_SMS) bn = 128;
+    else if (t256 >= 2L * PD_NUM_SMS && kb0 >= 4) bn = 256;
+    else if (t256 >= PD_NUM_SMS) bn = 256;
+    else if (t128 >= PD_NUM_SMS) bn = 128;
+    else bn = 64;
+    const long tiles = (long)tiles_m * ((N + bn - 1) / bn);
+    int split = 1;
+    if ((tiles < PD_NUM_SMS && kb0 >= 32) || (tiles < 2 * PD_NUM_SMS && kb0 >= 128)) {
+        split = (int)((2 * PD_NUM_SMS + tiles - 1) / tiles);
+        if (split > kb0 / 8) split = kb0 / 8;
+        if (split < 1) split = 1;
+    }
+    const int kb_per = (kb0 + split - 1) / split;
+    return (kb0 + kb_per - 1) / kb_per;
 }
 
 PD_API int pd_gemm_tf32_cfg(const float* A, long sam, long sak, const float* B, long sbk, long sbn, float* C, long ldc,

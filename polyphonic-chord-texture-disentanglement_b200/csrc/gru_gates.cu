@@ -98,6 +98,7 @@ struct GateBwd {
     const int* lengths; int t;
     int B, H;
     const int* nrows;                  // packed note level: DEVICE count of live rows (a prefix); nullptr = all B
+    float* zero_out; long ldzo;        // optional (B,H) buffer to clear: the output of the split-K dgh.W_hh GEMM that follows
 };
 
 __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
     if (idx >= (long)a.B * hq) return;
     const int b = (int)(idx / hq), j = (int)(idx % hq) * 4;
     if (a.nrows != nullptr && b >= *a.nrows) return;
+    if (a.zero_out) *reinterpret_cast<float4*>(a.zero_out + (long)b * a.ldzo + j) = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 d = a.dh ? *reinterpret_cast<const float4*>(a.dh + (long)b * a.lddh + j) : make_float4(0, 0, 0, 0);
     if (a.dh2) {
         float4 e = *reinterpret_cast<const float4*>(a.dh2 + (long)b * a.lddh2 + j);
@@ -195,15 +197,17 @@ PD_API int pd_gru_gates_fwd_split3(const float* gi, long ldgi, const float* gi2,
 static int gates_bwd_launch(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3,
                             long lddh3, const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
                             long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
-                            long lddgi2, const int* lengths, int t, int B, int H, const int* nrows, void* stream) {
+                            long lddgi2, const int* lengths, int t, int B, int H, const int* nrows, void* stream,
+                            float* zero_out = nullptr, long ldzo = 0) {
     if (B <= 0) return 0;
+    if (zero_out && !al4(zero_out, ldzo)) return PD_BAD_ARG;
     if ((H & 3) || (dh && !al4(dh, lddh)) || (dh2 && !al4(dh2, lddh2)) || (dh3 && !al4(dh3, lddh3)) ||
         !al4(rzn, ldrzn) || !al4(hn, ldhn) ||
         (hprev && !al4(hprev, ldhp)) || !al4(dgi, lddgi) || !al4(dgh, lddgh) || !al4(dhprev, lddhp) ||
         (dgi2 && !al4(dgi2, lddgi2)))
         return PD_BAD_ARG;
     GateBwd a{dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh,
-              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H, nrows};
+              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H, nrows, zero_out, ldzo};
     long n = (long)B * (H >> 2);
     gru_gates_bwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return pd_launch_status();
@@ -225,4 +229,15 @@ PD_API int pd_gru_gates_bwd_rows(const float* dh, long lddh, const float* dh2, l
     if (nrows == nullptr) return PD_BAD_ARG;
     return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
                             lddhp, nullptr, 0, nullptr, 0, B, H, nrows, stream);
+}
+
+// pd_gru_gates_bwd that also clears zero_out (B,H; row stride ldzo): the accumulator of the split-K dgh . W_hh GEMM of the
+// same step, which then runs in accumulate mode without its own zero-fill node (batch-sized recurrences: one graph node
+// less on each of their serial backward steps)
+PD_API int pd_gru_gates_bwd_z(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                              const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp,
+                              float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, const int* lengths,
+                              int t, int B, int H, float* zero_out, long ldzo, void* stream) {
+    return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
+                            lddhp, nullptr, 0, lengths, t, B, H, nullptr, stream, zero_out, ldzo);
 }

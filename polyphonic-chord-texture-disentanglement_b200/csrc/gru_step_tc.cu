@@ -230,7 +230,8 @@ constexpr int N_OUTB = 5;          // separate result buffers (OUTB variant): h'
 // A2 (B x K2: the step's input rows) . B2 (3H x K2: W_ih) follows the h segment through the same stage ring; its r / z
 // products accumulate onto the h-projection's r / z columns, its n product goes to a fourth 64-column block (the GRU
 // needs W_in x and W_hn h apart: n = tanh(i_n + r * h_n)).  Accumulator = 256 TMEM columns; no gi tensor exists.
-template <int STAGES, int NSETS, bool OUTB, bool PRECISE, bool SEG2>
+// UNT: hidden units per tile (64; 32 gives the batch-sized recurrences -- 4 row tiles -- a full wave of CTAs)
+template <int STAGES, int NSETS, bool OUTB, bool PRECISE, bool SEG2, int UNT = 64>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
@@ -238,6 +239,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmRzn, const __grid_constant__ CUtensorMap tmHn,
                     const __grid_constant__ CUtensorMap tmH3, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB2, StepIo g, int tiles_m, int tiles_u) {
+    constexpr int UN = UNT, BN3 = 3 * UNT;                             // (shadow the file-level tile constants)
     constexpr int ACC = SEG2 ? 4 * UN : BN3;                           // TMEM columns per accumulator
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     constexpr int A_BYTES = BM * 128, B_BYTES = BN3 * 128;
@@ -561,8 +563,28 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr};
     const CUtensorMap th3 = tho;
     constexpr bool kPrecise = false;
-    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
-    const long items = (long)tiles_m * tiles_u;
+    int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    long items = (long)tiles_m * tiles_u;
+    if (g_step_variant == 0 && items < PD_NUM_SMS && H % 32 == 0) {
+        // batch-sized recurrence (e.g. 512 x 1024: 64 tiles of 64 units): 32-unit tiles fill the machine in one wave and
+        // leave room for a 4-stage ring
+        rc = make_map(&tb, w_hh, 4, H, 3L * H, ldw, 32, false);
+        if (rc) return rc;
+        tiles_u = H / 32;
+        items = (long)tiles_m * tiles_u;
+        const int grid32 = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+        constexpr int ST = 4, NS = 1;
+        constexpr int smem = ST * (BM * 128 + 96 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+        static unsigned long long attr32 = 0;
+        if (pd_first_use_on_device(attr32)) {
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, kPrecise, false, 32>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        gru_step_tma_kernel<ST, NS, true, kPrecise, false, 32><<<grid32, NUM_THREADS, smem, (cudaStream_t)stream>>>(
+            ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u);
+        return pd_launch_status();
+    }
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
     // variant 0 (default): 3-stage main loop, one operand set per epilogue warp reloaded as soon as its values are in
     // registers, results through separate buffers; variant 1: round-1 layout (4 stages, results written back into the

@@ -104,6 +104,7 @@ def fork_join(fns):
 # stream (the engine has made that stream wait for the op's backward).  In a captured step the jobs become parallel
 # branches of the graph that join before the clip.  Results are the in-line ones (same kernels, same operands).
 DEFER_WGRAD = True
+SMALL_GEMM_CFG = 0
 BG_GEMM_CFG = 0        # launch configuration of GEMMs issued on the weight-gradient stream (0: the usual heuristic)
 DBG_WS_OFF = DBG_PIN_OFF = DBG_INLINE = False
 DBG_WS_SKIP = set()
@@ -265,7 +266,7 @@ FUSED_GRU_STEP = False
 # gate kernel (max |dh| 7e-7) and 108 vs 147 us on the note-GRU step (16384 x 512); equal or slower on the 512-row
 # recurrences (31.5 vs 29.5 us), hence the row threshold.
 FUSED_GRU_STEP_TMA = True
-FUSED_GRU_STEP_TMA_MIN_ROWS = 4096
+FUSED_GRU_STEP_TMA_MIN_ROWS = 256
 # Fold the per-step x-projection into the fused step as a second K segment (pd_gru_step_tmax): for the teacher-forced note
 # GRU the (32*B, 16, 1536) projection of the note embeddings (1.6 GB at batch 512) is then never written or read -- the
 # producing GEMM skips those columns (linear_split(skip_tail=)), each step multiplies its 128-wide embedding rows itself.
@@ -343,6 +344,11 @@ def _gemm(a, sam, sak, b, sbk, sbn, out, bias, M, N, K, accumulate, a3=None, row
         return out
     if tc_ok and PRECISION == "tf32":
         name = "pd_gemm_tf32"
+        if SMALL_GEMM_CFG and M <= 1024 and N > 128:
+            # tile configuration of the batch-sized (M = batch) recurrent GEMMs (tuning switch; 0 = library heuristic)
+            _call("pd_gemm_tf32_cfg", _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
+                  int(accumulate), int(SMALL_GEMM_CFG), _stream())
+            return out
         if BG_GEMM_CFG and _on_wgrad_stream():
             # deferred weight-gradient GEMM: the "background" launch shape (see csrc/gemm_tc.cu launch())
             _call("pd_gemm_tf32_cfg", _ptr(a), sam, sak, _ptr(b), sbk, sbn, _ptr(out), out.stride(0), _ptr(bias), M, N, K,
@@ -897,11 +903,24 @@ def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0
     dz_a, dz_b, dm_a, dm_b = bufs[0], bufs[1], bufs[2], bufs[3]
     dz = dm = None
     st = _stream()
+    # batch-sized recurrences run their dgh.W_hh GEMM split over K (zero-fill + red.add epilogue): the gate kernel of the
+    # step clears the accumulator instead, one graph node less on every serial step
+    fold_zero = (PRECISION == "tf32" and w_hh.stride(1) == 1 and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0
+                 and _lib.lib.pd_gemm_tf32_splits(B, H, 3 * H) > 1)
     for i in range(T - 1, -1, -1):
         t = order[i]
         hprev = h_all[:, order[i - 1]] if i > 0 else h0
         nz = dz_b if dz is dz_a else dz_a
         nm = dm_b if dm is dm_a else dm_a
+        if fold_zero and hprev is not None:
+            _call("pd_gru_gates_bwd_z", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
+                  dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+                  _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), hprev.stride(0),
+                  _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
+                  _ptr(lengths), t, B, H, _ptr(nm), nm.stride(0), st)
+            gemm_nn(dgh[:, t], w_hh, nm, accumulate=True)
+            dz, dm = nz, nm
+            continue
         _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
               dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
               _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
@@ -1167,9 +1186,11 @@ def note_gru_packed(emb, w_x, gi_s, h0, w_hh, b_hh, table):
 
 
 def packed_ok(R, H, K2):
-    """Can a batch of R (segment, time step) rows take the packed note level?  (TF32 tensor-core mode; TMA-addressable
-    shapes; 32-row groups must not straddle slots.)"""
-    return (PACKED_NOTES and PRECISION == "tf32" and FUSED_GRU_STEP_TMA and R % 32 == 0 and H % 64 == 0 and K2 % 4 == 0
+    """Can a batch of R (segment, time step) rows take the packed note level?  TF32 tensor-core mode, TMA-addressable
+    shapes, and R a multiple of 128 (batch a multiple of 4): the kernels skip work per 128-row tile, and a tile must not
+    straddle two note slots -- rows of a dead slot inside a live tile would be written with values computed from
+    unwritten inputs.  Other batch sizes take the dense path."""
+    return (PACKED_NOTES and PRECISION == "tf32" and FUSED_GRU_STEP_TMA and R % 128 == 0 and H % 64 == 0 and K2 % 4 == 0
             and torch.is_grad_enabled())
 
 

@@ -361,6 +361,12 @@ class CpuBackend:
         W[130:] += T[:, 1:].astype(np.float32).T @ G
         _arr(db, (128,), (1,))[...] += G.sum(0)
 
+    def pd_gru_gates_bwd_z(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                           dhp, lddhp, lengths, t, B, H, zero_out, ldzo, st):
+        self.pd_gru_gates_bwd(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                              dhp, lddhp, None, 0, lengths, t, B, H, st)
+        _arr(zero_out, (B, H), (ldzo, 1))[...] = 0
+
     # ---- pianotree misc ----
     def pd_grid_prepare(self, x, steps, tok, lengths, pt, dt, st):
         X = _arr(x, (steps, 16, 6), (96, 6, 1), np.int64)

@@ -629,7 +629,8 @@ def test_gru_gates_fwd_split3():
     assert torch.allclose(hi + lo, c3[:, :H] + c3[:, 2 * H:3 * H], atol=3e-6) and torch.equal(g3[:, 3 * H:], c3[:, 3 * H:])
 
 
-@pytest.mark.parametrize("B,H,bcast,save", [(300, 128, True, True), (4100, 512, True, True), (129, 64, False, False)])
+@pytest.mark.parametrize("B,H,bcast,save", [(300, 128, True, True), (4100, 512, True, True), (129, 64, False, False),
+                                             (512, 1024, True, True), (512, 512, False, True)])
 def test_gru_step_tma(B, H, bcast, save):
     """Persistent fused GRU step with TMA epilogue I/O (pd_gru_step_tma) vs the numpy restatement."""
     _dev()
