@@ -376,6 +376,46 @@ def run_b200(args):
     step_bytes = R * (9 * H_ + K2_) * 4 + 3 * H_ * (H_ + K2_) * 4
     step_gbs = step_bytes / (ms_fstep * 1e-3) / 1e9
     del x_, gi2_, h_, rzn_, hn_
+    # the kernel family with the largest share of the packed step (profiles/r02_v4_train_step_launches.txt): the
+    # dgh . W_hh GEMM of the batch-sized recurrences' backward steps (time GRU, both encoder bi-GRUs, chord decoder):
+    # [B x 3H] . [3H x H], H = 1024, split over K with a red.add epilogue into an accumulator the gate kernel cleared.
+    # 32 launches over distinct gate-gradient slices (as in the 32-step time GRU), W_hh stays L2-resident as in the step.
+    Hh = 1024
+    dgh_ = torch.randn(32, B, 3 * Hh, device=dev)
+    w_hh_ = torch.randn(3 * Hh, Hh, device=dev) * 0.03
+    dm_ = torch.zeros(2, B, Hh, device=dev)
+
+    def dh_seq():
+        for t_ in range(32):
+            ops.gemm_nn(dgh_[t_], w_hh_, dm_[t_ & 1], accumulate=True)
+    dh_seq()
+    ms_dh = timed(dh_seq, 5) / 32
+    dh_flop = 2.0 * B * 3 * Hh * Hh
+    dh_tflops = dh_flop / (ms_dh * 1e-3) / 1e12
+    del dgh_, dm_
+    # ... and of their forward steps: the fused step kernel with 32-unit tiles (recurrent GEMM [B x H] . [H x 3H] on tcgen05 +
+    # gate math in the epilogue, operands / results as TMA boxes) -- the single kernel with the largest share of the step
+    gi_b = torch.randn(B, 33, 3 * Hh, device=dev)
+    h_b = torch.randn(B, 33, Hh, device=dev) * 0.3
+    rzn_b = torch.empty(B, 32, 3 * Hh, device=dev)
+    hn_b = torch.empty(B, 32, Hh, device=dev)
+    b_b = torch.randn(3 * Hh, device=dev) * 0.1
+
+    def fwd_seq():
+        for t_ in range(32):
+            ops._call("pd_gru_step_tma", h_b[:, t_].data_ptr(), h_b.stride(0), w_hh_.data_ptr(), Hh, b_b.data_ptr(),
+                      gi_b[:, t_].data_ptr(), gi_b.stride(0), None, 0, h_b[:, t_ + 1].data_ptr(), h_b.stride(0),
+                      rzn_b[:, t_].data_ptr(), rzn_b.stride(0), hn_b[:, t_].data_ptr(), hn_b.stride(0), B, Hh,
+                      torch.cuda.current_stream().cuda_stream)
+    fwd_seq()
+    ms_bstep = timed(fwd_seq, 5) / 32
+    bstep_tflops = dh_flop / (ms_bstep * 1e-3) / 1e12
+    del gi_b, h_b, rzn_b, hn_b
+    # live share of the note level in THIS batch (device table of the packed path): executed work, not the dense count
+    tok_, len_, _, _ = ops.grid_prepare(x)
+    tab_ = ops.Packed(tok_, len_).table.cpu()
+    live_frac = float(tab_[18:33].sum()) / (15.0 * R)
+    del tok_, len_
 
     def leave():
         # a process group whose collectives were captured in CUDA graphs can block in
@@ -393,7 +433,10 @@ def run_b200(args):
         return
     peak_tf, peak_hbm, peak_src = _peaks()
     sps = world * B / (ms_step * 1e-3)
-    achieved = TRAIN_GFLOP_PER_SAMPLE * B / (ms_step * 1e-3) / 1e3      # TFLOP/s per GPU
+    # executed algorithmic work: 66.5 % of the dense minimum (603.7 of 908.2 M MAC: note GRU, heads, duration decoder) is
+    # note-level and only its live share is computed in loss mode (packed note level)
+    gflop_exec = TRAIN_GFLOP_PER_SAMPLE * (1.0 - 0.6647 * (1.0 - live_frac))
+    achieved = gflop_exec * B / (ms_step * 1e-3) / 1e3                   # TFLOP/s per GPU
     out = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
@@ -402,6 +445,8 @@ def run_b200(args):
                                   "teacher-forced PianoTree decoder, batch 512 per GPU (BASELINE configs[1])",
                       "batch_per_gpu": B, "global_batch": world * B, "tfr": [1, 1, 1],
                       "l2_policy": "working set per step (>5 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                      "note_level": "packed: rows sorted by token count, note slots whose target is PAD are not computed in "
+                                    "loss mode (losses and gradients unchanged; tests/test_gpu_model.py)",
                       "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
                       "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else "torch clip_grad_norm_ + Adam(fused)"},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
@@ -419,18 +464,37 @@ def run_b200(args):
                       "fp32_ffma_value": world * Bd / (dec_ms["fp32"] * 1e-3),
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True,
                       "latency_16_segments_ms": ms_dec16, "e2e": dec_e2e},
-           "roofline": {"bound": "hbm", "achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
-                        "frac": step_gbs / peak_hbm, "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1>"),
+           "roofline": {"bound": "tensor", "achieved": bstep_tflops, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": bstep_tflops / peak_tf, "traffic": _measured_traffic("gru_step_tma_kernel<4, 1, 1, 0, 0, 32>"),
                         "peak_source": peak_src,
-                        "kernel": "gru_step_tma_kernel<SEG2> via pd_gru_step_tmax (fused note-GRU step: tcgen05 recurrent GEMM + folded x-projection + gate math, 32B x 512)",
-                        "ms_per_launch": ms_fstep, "algorithmic_bytes_per_launch": step_bytes,
-                        "what": "dominant kernel timed alone with CUDA events (15 launches over distinct slices, 3 rounds): "
-                                "(9 x H + 128) x 4 algorithmic bytes per row-step (h_prev, gi2 in; h, r|z|n, W_hn.h out; x rows) "
-                                "/ launch time, vs the measured HBM copy bandwidth; traffic = ncu dram bytes per launch of the "
-                                "same variant (profiles/r02_kernel_traffic.json)",
+                        "kernel": "gru_step_tma_kernel<32-unit tiles> via pd_gru_step_tma: one forward step of a batch-sized "
+                                  "recurrence (time GRU / encoders / chord decoder), [B x 1024] . [1024 x 3072] on tcgen05 + "
+                                  "gate math in the epilogue",
+                        "ms_per_launch": ms_bstep, "algorithmic_flop_per_launch": dh_flop,
+                        "what": "the kernel with the largest share of the packed step (profiles/r02_v4_train_step_launches.txt: "
+                                "68 launches, 11.9 %), timed alone with CUDA events (32 launches over distinct slices of a "
+                                "(B,33,.) sequence, 5 rounds): 2 M N K / launch time vs the measured sustained bf16 tensor peak. "
+                                "TF32 multiplies run at half that rate, and at batch 512 the kernel is ONE wave of 128 CTAs with "
+                                "32 dependent k-blocks: bound by launch + TMA pipeline latency, not by the tensor pipe; "
+                                "traffic = ncu dram bytes per launch (profiles/r02_kernel_traffic.json)",
+                        "recurrent_dh_gemm": {"achieved": dh_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": dh_tflops / peak_tf,
+                                              "ms_per_launch": ms_dh,
+                                              "traffic": _measured_traffic("gemm_tf32_kernel<4, 1, 64, 3, 3, 0, 1>"),
+                                              "kernel": "gemm_tf32_kernel<64-wide, 3 stages, NN>: dgh . W_hh of the same recurrences' "
+                                                        "backward steps, [B x 3072] . [3072 x 1024], split-K red.add epilogue "
+                                                        "(82 launches, 10.1 %)"},
+                        "fused_note_step_hbm": {"achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
+                                                "frac": step_gbs / peak_hbm,
+                                                "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1>"),
+                                                "kernel": "gru_step_tma_kernel<SEG2> (fused note-GRU step, all 32B rows live)",
+                                                "ms_per_launch": ms_fstep, "algorithmic_bytes_per_launch": step_bytes},
                         "whole_step_tensor": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                                              "frac": achieved / peak_tf,
-                                              "what": "5.45 algorithmic GFLOP/sample x batch / step time vs sustained bf16 peak"},
+                                              "frac": achieved / peak_tf, "gflop_per_sample_executed": gflop_exec,
+                                              "gflop_per_sample_dense": TRAIN_GFLOP_PER_SAMPLE,
+                                              "note_level_live_fraction": live_frac,
+                                              "what": "EXECUTED algorithmic GFLOP/sample x batch / step time vs sustained bf16 "
+                                                      "peak; dense = the reference's work incl. the PAD-target note slots the "
+                                                      "packed path does not compute"},
                         "note_gemm_alone": {"name": "note-GRU recurrent GEMM [32B x 512].[512 x 1536] (unfused route)",
                                             "ms": ms_gemm, "achieved": gemm_tflops, "frac": gemm_tflops / peak_tf,
                                             "traffic": _measured_traffic("gemm_tf32_persistent")}},

@@ -203,6 +203,8 @@ struct BwdArgs {
     float* dgi; long gr, gt;              // (R, T, 384) [dr | dz | dn]      (zeros where masked)
     float* dgh; long qr, qt;              // (R, T, 384) [dr | dz | dn*r]
     long R; int T; int reverse;
+    const int* cp;                        // packed note level (rows sorted by length): masked dgi entries of step t are
+                                          // only zero-filled for rows < cp[t]; the consumers skip the rest.  nullptr: all
 };
 
 // Backward of the recurrence for a tile of 16 sequences, walking the steps in reverse processing order.  The
@@ -298,10 +300,12 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_bwd_kernel(BwdArgs a) {
                         }
                         dh[nt][half] = d;                          // masked: pass-through; active: direct z path
                         const long rr = r0 + row;
-                        float* gi = a.dgi + rr * a.gr + (long)t * a.gt + u;
-                        *reinterpret_cast<float2*>(gi) = dr;
-                        *reinterpret_cast<float2*>(gi + H) = dz;
-                        *reinterpret_cast<float2*>(gi + 2 * H) = dn;
+                        if (t < lens[half] || a.cp == nullptr || rr < a.cp[t]) {
+                            float* gi = a.dgi + rr * a.gr + (long)t * a.gt + u;
+                            *reinterpret_cast<float2*>(gi) = dr;
+                            *reinterpret_cast<float2*>(gi + H) = dz;
+                            *reinterpret_cast<float2*>(gi + 2 * H) = dn;
+                        }
                         float* gq = a.dgh + rr * a.qr + (long)t * a.qt + u;
                         *reinterpret_cast<float2*>(gq) = dr;
                         *reinterpret_cast<float2*>(gq + H) = dz;
@@ -376,13 +380,14 @@ PD_API int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths
 }
 
 // dgi, dgh (R,T,384) <- dout (R,T,128) and the forward saves; BPTT with dh resident per tile (TF32 matvecs).
-PD_API int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
-                         long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
-                         float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse, void* stream) {
+static int gru128_bwd_impl(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
+                           long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
+                           float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp,
+                           void* stream) {
     if (R <= 0 || T <= 0) return 0;
     const uintptr_t ptrs = (uintptr_t)dout | (uintptr_t)h_all | (uintptr_t)rzn | (uintptr_t)hn | (uintptr_t)dgi | (uintptr_t)dgh;
     if (((uintptr_t)w_hh & 15) || (ptrs & 7) || ((dr | dt | hr | ht | zr | zt | nr | nt | gr | gt | qr | qt) & 1)) return PD_BAD_ARG;
-    BwdArgs a{dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T, reverse};
+    BwdArgs a{dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T, reverse, cp};
     constexpr int smem = (G3 * H + 16 * GS) * (int)sizeof(float);
     static unsigned long long attr = 0;
     if (pd_first_use_on_device(attr)) {
@@ -393,4 +398,23 @@ PD_API int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all
     unsigned grid = (unsigned)(tiles < PD_NUM_SMS ? tiles : PD_NUM_SMS);
     gru128_bwd_kernel<<<grid, NTHR, smem, (cudaStream_t)stream>>>(a);
     return pd_launch_status();
+}
+
+PD_API int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
+                         long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
+                         float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse, void* stream) {
+    return gru128_bwd_impl(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
+                           reverse, nullptr, stream);
+}
+
+// Packed note level: rows sorted by length, dgi a slot-major gradient slab whose consumers skip dead rows -- the masked
+// (row, step) entries of dgi are zero-filled only for rows < cp[t] (T ints, device), the others are left unwritten.
+// dgh is written in full.
+PD_API int pd_gru128_bwd_rows(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
+                              long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
+                              float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse,
+                              const int* cp, void* stream) {
+    if (cp == nullptr) return PD_BAD_ARG;
+    return gru128_bwd_impl(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
+                           reverse, cp, stream);
 }

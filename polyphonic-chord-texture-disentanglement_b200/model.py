@@ -136,7 +136,7 @@ class DisentangleVAE(PytorchModel):
         (pitch_outs, dur_outs), (recon_root, recon_chroma, recon_bass) = ops.fork_join([
             (lambda: self.decoder.decode_packed(dec_z, *pre)) if packed else
             lambda: self.decoder(dec_z, False, embedded_x, lengths, tfr1, tfr2, pre=pre,
-                                 plan_dev=None if plan_dev is None else plan_dev[:479]),
+                                 plan_dev=None if plan_dev is None else plan_dev[:479], loss_mode=_packed),
             lambda: self.chd_decoder(z_chd, False, tfr3, c, plan_dev=None if plan_dev is None else plan_dev[479:])])
         return pitch_outs, dur_outs, dist_chd, dist_rhy, recon_root, recon_chroma, recon_bass
 

@@ -975,7 +975,13 @@ class _GruSeq(torch.autograd.Function):
         order = list(range(T - 1, -1, -1) if ctx.reverse else range(T))
         want_dh0 = h0 is not None and ctx.needs_input_grad[2]
         dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if want_dh0 else None
-        if ctx.resident:
+        slab_rows = ctx.slab[4] if ctx.slab is not None and len(ctx.slab) > 4 else None
+        if ctx.resident and slab_rows is not None:
+            _call("pd_gru128_bwd_rows", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
+                  h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
+                  _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
+                  dgh.stride(1), B, T, int(ctx.reverse), _ptr(slab_rows[0]), _stream())
+        elif ctx.resident:
             _call("pd_gru128_bwd", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
                   h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
                   _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
@@ -1066,6 +1072,16 @@ class Packed:
         self.lengths = torch.empty(R, device=dev, dtype=torch.int32)              # of the sorted rows (descending)
         _call("pd_pack_grid", _ptr(tok), _ptr(lengths32), _ptr(self.perm), R, _ptr(self.tok), _ptr(self.pitch_tgt),
               _ptr(self.dur_tgt), _ptr(self.lengths), _stream())
+
+    def slot_major_tokens(self, tok):
+        """Another token grid of the same rows (R*16, 6) int32 -- e.g. the tokens a scheduled-sampling pass fed -- in this
+        order's slot-major layout (16*R, 6)."""
+        R = self.R
+        out = torch.empty(16 * R, 6, device=tok.device, dtype=torch.int32)
+        scratch = torch.empty(15 * R * 6 + R, device=tok.device, dtype=torch.int32)     # targets / lengths of THAT grid: unused
+        _call("pd_pack_grid", _ptr(tok), _ptr(self.lengths), _ptr(self.perm), R, _ptr(out), _ptr(scratch), _ptr(scratch[15 * R:]),
+              _ptr(scratch[:R]), _stream())
+        return out
 
     def rows(self, t0):
         """Live-row predicate (cp tensor, slot_rows) of slot-major buffers whose slot 0 needs tokens beyond position ``t0``:
@@ -1407,13 +1423,15 @@ def _slab_of(t, width):
     return slab if slab is not None and slab[2] == width else None
 
 
-def slot_major_seq(g, T, R):
+def slot_major_seq(g, T, R, rows=None):
     """A head of a ``linear_split`` over slot-major rows (T*R, n) as the (R, T, n) sequence view the GRU ops take; the
-    gradient-slab tag follows (the recurrence's backward then writes its input gradient in place, slot-major)."""
+    gradient-slab tag follows (the recurrence's backward then writes its input gradient in place, slot-major).
+    ``rows``: the live-row predicate the producing ``linear_split`` was given -- dead (row, step) entries of g are unwritten
+    (the masked recurrences never read them) and their gradient need not be written."""
     v = g.view(T, R, -1).permute(1, 0, 2)
     tag = getattr(g, "_pd_slab", None)
     if tag is not None:
-        v._pd_slab = tag + ("slot_major",)
+        v._pd_slab = tag + ("slot_major", rows)
     return v
 
 

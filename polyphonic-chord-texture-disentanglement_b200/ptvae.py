@@ -374,8 +374,9 @@ class PtvaeDecoder(nn.Module):
         (wf, _, bf, _), (wb, _, bb, _) = eg.dir(False), eg.dir(True)
         with ops.weight_space("prologue"):
             w_cat, b_cat = ops.wmark(torch.cat([wf, wb], 0), torch.cat([bf, bb], 0))
-        gi_f, gi_b = ops.linear_split(emb.view(self.max_simu_note * R, -1), w_cat, b_cat, (wf.shape[0], wb.shape[0]))
-        as_seq = lambda g: ops.slot_major_seq(g, self.max_simu_note, R)            # (R,16,384) view of the slot-major rows
+        rows0 = pk.rows(0)          # slot n of a row is a real token iff the row has more than n tokens
+        gi_f, gi_b = ops.linear_split(emb.view(self.max_simu_note * R, -1), w_cat, b_cat, (wf.shape[0], wb.shape[0]), rows=rows0)
+        as_seq = lambda g: ops.slot_major_seq(g, self.max_simu_note, R, rows0)     # (R,16,384) view of the slot-major rows
         with ops.rows_sorted():
             summ_s = _bigru_final(eg, None, pk.lengths, gi=(as_seq(gi_f), as_seq(gi_b)))           # sorted order
         summ = ops.gather_rows(summ_s, pk.inv, pk.perm).view(B, self.num_step, -1)                  # back to (b,t) order
@@ -426,7 +427,9 @@ class PtvaeDecoder(nn.Module):
     #: Set to False for the step-wise path (one autograd node chain per note slot).
     batched_sampling = True
 
-    def _decode_sampled_batched(self, z, x, lengths32, plan_note, plan_time):
+    def _decode_sampled_batched(self, z, x, lengths32, plan_note, plan_time, loss_mode=False):
+        """``loss_mode``: only the losses will leave the model -- the teacher-forced phases then run over the packed note
+        level (``decode_packed``: liveness of a slot is a property of the GROUND-TRUTH grid, whatever token was fed)."""
         B, T, NS = z.size(0), self.num_step, self.max_simu_note
         R = B * T
         gt_tok = x._pd_tok.view(B, T, NS, 6)                                        # int32 ground-truth tokens
@@ -462,6 +465,12 @@ class PtvaeDecoder(nn.Module):
             summ = torch.where(m_time, summ_gt, summ_pred)
         else:
             summ = summ_pred
+        if loss_mode and ops.packed_ok(R, self.dec_notes_hid_size, self.note_emb_size):
+            pk = ops.Packed(gt_tok.reshape(R * NS, 6), lengths32)
+            mix_tok_all = mix_tok if any(any(r) for r in plan_note) else pred_tok
+            tok_s = pk.slot_major_tokens(mix_tok_all.reshape(R * NS, 6).contiguous())
+            emb_s = ops.note_embed(tok_s, w, b, rows=pk.rows(0)).view(NS, R, -1)
+            return self.decode_packed(z, pk, emb_s, summ)
         wn_ih = self.dec_notes_gru.dir()[0]
         with ops.weight_space("sampled"):
             w_tok_n = ops.wmark(wn_ih[:, self.dec_time_hid_size:])
@@ -565,7 +574,8 @@ class PtvaeDecoder(nn.Module):
                 plan_time.append(random.random() < tfr1)
         return plan_note, plan_time
 
-    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None):
+    def decoder(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None,
+                loss_mode=False):
         """z (B,512); x embedded grid (B,32,16,128) + lengths (B,32), or None/None at inference.
         -> pitch logits (B,32,15,130), dur logits (B,32,15,5,2).               ptvae.py:430-491
         ``pre``: result of ``teacher_forced_prologue`` computed ahead by the caller (optional)."""
@@ -585,11 +595,12 @@ class PtvaeDecoder(nn.Module):
             return self._decode_teacher_forced(z, x, lengths32, pre)
         if (self.batched_sampling and not inference and torch.is_grad_enabled()
                 and getattr(x, "_pd_tok", None) is not None):
-            return self._decode_sampled_batched(z, x, lengths32, plan_note, plan_time)
+            return self._decode_sampled_batched(z, x, lengths32, plan_note, plan_time, loss_mode)
         return self._decode_stepwise(z, inference, x, lengths32, plan_note, plan_time)
 
-    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None):
-        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre, plan_dev)
+    def forward(self, z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre=None, plan_dev=None,
+                loss_mode=False):
+        return self.decoder(z, inference, x, lengths, teacher_forcing_ratio1, teacher_forcing_ratio2, pre, plan_dev, loss_mode)
 
     def greedy_tokens(self, z):
         """Greedy decode returning only the int tokens (B,32,15,6) int32 on device -- the logits the

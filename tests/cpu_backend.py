@@ -361,6 +361,17 @@ class CpuBackend:
         W[130:] += T[:, 1:].astype(np.float32).T @ G
         _arr(db, (128,), (1,))[...] += G.sum(0)
 
+    def pd_gru128_bwd_rows(self, dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr,
+                           qt, R, T, reverse, cp, st):
+        GI = _arr(dgi, (R, T, 384), (gr, gt, 1))
+        keep = GI.copy()
+        self.pd_gru128_bwd(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
+                           reverse, st)
+        L = np.minimum(_arr(lengths, (R,), (1,), np.int32), T)
+        CP = _arr(cp, (T,), (1,), np.int32)
+        skip = (np.arange(T)[None, :] >= L[:, None]) & (np.arange(R)[:, None] >= CP[None, :])      # masked and not padded-live
+        GI[skip] = keep[skip]
+
     def pd_gru_gates_bwd_z(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                            dhp, lddhp, lengths, t, B, H, zero_out, ldzo, st):
         self.pd_gru_gates_bwd(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,

@@ -114,6 +114,34 @@ def test_packed_loss_mode_matches_oracle(B):
         assert err <= 1e-2, (name, err)
 
 
+@pytest.mark.parametrize("tfr", [0., 0.5])
+def test_packed_scheduled_sampling_equals_dense_phases(tfr, monkeypatch):
+    """Scheduled sampling / free-running training in loss mode: the greedy pass is shared, the batched phases over the
+    mixed inputs run packed (liveness is a property of the ground-truth grid) -- losses and all gradients must equal
+    those of the dense phases on the same fed tokens (TF32 both ways: reassociation-level differences only)."""
+    dev = _dev()
+    from polydis_b200 import ops
+    B = 16
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 29))
+    torch.manual_seed(8)
+    eps = (torch.randn(B, 256, device=dev), torch.randn(B, 256, device=dev))
+    res = {}
+    for packed in (False, True):
+        monkeypatch.setattr(ops, "PACKED_NOTES", packed)
+        m = _model(dev, 1, 2.0, 3.0)
+        m.train()
+        random.seed(13)
+        losses = m('train', x, c, pr, tfr1=tfr, tfr2=tfr, tfr3=tfr, beta=0.1, weights=(1, 0.5), eps=eps)
+        losses[0].backward()
+        torch.cuda.synchronize()
+        res[packed] = (torch.stack([v.detach() for v in losses]).cpu(), {n: p.grad.detach().cpu() for n, p in m.named_parameters()})
+    assert torch.allclose(res[True][0], res[False][0], rtol=1e-4, atol=1e-6), (res[True][0], res[False][0])
+    for n, g in res[False][1].items():
+        gp = res[True][1][n]
+        assert bool(torch.isfinite(gp).all()), n
+        assert float((gp - g).norm()) <= 2e-3 * float(g.norm()) + 1e-9, (n, float((gp - g).norm() / g.norm()))
+
+
 @pytest.mark.parametrize("tfr", [(1.0, 1.0, 1.0), (0.5, 0.5, 0.5)])
 def test_training_matches_oracle_full_gradients(tfr):
     dev = _dev()

@@ -98,8 +98,8 @@ def test_training_matches_reference_golden(golden_dir, monkeypatch, tag):
     assert random.random() == expect
 
 
-@pytest.mark.parametrize("B,defer", [(8, True), (4, False), (12, True)])
-def test_packed_loss_mode_equals_dense_path(monkeypatch, B, defer):
+@pytest.mark.parametrize("B,defer,tfr", [(8, True, 1.), (4, False, 1.), (12, True, 1.), (8, True, 0.), (8, False, 0.5)])
+def test_packed_loss_mode_equals_dense_path(monkeypatch, B, defer, tfr):
     """Loss mode through the packed note level (rows sorted by token count, slot-major buffers, dead note slots skipped)
     gives the losses and all 81 gradients of the dense path (which the test above pins to the reference goldens).  Every
     ``torch.empty`` is NaN-filled, so a dead row leaking into any result fails the comparison.  Batches that are not a
@@ -120,8 +120,9 @@ def test_packed_loss_mode_equals_dense_path(monkeypatch, B, defer):
         with monkeypatch.context() as mp:
             if packed:
                 cpu_backend.poison_empty(mp)
-            losses = m('train', x, c, pr, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5), eps=eps)
+            losses = m('train', x, c, pr, tfr1=tfr, tfr2=tfr, tfr3=tfr, beta=0.1, weights=(1, 0.5), eps=eps)
             losses[0].backward()
+        # (tfr < 1: scheduled sampling as a greedy pass + the batched phases over mixed inputs, packed as well)
         assert (be.calls.count("pd_gru_step_tmax_rows") == 15) == packed
         res[packed] = ([float(v.detach()) for v in losses], {n: p.grad.clone() for n, p in m.named_parameters()})
     np.testing.assert_allclose(res[True][0], res[False][0], rtol=1e-5, atol=1e-7)

@@ -67,6 +67,8 @@ for rep in range(2):
     ops.gemm_nn(dgh[:, 3], W, dh)
     ops.gemm_tn(dgh.view(R * T, 3 * H), h[:, :T].reshape(R * T, H), dW)
     # one step of a batch-sized (512-row) recurrence, H = 1024: forward GEMM + gates, backward gates + split-K dh GEMM
+    ops._call("pd_gru_step_tma", P(hs[:, 2]), hs.stride(0), P(Ws), Hs, P(bs), P(gis[:, 3]), gis.stride(0), None, 0,
+              P(hs[:, 3]), hs.stride(0), P(rzns[:, 3]), rzns.stride(0), P(hns[:, 3]), hns.stride(0), Bs, Hs, st)
     ops.gemm_nt(hs[:, 2], Ws, ghs, bs)
     ops._gates_fwd(gis[:, 3], None, ghs, hs[:, 2], hs[:, 3], rzns[:, 3], hns[:, 3], None, 3)
     ops.gemm_nn(dghs, Ws, dhs)
