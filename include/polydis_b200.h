@@ -279,11 +279,13 @@ int pd_dur_decode_bwd_rows(const float* S, const float* dlogits, long Q, const f
 int pd_note_embed_bwd_rows(const int* tok, long R, const float* g, long ldg, float* dWT, float* dbias, const int* cp,
                            int slot_rows, void* stream);
 
-/* pd_gru128_bwd over length-sorted rows whose dgi is a slot-major slab with skipping consumers: masked (row, step)
- * entries of dgi are zero-filled only for rows < cp[t] */
+/* pd_gru128_bwd for the note summarisers.  cp (nullable): length-sorted rows whose dgi is a slot-major slab with skipping
+ * consumers -- masked (row, step) entries of dgi are zero-filled only for rows < cp[t].  dout_step >= 0: dout is the (R,128)
+ * gradient of that step's output alone (-1: dout is (R,T,128)). */
 int pd_gru128_bwd_rows(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn, long zr,
                        long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh, float* dgi, long gr,
-                       long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp, void* stream);
+                       long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp, int dout_step,
+                       void* stream);
 
 /* pd_gru_gates_bwd that also clears zero_out (B,H): the accumulator of the split-K dgh.W_hh GEMM that follows, which then
  * runs with accumulate = 1 and no zero-fill node of its own.  pd_gemm_tf32_splits: the number of K splits pd_gemm_tf32

@@ -205,6 +205,8 @@ struct BwdArgs {
     long R; int T; int reverse;
     const int* cp;                        // packed note level (rows sorted by length): masked dgi entries of step t are
                                           // only zero-filled for rows < cp[t]; the consumers skip the rest.  nullptr: all
+    int dout_step;                        // >= 0: dout is (R, 128) and is the gradient of step dout_step's output only (the
+                                          // final state of a summariser); -1: dout is (R, T, 128)
 };
 
 // Backward of the recurrence for a tile of 16 sequences, walking the steps in reverse processing order.  The
@@ -263,7 +265,8 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_bwd_kernel(BwdArgs a) {
                     const long rr = r0 + rows[half];
                     const int u = u0 + nt * 8 + 2 * tig;
                     Saves& x = q[nt][half];
-                    x.d = __ldg(reinterpret_cast<const float2*>(a.dout + rr * a.dr + (long)t * a.dt + u));
+                    if (a.dout_step < 0) x.d = __ldg(reinterpret_cast<const float2*>(a.dout + rr * a.dr + (long)t * a.dt + u));
+                    else x.d = (t == a.dout_step) ? __ldg(reinterpret_cast<const float2*>(a.dout + rr * a.dr + u)) : make_float2(0.f, 0.f);
                     if (t < lens[half]) {
                         const float* p = a.rzn + rr * a.zr + (long)t * a.zt + u;
                         x.r = __ldg(reinterpret_cast<const float2*>(p));
@@ -383,11 +386,12 @@ PD_API int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths
 static int gru128_bwd_impl(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
                            long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
                            float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp,
-                           void* stream) {
+                           int dout_step, void* stream) {
     if (R <= 0 || T <= 0) return 0;
+    if (dout_step >= T) return PD_BAD_ARG;
     const uintptr_t ptrs = (uintptr_t)dout | (uintptr_t)h_all | (uintptr_t)rzn | (uintptr_t)hn | (uintptr_t)dgi | (uintptr_t)dgh;
     if (((uintptr_t)w_hh & 15) || (ptrs & 7) || ((dr | dt | hr | ht | zr | zt | nr | nt | gr | gt | qr | qt) & 1)) return PD_BAD_ARG;
-    BwdArgs a{dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T, reverse, cp};
+    BwdArgs a{dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T, reverse, cp, dout_step};
     constexpr int smem = (G3 * H + 16 * GS) * (int)sizeof(float);
     static unsigned long long attr = 0;
     if (pd_first_use_on_device(attr)) {
@@ -404,17 +408,17 @@ PD_API int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all
                          long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
                          float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse, void* stream) {
     return gru128_bwd_impl(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
-                           reverse, nullptr, stream);
+                           reverse, nullptr, -1, stream);
 }
 
-// Packed note level: rows sorted by length, dgi a slot-major gradient slab whose consumers skip dead rows -- the masked
-// (row, step) entries of dgi are zero-filled only for rows < cp[t] (T ints, device), the others are left unwritten.
-// dgh is written in full.
+// Variant for the note summarisers.  cp (nullable; packed note level): rows sorted by length, dgi a slot-major gradient slab
+// whose consumers skip dead rows -- the masked (row, step) entries of dgi are zero-filled only for rows < cp[t] (T ints,
+// device), the others are left unwritten; dgh is written in full.  dout_step >= 0: only the state of that step was used
+// (the summary), dout is its (R,128) gradient (row stride dr; dt ignored) -- no (R,T,128) gradient tensor of zeros.
 PD_API int pd_gru128_bwd_rows(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn,
                               long zr, long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh,
                               float* dgi, long gr, long gt, float* dgh, long qr, long qt, long R, int T, int reverse,
-                              const int* cp, void* stream) {
-    if (cp == nullptr) return PD_BAD_ARG;
+                              const int* cp, int dout_step, void* stream) {
     return gru128_bwd_impl(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
-                           reverse, cp, stream);
+                           reverse, cp, dout_step, stream);
 }

@@ -894,9 +894,16 @@ def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fuse
 
 
 def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0):
-    """BPTT over all steps for one block of rows; dh0 (or None) receives the gradient of the initial state."""
+    """BPTT over all steps for one block of rows; dh0 (or None) receives the gradient of the initial state.
+    ``dout``: (B,T,H) gradient of every step's output, or (d (B,H), step): only that step's output was used."""
     B, T, H = h_all.shape
-    dev = dout.device
+    dev = h_all.device
+    final = dout if isinstance(dout, tuple) else None
+
+    def dout_of(t):
+        if final is None:
+            return dout[:, t], dout.stride(0)
+        return (final[0], final[0].stride(0)) if t == final[1] else (None, 0)
     # the recurrent gradient arrives in two pieces: dh*z (written by the gate kernel of the later step)
     # and dgh @ W_hh (written by that step's GEMM); the next gate kernel sums both with dout[:, t]
     bufs = torch.empty(4, B, H, device=dev, dtype=torch.float32)
@@ -912,17 +919,18 @@ def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0
         hprev = h_all[:, order[i - 1]] if i > 0 else h0
         nz = dz_b if dz is dz_a else dz_a
         nm = dm_b if dm is dm_a else dm_a
+        d_t, ld_t = dout_of(t)
         if fold_zero and hprev is not None:
-            _call("pd_gru_gates_bwd_z", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
-                  dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+            _call("pd_gru_gates_bwd_z", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(d_t),
+                  ld_t, _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
                   _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), hprev.stride(0),
                   _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
                   _ptr(lengths), t, B, H, _ptr(nm), nm.stride(0), st)
             gemm_nn(dgh[:, t], w_hh, nm, accumulate=True)
             dz, dm = nz, nm
             continue
-        _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(dout[:, t]),
-              dout.stride(0), _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+        _call("pd_gru_gates_bwd", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(d_t),
+              ld_t, _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
               _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), 0 if hprev is None else hprev.stride(0),
               _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
               None, 0, _ptr(lengths), t, B, H, st)
@@ -944,10 +952,12 @@ class _GruSeq(torch.autograd.Function):
     duration / chord GRUs and (with ``lengths``) the packed note-summary bi-GRU."""
 
     @staticmethod
-    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None, xsrc=None, wg=None):
+    def forward(ctx, gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps=None, slab=None, xsrc=None, wg=None, final_only=False):
         _chk(gi, "gi")
         ctx.slab = slab
         ctx.wg = wg
+        ctx.final_only = final_only      # return only the state after the last processed step (a summariser's output):
+        #                                  its backward then takes an (B,H) gradient -- no (B,T,H) tensor of zeros
         save = {}
         h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps, xsrc)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
@@ -955,6 +965,8 @@ class _GruSeq(torch.autograd.Function):
         ctx.reverse = reverse
         ctx.has_gi2 = gi2 is not None
         ctx.t_full = gi.shape[1]
+        if final_only:
+            return h_all[:, 0 if reverse else h_all.shape[1] - 1].contiguous()
         return h_all
 
     @staticmethod
@@ -964,6 +976,7 @@ class _GruSeq(torch.autograd.Function):
         dev = dout.device
         if not dout.is_contiguous():
             dout = dout.contiguous()
+        last = (0 if ctx.reverse else T - 1) if ctx.final_only else -1
         if ctx.slab is not None:       # gi is a head of a linear_split: its gradient goes straight into that op's slab
             dgi = ctx.slab[0].block(ctx.slab[1], ctx.slab[2], (B, ctx.t_full), slot_major=len(ctx.slab) > 3)
         else:
@@ -976,11 +989,11 @@ class _GruSeq(torch.autograd.Function):
         want_dh0 = h0 is not None and ctx.needs_input_grad[2]
         dh0 = torch.empty(B, H, device=dev, dtype=torch.float32) if want_dh0 else None
         slab_rows = ctx.slab[4] if ctx.slab is not None and len(ctx.slab) > 4 else None
-        if ctx.resident and slab_rows is not None:
-            _call("pd_gru128_bwd_rows", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
-                  h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
-                  _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
-                  dgh.stride(1), B, T, int(ctx.reverse), _ptr(slab_rows[0]), _stream())
+        if ctx.resident and (slab_rows is not None or last >= 0):
+            _call("pd_gru128_bwd_rows", _ptr(dout), dout.stride(0), dout.stride(1) if last < 0 else 0, _ptr(h_all),
+                  h_all.stride(0), h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0),
+                  hn.stride(1), _ptr(lengths), _ptr(w_hh), _ptr(dgi), dgi.stride(0), dgi.stride(1), _ptr(dgh), dgh.stride(0),
+                  dgh.stride(1), B, T, int(ctx.reverse), None if slab_rows is None else _ptr(slab_rows[0]), last, _stream())
         elif ctx.resident:
             _call("pd_gru128_bwd", _ptr(dout), dout.stride(0), dout.stride(1), _ptr(h_all), h_all.stride(0),
                   h_all.stride(1), _ptr(rzn), rzn.stride(0), rzn.stride(1), _ptr(hn), hn.stride(0), hn.stride(1),
@@ -988,8 +1001,8 @@ class _GruSeq(torch.autograd.Function):
                   dgh.stride(1), B, T, int(ctx.reverse), _stream())
         else:
             def run(sl):
-                _gru_steps_bwd(dout[sl], rzn[sl], hn[sl], h_all[sl], _sl(h0, sl), w_hh, _sl(lengths, sl), order,
-                               dgi[sl], dgh[sl], _sl(dh0, sl))
+                _gru_steps_bwd(dout[sl] if last < 0 else (dout[sl], last), rzn[sl], hn[sl], h_all[sl], _sl(h0, sl), w_hh,
+                               _sl(lengths, sl), order, dgi[sl], dgh[sl], _sl(dh0, sl))
             _over_row_chunks(B, 3 * H, run)
         dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)
@@ -1026,12 +1039,13 @@ class _GruSeq(torch.autograd.Function):
             ctx.wg.set(wgrads, keep=(dgh, h_all, h0))     # off the chain: on the weight-gradient stream (ops.defer)
         else:
             wgrads()
-        return dgi, dgi2, dh0, dw, db, None, None, None, None, None, None
+        return dgi, dgi2, dh0, dw, db, None, None, None, None, None, None, None
 
 
-def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None, xsrc=None):
+def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=None, xsrc=None, final_only=False):
     """Autograd-aware GRU over (B,T,3H) input projections; falls to the no-grad loop when nothing
-    requires grad (inference).  ``xsrc``: see ``gru_sequence_nograd`` (gi then only routes the gradient)."""
+    requires grad (inference).  ``xsrc``: see ``gru_sequence_nograd`` (gi then only routes the gradient).
+    ``final_only``: return the (B,H) state after the last processed step (index 0 when reversed) instead of all states."""
     if xsrc is not None:
         xsrc = (xsrc[0].detach(), xsrc[1].detach())           # gradients flow through gi's producer (linear_split)
     if torch.is_grad_enabled() and (gi.requires_grad or w_hh.requires_grad or
@@ -1039,8 +1053,10 @@ def gru_sequence(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, n_steps=N
         wg = None
         if gi.shape[0] * gi.shape[1] >= DEFER_MIN_ROWS:
             w_hh, b_hh, wg = defer(w_hh, b_hh)
-        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc, wg)
-    return gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps, xsrc)
+        return _GruSeq.apply(gi, gi2, h0, w_hh, b_hh, lengths, reverse, n_steps, _slab_of(gi, gi.shape[-1]), xsrc, wg,
+                             final_only)
+    h = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, None, n_steps, xsrc)
+    return h[:, 0 if reverse else h.shape[1] - 1] if final_only else h
 
 
 # ------------------------------------------------------------------------------------------------

@@ -71,8 +71,7 @@ def _bigru_final(gru, x, lengths=None, gi=None):
     def one(rev):
         w_ih, w_hh, b_ih, b_hh = gru.dir(rev)
         g = ops.linear(x, w_ih, b_ih) if gi is None else gi[int(rev)]
-        h = ops.gru_sequence(g, None, None, w_hh, b_hh, lengths, rev)
-        return h[:, 0] if rev else h[:, -1]
+        return ops.gru_sequence(g, None, None, w_hh, b_hh, lengths, rev, final_only=True)
     return torch.cat(ops.fork_join([lambda: one(False), lambda: one(True)]), -1)
 
 

@@ -362,11 +362,17 @@ class CpuBackend:
         _arr(db, (128,), (1,))[...] += G.sum(0)
 
     def pd_gru128_bwd_rows(self, dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr,
-                           qt, R, T, reverse, cp, st):
+                           qt, R, T, reverse, cp, dout_step, st):
         GI = _arr(dgi, (R, T, 384), (gr, gt, 1))
         keep = GI.copy()
+        if dout_step >= 0:                                   # (R,128) gradient of one step's output
+            full = np.zeros((R, T, 128), np.float32)
+            full[:, dout_step] = _arr(dout, (R, 128), (dr, 1))
+            dout, dr, dt = full.ctypes.data, T * 128, 128
         self.pd_gru128_bwd(dout, dr, dt, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, lengths, w_hh, dgi, gr, gt, dgh, qr, qt, R, T,
                            reverse, st)
+        if cp is None:
+            return
         L = np.minimum(_arr(lengths, (R,), (1,), np.int32), T)
         CP = _arr(cp, (T,), (1,), np.int32)
         skip = (np.arange(T)[None, :] >= L[:, None]) & (np.arange(R)[:, None] >= CP[None, :])      # masked and not padded-live

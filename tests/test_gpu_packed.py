@@ -200,3 +200,34 @@ def test_row_reductions_gather_and_embed_bwd():
         return ([tok, 16 * R, g_, 128, dwt, db, tab0[17:], R, None], [dwt, db])
     for g, c in _both("pd_note_embed_bwd_rows", mk4):
         assert bool(torch.isfinite(g).all()) and torch.allclose(g, c, atol=2e-3, rtol=1e-4), float((g - c).abs().max())
+
+
+@pytest.mark.parametrize("reverse,final", [(0, False), (1, False), (0, True), (1, True)])
+def test_gru128_bwd_rows_sorted_lengths(reverse, final):
+    """Resident summary-GRU backward over length-sorted rows with a slot-major dgi slab: masked (row, step) entries of dgi
+    are zero-filled only inside the padded live prefix of each step, everything else keeps its contents."""
+    _dev()
+    from tests.cpu_backend import CpuBackend
+    cpu = CpuBackend()
+    R, T, H = 512, 16, 128
+    torch.manual_seed(4)
+    w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+    rng = np.random.RandomState(3)
+    lengths = torch.from_numpy(np.sort(np.where(rng.rand(R) < 0.4, 2, rng.randint(3, 12, R)))[::-1].astype(np.int32).copy())
+    tab = _table(R, [int((lengths > t).sum()) for t in range(17)])
+    gi = torch.randn(R, T, 3 * H)
+    h_all, rzn, hn = torch.zeros(R, T, H), torch.zeros(R, T, 3 * H), torch.zeros(R, T, H)
+    cpu.pd_gru128_fwd(gi.data_ptr(), T * 3 * H, 3 * H, lengths.data_ptr(), w.data_ptr(), b.data_ptr(), h_all.data_ptr(), T * H, H,
+                      rzn.data_ptr(), T * 3 * H, 3 * H, hn.data_ptr(), T * H, H, R, T, reverse, 1, None)
+
+    def mkb():
+        slab = torch.full((T, R, 3 * H), 6.0)                        # slot-major storage, (R,T,.) strides (3H, R*3H)
+        dgh = torch.zeros(R, T, 3 * H)
+        # final: only the summary (the state after the last processed step) carried gradient -> an (R,H) dout
+        dout = torch.randn(R, H) if final else torch.randn(R, T, H)
+        step = (0 if reverse else T - 1) if final else -1
+        return ([dout, H if final else T * H, 0 if final else H, h_all, T * H, H, rzn, T * 3 * H, 3 * H, hn, T * H, H, lengths,
+                 w, slab, 3 * H, R * 3 * H, dgh, T * 3 * H, 3 * H, R, T, reverse, tab[17:], step, None], [slab, dgh])
+    (gs, cs), (gh, ch) = _both("pd_gru128_bwd_rows", mkb)
+    assert torch.allclose(gs, cs, atol=5e-3, rtol=1e-3) and torch.allclose(gh, ch, atol=5e-3, rtol=1e-3)
+    assert bool((cs == 6.0).any())
