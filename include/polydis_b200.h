@@ -287,6 +287,18 @@ int pd_gru128_bwd_rows(const float* dout, long dr, long dt, const float* h_all, 
                        long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp, int dout_step,
                        void* stream);
 
+/* bf16-operand step of the batch-sized recurrences (BASELINE configs[1] "bf16 / fp32-accumulate"): hb_prev / wb are bf16
+ * copies of h_prev (B x H) and W_hh (3H x H) (strides in elements); accumulators, gate math, the h_prev of the blend and all
+ * saved arrays are fp32; hb_out receives the bf16 copy of the new state.  pd_gru_gates_bwd_zb: pd_gru_gates_bwd_z that also
+ * writes a bf16 copy of dgh, the A operand of the bf16 dgh.W_hh GEMM (pd_gemm_bf16). */
+int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
+                         long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
+                         void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H, void* stream);
+int pd_gru_gates_bwd_zb(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                        const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
+                        long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, const int* lengths, int t, int B, int H,
+                        float* zero_out, long ldzo, void* dgh_b, long lddghb, void* stream);
+
 /* pd_gru_gates_bwd that also clears zero_out (B,H): the accumulator of the split-K dgh.W_hh GEMM that follows, which then
  * runs with accumulate = 1 and no zero-fill node of its own.  pd_gemm_tf32_splits: the number of K splits pd_gemm_tf32
  * uses for a problem (returns the count, not a status). */

@@ -99,6 +99,7 @@ struct GateBwd {
     int B, H;
     const int* nrows;                  // packed note level: DEVICE count of live rows (a prefix); nullptr = all B
     float* zero_out; long ldzo;        // optional (B,H) buffer to clear: the output of the split-K dgh.W_hh GEMM that follows
+    uint16_t* dgh_b; long lddghb;      // optional bf16 copy of dgh (B,3H): the A operand of a bf16 dgh.W_hh GEMM
 };
 
 __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
@@ -121,6 +122,11 @@ __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
     float* dgh = a.dgh + (long)b * a.lddgh + j;
     if (a.lengths && a.t >= a.lengths[b]) {
         float4 zero = make_float4(0, 0, 0, 0);
+        if (a.dgh_b) {
+            uint16_t* q = a.dgh_b + (long)b * a.lddghb + j;
+            *reinterpret_cast<uint2*>(q) = make_uint2(0u, 0u); *reinterpret_cast<uint2*>(q + a.H) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(q + 2 * a.H) = make_uint2(0u, 0u);
+        }
         *reinterpret_cast<float4*>(dgi) = zero; *reinterpret_cast<float4*>(dgi + a.H) = zero;
         *reinterpret_cast<float4*>(dgi + 2 * a.H) = zero;
         *reinterpret_cast<float4*>(dgh) = zero; *reinterpret_cast<float4*>(dgh + a.H) = zero;
@@ -147,6 +153,17 @@ __global__ void __launch_bounds__(256) gru_gates_bwd_kernel(GateBwd a) {
     *reinterpret_cast<float4*>(dgi + 2 * a.H) = dn;
     *reinterpret_cast<float4*>(dgh) = dr; *reinterpret_cast<float4*>(dgh + a.H) = dz;
     *reinterpret_cast<float4*>(dgh + 2 * a.H) = dnr;
+    if (a.dgh_b) {
+        auto pack = [](float4 v) {
+            uint2 o;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(v.y), "f"(v.x));
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(v.w), "f"(v.z));
+            return o;
+        };
+        uint16_t* q = a.dgh_b + (long)b * a.lddghb + j;
+        *reinterpret_cast<uint2*>(q) = pack(dr); *reinterpret_cast<uint2*>(q + a.H) = pack(dz);
+        *reinterpret_cast<uint2*>(q + 2 * a.H) = pack(dnr);
+    }
     *reinterpret_cast<float4*>(a.dhprev + (long)b * a.lddhp + j) = dp;
     if (a.dgi2) {
         float* q = a.dgi2 + (long)b * a.lddgi2 + j;
@@ -198,16 +215,17 @@ static int gates_bwd_launch(const float* dh, long lddh, const float* dh2, long l
                             long lddh3, const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
                             long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, float* dgi2,
                             long lddgi2, const int* lengths, int t, int B, int H, const int* nrows, void* stream,
-                            float* zero_out = nullptr, long ldzo = 0) {
+                            float* zero_out = nullptr, long ldzo = 0, void* dgh_b = nullptr, long lddghb = 0) {
     if (B <= 0) return 0;
     if (zero_out && !al4(zero_out, ldzo)) return PD_BAD_ARG;
+    if (dgh_b && (((uintptr_t)dgh_b & 7) || (lddghb & 3))) return PD_BAD_ARG;
     if ((H & 3) || (dh && !al4(dh, lddh)) || (dh2 && !al4(dh2, lddh2)) || (dh3 && !al4(dh3, lddh3)) ||
         !al4(rzn, ldrzn) || !al4(hn, ldhn) ||
         (hprev && !al4(hprev, ldhp)) || !al4(dgi, lddgi) || !al4(dgh, lddgh) || !al4(dhprev, lddhp) ||
         (dgi2 && !al4(dgi2, lddgi2)))
         return PD_BAD_ARG;
     GateBwd a{dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh,
-              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H, nrows, zero_out, ldzo};
+              dhprev, lddhp, dgi2, lddgi2, lengths, t, B, H, nrows, zero_out, ldzo, (uint16_t*)dgh_b, lddghb};
     long n = (long)B * (H >> 2);
     gru_gates_bwd_kernel<<<pd_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(a);
     return pd_launch_status();
@@ -240,4 +258,15 @@ PD_API int pd_gru_gates_bwd_z(const float* dh, long lddh, const float* dh2, long
                               int t, int B, int H, float* zero_out, long ldzo, void* stream) {
     return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
                             lddhp, nullptr, 0, lengths, t, B, H, nullptr, stream, zero_out, ldzo);
+}
+
+// pd_gru_gates_bwd_z that additionally writes dgh_b, a bf16 copy of dgh (B,3H; row stride lddghb elements): the A operand
+// of the bf16 dgh . W_hh GEMM of the batch-sized recurrences (pd_gemm_bf16)
+PD_API int pd_gru_gates_bwd_zb(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
+                               const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp,
+                               float* dgi, long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, const int* lengths,
+                               int t, int B, int H, float* zero_out, long ldzo, void* dgh_b, long lddghb, void* stream) {
+    if (dgh_b == nullptr) return PD_BAD_ARG;
+    return gates_bwd_launch(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hprev, ldhp, dgi, lddgi, dgh, lddgh, dhprev,
+                            lddhp, nullptr, 0, lengths, t, B, H, nullptr, stream, zero_out, ldzo, dgh_b, lddghb);
 }

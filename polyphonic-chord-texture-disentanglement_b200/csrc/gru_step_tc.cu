@@ -203,6 +203,8 @@ struct StepIo {
     int K2;          // SEG2 kernels: columns of the second A operand (the step's input x, e.g. the note embedding)
     const int* nrows;   // packed note level: DEVICE count of live rows of this step (rows are length-sorted, so they are a
                         // prefix; nullptr = all B).  Whole 128-row tiles up to the count are processed, the rest untouched.
+    uint16_t* hb_out;   // bf16 variant: bf16 copy of the new state (row stride ldhb elements), the next step's A operand
+    long ldhb;
 };
 
 constexpr int IOB = 2048;          // one epilogue buffer: 32 rows x 16 fp32 (64-byte rows, SWIZZLE_64B)
@@ -231,7 +233,9 @@ constexpr int N_OUTB = 5;          // separate result buffers (OUTB variant): h'
 // products accumulate onto the h-projection's r / z columns, its n product goes to a fourth 64-column block (the GRU
 // needs W_in x and W_hn h apart: n = tanh(i_n + r * h_n)).  Accumulator = 256 TMEM columns; no gi tensor exists.
 // UNT: hidden units per tile (64; 32 gives the batch-sized recurrences -- 4 row tiles -- a full wave of CTAs)
-template <int STAGES, int NSETS, bool OUTB, bool PRECISE, bool SEG2, int UNT = 64>
+// EB: bytes per element of the main-loop operands (4: fp32 multiplied as TF32; 2: bf16 copies of h_prev / W_hh,
+// kind::f16 -- half the bytes and half the k-blocks of a step; accumulators, gate math and every epilogue array stay fp32)
+template <int STAGES, int NSETS, bool OUTB, bool PRECISE, bool SEG2, int UNT = 64, int EB = 4>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmGi, const __grid_constant__ CUtensorMap tmGi2,
@@ -256,7 +260,9 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t* tmem_slot = (uint32_t*)(io_bar + 4 * NSETS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb1 = (g.KA + 31) / 32, nkb2 = SEG2 ? (g.K2 + 31) / 32 : 0;
+    constexpr int BKE = 128 / EB;                                      // elements per 128-byte k-block row
+    static_assert(EB == 4 || !SEG2, "the folded x-projection is a TF32 path");
+    const int nkb1 = (g.KA + BKE - 1) / BKE, nkb2 = SEG2 ? (g.K2 + 31) / 32 : 0;
     const int nkb = nkb1 + nkb2;
     if (g.nrows != nullptr) {
         const int live = min(g.B, *g.nrows);
@@ -287,7 +293,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int m0 = (int)(item / tiles_u) * BM, u0 = (int)(item % tiles_u) * UN;
                 for (int i = 0; i < nkb; ++i, ++cnt) {
-                    const int s = (int)(cnt % STAGES), k0 = i * 32;
+                    const int s = (int)(cnt % STAGES), k0 = i * BKE;
                     if (cnt >= STAGES) mbar_wait(&empty[s], (uint32_t)((cnt / STAGES) - 1) & 1);
                     mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
                     const bool seg2 = SEG2 && i >= nkb1;
@@ -301,7 +307,7 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN3 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t idesc = (1u << 4) | (Elem<EB>::FMT << 7) | (Elem<EB>::FMT << 10) | ((uint32_t)(BN3 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t idesc_rz = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * UN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t idesc_n = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(UN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             long cnt = 0, j = 0;
@@ -326,8 +332,8 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            tc_mma_tf32(tmem_base + acc * ACC, make_desc(a + k * 32, 16, 1024, 2), make_desc(b + k * 32, 16, 1024, 2),
-                                        idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            tc_mma<EB>(tmem_base + acc * ACC, make_desc(a + k * 32, 16, 1024, 2), make_desc(b + k * 32, 16, 1024, 2),
+                                       idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(&empty[s]);
                 }
@@ -432,6 +438,19 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(b) : "f"(hp[i]));
                         ir[i] = __uint_as_float(b);
                         iz[i] = hp[i] - ir[i];
+                    }
+                }
+                if (EB == 2 && g.hb_out != nullptr) {
+                    // the next step's A operand: bf16 copy of h' (this thread: row `row + lane`, 16 columns = 32 bytes)
+                    const long r_ = (long)row + lane;
+                    if (r_ < g.B) {
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(pk[i]) : "f"(hp[2 * i + 1]), "f"(hp[2 * i]));
+                        uint4* dst = reinterpret_cast<uint4*>(g.hb_out + r_ * g.ldhb + col);
+                        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
                 }
                 uint8_t* ob = OUTB ? io_out + q * (N_OUTB * IOB) : bufs;
@@ -560,7 +579,7 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr};
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr, nullptr, 0};
     const CUtensorMap th3 = tho;
     constexpr bool kPrecise = false;
     int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
@@ -607,6 +626,50 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
 #undef PD_STEP_LAUNCH
 }
 
+// bf16-operand form for the batch-sized recurrences (time GRU, encoder bi-GRUs, chord decoder; BASELINE configs[1]
+// "bf16 / fp32-accumulate"): the A operand is a bf16 copy of h_prev (hb_prev: B x H, row stride ldhbp ELEMENTS), W a bf16
+// copy of W_hh (3H x H) -- half the bytes and half the k-blocks of the latency-bound main loop -- while the accumulators,
+// the gate math, h_prev in the blend and every saved array stay fp32.  Besides hout the kernel writes hb_out, the bf16
+// copy of the new state that the next step multiplies.  32-unit tiles; H % 64 == 0.
+PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
+                                long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
+                                void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H,
+                                void* stream) {
+    if (B <= 0) return 0;
+    if (H % 64 != 0 || hb_prev == nullptr || hprev == nullptr || hout == hprev || hb_out == hb_prev || hb_out == nullptr)
+        return PD_BAD_ARG;
+    if (!al16(hprev, ldhp) || !al16(gi, ldgi) || (gi2 && !al16(gi2, ldgi2)) || !al16(hout, ldho) || (rzn && !al16(rzn, ldrzn)) ||
+        (hn && !al16(hn, ldhn)) || ((uintptr_t)b_hh & 15) || ((uintptr_t)hb_prev & 15) || ((uintptr_t)wb & 15) ||
+        ((uintptr_t)hb_out & 31) || (ldhbp & 7) || (ldwb & 7) || (ldhbo & 15))
+        return PD_BAD_ARG;
+    CUtensorMap ta, tb, tgi, tgi2, thp, tho, trzn, thn;
+    int rc = make_map(&ta, hb_prev, 2, H, B, ldhbp, BM, false);
+    if (!rc) rc = make_map(&tb, wb, 2, H, 3L * H, ldwb, 32, false);
+    if (!rc) rc = make_map_io(&tgi, gi, 3L * H, B, ldgi);
+    if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
+    if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
+    tgi2 = tgi; trzn = tho; thn = tho;
+    if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
+    if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
+    if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
+    if (rc) return rc;
+    StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr, (uint16_t*)hb_out, ldhbo};
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / 32;
+    const long items = (long)tiles_m * tiles_u;
+    const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    constexpr int ST = 4, NS = 1;
+    constexpr int smem = ST * (BM * 128 + 96 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+    static unsigned long long attr = 0;
+    if (pd_first_use_on_device(attr)) {
+        cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, false, false, 32, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    gru_step_tma_kernel<ST, NS, true, false, false, 32, 2><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
+        ta, tb, tgi, tgi2, thp, tho, trzn, thn, tho, ta, tb, g, tiles_m, tiles_u);
+    return pd_launch_status();
+}
+
 // Training form with the x-projection folded in (SEG2, TF32 single pass): gi = W_x x is computed inside the kernel as a
 // second K segment (x: B x K2 rows of the step's input, w_x: 3H x K2), so the (B,T,3H) x-projection of the sequence is never
 // materialised.  gi2 (B,3H) carries the rest of the input projection incl. b_ih.  Teacher-forced note GRU (ptvae.py:396-398):
@@ -631,7 +694,7 @@ static int gru_step_tmax_impl(const float* hprev, long ldhp, const float* w_hh, 
     if (!rc && rzn) rc = make_map_io(&trzn, rzn, 3L * H, B, ldrzn);
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
-    StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2, nrows};
+    StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2, nrows, nullptr, 0};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -688,7 +751,7 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
     tgi2 = tgi; trzn = tho; thn = tho;
     if (!rc && gi2) rc = make_map_io(&tgi2, gi2, 3L * H, B, ldgi2);
     if (rc) return rc;
-    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1, 0, nullptr};
+    StepIo g{b_hh, gi2 != nullptr, 0, 0, B, H, 3 * H, 1, 0, nullptr, nullptr, 0};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -730,7 +793,7 @@ PD_API int pd_gru_step_tma3x(const float* a3, long lda3, const float* w3, long l
     if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
     if (!rc) rc = make_map_io(&th3, h3out, 3L * H, B, ldh3);
     if (rc) return rc;
-    StepIo g{b_hh, 1, 0, 0, B, H, 3 * H, 1, K2, nullptr};
+    StepIo g{b_hh, 1, 0, 0, B, H, 3 * H, 1, K2, nullptr, nullptr, 0};
     const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);

@@ -271,6 +271,12 @@ FUSED_GRU_STEP_TMA_MIN_ROWS = 256
 # GRU the (32*B, 16, 1536) projection of the note embeddings (1.6 GB at batch 512) is then never written or read -- the
 # producing GEMM skips those columns (linear_split(skip_tail=)), each step multiplies its 128-wide embedding rows itself.
 FUSED_GRU_STEP_X = True
+# bf16 operands (fp32 accumulate / gate math / state) for the recurrent GEMMs of the batch-sized recurrences in training --
+# time GRU, encoder bi-GRUs, chord decoder: their per-step kernels are bound by launch + TMA-pipeline latency, which scales
+# with the bytes and k-blocks of the main loop.  BASELINE configs[1] "bf16/fp32-accum"; gradient error of these operands
+# alone vs the fp32 reference: 1.0e-3 (tolerance 1e-2; measured on the CPU emulation, all-TF32: 7e-4).
+BF16_RECURRENT = True
+BF16_RECURRENT_MAX_ROWS = 4096
 
 
 def fold_x_ok(rows, H, x, w_x):
@@ -825,7 +831,7 @@ def gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths=None, reverse=False, sa
 
     def run(sl):
         _gru_steps_fwd(gi[sl], _sl(gi2, sl), _sl(h0, sl), w_hh, b_hh, _sl(lengths, sl), order, h_all[sl], _sl(rzn, sl),
-                       _sl(hn, sl), fused_ok)
+                       _sl(hn, sl), fused_ok, save)
     _over_row_chunks(B, H3, run)
     return h_all
 
@@ -861,14 +867,44 @@ def _over_row_chunks(B, H3, run):
     fork_join([lane(l) for l in range(min(ROW_CHUNK_LANES, len(starts)))])
 
 
-def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fused_ok):
+def to_bf16(x):
+    """fp32 (rows, cols) with unit inner stride -> bf16 copy (round to nearest even)."""
+    rows, cols = x.shape
+    out = torch.empty(rows, cols, device=x.device, dtype=torch.bfloat16)
+    _call("pd_f32_to_bf16", _ptr(x), x.stride(0), rows, cols, _ptr(out), out.stride(0), _stream())
+    return out
+
+
+def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fused_ok, save=None):
     """All steps of the recurrence for one block of rows (every argument already row-sliced)."""
     B, H = h_all.shape[0], h_all.shape[2]
     gh = torch.empty(B, 3 * H, device=gi.device, dtype=torch.float32)
     hprev = h0
+    # bf16 copies of W_hh and of the running state for the batch-sized recurrences in training (BF16_RECURRENT)
+    use_bf16 = (fused_ok and BF16_RECURRENT and save is not None and rzn is not None and lengths is None
+                and FUSED_GRU_STEP_TMA and FUSED_GRU_STEP_TMA_MIN_ROWS <= B <= BF16_RECURRENT_MAX_ROWS and H % 64 == 0
+                and w_hh.stride(1) == 1)
+    wb = hb = None
+    if use_bf16:
+        wb = to_bf16(w_hh)
+        save["wb"] = wb                                   # the backward's dgh . W_hh GEMM multiplies the same copy
+        hb = torch.empty(2, B, H, device=gi.device, dtype=torch.bfloat16)      # ping-pong: state in / state out
+        hb_cur = 0
+        hb_valid = False
     for t in order:
         if (fused_ok and hprev is not None and hprev.stride(1) == 1 and hprev.stride(0) % 4 == 0
                 and hprev.data_ptr() % 16 == 0):
+            if use_bf16:
+                if not hb_valid:                          # first fused step: the incoming state has no bf16 copy yet
+                    _call("pd_f32_to_bf16", _ptr(hprev), hprev.stride(0), B, H, _ptr(hb[hb_cur]), H, _stream())
+                _call("pd_gru_step_tma_bf16", _ptr(hb[hb_cur]), H, _ptr(wb), wb.stride(0), _ptr(b_hh), _ptr(gi[:, t]),
+                      gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0), _ptr(hprev), hprev.stride(0),
+                      _ptr(h_all[:, t]), h_all.stride(0), _ptr(hb[hb_cur ^ 1]), H, _ptr(rzn[:, t]), rzn.stride(0),
+                      _ptr(hn[:, t]), hn.stride(0), B, H, _stream())
+                hb_cur ^= 1
+                hb_valid = True
+                hprev = h_all[:, t]
+                continue
             if FUSED_GRU_STEP_TMA and lengths is None and B >= FUSED_GRU_STEP_TMA_MIN_ROWS:
                 _call("pd_gru_step_tma", _ptr(hprev), hprev.stride(0), _ptr(w_hh), w_hh.stride(0), _ptr(b_hh),
                       _ptr(gi[:, t]), gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0),
@@ -893,7 +929,7 @@ def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fuse
         hprev = h_all[:, t]
 
 
-def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0):
+def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0, wb=None):
     """BPTT over all steps for one block of rows; dh0 (or None) receives the gradient of the initial state.
     ``dout``: (B,T,H) gradient of every step's output, or (d (B,H), step): only that step's output was used."""
     B, T, H = h_all.shape
@@ -914,12 +950,23 @@ def _gru_steps_bwd(dout, rzn, hn, h_all, h0, w_hh, lengths, order, dgi, dgh, dh0
     # step clears the accumulator instead, one graph node less on every serial step
     fold_zero = (PRECISION == "tf32" and w_hh.stride(1) == 1 and w_hh.stride(0) % 4 == 0 and w_hh.data_ptr() % 16 == 0
                  and _lib.lib.pd_gemm_tf32_splits(B, H, 3 * H) > 1)
+    dghb = torch.empty(B, 3 * H, device=dev, dtype=torch.bfloat16) if (wb is not None and fold_zero) else None
     for i in range(T - 1, -1, -1):
         t = order[i]
         hprev = h_all[:, order[i - 1]] if i > 0 else h0
         nz = dz_b if dz is dz_a else dz_a
         nm = dm_b if dm is dm_a else dm_a
         d_t, ld_t = dout_of(t)
+        if dghb is not None and hprev is not None:
+            # bf16 operands for dgh . W_hh (the forward multiplied the same bf16 W_hh): the gate kernel emits the bf16 copy
+            _call("pd_gru_gates_bwd_zb", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(d_t),
+                  ld_t, _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
+                  _ptr(hn[:, t]), hn.stride(0), _ptr(hprev), hprev.stride(0),
+                  _ptr(dgi[:, t]), dgi.stride(0), _ptr(dgh[:, t]), dgh.stride(0), _ptr(nz), nz.stride(0),
+                  _ptr(lengths), t, B, H, _ptr(nm), nm.stride(0), _ptr(dghb), 3 * H, st)
+            _call("pd_gemm_bf16", _ptr(dghb), 3 * H, 1, _ptr(wb), wb.stride(0), 1, _ptr(nm), nm.stride(0), None, B, H, 3 * H, 1, st)
+            dz, dm = nz, nm
+            continue
         if fold_zero and hprev is not None:
             _call("pd_gru_gates_bwd_z", _ptr(dz), 0 if dz is None else dz.stride(0), _ptr(d_t),
                   ld_t, _ptr(dm), 0 if dm is None else dm.stride(0), _ptr(rzn[:, t]), rzn.stride(0),
@@ -961,6 +1008,7 @@ class _GruSeq(torch.autograd.Function):
         save = {}
         h_all = gru_sequence_nograd(gi, gi2, h0, w_hh, b_hh, lengths, reverse, save, n_steps, xsrc)
         ctx.save_for_backward(save["rzn"], save["hn"], h_all, h0, w_hh, lengths)
+        ctx.wb = save.get("wb")           # bf16 copy of W_hh the forward multiplied (batch-sized recurrences), or None
         ctx.resident = bool(save.get("resident"))
         ctx.reverse = reverse
         ctx.has_gi2 = gi2 is not None
@@ -1002,7 +1050,7 @@ class _GruSeq(torch.autograd.Function):
         else:
             def run(sl):
                 _gru_steps_bwd(dout[sl] if last < 0 else (dout[sl], last), rzn[sl], hn[sl], h_all[sl], _sl(h0, sl), w_hh,
-                               _sl(lengths, sl), order, dgi[sl], dgh[sl], _sl(dh0, sl))
+                               _sl(lengths, sl), order, dgi[sl], dgh[sl], _sl(dh0, sl), ctx.wb)
             _over_row_chunks(B, 3 * H, run)
         dgh_flat = dgh.view(B * T, 3 * H)
         db = torch.empty(3 * H, device=dev, dtype=torch.float32)

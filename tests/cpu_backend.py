@@ -378,6 +378,26 @@ class CpuBackend:
         skip = (np.arange(T)[None, :] >= L[:, None]) & (np.arange(R)[:, None] >= CP[None, :])      # masked and not padded-live
         GI[skip] = keep[skip]
 
+    @staticmethod
+    def _to_bf16_bits(x):
+        bits = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+        return ((bits + 0x7FFF + ((bits >> 16) & 1)) >> 16).astype(np.uint16)
+
+    def pd_gru_step_tma_bf16(self, hb, ldhb, wb, ldwb, b_hh, gi, ldgi, gi2, ldgi2, hp, ldhp, ho, ldho, hbo, ldhbo, rzn, ldrzn,
+                             hn, ldhn, B, H, st):
+        HB = self._bf16_to_f32(hb, (B, H), (ldhb, 1))
+        WB = self._bf16_to_f32(wb, (3 * H, H), (ldwb, 1))
+        gh = (HB @ WB.T + _arr(b_hh, (3 * H,), (1,))).astype(np.float32)
+        self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh.ctypes.data, 3 * H, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn, None, 0,
+                              B, H, st)
+        _arr(hbo, (B, H), (ldhbo, 1), np.uint16)[...] = self._to_bf16_bits(_arr(ho, (B, H), (ldho, 1)))
+
+    def pd_gru_gates_bwd_zb(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                            dhp, lddhp, lengths, t, B, H, zero_out, ldzo, dgh_b, lddghb, st):
+        self.pd_gru_gates_bwd_z(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
+                                dhp, lddhp, lengths, t, B, H, zero_out, ldzo, st)
+        _arr(dgh_b, (B, 3 * H), (lddghb, 1), np.uint16)[...] = self._to_bf16_bits(_arr(dgh, (B, 3 * H), (lddgh, 1)))
+
     def pd_gru_gates_bwd_z(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                            dhp, lddhp, lengths, t, B, H, zero_out, ldzo, st):
         self.pd_gru_gates_bwd(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,

@@ -647,6 +647,47 @@ def test_gru_step_tma(B, H, bcast, save):
         assert torch.allclose(g, c, atol=4e-3, rtol=0), float((g - c).abs().max())
 
 
+@pytest.mark.parametrize("B,H,bcast", [(512, 1024, True), (512, 512, False), (300, 128, True), (2048, 1024, False)])
+def test_gru_step_tma_bf16_operands(B, H, bcast):
+    """Fused step with bf16 copies of h_prev / W_hh as the tcgen05 operands (kind::f16, fp32 accumulate; the batch-sized
+    recurrences in training): both sides multiply the SAME bf16 values, so the comparison is tight; the kernel also emits
+    the bf16 copy of the new state."""
+    _dev()
+    torch.manual_seed(5)
+    w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
+    hp = torch.randn(B, H)
+    wb, hb = w.to(torch.bfloat16), hp.to(torch.bfloat16)
+
+    def mk():
+        ho, hbo = torch.zeros(B, H), torch.zeros(B, H, dtype=torch.bfloat16)
+        rzn, hn = torch.zeros(B, 3 * H), torch.zeros(B, H)
+        return ([hb, H, wb, H, b, torch.randn(B, 3 * H), 3 * H, torch.randn(B, 3 * H) if bcast else None, 3 * H, hp, H, ho, H,
+                 hbo, H, rzn, 3 * H, hn, H, B, H, None], [ho, hbo, rzn, hn])
+    (gh, ch), (gb, cb), (gr, cr), (gn, cn) = _both("pd_gru_step_tma_bf16", mk)
+    assert torch.allclose(gh, ch, atol=2e-5, rtol=0), float((gh - ch).abs().max())
+    assert torch.allclose(gr, cr, atol=2e-5, rtol=0) and torch.allclose(gn, cn, atol=2e-5, rtol=0)
+    assert float((gb.float() - cb.float()).abs().max()) <= 2 ** -7           # (one bf16 ulp where h' straddles a boundary)
+    assert float((gb.float() - gh).abs().max()) <= 2 ** -8 * float(gh.abs().max())
+
+
+def test_gru_gates_bwd_zb_bf16_copy():
+    """Gate-gradient kernel that also clears the split-K accumulator and writes the bf16 copy of dgh."""
+    _dev()
+    B, H = 512, 1024
+
+    def mk():
+        dgi, dgh, dhp = torch.zeros(B, 3 * H), torch.zeros(B, 3 * H), torch.zeros(B, H)
+        zo, gb = torch.full((B, H), 3.0), torch.zeros(B, 3 * H, dtype=torch.bfloat16)
+        rzn = torch.rand(B, 3 * H) * 0.9 + 0.05
+        return ([torch.randn(B, H), H, torch.randn(B, H), H, torch.randn(B, H), H, rzn, 3 * H, torch.randn(B, H), H,
+                 torch.randn(B, H), H, dgi, 3 * H, dgh, 3 * H, dhp, H, None, 0, B, H, zo, H, gb, 3 * H, None], [dgi, dgh, dhp, zo, gb])
+    res = _both("pd_gru_gates_bwd_zb", mk)
+    for g, c in res[:4]:
+        assert torch.allclose(g, c, atol=1e-5, rtol=1e-5)
+    assert float(res[3][0].abs().max()) == 0.0
+    assert float((res[4][0].float() - res[4][1].float()).abs().max()) <= 2 ** -7 * float(res[1][0].abs().max())
+
+
 @pytest.mark.parametrize("B,H,bcast", [(700, 128, True), (4100, 512, True), (513, 1024, False)])
 def test_gru_step_tma3_split3_inference(B, H, bcast):
     """Fused inference step of the 3xTF32 decode path (pd_gru_step_tma3): [hi|hi|lo] . [hi|lo|hi] on tcgen05, expf / tanhf
