@@ -385,9 +385,14 @@ def run_b200(args):
     w_hh_ = torch.randn(3 * Hh, Hh, device=dev) * 0.03
     dm_ = torch.zeros(2, B, Hh, device=dev)
 
+    dghb_ = dgh_.to(torch.bfloat16)
+    wbb_ = ops.to_bf16(w_hh_)
+
     def dh_seq():
+        # as ops._gru_steps_bwd issues it in training: bf16 copies of dgh (written by the gate kernel) and W_hh
         for t_ in range(32):
-            ops.gemm_nn(dgh_[t_], w_hh_, dm_[t_ & 1], accumulate=True)
+            ops._call("pd_gemm_bf16", dghb_[t_].data_ptr(), 3 * Hh, 1, wbb_.data_ptr(), Hh, 1, dm_[t_ & 1].data_ptr(), Hh, None,
+                      B, Hh, 3 * Hh, 1, torch.cuda.current_stream().cuda_stream)
     dh_seq()
     ms_dh = timed(dh_seq, 5) / 32
     dh_flop = 2.0 * B * 3 * Hh * Hh
@@ -401,10 +406,16 @@ def run_b200(args):
     hn_b = torch.empty(B, 32, Hh, device=dev)
     b_b = torch.randn(3 * Hh, device=dev) * 0.1
 
+    wb_b = ops.to_bf16(w_hh_)
+    hb_b = torch.empty(2, B, Hh, device=dev, dtype=torch.bfloat16)
+    hb_b[0].copy_(h_b[:, 0])
+
     def fwd_seq():
+        # the call ops._gru_steps_fwd issues for these recurrences in training: bf16 copies of h / W_hh as tcgen05 operands
         for t_ in range(32):
-            ops._call("pd_gru_step_tma", h_b[:, t_].data_ptr(), h_b.stride(0), w_hh_.data_ptr(), Hh, b_b.data_ptr(),
-                      gi_b[:, t_].data_ptr(), gi_b.stride(0), None, 0, h_b[:, t_ + 1].data_ptr(), h_b.stride(0),
+            ops._call("pd_gru_step_tma_bf16", hb_b[t_ & 1].data_ptr(), Hh, wb_b.data_ptr(), Hh, b_b.data_ptr(),
+                      gi_b[:, t_].data_ptr(), gi_b.stride(0), None, 0, h_b[:, t_].data_ptr(), h_b.stride(0),
+                      h_b[:, t_ + 1].data_ptr(), h_b.stride(0), hb_b[(t_ & 1) ^ 1].data_ptr(), Hh,
                       rzn_b[:, t_].data_ptr(), rzn_b.stride(0), hn_b[:, t_].data_ptr(), hn_b.stride(0), B, Hh,
                       torch.cuda.current_stream().cuda_stream)
     fwd_seq()
@@ -439,8 +450,9 @@ def run_b200(args):
     achieved = gflop_exec * B / (ms_step * 1e-3) / 1e3                   # TFLOP/s per GPU
     out = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
-           "dtype_note": "fp32 storage; GEMM operands rounded to TF32 on the tensor cores, fp32 accumulation and gate math",
+           "vs_baseline": None, "dtype": "tf32+bf16", "data": "synthetic",
+           "dtype_note": "fp32 storage, accumulation, gate math and recurrent state; GEMM operands rounded to TF32 on the tensor "
+                         "cores, bf16 operand copies (W_hh, h, dgh) for the recurrent GEMMs of the batch-sized recurrences",
            "config": {"workload": "PolyDisVAE training step (zero_grad+fwd+loss+bwd+clip_grad_norm+Adam), "
                                   "teacher-forced PianoTree decoder, batch 512 per GPU (BASELINE configs[1])",
                       "batch_per_gpu": B, "global_batch": world * B, "tfr": [1, 1, 1],
@@ -465,24 +477,24 @@ def run_b200(args):
                       "tf32_value": world * Bd / (dec_ms["tf32"] * 1e-3), "cuda_graph": True,
                       "latency_16_segments_ms": ms_dec16, "e2e": dec_e2e},
            "roofline": {"bound": "tensor", "achieved": bstep_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                        "frac": bstep_tflops / peak_tf, "traffic": _measured_traffic("gru_step_tma_kernel<4, 1, 1, 0, 0, 32>"),
+                        "frac": bstep_tflops / peak_tf, "traffic": _measured_traffic("gru_step_tma_kernel<4, 1, 1, 0, 0, 32, 2>"),
                         "peak_source": peak_src,
-                        "kernel": "gru_step_tma_kernel<32-unit tiles> via pd_gru_step_tma: one forward step of a batch-sized "
-                                  "recurrence (time GRU / encoders / chord decoder), [B x 1024] . [1024 x 3072] on tcgen05 + "
-                                  "gate math in the epilogue",
+                        "kernel": "gru_step_tma_kernel<32-unit tiles, bf16 operands> via pd_gru_step_tma_bf16: one forward step of a "
+                                  "batch-sized recurrence (time GRU / encoders / chord decoder), [B x 1024] . [1024 x 3072] on "
+                                  "tcgen05 (kind::f16, fp32 accumulate) + gate math in the epilogue",
                         "ms_per_launch": ms_bstep, "algorithmic_flop_per_launch": dh_flop,
                         "what": "the kernel with the largest share of the packed step (profiles/r02_v4_train_step_launches.txt: "
                                 "68 launches, 11.9 %), timed alone with CUDA events (32 launches over distinct slices of a "
                                 "(B,33,.) sequence, 5 rounds): 2 M N K / launch time vs the measured sustained bf16 tensor peak. "
-                                "TF32 multiplies run at half that rate, and at batch 512 the kernel is ONE wave of 128 CTAs with "
-                                "32 dependent k-blocks: bound by launch + TMA pipeline latency, not by the tensor pipe; "
+                                "At batch 512 the kernel is ONE wave of 128 CTAs with 16 dependent k-blocks: bound by launch + TMA "
+                                "pipeline latency, not by the tensor pipe; "
                                 "traffic = ncu dram bytes per launch (profiles/r02_kernel_traffic.json)",
                         "recurrent_dh_gemm": {"achieved": dh_tflops, "peak": peak_tf, "unit": "TFLOP/s", "frac": dh_tflops / peak_tf,
                                               "ms_per_launch": ms_dh,
-                                              "traffic": _measured_traffic("gemm_tf32_kernel<4, 1, 64, 3, 3, 0, 1>"),
-                                              "kernel": "gemm_tf32_kernel<64-wide, 3 stages, NN>: dgh . W_hh of the same recurrences' "
-                                                        "backward steps, [B x 3072] . [3072 x 1024], split-K red.add epilogue "
-                                                        "(82 launches, 10.1 %)"},
+                                              "traffic": _measured_traffic("gemm_tf32_kernel<2, 1, 64, 3, 3, 0, 1>"),
+                                              "kernel": "gemm_tf32_kernel<bf16 operands, 64-wide, 3 stages, NN>: dgh . W_hh of the same "
+                                                        "recurrences' backward steps, [B x 3072] . [3072 x 1024], split-K red.add "
+                                                        "epilogue (82 launches)"},
                         "fused_note_step_hbm": {"achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
                                                 "frac": step_gbs / peak_hbm,
                                                 "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1>"),

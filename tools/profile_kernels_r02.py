@@ -39,6 +39,9 @@ rzns = torch.empty(Bs, 32, 3 * Hs, device=dev)
 hns = torch.empty(Bs, 32, Hs, device=dev)
 dghs = torch.randn(Bs, 3 * Hs, device=dev)
 dhs = torch.empty(Bs, Hs, device=dev)
+Wbs = ops.to_bf16(Ws)
+hbs = torch.zeros(2, Bs, Hs, device=dev, dtype=torch.bfloat16)
+dghbs = dghs.to(torch.bfloat16)
 Q = R * T
 h0 = torch.randn(Q, 64, device=dev)
 par = [torch.randn(192, 5, device=dev) * 0.3, torch.randn(192, device=dev) * 0.1, torch.randn(192, 64, device=dev) * 0.2,
@@ -69,6 +72,10 @@ for rep in range(2):
     # one step of a batch-sized (512-row) recurrence, H = 1024: forward GEMM + gates, backward gates + split-K dh GEMM
     ops._call("pd_gru_step_tma", P(hs[:, 2]), hs.stride(0), P(Ws), Hs, P(bs), P(gis[:, 3]), gis.stride(0), None, 0,
               P(hs[:, 3]), hs.stride(0), P(rzns[:, 3]), rzns.stride(0), P(hns[:, 3]), hns.stride(0), Bs, Hs, st)
+    ops._call("pd_gru_step_tma_bf16", P(hbs[0]), Hs, P(Wbs), Hs, P(bs), P(gis[:, 3]), gis.stride(0), None, 0, P(hs[:, 2]),
+              hs.stride(0), P(hs[:, 3]), hs.stride(0), P(hbs[1]), Hs, P(rzns[:, 3]), rzns.stride(0), P(hns[:, 3]), hns.stride(0),
+              Bs, Hs, st)
+    ops._call("pd_gemm_bf16", P(dghbs), 3 * Hs, 1, P(Wbs), Hs, 1, P(dhs), Hs, None, Bs, Hs, 3 * Hs, 1, st)
     ops.gemm_nt(hs[:, 2], Ws, ghs, bs)
     ops._gates_fwd(gis[:, 3], None, ghs, hs[:, 2], hs[:, 3], rzns[:, 3], hns[:, 3], None, 3)
     ops.gemm_nn(dghs, Ws, dhs)
