@@ -287,6 +287,13 @@ int pd_gru128_bwd_rows(const float* dout, long dr, long dt, const float* h_all, 
                        long gt, float* dgh, long qr, long qt, long R, int T, int reverse, const int* cp, int dout_step,
                        void* stream);
 
+/* texture front end, training form: the forward also writes the pooled arg-max position of every output (int8, -1 = ReLU
+ * inactive; same layout as out), the backward reads it instead of recomputing the convolution */
+int pd_texture_frontend_fwd_ix(const float* pr_mat, const float* w, const float* bias, int B, int C, float* out,
+                               signed char* amax, void* stream);
+int pd_texture_frontend_bwd_ix(const float* pr_mat, const signed char* amax, int B, int C, const float* gout, float* dw,
+                               float* dbias, void* stream);
+
 /* bf16-operand step of the batch-sized recurrences (BASELINE configs[1] "bf16 / fp32-accumulate"): hb_prev / wb are bf16
  * copies of h_prev (B x H) and W_hh (3H x H) (strides in elements); accumulators, gate math, the h_prev of the blend and all
  * saved arrays are fp32; hb_out receives the bf16 copy of the new state.  pd_gru_gates_bwd_zb: pd_gru_gates_bwd_z that also

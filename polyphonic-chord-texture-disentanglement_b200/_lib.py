@@ -80,6 +80,8 @@ SIGNATURES = {
     "pd_note_embed_bwd_rows": [_P, _L, _P, _L, _P, _P, _P, _I, _P],
     "pd_gru128_bwd_rows": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P, _I, _P],
     "pd_gru_gates_bwd_z": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P],
+    "pd_texture_frontend_fwd_ix": [_P, _P, _P, _I, _I, _P, _P, _P],
+    "pd_texture_frontend_bwd_ix": [_P, _P, _I, _I, _P, _P, _P, _P],
     "pd_gru_step_tma_bf16": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
     "pd_gru_gates_bwd_zb": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P,
                             _L, _P],

@@ -14,7 +14,8 @@ namespace {
 constexpr int KH = 4, KW = 12, W_IN = 128, W_POOL = 29, MAXC = 16;
 
 __global__ void __launch_bounds__(320) texture_fwd_kernel(const float* __restrict__ pr, const float* __restrict__ w,
-                                                          const float* __restrict__ bias, int C, float* out) {
+                                                          const float* __restrict__ bias, int C, float* out,
+                                                          signed char* amax) {
     __shared__ float band[KH][W_IN];
     __shared__ float ws[MAXC * KH * KW];
     __shared__ float bs[MAXC];
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(320) texture_fwd_kernel(const float* __restric
         const int ch = o / W_POOL, wp = o % W_POOL;
         const float* f = ws + ch * KH * KW;
         float best = 0.0f;   // relu floor
+        int bq = -1;         // pooled arg-max position; -1: relu inactive everywhere (no gradient flows)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float s = bs[ch];
@@ -36,9 +38,10 @@ __global__ void __launch_bounds__(320) texture_fwd_kernel(const float* __restric
             for (int dr = 0; dr < KH; ++dr)
 #pragma unroll
                 for (int dc = 0; dc < KW; ++dc) s = fmaf(f[dr * KW + dc], band[dr][w0 + dc], s);
-            best = fmaxf(best, s);
+            if (s > best) { best = s; bq = q; }          // first maximum wins (max_pool2d backward convention)
         }
         out[(((long)b * C + ch) * 8 + i) * W_POOL + wp] = best;
+        if (amax) amax[(((long)b * C + ch) * 8 + i) * W_POOL + wp] = (signed char)bq;
     }
 }
 
@@ -51,15 +54,18 @@ __global__ void __launch_bounds__(320) texture_fwd_kernel(const float* __restric
 constexpr int BWD_THREADS = 512;
 __global__ void __launch_bounds__(BWD_THREADS) texture_bwd_kernel(const float* __restrict__ pr, const float* __restrict__ w,
                                                                    const float* __restrict__ bias, int C, long n_items,
-                                                                   const float* __restrict__ gout, float* dw, float* dbias) {
+                                                                   const float* __restrict__ gout, float* dw, float* dbias,
+                                                                   const signed char* __restrict__ amax) {
     __shared__ float band[KH][W_IN];
     __shared__ float ws[MAXC * KH * KW];
     __shared__ float bs[MAXC];
     __shared__ float gq[MAXC * W_POOL];            // gout of the pooled output, 0 where no gradient flows
     __shared__ int qpos[MAXC * W_POOL];            // first column of its arg-max conv window
     const int t = threadIdx.x;
-    for (int k = t; k < C * KH * KW; k += BWD_THREADS) ws[k] = w[k];
-    if (t < C) bs[t] = bias[t];
+    if (amax == nullptr) {
+        for (int k = t; k < C * KH * KW; k += BWD_THREADS) ws[k] = w[k];
+        if (t < C) bs[t] = bias[t];
+    }
     const int ch_own = t / (KH * KW), tap = t % (KH * KW), dr_own = tap / KW, dc_own = tap % KW;
     const bool owner = t < C * KH * KW;
     float acc = 0.0f, dbacc = 0.0f;
@@ -75,7 +81,9 @@ __global__ void __launch_bounds__(BWD_THREADS) texture_bwd_kernel(const float* _
             const float g = gout[((b * C + ch) * 8 + i) * W_POOL + wp];
             float best = 0.0f;
             int bq = -1;                           // -1: relu inactive everywhere -> no gradient
-            if (g != 0.0f) {
+            if (amax != nullptr) {                 // the forward saved the arg-max: no recomputation of the conv windows
+                bq = amax[((b * C + ch) * 8 + i) * W_POOL + wp];
+            } else if (g != 0.0f) {
                 const float* f = ws + ch * KH * KW;
                 for (int q = 0; q < 4; ++q) {
                     float s = bs[ch];
@@ -113,19 +121,41 @@ PD_API int pd_texture_frontend_fwd(const float* pr_mat, const float* w, const fl
                                    float* out, void* stream) {
     if (B <= 0) return 0;
     if (C < 1 || C > MAXC) return PD_BAD_ARG;
-    texture_fwd_kernel<<<B * 8, 320, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C, out);
+    texture_fwd_kernel<<<B * 8, 320, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C, out, nullptr);
+    return pd_launch_status();
+}
+
+// Training form: also writes amax (B,C,8,29) int8, the pooled arg-max position of every output (-1: ReLU inactive), which
+// pd_texture_frontend_bwd_ix reads instead of recomputing the convolution (the recomputation, not the reduction, was the
+// cost of the backward: 182 of 204 us)
+PD_API int pd_texture_frontend_fwd_ix(const float* pr_mat, const float* w, const float* bias, int B, int C, float* out,
+                                      signed char* amax, void* stream) {
+    if (B <= 0) return 0;
+    if (C < 1 || C > MAXC || amax == nullptr) return PD_BAD_ARG;
+    texture_fwd_kernel<<<B * 8, 320, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C, out, amax);
     return pd_launch_status();
 }
 
 // dw (C*48) and dbias (C) are ACCUMULATED into (caller zeroes them).
-PD_API int pd_texture_frontend_bwd(const float* pr_mat, const float* w, const float* bias, int B, int C,
-                                   const float* gout, float* dw, float* dbias, void* stream) {
+static int texture_bwd_impl(const float* pr_mat, const float* w, const float* bias, int B, int C,
+                            const float* gout, float* dw, float* dbias, const signed char* amax, void* stream) {
     if (B <= 0) return 0;
     if (C < 1 || C > MAXC) return PD_BAD_ARG;
     if (C * KH * KW > BWD_THREADS) return PD_BAD_ARG;
     const long n_items = (long)B * 8;
     const long want = 2L * PD_NUM_SMS;
     texture_bwd_kernel<<<(unsigned)(n_items < want ? n_items : want), BWD_THREADS, 0, (cudaStream_t)stream>>>(pr_mat, w, bias, C,
-                                                                                                          n_items, gout, dw, dbias);
+                                                                                                          n_items, gout, dw, dbias, amax);
     return pd_launch_status();
+}
+
+PD_API int pd_texture_frontend_bwd(const float* pr_mat, const float* w, const float* bias, int B, int C,
+                                   const float* gout, float* dw, float* dbias, void* stream) {
+    return texture_bwd_impl(pr_mat, w, bias, B, C, gout, dw, dbias, nullptr, stream);
+}
+
+PD_API int pd_texture_frontend_bwd_ix(const float* pr_mat, const signed char* amax, int B, int C, const float* gout, float* dw,
+                                      float* dbias, void* stream) {
+    if (amax == nullptr) return PD_BAD_ARG;
+    return texture_bwd_impl(pr_mat, nullptr, nullptr, B, C, gout, dw, dbias, amax, stream);
 }

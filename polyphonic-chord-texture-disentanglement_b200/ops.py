@@ -62,33 +62,34 @@ def _empty_rows(rows, cols, dev):
 # lets them overlap -- also inside a captured CUDA graph, where the streams become parallel branches, and in
 # backward, because autograd replays each op on the stream its forward ran on.
 FORK_STREAMS = True
-_stream_pool = []
-_stream_depth = 0
+_stream_pool = {}          # parent stream handle -> its side streams
 
 
 def fork_join(fns):
     """Run the callables in list order (python side effects keep their order); all but the last go to side
-    streams forked from the current stream, the last runs on the current stream, then everything is joined."""
-    global _stream_depth
+    streams forked from the current stream, the last runs on the current stream, then everything is joined.
+
+    Every side stream belongs to ONE parent stream (the pool is keyed by the forking stream, so nested fork-joins under
+    different parents never share a side stream).  That is what makes the caching allocator safe here without
+    ``record_stream``: a tensor allocated on a side stream is consumed by its parent (or an ancestor) after the join; when
+    python frees it the block returns to the side stream's pool, and the side stream's next use starts with a wait on
+    that same parent -- i.e. after the consumer.  With a shared side stream a second parent could re-use the block while
+    the first parent's consumer was still queued (seen as a wrong first graph replay once buffer sizes lined up)."""
     if not FORK_STREAMS or len(fns) < 2 or not torch.cuda.is_available():
         return [f() for f in fns]
     cur = torch.cuda.current_stream()
     n_side = len(fns) - 1
-    while len(_stream_pool) < _stream_depth + n_side:
-        _stream_pool.append(torch.cuda.Stream(priority=-1))     # chain streams outrank the weight-gradient stream
-    side = _stream_pool[_stream_depth:_stream_depth + n_side]
-    _stream_depth += n_side
-    try:
-        outs = []
-        for f, st in zip(fns[:-1], side):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                outs.append(f())
-        outs.append(fns[-1]())
-        for st in side:
-            cur.wait_stream(st)
-    finally:
-        _stream_depth -= n_side
+    side = _stream_pool.setdefault(cur.cuda_stream, [])
+    while len(side) < n_side:
+        side.append(torch.cuda.Stream(priority=-1))     # chain streams outrank the weight-gradient stream
+    outs = []
+    for f, st in zip(fns[:-1], side):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            outs.append(f())
+    outs.append(fns[-1]())
+    for st in side[:n_side]:
+        cur.wait_stream(st)
     return outs
 
 
@@ -1415,25 +1416,32 @@ class _TextureFrontend(torch.autograd.Function):
         B, C = pr.shape[0], w.shape[0]
         out = torch.empty(B, C, 8, 29, device=pr.device, dtype=torch.float32)
         wc = w.contiguous()
-        _call("pd_texture_frontend_fwd", _ptr(pr), _ptr(wc), _ptr(b), B, C, _ptr(out), _stream())
-        ctx.save_for_backward(pr, wc, b)
+        if any(ctx.needs_input_grad):
+            # training: the forward also records the pooled arg-max positions; the backward reads them instead of
+            # recomputing the convolution windows
+            amax = torch.empty(B, C, 8, 29, device=pr.device, dtype=torch.int8)
+            _call("pd_texture_frontend_fwd_ix", _ptr(pr), _ptr(wc), _ptr(b), B, C, _ptr(out), _ptr(amax), _stream())
+            ctx.save_for_backward(pr, amax)
+        else:
+            _call("pd_texture_frontend_fwd", _ptr(pr), _ptr(wc), _ptr(b), B, C, _ptr(out), _stream())
+        ctx.wshape, ctx.bshape = w.shape, b.shape
         ctx.wg = wg
         return out
 
     @staticmethod
     def backward(ctx, g):
-        pr, w, b = ctx.saved_tensors
+        pr, amax = ctx.saved_tensors
         g = g.contiguous()
-        dw = torch.empty_like(w)
-        db = torch.empty_like(b)
+        dw = torch.empty(ctx.wshape, device=g.device, dtype=torch.float32)
+        db = torch.empty(ctx.bshape, device=g.device, dtype=torch.float32)
 
         def wgrads():                                      # (the piano-roll input needs no gradient)
             dw.zero_()
             db.zero_()
-            _call("pd_texture_frontend_bwd", _ptr(pr), _ptr(w), _ptr(b), pr.shape[0], w.shape[0], _ptr(g),
-                  _ptr(dw), _ptr(db), _stream())
+            _call("pd_texture_frontend_bwd_ix", _ptr(pr), _ptr(amax), pr.shape[0], ctx_c, _ptr(g), _ptr(dw), _ptr(db), _stream())
+        ctx_c = ctx.wshape[0]
         if ctx.wg is not None:
-            ctx.wg.set(wgrads, keep=(g, pr))
+            ctx.wg.set(wgrads, keep=(g, pr, amax))
         else:
             wgrads()
         return None, dw, db, None

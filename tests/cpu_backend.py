@@ -701,6 +701,26 @@ class CpuBackend:
         y = np.maximum(self._conv(P, _arr(w, (C, 48), (48, 1)), _arr(b, (C,), (1,))), 0)[..., :116]
         _arr(out, (B, C, 8, 29), (C * 232, 232, 29, 1))[...] = y.reshape(B, C, 8, 29, 4).max(-1)
 
+    def pd_texture_frontend_fwd_ix(self, pr, w, b, B, C, out, amax, st):
+        self.pd_texture_frontend_fwd(pr, w, b, B, C, out, st)
+        P = _arr(pr, (B, 32, 128), (4096, 128, 1))
+        y = self._conv(P, _arr(w, (C, 48), (48, 1)), _arr(b, (C,), (1,)))[..., :116].reshape(B, C, 8, 29, 4)
+        q = y.argmax(-1)                                       # first maximum
+        active = np.take_along_axis(y, q[..., None], -1)[..., 0] > 0
+        _arr(amax, (B, C, 8, 29), (C * 232, 232, 29, 1), np.int8)[...] = np.where(active, q, -1)
+
+    def pd_texture_frontend_bwd_ix(self, pr, amax, B, C, g, dw, db, st):
+        P = _arr(pr, (B, 32, 128), (4096, 128, 1))
+        A = _arr(amax, (B, C, 8, 29), (C * 232, 232, 29, 1), np.int8).astype(np.int64)
+        G = _arr(g, (B, C, 8, 29), (C * 232, 232, 29, 1))
+        gy = np.zeros((B, C, 8, 29, 4), np.float32)
+        np.put_along_axis(gy, np.maximum(A, 0)[..., None], np.where(A >= 0, G, 0)[..., None], -1)
+        gy = gy.reshape(B, C, 8, 116)
+        bands = P.reshape(B, 8, 4, 128)
+        win = np.lib.stride_tricks.sliding_window_view(bands, 12, axis=3)[:, :, :, :116]   # (B,8,4,116,12)
+        _arr(dw, (C, 4, 12), (48, 12, 1))[...] += np.einsum("bciw,bidwk->cdk", gy, win)
+        _arr(db, (C,), (1,))[...] += gy.sum((0, 2, 3))
+
     def pd_texture_frontend_bwd(self, pr, w, b, B, C, g, dw, db, st):
         P = _arr(pr, (B, 32, 128), (4096, 128, 1))
         y = self._conv(P, _arr(w, (C, 48), (48, 1)), _arr(b, (C,), (1,)))[..., :116].reshape(B, C, 8, 29, 4)

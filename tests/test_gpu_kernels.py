@@ -308,6 +308,21 @@ def test_texture_frontend(NB):
                 None], [dw, db]
     for g, c in _both("pd_texture_frontend_bwd", mkb):
         assert torch.allclose(g, c, atol=5e-3 * np.sqrt(NB / 6), rtol=1e-4), float((g - c).abs().max())
+    # training form: the forward records the pooled arg-max, the backward reads it
+    wt, bt = torch.randn(10, 48) * 0.2, torch.randn(10) * 0.1
+
+    def mki():
+        out, am = torch.zeros(NB, 10, 8, 29), torch.zeros(NB, 10, 8, 29, dtype=torch.int8)
+        return [pr, wt, bt, NB, 10, out, am, None], [out, am]
+    (go, co), (ga, ca) = _both("pd_texture_frontend_fwd_ix", mki)
+    assert torch.allclose(go, co, atol=1e-4) and float((ga != ca).float().mean()) < 1e-3      # (exact ties aside)
+    gout = torch.randn(NB, 10, 8, 29)
+
+    def mkbi():
+        dw, db = torch.zeros(10, 48), torch.zeros(10)
+        return [pr, ca, NB, 10, gout, dw, db, None], [dw, db]
+    for g, c in _both("pd_texture_frontend_bwd_ix", mkbi):
+        assert torch.allclose(g, c, atol=5e-3 * np.sqrt(NB / 6), rtol=1e-4), float((g - c).abs().max())
 
 
 @pytest.mark.parametrize("R,C,ignore", [(4001, 130, 130), (9000, 2, 2), (333, 12, -100)])

@@ -26,7 +26,11 @@ def run(spec):
         setattr(ops, k, type(saved[k])(float(v)) if not isinstance(saved[k], bool) else bool(int(v)))
     torch.manual_seed(0); random.seed(0)
     m = DisentangleVAE.init_model(device=dev).to(dev)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
+    if os.environ.get("PD_AB_FUSED_OPT"):       # the repo's clip + Adam + LR decay on the reducer's flat buckets
+        from polydis_b200.optim import FusedClipAdam
+        opt = FusedClipAdam(list(m.parameters()), lr=1e-3, clip=1.0, lr_gamma=0.9999, lr_min=1e-5)
+    else:
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=True)
     g = GraphedTrainStep(m, opt, B, warmup=2, inject_eps=True).capture(x, c, pr)
     l0 = float(g(x, c, pr)[0])
     for _ in range(3):
