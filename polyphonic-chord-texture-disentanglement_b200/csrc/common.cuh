@@ -93,6 +93,31 @@ struct PdLiveBlocks {
     }
 };
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------------
+// The step's critical path is a chain of ~150 dependent 10-20 us kernels; with PDL the CTAs of kernel N+1 are scheduled
+// while kernel N drains and run their prologue (barrier init, TMEM allocation, tensor-map prefetch) before blocking in
+// pd_grid_dependency_wait(), which returns once every prerequisite grid has completed and its writes are visible.
+// Kernels that opt in call pd_grid_launch_dependents() first (lets the runtime schedule the dependent grid early) and
+// pd_grid_dependency_wait() before their first access to global memory; both are no-ops for ordinary launches.
+__device__ __forceinline__ void pd_grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pd_grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+extern int g_pd_pdl;       // 0 = ordinary launches (default), 1 = launch the opted-in kernels with the PDL attribute
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pd_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_pd_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float pd_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 // MUFU forms for the TF32-mode recurrent kernels, which are instruction-bound on the gate math: ex2.approx +
 // rcp.approx, absolute error ~1e-6 (three orders below the TF32 operand rounding of the matvec next to them);

@@ -78,3 +78,10 @@ PD_API int pd_adam_clip_step(float* p, const float* g, float* m, float* v, long 
                                                                          b1, b2, eps, clip);
     return pd_launch_status();
 }
+
+// ---- library-wide switch: programmatic dependent launch for the opted-in kernels (common.cuh) -----------------------------
+int g_pd_pdl = 0;
+PD_API int pd_set_pdl(int on) {
+    g_pd_pdl = on ? 1 : 0;
+    return 0;
+}
