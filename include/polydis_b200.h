@@ -315,6 +315,11 @@ int pd_gru_gates_bwd_z(const float* dh, long lddh, const float* dh2, long lddh2,
                        float* zero_out, long ldzo, void* stream);
 int pd_gemm_tf32_splits(int M, int N, int K);
 
+/* Library-wide switch: launch the kernels of the recurrent chain (fused step, gate gradients, the tcgen05 GEMM) with the
+ * programmatic-dependent-launch attribute, so that a kernel's prologue overlaps its predecessor's tail (csrc/common.cuh).
+ * 0 (default) = ordinary launches. */
+int pd_set_pdl(int on);
+
 #ifdef __cplusplus
 }
 #endif

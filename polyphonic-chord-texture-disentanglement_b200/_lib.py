@@ -85,6 +85,7 @@ SIGNATURES = {
     "pd_gru_step_tma_bf16": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
     "pd_gru_gates_bwd_zb": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P,
                             _L, _P],
+    "pd_set_pdl": [_I],
     "pd_gemm_tf32_splits": [_I, _I, _I],          # (returns the split count, not a status: call through ``lib``)
 }
 

@@ -259,16 +259,12 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* io_bar = tmem_empty + 2;                                 // [4][NSETS]: epilogue operands of a warp's set landed
     uint32_t* tmem_slot = (uint32_t*)(io_bar + 4 * NSETS);
 
+    pd_grid_launch_dependents();        // (PDL launches: the next kernel of the chain may be scheduled while this one runs)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int BKE = 128 / EB;                                      // elements per 128-byte k-block row
     static_assert(EB == 4 || !SEG2, "the folded x-projection is a TF32 path");
     const int nkb1 = (g.KA + BKE - 1) / BKE, nkb2 = SEG2 ? (g.K2 + 31) / 32 : 0;
     const int nkb = nkb1 + nkb2;
-    if (g.nrows != nullptr) {
-        const int live = min(g.B, *g.nrows);
-        tiles_m = (live + BM - 1) / BM;
-    }
-    const long n_items = (long)tiles_m * tiles_u;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -285,7 +281,14 @@ gru_step_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pd_grid_dependency_wait();          // prologue done; from here on the kernel touches data of its predecessors
     const uint32_t tmem_base = *tmem_slot;
+    if (g.nrows != nullptr) {
+        const int live = min(g.B, *g.nrows);
+        tiles_m = (live + BM - 1) / BM;
+    }
+    const long n_items = (long)tiles_m * tiles_u;
+
 
     if (warp == 0) {
         if (lane == 0) {
@@ -600,8 +603,8 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             if (e != cudaSuccess) return (int)e;
         }
-        gru_step_tma_kernel<ST, NS, true, kPrecise, false, 32><<<grid32, NUM_THREADS, smem, (cudaStream_t)stream>>>(
-            ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u);
+        { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, kPrecise, false, 32>, dim3(grid32), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+            ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
         return pd_launch_status();
     }
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
@@ -616,8 +619,12 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
             cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, OB, kPrecise, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
             if (e != cudaSuccess) return (int)e;                                                                            \
         }                                                                                                                   \
-        gru_step_tma_kernel<ST, NS, OB, kPrecise, false><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ta, tb, tgi, tgi2, thp, \
-                                                                                  tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u); \
+        {                                                                                                                   \
+            cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, OB, kPrecise, false>, dim3(grid), dim3(NUM_THREADS),     \
+                                           (size_t)smem, (cudaStream_t)stream, ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, \
+                                           tb, g, tiles_m, tiles_u);                                                        \
+            if (le != cudaSuccess) return (int)le;                                                                          \
+        }                                                                                                                   \
         return pd_launch_status();                                                                                          \
     }
     if (g_step_variant == 1) PD_STEP_LAUNCH(4, 1, false)
@@ -665,8 +672,8 @@ PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    gru_step_tma_kernel<ST, NS, true, false, false, 32, 2><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
-        ta, tb, tgi, tgi2, thp, tho, trzn, thn, tho, ta, tb, g, tiles_m, tiles_u);
+    { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, false, false, 32, 2>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+            ta, tb, tgi, tgi2, thp, tho, trzn, thn, tho, ta, tb, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
     return pd_launch_status();
 }
 
@@ -705,8 +712,8 @@ static int gru_step_tmax_impl(const float* hprev, long ldhp, const float* w_hh, 
         cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    gru_step_tma_kernel<ST, NS, true, false, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
-        ta, tb, tgi2, tgi2, thp, tho, trzn, thn, tho, ta2, tb2, g, tiles_m, tiles_u);
+    { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, false, true>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+            ta, tb, tgi2, tgi2, thp, tho, trzn, thn, tho, ta2, tb2, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
     return pd_launch_status();
 }
 
@@ -762,8 +769,8 @@ PD_API int pd_gru_step_tma3(const float* a3, long lda3, const float* w3, long ld
         cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    gru_step_tma_kernel<ST, NS, true, true, false><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
-        ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u);
+    { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, true, false>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+            ta, tb, tgi, tgi2, thp, tho, trzn, thn, th3, ta, tb, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
     return pd_launch_status();
 }
 
@@ -804,8 +811,8 @@ PD_API int pd_gru_step_tma3x(const float* a3, long lda3, const float* w3, long l
         cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
     }
-    gru_step_tma_kernel<ST, NS, true, true, true><<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(
-        ta, tb, tgi2, tgi2, thp, tho, tho, tho, th3, ta2, tb2, g, tiles_m, tiles_u);
+    { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, true, true>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+            ta, tb, tgi2, tgi2, thp, tho, tho, tho, th3, ta2, tb2, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
     return pd_launch_status();
 }
 

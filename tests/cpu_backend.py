@@ -404,6 +404,9 @@ class CpuBackend:
                               dhp, lddhp, None, 0, lengths, t, B, H, st)
         _arr(zero_out, (B, H), (ldzo, 1))[...] = 0
 
+    def pd_set_pdl(self, on):
+        pass
+
     # ---- pianotree misc ----
     def pd_grid_prepare(self, x, steps, tok, lengths, pt, dt, st):
         X = _arr(x, (steps, 16, 6), (96, 6, 1), np.int64)

@@ -19,6 +19,10 @@ x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 0))
 
 
 def run(spec):
+    from polydis_b200 import _lib
+    pdl = "PDL=1" in spec
+    _lib.lib.pd_set_pdl(1 if pdl else 0)
+    spec = ",".join(kv for kv in spec.split(",") if not kv.startswith("PDL="))
     saved = {}
     for kv in filter(None, spec.split(",")):
         k, v = kv.split("=")
@@ -40,7 +44,7 @@ def run(spec):
     for _ in range(20):
         g(x, c, pr)
     e1.record(); torch.cuda.synchronize()
-    print(f"{spec or 'default':50s} {e0.elapsed_time(e1) / 20:7.3f} ms/step   first loss {l0:.6f}", flush=True)
+    print(f"{(spec or 'default') + (' PDL' if pdl else ''):50s} {e0.elapsed_time(e1) / 20:7.3f} ms/step   first loss {l0:.6f}", flush=True)
     for k, v in saved.items():
         setattr(ops, k, v)
     del g, m, opt
