@@ -115,16 +115,34 @@ _warn_off = False
 _ws_active = []
 
 
-def wgrad_stream():
-    """The low-priority side stream of the deferred weight-gradient jobs (None without CUDA)."""
+#: number of weight-gradient streams the deferred jobs are dealt onto (round robin per tagged op).  The jobs are
+#: independent of each other; on ONE in-order stream the last dozen small ones (encoder-side gradients that only exist
+#: when backward ends) serialise into a ~1 ms tail after the chain has finished.
+DEFER_STREAMS = 4
+_wg_extra = []
+_wg_next = 0
+
+
+def wgrad_stream(i=0):
+    """The low-priority side streams of the deferred weight-gradient jobs (None without CUDA).  Stream 0 also hosts the
+    weight-space nodes (``weight_space``) and the parameters' gradient accumulation (``pin_leaf_streams``)."""
     global _wg_stream
-    if _wg_stream is None and torch.cuda.is_available():
+    if not torch.cuda.is_available():
+        return None
+    if _wg_stream is None:
         _wg_stream = torch.cuda.Stream()
-    return _wg_stream
+    if i == 0:
+        return _wg_stream
+    while len(_wg_extra) < i:
+        _wg_extra.append(torch.cuda.Stream())
+    return _wg_extra[i - 1]
 
 
 def _on_wgrad_stream():
-    return _wg_stream is not None and torch.cuda.current_stream() == _wg_stream
+    if _wg_stream is None:
+        return False
+    cur = torch.cuda.current_stream()
+    return cur == _wg_stream or any(cur == s for s in _wg_extra)
 
 
 class weight_space:
@@ -172,8 +190,9 @@ def pin_leaf_streams(params):
     """Create the parameters' AccumulateGrad nodes under the weight-gradient stream (a node runs on the stream that was
     current when it was created; they are created on a parameter's first use and die with the graph).  Without this
     the engine makes the stream of a parameter's first forward use -- the chain's -- wait for the deferred job."""
-    global _leaf_pins
+    global _leaf_pins, _wg_next
     _leaf_pins = []
+    _wg_next = 0                # the same op -> stream assignment in every forward pass
     s = wgrad_stream()
     if not (DEFER_WGRAD and s is not None and torch.is_grad_enabled()) or _on_wgrad_stream() or DBG_PIN_OFF:
         return
@@ -187,15 +206,16 @@ def pin_leaf_streams(params):
 
 
 class _WGradJob:
-    __slots__ = ("job",)
+    __slots__ = ("job", "stream")
 
-    def __init__(self):
+    def __init__(self, stream=None):
         self.job = None
+        self.stream = stream
 
     def set(self, job, keep=()):
         """``job()`` launches the weight-gradient kernels (it runs under the weight-gradient stream); ``keep``: device
         buffers it reads that the calling backward may release before the job has executed."""
-        s = _wg_stream
+        s = self.stream
         if s is not None:
             for t in keep:
                 if torch.is_tensor(t) and t.is_cuda:
@@ -236,8 +256,12 @@ def defer(*ws):
     idx = [i for i, w in enumerate(ws) if torch.is_tensor(w) and w.requires_grad]
     if not idx or not all(_deferrable(ws[i]) for i in idx):
         return ws + (None,)
-    wg = _WGradJob()
-    s = wgrad_stream() if ws[idx[0]].is_cuda else None
+    global _wg_next
+    s = None
+    if ws[idx[0]].is_cuda:
+        s = wgrad_stream(_wg_next % max(1, DEFER_STREAMS))
+        _wg_next += 1
+    wg = _WGradJob(s)
     if s is not None:
         with torch.cuda.stream(s):
             tagged = _DeferTag.apply(wg, *[ws[i] for i in idx])
