@@ -222,6 +222,23 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / n
 
+    def timed_graph(fn, n):
+        """ms per replay of a CUDA graph of fn() -- how the step itself issues its kernels (eager launches of the TMA kernels
+        are host-bound: every launch encodes its tensor maps on the CPU)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            fn()
+        gr.replay()
+        ms = timed(gr.replay, n)
+        del gr
+        return ms
+
     mark("model + reducer ready")
     graphed = None
     if not args.eager:
@@ -371,7 +388,7 @@ def run_b200(args):
                       h_[:, t_ + 1].data_ptr(), h_.stride(0), rzn_[:, t_].data_ptr(), rzn_.stride(0), hn_[:, t_].data_ptr(),
                       hn_.stride(0), R, H_, torch.cuda.current_stream().cuda_stream)
     step_seq()
-    ms_fstep = timed(step_seq, 3) / T_
+    ms_fstep = timed_graph(step_seq, 5) / T_
     # h_prev + gi2(3) in, h + rzn(3) + hn out = 9 H floats per row-step, + the step's 128 embedding floats, + W_hh | W_x
     step_bytes = R * (9 * H_ + K2_) * 4 + 3 * H_ * (H_ + K2_) * 4
     step_gbs = step_bytes / (ms_fstep * 1e-3) / 1e9
@@ -394,7 +411,7 @@ def run_b200(args):
             ops._call("pd_gemm_bf16", dghb_[t_].data_ptr(), 3 * Hh, 1, wbb_.data_ptr(), Hh, 1, dm_[t_ & 1].data_ptr(), Hh, None,
                       B, Hh, 3 * Hh, 1, torch.cuda.current_stream().cuda_stream)
     dh_seq()
-    ms_dh = timed(dh_seq, 5) / 32
+    ms_dh = timed_graph(dh_seq, 10) / 32
     dh_flop = 2.0 * B * 3 * Hh * Hh
     dh_tflops = dh_flop / (ms_dh * 1e-3) / 1e12
     del dgh_, dm_
@@ -419,7 +436,7 @@ def run_b200(args):
                       rzn_b[:, t_].data_ptr(), rzn_b.stride(0), hn_b[:, t_].data_ptr(), hn_b.stride(0), B, Hh,
                       torch.cuda.current_stream().cuda_stream)
     fwd_seq()
-    ms_bstep = timed(fwd_seq, 5) / 32
+    ms_bstep = timed_graph(fwd_seq, 10) / 32
     bstep_tflops = dh_flop / (ms_bstep * 1e-3) / 1e12
     del gi_b, h_b, rzn_b, hn_b
     # live share of the note level in THIS batch (device table of the packed path): executed work, not the dense count
@@ -483,9 +500,10 @@ def run_b200(args):
                                   "batch-sized recurrence (time GRU / encoders / chord decoder), [B x 1024] . [1024 x 3072] on "
                                   "tcgen05 (kind::f16, fp32 accumulate) + gate math in the epilogue",
                         "ms_per_launch": ms_bstep, "algorithmic_flop_per_launch": dh_flop,
-                        "what": "the kernel with the largest share of the packed step (profiles/r02_v4_train_step_launches.txt: "
-                                "68 launches, 11.9 %), timed alone with CUDA events (32 launches over distinct slices of a "
-                                "(B,33,.) sequence, 5 rounds): 2 M N K / launch time vs the measured sustained bf16 tensor peak. "
+                        "what": "the kernel with the largest share of the packed step (profiles/r02_v5_train_step_launches.txt: "
+                                "68 launches, 10.4 %), timed alone with CUDA events as a captured graph of 32 dependent launches "
+                                "over the slices of a (B,33,.) sequence (10 replays): 2 M N K / launch time vs the measured "
+                                "sustained bf16 tensor peak. "
                                 "At batch 512 the kernel is ONE wave of 128 CTAs with 16 dependent k-blocks: bound by launch + TMA "
                                 "pipeline latency, not by the tensor pipe; "
                                 "traffic = ncu dram bytes per launch (profiles/r02_kernel_traffic.json)",
@@ -497,7 +515,7 @@ def run_b200(args):
                                                         "epilogue (82 launches)"},
                         "fused_note_step_hbm": {"achieved": step_gbs, "peak": peak_hbm, "unit": "GB/s",
                                                 "frac": step_gbs / peak_hbm,
-                                                "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1>"),
+                                                "traffic": _measured_traffic("gru_step_tma_kernel<3, 1, 1, 0, 1, 64, 4>"),
                                                 "kernel": "gru_step_tma_kernel<SEG2> (fused note-GRU step, all 32B rows live)",
                                                 "ms_per_launch": ms_fstep, "algorithmic_bytes_per_launch": step_bytes},
                         "whole_step_tensor": {"achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
