@@ -24,6 +24,12 @@ import sys
 import threading
 import time
 
+EXCHANGE_NOTE = {
+    "p2p": "polydis_b200 allreduce_p2p_kernel: one kernel per bucket gathers the gradients, two-shot all-reduce with peer "
+           "loads / stores over NVLink (CUDA IPC symmetric region), clip-norm partials; captured in the step graph",
+    "nccl": "multi-tensor gather + ncclAllReduce(AVG) per bucket on a side stream, captured in the step graph",
+}
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -177,7 +183,16 @@ def run_b200(args):
         from polydis_b200.ddp import BucketedGradAllReduce
         for p in params:                                   # identical initial weights on every rank
             dist.broadcast(p.data, 0)
-        reducer = BucketedGradAllReduce(params, bucket_mb=8)
+        exchange = args.exchange
+        if exchange == "p2p":           # the repo's peer-memory kernel; NCCL only if the node offers no CUDA IPC / P2P
+            try:
+                reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb, impl="p2p")
+            except RuntimeError as ex:
+                if rank == 0:
+                    print(f"bench: p2p exchange unavailable, using NCCL: {ex}", file=sys.stderr, flush=True)
+                exchange = "nccl"
+        if exchange == "nccl":
+            reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb)
     fused_opt = args.fused_optim
     if fused_opt:
         from polydis_b200.optim import FusedClipAdam
@@ -199,7 +214,10 @@ def run_b200(args):
         if reducer is not None:
             reducer.finish()
         if not fused_opt:
-            torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
+            if getattr(reducer, "impl", None) == "p2p":
+                reducer.clip_grad_norm_(1.0)
+            else:
+                torch.nn.utils.clip_grad_norm_(params, 1.0, foreach=True)
         opt.step()
         return losses[0]
 
@@ -477,7 +495,8 @@ def run_b200(args):
                       "note_level": "packed: rows sorted by token count, note slots whose target is PAD are not computed in "
                                     "loss mode (losses and gradients unchanged; tests/test_gpu_model.py)",
                       "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else "torch clip_grad_norm_ + Adam(fused)"},
+                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else "torch clip_grad_norm_ + Adam(fused)",
+                      **({"gradient_exchange": EXCHANGE_NOTE[reducer.impl], "bucket_mb": args.bucket_mb} if reducer is not None and world > 1 else {})},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4,
                    "how": ("GraphedTrainStep.prefetch/step_prefetched: each step copies one full batch from pinned host "
@@ -553,6 +572,9 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--decode-batch", type=int, default=16384)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="gradient exchange under --gpus N>1: the repo's peer-memory all-reduce kernel (default) or NCCL")
+    ap.add_argument("--bucket-mb", type=float, default=8.0)
     ap.add_argument("--no-tfr0", action="store_true", help="skip the free-running (tfr=0) training measurement")
     ap.add_argument("--no-decode-e2e", action="store_true", help="skip the 65,536-segment end-to-end decode measurement")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] strong-scaling point under --gpus N>1")

@@ -21,21 +21,72 @@ Design (round 2):
 * every operation is a stream operation, so the whole exchange is captured inside the training step's CUDA graph;
 * ``finish()`` joins the communication stream before the global-norm clip and the optimizer step (which therefore
   see identical gradients on every rank).
+
+``impl="p2p"`` (CUDA, world 2..8 on one NVLink / NVSwitch node) replaces the per-bucket multi-tensor copy + NCCL call by
+ONE kernel of the repo's library (``csrc/allreduce_p2p.cu``): the buckets live in a CUDA-IPC "symmetric" region every
+peer has mapped; the kernel gathers the bucket from the producers' buffers, reduces this rank's slice with peer loads
+over NVLink, stores the average into every rank's copy and leaves the squared-norm partials of the clip
+(``clip_grad_norm_``).  Measured reason (2 GPUs, ``tools/ddp_trace.py``): with the deferred weight gradients most
+buckets complete only when backward ends, so the exchange is an exposed tail of copy + ``ncclAllReduce`` (RING_LL,
+15-70 us per 8 MB bucket) launches -- 0.75 ms of an 8.57 ms step.
 """
+import ctypes
+import os
+
 import torch
 import torch.distributed as dist
 
 
+class _DeviceRegion:
+    """A raw device allocation exposed through ``__cuda_array_interface__`` (``torch.as_tensor`` wraps it, no copy)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def observe_ready_order(params, run_backward):
+    """Run ``run_backward()`` (one forward + backward) and return the parameters in the order autograd finished
+    accumulating their gradients -- the bucket order that lets each all-reduce start as early as possible (the deferred
+    weight-gradient jobs of ``ops.defer`` make this differ from reverse registration order).  Gradients are dropped."""
+    params = [p for p in params if p.requires_grad]
+    seen, handles = [], []
+    for p in params:
+        handles.append(p.register_post_accumulate_grad_hook(lambda q, seen=seen: seen.append(q)))
+    for p in params:
+        p.grad = None
+    run_backward()
+    for h in handles:
+        h.remove()
+    for p in params:
+        p.grad = None
+    out, ids = [], set()
+    for p in seen:
+        if id(p) not in ids:
+            ids.add(id(p))
+            out.append(p)
+    return out + [p for p in reversed(params) if id(p) not in ids]
+
+
 class BucketedGradAllReduce:
-    def __init__(self, params, bucket_mb=8, group=None):
+    def __init__(self, params, bucket_mb=8, group=None, ready_order=None, comm_priority=0, impl="nccl", ar_blocks=None):
+        """``ready_order``: the parameters in the order their gradients become ready (``observe_ready_order``); default
+        reverse registration order.  ``comm_priority``: CUDA priority of the communication stream (negative = higher).
+        ``impl``: "nccl" | "p2p" (the library's peer-memory kernel; falls back to "nccl" semantics only by raising)."""
         self.group = group
+        self.impl = impl
+        assert impl in ("nccl", "p2p")
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.cuda = self.params[0].is_cuda
         cap = int(bucket_mb * (1 << 20) // 4)
         self.buckets = []                  # dicts: flat, params, views, pending, events, adopted
         cur, cur_n = [], 0
-        for p in reversed(self.params):
+        if ready_order is not None:
+            order = [p for p in ready_order if p.requires_grad]
+            assert len(order) == len(self.params) and {id(p) for p in order} == {id(p) for p in self.params}
+        else:
+            order = list(reversed(self.params))
+        for p in order:
             if cur and cur_n + p.numel() > cap:
                 self._close(cur)
                 cur, cur_n = [], 0
@@ -43,7 +94,9 @@ class BucketedGradAllReduce:
             cur_n += p.numel()
         if cur:
             self._close(cur)
-        self.comm = torch.cuda.Stream() if self.cuda else None
+        if impl == "p2p":
+            self._setup_p2p(ar_blocks)
+        self.comm = torch.cuda.Stream(priority=comm_priority) if self.cuda else None
         self._handles = []
         for bi, b in enumerate(self.buckets):
             for pi, p in enumerate(b["params"]):
@@ -52,14 +105,98 @@ class BucketedGradAllReduce:
 
     def _close(self, plist):
         n = sum(-(-p.numel() // 4) * 4 for p in plist)             # 16-byte aligned slots
-        flat = torch.zeros(n, device=plist[0].device, dtype=torch.float32)
-        views, off = [], 0
-        for p in plist:
-            views.append(flat[off:off + p.numel()].view_as(p))
-            off += -(-p.numel() // 4) * 4
+        flat = None if self.impl == "p2p" else torch.zeros(n, device=plist[0].device, dtype=torch.float32)
         events = [torch.cuda.Event() for _ in plist] if plist[0].is_cuda else None
-        self.buckets.append({"flat": flat, "params": plist, "views": views, "pending": len(plist), "events": events,
-                             "adopted": None})
+        b = {"flat": flat, "n": n, "params": plist, "views": None, "pending": len(plist), "events": events, "adopted": None,
+             "index": len(self.buckets)}
+        if flat is not None:
+            self._bind(b, flat)
+        self.buckets.append(b)
+
+    @staticmethod
+    def _bind(b, flat):
+        views, offs, off = [], [], 0
+        for p in b["params"]:
+            views.append(flat[off:off + p.numel()].view_as(p))
+            offs.append(off)
+            off += -(-p.numel() // 4) * 4
+        b["flat"], b["views"], b["offs"] = flat, views, offs
+
+    def _setup_p2p(self, ar_blocks):
+        """Allocate this rank's symmetric region, exchange the IPC handles, map the peers' regions."""
+        from ._lib import lib
+        if not (self.cuda and dist.is_initialized() and 2 <= self.world <= lib.pd_ar_limit(0)):
+            raise RuntimeError("impl='p2p' needs CUDA parameters and a process group of 2..8 ranks on one node")
+        self._lib = lib
+        self.rank = dist.get_rank(self.group)
+        self.ar_blocks = int(ar_blocks or os.environ.get("PD_AR_BLOCKS", "48"))
+        assert 1 <= self.ar_blocks <= lib.pd_ar_limit(1)
+        self.max_src = lib.pd_ar_limit(2)
+        dev = self.params[0].device
+        self.flag_bytes = lib.pd_ar_flag_bytes(len(self.buckets))
+        total = sum(b["n"] for b in self.buckets)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        with torch.cuda.device(dev):
+            rc = lib.pd_ipc_alloc(self.flag_bytes + total * 4, ctypes.byref(ptr), handle)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, (rc, bytes(handle.raw)), group=self.group)
+            self._region = ptr.value
+            self._peer_ptrs = (ctypes.c_void_p * self.world)()
+            self._opened = []
+            why = "" if rc == 0 else f"pd_ipc_alloc -> {rc}"
+            if all(h[0] == 0 for h in handles):
+                for r, (_, h) in enumerate(handles):
+                    if r == self.rank:
+                        self._peer_ptrs[r] = ptr.value
+                        continue
+                    q = ctypes.c_void_p()
+                    rc = lib.pd_ipc_open(ctypes.create_string_buffer(h, 64), ctypes.byref(q))
+                    if rc != 0:
+                        why = f"pd_ipc_open(rank {r}) -> cudaError {rc}"
+                        break
+                    self._peer_ptrs[r] = q.value
+                    self._opened.append(q.value)
+            data = None
+            if not why:
+                try:
+                    self._mem = _DeviceRegion(ptr.value + self.flag_bytes, total)
+                    data = torch.as_tensor(self._mem, device=dev)
+                    assert data.data_ptr() == ptr.value + self.flag_bytes and data.dtype == torch.float32
+                except Exception as e:                  # noqa: BLE001 -- reported to every rank below
+                    why = f"wrapping the region as a tensor failed: {e!r}"
+            # every rank learns whether ALL ranks are set up (a rank raising alone would leave the others in a collective)
+            whys = [None] * self.world
+            dist.all_gather_object(whys, why, group=self.group)
+            if any(whys):
+                raise RuntimeError("impl='p2p' unavailable: " + "; ".join(f"rank {r}: {w}" for r, w in enumerate(whys) if w))
+        self.flat_all = data
+        off = 0
+        for b in self.buckets:
+            b["off"] = off
+            self._bind(b, data[off:off + b["n"]])
+            off += b["n"]
+        self._epoch = torch.zeros(lib.pd_ar_limit(1), device=dev, dtype=torch.int32)
+        self._err = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
+        dist.barrier(group=self.group)          # every rank has mapped every region before the first kernel touches one
+
+    def _exchange_p2p(self, bi, b, grads):
+        """One kernel: gather ``grads`` into the bucket, all-reduce (average) it over the peers, leave the norm partials."""
+        lib = self._lib
+        ok = len(grads) <= self.max_src and all(g.is_contiguous() and g.dtype == torch.float32 and g.data_ptr() % 4 == 0
+                                                and g.numel() == p.numel() for g, p in zip(grads, b["params"]))
+        if ok:
+            n_src = len(grads)
+            src = (ctypes.c_void_p * n_src)(*[g.data_ptr() for g in grads])
+            soff = (ctypes.c_long * n_src)(*b["offs"])
+            sn = (ctypes.c_long * n_src)(*[g.numel() for g in grads])
+        else:
+            torch._foreach_copy_(b["views"], grads)
+            n_src, src, soff, sn = 0, None, None, None
+        from . import _lib
+        _lib.call("pd_allreduce_p2p", self._peer_ptrs, self.rank, self.world, self.flag_bytes, b["off"], b["n"],
+                  1.0 / self.world, self._epoch.data_ptr(), self._err.data_ptr(), bi, self.ar_blocks, src, soff, sn, n_src,
+                  torch.cuda.current_stream().cuda_stream)
 
     def _make_hook(self, bi, pi):
         def hook(_p):
@@ -81,9 +218,12 @@ class BucketedGradAllReduce:
             for ev in b["events"]:
                 self.comm.wait_event(ev)
             with torch.cuda.stream(self.comm):
-                torch._foreach_copy_(b["views"], grads)
-                if self.world > 1:
-                    dist.all_reduce(b["flat"], op=dist.ReduceOp.AVG, group=self.group)
+                if self.impl == "p2p":
+                    self._exchange_p2p(b["index"], b, grads)
+                else:
+                    torch._foreach_copy_(b["views"], grads)
+                    if self.world > 1:
+                        dist.all_reduce(b["flat"], op=dist.ReduceOp.AVG, group=self.group)
             b["adopted"] = grads           # keep the producers' buffers alive until finish() has joined ``comm``
         else:                                                       # gloo (CPU tests): no streams, no AVG
             torch._foreach_copy_(b["views"], grads)
@@ -112,6 +252,26 @@ class BucketedGradAllReduce:
             b["adopted"] = None
         self.check_grad_views()
 
+    def clip_grad_norm_(self, max_norm):
+        """Global-norm clip of the averaged gradients (call after ``finish()``): torch's ``clip_grad_norm_`` semantics
+        (coef = max_norm / (norm + 1e-6), capped at 1, always applied).  With ``impl="p2p"`` the squared norm comes from
+        the partials the exchange kernels left (no pass over the gradients); returns the norm as a device scalar."""
+        flats = [b["flat"] for b in self.buckets]
+        if self.impl == "p2p":
+            from . import _lib
+            _lib.call("pd_ar_norm_total", self._region, len(self.buckets), self.world, self.ar_blocks,
+                      self._sumsq.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            norm = self._sumsq.sqrt().squeeze(0)
+        else:
+            norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(flats)))
+        coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
+        torch._foreach_mul_(flats, coef)
+        return norm
+
+    def peer_error(self):
+        """True if an exchange kernel gave up waiting for a peer (synchronises; not for use inside a capture)."""
+        return self.impl == "p2p" and bool(self._err.item())
+
     def check_grad_views(self):
         """Every ``p.grad`` must be its bucket view: a stray ``zero_grad(set_to_none=True)`` / foreign optimizer would
         otherwise leave the optimizer stepping on stale bucket contents without any error."""
@@ -124,3 +284,10 @@ class BucketedGradAllReduce:
     def remove(self):
         for h in self._handles:
             h.remove()
+        if self.impl == "p2p" and getattr(self, "_region", None):
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)      # no peer is still inside an exchange kernel on this region
+            for q in self._opened:
+                self._lib.pd_ipc_close(q)
+            # the region itself stays allocated while tensors view it (``flat_all``); it is freed with the process

@@ -65,7 +65,10 @@ class GraphedTrainStep:
         if self.reducer is not None:
             self.reducer.finish()
         if self.clip and not self.fused:
-            torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
+            if getattr(self.reducer, "impl", None) == "p2p":
+                self.reducer.clip_grad_norm_(self.clip)     # norm from the exchange kernels' partials
+            else:
+                torch.nn.utils.clip_grad_norm_(self.params, self.clip, foreach=True)
         self.opt.step()
         return torch.stack([l.detach() for l in losses])
 

@@ -28,7 +28,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, impl="nccl"):
     try:
         sys.path.insert(0, ROOT)
         import torch.distributed as dist
@@ -42,6 +42,36 @@ def _worker(rank, world, port, q):
         from polydis_b200.model import DisentangleVAE
         from polydis_b200.synth import synth_batch
         from polydis_b200.weights import make_state_dict
+
+        if impl == "p2p":
+            # the exchange kernel alone: odd-sized parameters, sources that are only 4-byte aligned, several rounds on the
+            # same flags (epochs), exact expected values; norm partials vs torch
+            sizes = (5, 1024, 3, 77777, 1, 4096 * 33 + 2, 130)
+            ps = [torch.nn.Parameter(torch.zeros(n, device=dev)) for n in sizes]
+            redk = BucketedGradAllReduce(ps, bucket_mb=0.3, impl="p2p")
+            assert len(redk.buckets) >= 3
+            for rnd in range(3):
+                redk.reset()
+                keep = []
+                for i, p_ in enumerate(ps):
+                    base = torch.arange(p_.numel() + 1, device=dev, dtype=torch.float32) * (rank + 1) + (rnd + i)
+                    keep.append(base)
+                    p_.grad = base[1:] if i % 2 else base[1:].clone()      # odd ones: data_ptr % 16 == 4
+                for b in redk.buckets:
+                    b["pending"] = 0
+                    redk._launch(b)
+                redk.finish()
+                total = redk.clip_grad_norm_(1e30)
+                torch.cuda.synchronize()
+                assert not redk.peer_error()
+                ref_sq = 0.0
+                for i, p_ in enumerate(ps):
+                    want = (torch.arange(p_.numel() + 1, device=dev, dtype=torch.float64)[1:] * (sum(range(1, world + 1)) / world)
+                            + (rnd + i)).float()
+                    assert torch.equal(p_.grad, want), (rnd, i, float((p_.grad - want).abs().max()))
+                    ref_sq += float(want.double().pow(2).sum())
+                assert abs(float(total) - ref_sq ** 0.5) <= 1e-5 * ref_sq ** 0.5, (float(total), ref_sq ** 0.5)
+            redk.remove()
 
         B = 4
         shards = [[torch.from_numpy(a) for a in synth_batch(B, 60 + r)] for r in range(world)]
@@ -63,7 +93,7 @@ def _worker(rank, world, port, q):
         e = tuple(t.to(dev) for t in eps[rank])
         # 1. eager, bucketed all-reduce
         m = fresh()
-        red = BucketedGradAllReduce(list(m.parameters()), bucket_mb=8)
+        red = BucketedGradAllReduce(list(m.parameters()), bucket_mb=8, impl=impl)
         for _ in range(2):                               # twice: reset() must re-arm everything
             red.reset()
             random.seed(0)
@@ -80,7 +110,7 @@ def _worker(rank, world, port, q):
         # 2. the same exchange inside the step's CUDA graph + Adam; reference = single-process Adam on the averaged grads
         m2 = fresh()
         params2 = list(m2.parameters())
-        red2 = BucketedGradAllReduce(params2, bucket_mb=8)
+        red2 = BucketedGradAllReduce(params2, bucket_mb=8, impl=impl)
         opt2 = torch.optim.Adam(params2, lr=1e-3, fused=True, capturable=True)
         random.seed(0)
         g = GraphedTrainStep(m2, opt2, B, reducer=red2, warmup=11, inject_eps=True, clip=1.0).capture(x, c, pr)
@@ -122,20 +152,21 @@ def _worker(rank, world, port, q):
         os._exit(0)
 
 
-def test_two_rank_nccl_gradients_match_per_shard_oracle_mean():
+@pytest.mark.parametrize("impl", ["nccl", "p2p"])
+def test_two_rank_nccl_gradients_match_per_shard_oracle_mean(impl):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, impl)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=900) for _ in procs]
     for p in procs:
         p.join(timeout=120)
-    print("2-rank NCCL (rank, status, oracle err, graph-vs-eager err, step err, rank diff):", res)
+    print(f"2-rank {impl} (rank, status, oracle err, graph-vs-eager err, step err, rank diff):", res)
     for rank, status, worst, graph_err, step_err, rank_diff in res:
         assert status == "ok", status
         assert worst <= 1e-2, (rank, worst)                  # N-rank gradients == mean of per-shard oracle gradients
