@@ -184,15 +184,26 @@ def run_b200(args):
         for p in params:                                   # identical initial weights on every rank
             dist.broadcast(p.data, 0)
         exchange = args.exchange
+        # buckets in the order the gradients become ready (one observed backward; rank 0's order for everybody)
+        from polydis_b200.ddp import observe_ready_order
+        xo, co, po = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 7))     # the real batch size: which ops defer depends on it
+
+        def _one_backward():
+            model('train', xo, co, po, tfr1=1., tfr2=1., tfr3=1., beta=0.1, weights=(1, 0.5))[0].backward()
+            torch.cuda.synchronize()
+        seen = observe_ready_order(params, _one_backward)
+        idx = [[next(i for i, q in enumerate(params) if q is p) for p in seen]]
+        dist.broadcast_object_list(idx, 0)
+        order = [params[i] for i in idx[0]]
         if exchange == "p2p":           # the repo's peer-memory kernel; NCCL only if the node offers no CUDA IPC / P2P
             try:
-                reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb, impl="p2p")
+                reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb, impl="p2p", ready_order=order)
             except RuntimeError as ex:
                 if rank == 0:
                     print(f"bench: p2p exchange unavailable, using NCCL: {ex}", file=sys.stderr, flush=True)
                 exchange = "nccl"
         if exchange == "nccl":
-            reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb)
+            reducer = BucketedGradAllReduce(params, bucket_mb=args.bucket_mb, ready_order=order)
     fused_opt = args.fused_optim
     if fused_opt:
         from polydis_b200.optim import FusedClipAdam
@@ -574,7 +585,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="gradient exchange under --gpus N>1: the repo's peer-memory all-reduce kernel (default) or NCCL")
-    ap.add_argument("--bucket-mb", type=float, default=8.0)
+    ap.add_argument("--bucket-mb", type=float, default=16.0)
     ap.add_argument("--no-tfr0", action="store_true", help="skip the free-running (tfr=0) training measurement")
     ap.add_argument("--no-decode-e2e", action="store_true", help="skip the 65,536-segment end-to-end decode measurement")
     ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] strong-scaling point under --gpus N>1")

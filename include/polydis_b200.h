@@ -328,11 +328,13 @@ int pd_set_pdl(int on);
  * A rank's "region" = pd_ar_flag_bytes(n_buckets) bytes of flags followed by the flat fp32 buckets, allocated with
  * pd_ipc_alloc (cudaMalloc + zero fill + 64-byte cudaIpcMemHandle_t) and mapped by every peer with pd_ipc_open.
  * pd_allreduce_p2p: peers[p] = rank p's region as mapped here (own region for p == rank); off / n: element offset and
- * count of the bucket in the data part (multiples of 4); epoch: pd_ar_limit(1) zeroed uint32 of this rank; err: set to 1
- * if a peer did not answer within ~4 s (the kernel then gives up instead of hanging); norm_slot >= 0: bucket index for the
- * norm partials (pd_ar_norm_total sums the first n_slots buckets' partials into out[0], same bits on every rank);
- * nblocks <= pd_ar_limit(1), identical on all ranks; src / src_off / src_n / n_src: the gather table (n_src = 0: the
- * bucket is already in place).  All ranks must issue their buckets in the same order on one stream each. */
+ * count of the bucket in the data part (multiples of 4); bucket: the flag slot / epoch row of this exchange (exchanges of
+ * different buckets may overlap on different streams; those of one bucket are issued in the same order on every rank);
+ * epoch: n_buckets x pd_ar_limit(1) zeroed uint32 of this rank; err: set to 1 if a peer did not answer within ~4 s (the
+ * kernel then gives up instead of hanging); with_norm: leave the squared-norm partials of the averaged bucket
+ * (pd_ar_norm_total sums the first n_slots buckets' partials into out[0], same bits on every rank); nblocks <=
+ * pd_ar_limit(1), identical on all ranks; src / src_off / src_n / n_src: the gather table (n_src = 0: the bucket is
+ * already in place). */
 int pd_ar_flag_bytes(int n_buckets);
 int pd_ar_limit(int which);
 int pd_ipc_alloc(long bytes, void** ptr, void* handle64);
@@ -340,8 +342,8 @@ int pd_ipc_open(const void* handle64, void** ptr);
 int pd_ipc_close(void* ptr);
 int pd_ipc_free(void* ptr);
 int pd_allreduce_p2p(const void* const* peers, int rank, int world, long flag_bytes, long off, long n, float scale,
-                     void* epoch, int* err, int norm_slot, int nblocks, const void* const* src, const long* src_off,
-                     const long* src_n, int n_src, void* stream);
+                     void* epoch, int* err, int bucket, int with_norm, int nblocks, const void* const* src,
+                     const long* src_off, const long* src_n, int n_src, void* stream);
 int pd_ar_norm_total(const void* region, int n_slots, int world, int nblocks, float* out, void* stream);
 
 #ifdef __cplusplus

@@ -92,7 +92,7 @@ SIGNATURES = {
     "pd_ipc_open": [_P, _P],
     "pd_ipc_close": [_P],
     "pd_ipc_free": [_P],
-    "pd_allreduce_p2p": [_P, _I, _I, _L, _L, _L, _F, _P, _P, _I, _I, _P, _P, _P, _I, _P],
+    "pd_allreduce_p2p": [_P, _I, _I, _L, _L, _L, _F, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P],
     "pd_ar_norm_total": [_P, _I, _I, _I, _P, _P],
     "pd_gemm_tf32_splits": [_I, _I, _I],          # (returns the split count, not a status: call through ``lib``)
 }

@@ -21,14 +21,18 @@
 // port (900 GB/s per direction), latency-bound for the 8 MB buckets used here; grid and unroll are sized to keep
 // ~2 MB of peer loads in flight.
 #include "common.cuh"
-#include <stdlib.h>
 #include <string.h>
 
 #define PD_AR_MAX_RANKS 8
-#define PD_AR_MAX_BLOCKS 160
+#define PD_AR_MAX_BLOCKS 64
 #define PD_AR_MAX_SRC 40
-// flag area (uint32): start[b][src], done[b][src], then W * PD_AR_MAX_BLOCKS norm partials per bucket slot
-#define PD_AR_FLAG_WORDS (2 * PD_AR_MAX_BLOCKS * PD_AR_MAX_RANKS)
+// 512-thread blocks: 32 of them keep ~1 MB of peer loads in flight per exchange (256-thread blocks halve the bandwidth of
+// an exchange and did not make the step faster, profiles/r02_ddp_ab_2gpu.txt)
+#define PD_AR_THREADS 512
+// flag slot of ONE bucket (uint32 words): start[b][src], done[b][src], norm partials [src][b] (floats).  A slot per bucket,
+// so exchanges of different buckets may be in flight at the same time (on different streams).
+#define PD_AR_NORM_OFF (2 * PD_AR_MAX_BLOCKS * PD_AR_MAX_RANKS)
+#define PD_AR_SLOT_WORDS (PD_AR_NORM_OFF + PD_AR_MAX_RANKS * PD_AR_MAX_BLOCKS)
 
 namespace {
 
@@ -46,31 +50,24 @@ struct ArGather {
     int count;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// STRONG: sys-scope relaxed accesses; otherwise weak L1-bypassing ones (ordered by the flag barriers around them: the
-// acquire in the start barrier + __syncthreads before, __threadfence_system + release in the end barrier after)
-template <bool STRONG>
+// Weak L1-bypassing accesses, ordered by the flag barriers around them (the acquire of the start barrier + __syncthreads
+// before, __syncthreads + __threadfence_system + flag store of the end barrier after).  Sys-scope strong accesses
+// measured the same (tools/ar_bench.py, profiles/r02_ar_bench_2gpu.txt).
 __device__ __forceinline__ float4 ld_peer(const float4* p) {
     float4 v;
-    if (STRONG)
-        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    else
-        asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
-template <bool STRONG>
 __device__ __forceinline__ void st_peer(float4* p, float4 v) {
-    if (STRONG)
-        asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-    else
-        asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -120,7 +117,7 @@ __device__ __forceinline__ void gather_local(const ArGather& G, float* dst, long
     }
 }
 
-template <int W, int U, bool STRONG>
+template <int W, int U>
 __device__ __forceinline__ void reduce_slice(const ArPeers& P, long off4, long lo, long hi, float scale, float& ss) {
     const long stride = (long)gridDim.x * blockDim.x;
     long i = first_owned(lo, (long)blockIdx.x * blockDim.x + threadIdx.x, stride);
@@ -129,7 +126,7 @@ __device__ __forceinline__ void reduce_slice(const ArPeers& P, long off4, long l
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int p = 0; p < W; ++p) v[u][p] = ld_peer<STRONG>(reinterpret_cast<const float4*>(P.data[p]) + off4 + i + u * stride);
+            for (int p = 0; p < W; ++p) v[u][p] = ld_peer(reinterpret_cast<const float4*>(P.data[p]) + off4 + i + u * stride);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             float4 a = v[u][0];
@@ -138,28 +135,29 @@ __device__ __forceinline__ void reduce_slice(const ArPeers& P, long off4, long l
             a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
             ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
 #pragma unroll
-            for (int p = 0; p < W; ++p) st_peer<STRONG>(reinterpret_cast<float4*>(P.data[p]) + off4 + i + u * stride, a);
+            for (int p = 0; p < W; ++p) st_peer(reinterpret_cast<float4*>(P.data[p]) + off4 + i + u * stride, a);
         }
     }
     for (; i < hi; i += stride) {
-        float4 a = ld_peer<STRONG>(reinterpret_cast<const float4*>(P.data[0]) + off4 + i);
+        float4 a = ld_peer(reinterpret_cast<const float4*>(P.data[0]) + off4 + i);
 #pragma unroll
         for (int p = 1; p < W; ++p) {
-            float4 b = ld_peer<STRONG>(reinterpret_cast<const float4*>(P.data[p]) + off4 + i);
+            float4 b = ld_peer(reinterpret_cast<const float4*>(P.data[p]) + off4 + i);
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         }
         a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
         ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
 #pragma unroll
-        for (int p = 0; p < W; ++p) st_peer<STRONG>(reinterpret_cast<float4*>(P.data[p]) + off4 + i, a);
+        for (int p = 0; p < W; ++p) st_peer(reinterpret_cast<float4*>(P.data[p]) + off4 + i, a);
     }
 }
 
-// norm_slot < 0: no sum of squares.  Else every rank ends up with the same W * gridDim.x partials at
-// norm area [norm_slot][src rank][block] of ITS flag region (floats stored after PD_AR_FLAG_WORDS).
-template <int W, bool STRONG, int UMUL>
-__global__ void __launch_bounds__(512) allreduce_p2p_kernel(ArPeers P, int rank, long off4, long n4, float scale,
-                                                            unsigned* epoch, int* err, int norm_slot,
+// P.flags[p] = rank p's flag slot OF THIS BUCKET (start[b][src] | done[b][src] | norm partials [src][b]); epoch likewise.
+// Only the W signalling threads of a block fence (after the block barrier that makes the block's writes theirs to
+// publish -- the cooperative-groups grid-barrier pattern); a fence per thread costs ~10 us per exchange.
+template <int W>
+__global__ void __launch_bounds__(PD_AR_THREADS) allreduce_p2p_kernel(ArPeers P, int rank, long off4, long n4, float scale,
+                                                            unsigned* epoch, int* err, int with_norm,
                                                             const __grid_constant__ ArGather G) {
     const int b = blockIdx.x;
     __shared__ unsigned e_s;
@@ -169,20 +167,20 @@ __global__ void __launch_bounds__(512) allreduce_p2p_kernel(ArPeers P, int rank,
     const unsigned e = e_s;
     if (G.count > 0) {
         gather_local(G, P.data[rank] + off4 * 4, (long)b * blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
-        __threadfence_system();
         __syncthreads();
     }
     if (threadIdx.x < W) {
         const int p = threadIdx.x;
-        st_release_sys(P.flags[p] + (b * PD_AR_MAX_RANKS + rank), e);
+        if (G.count > 0) __threadfence_system();
+        st_relaxed_sys(P.flags[p] + (b * PD_AR_MAX_RANKS + rank), e);
         wait_flag(P.flags[rank] + (b * PD_AR_MAX_RANKS + p), e, err);
     }
     __syncthreads();
     const long per = (n4 + W - 1) / W;
     const long lo = (long)rank * per, hi = (lo + per < n4) ? lo + per : n4;
     float ss = 0.0f;
-    if (lo < hi) reduce_slice<W, UMUL * (W <= 2 ? 4 : (W <= 4 ? 2 : 1)), STRONG>(P, off4, lo, hi, scale, ss);
-    if (norm_slot >= 0) {
+    if (lo < hi) reduce_slice<W, (W <= 2 ? 4 : (W <= 4 ? 2 : 1))>(P, off4, lo, hi, scale, ss);
+    if (with_norm) {
         ss = warp_sum(ss);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
         __syncthreads();
@@ -190,17 +188,16 @@ __global__ void __launch_bounds__(512) allreduce_p2p_kernel(ArPeers P, int rank,
             float a = 0.0f;
             for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += red[k];
             for (int p = 0; p < W; ++p) {
-                float* dst = reinterpret_cast<float*>(P.flags[p] + PD_AR_FLAG_WORDS) +
-                             ((long)norm_slot * W + rank) * PD_AR_MAX_BLOCKS + b;
+                float* dst = reinterpret_cast<float*>(P.flags[p] + PD_AR_NORM_OFF) + rank * PD_AR_MAX_BLOCKS + b;
                 asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(a) : "memory");
             }
         }
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x < W) {
         const int p = threadIdx.x;
-        st_release_sys(P.flags[p] + ((PD_AR_MAX_BLOCKS + b) * PD_AR_MAX_RANKS + rank), e);
+        __threadfence_system();
+        st_relaxed_sys(P.flags[p] + ((PD_AR_MAX_BLOCKS + b) * PD_AR_MAX_RANKS + rank), e);
         wait_flag(P.flags[rank] + ((PD_AR_MAX_BLOCKS + b) * PD_AR_MAX_RANKS + p), e, err);
     }
     __syncthreads();
@@ -208,13 +205,14 @@ __global__ void __launch_bounds__(512) allreduce_p2p_kernel(ArPeers P, int rank,
 }
 
 // sum of the norm partials of n_slots buckets (W ranks x nblocks each), fixed order -> identical on every rank
-__global__ void __launch_bounds__(256) ar_norm_total_kernel(const float* parts, int n_slots, int W, int nblocks, float* out) {
+__global__ void __launch_bounds__(256) ar_norm_total_kernel(const unsigned* region, int n_slots, int W, int nblocks, float* out) {
     __shared__ float sh[256];
     float s = 0.0f;
     const int per_slot = W * PD_AR_MAX_BLOCKS;
     for (int i = threadIdx.x; i < n_slots * per_slot; i += 256) {
-        const int blk = i % PD_AR_MAX_BLOCKS;
-        if (blk < nblocks) s += parts[i];
+        const int slot = i / per_slot, j = i % per_slot;
+        if (j % PD_AR_MAX_BLOCKS < nblocks)
+            s += reinterpret_cast<const float*>(region + (long)slot * PD_AR_SLOT_WORDS + PD_AR_NORM_OFF)[j];
     }
     sh[threadIdx.x] = s;
     __syncthreads();
@@ -230,7 +228,7 @@ __global__ void __launch_bounds__(256) ar_norm_total_kernel(const float* parts, 
 // bytes of the flag area in front of the gradient data of a symmetric region that serves n_buckets buckets
 // (returns the byte count, not a status)
 PD_API int pd_ar_flag_bytes(int n_buckets) {
-    long words = PD_AR_FLAG_WORDS + (long)n_buckets * PD_AR_MAX_RANKS * PD_AR_MAX_BLOCKS;
+    long words = (long)n_buckets * PD_AR_SLOT_WORDS;
     return (int)(((words * 4 + 255) / 256) * 256);
 }
 
@@ -264,15 +262,17 @@ PD_API int pd_ipc_free(void* ptr) { return (int)cudaFree(ptr); }
 
 // In-place average of n floats at element offset `off` of the data part of every rank's region.
 // peers[p] = base address of rank p's region AS MAPPED IN THIS PROCESS (own region for p == rank); data starts
-// flag_bytes after it.  off and n must be multiples of 4.  epoch: PD_AR_MAX_BLOCKS zero-initialised uint32 of THIS rank
-// (shared by all buckets of a communicator, which must be launched in the same order on one stream on every rank).
+// flag_bytes after it.  off and n must be multiples of 4.  bucket: which flag slot / epoch row this exchange uses (every
+// rank must issue the exchanges of one bucket in the same order; different buckets are independent).  epoch: n_buckets x
+// pd_ar_limit(1) zero-initialised uint32 of THIS rank.
 // n_src > 0: the bucket is first gathered from n_src (<= pd_ar_limit(2)) contiguous fp32 buffers: src[k] holds src_n[k]
 // elements that go to bucket element src_off[k] (a multiple of 4; the padding up to the next slot is zero-filled).
 PD_API int pd_allreduce_p2p(const void* const* peers, int rank, int world, long flag_bytes, long off, long n, float scale,
-                            void* epoch, int* err, int norm_slot, int nblocks, const void* const* src,
+                            void* epoch, int* err, int bucket, int with_norm, int nblocks, const void* const* src,
                             const long* src_off, const long* src_n, int n_src, void* stream) {
     if (world < 2 || world > PD_AR_MAX_RANKS || rank < 0 || rank >= world || (off & 3) || (n & 3) || n <= 0 ||
-        nblocks < 1 || nblocks > PD_AR_MAX_BLOCKS || n_src < 0 || n_src > PD_AR_MAX_SRC)
+        nblocks < 1 || nblocks > PD_AR_MAX_BLOCKS || n_src < 0 || n_src > PD_AR_MAX_SRC || bucket < 0 ||
+        (long)(bucket + 1) * PD_AR_SLOT_WORDS * 4 > flag_bytes)
         return PD_BAD_ARG;
     ArGather G;
     G.count = n_src;
@@ -287,29 +287,13 @@ PD_API int pd_allreduce_p2p(const void* const* peers, int rank, int world, long 
     ArPeers P;
     for (int p = 0; p < PD_AR_MAX_RANKS; ++p) {
         char* base = (char*)const_cast<void*>(peers[p < world ? p : 0]);
-        P.flags[p] = reinterpret_cast<unsigned*>(base);
+        P.flags[p] = reinterpret_cast<unsigned*>(base) + (long)bucket * PD_AR_SLOT_WORDS;
         P.data[p] = reinterpret_cast<float*>(base + flag_bytes);
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long off4 = off / 4, n4 = n / 4;
-    // tuning switch (tools/ar_bench.py): bit 0 = sys-scope strong accesses instead of weak ones, bit 1 = half the unroll
-    static int variant = -1;
-    if (variant < 0) {
-        const char* v = getenv("PD_AR_VARIANT");
-        variant = v ? atoi(v) : 0;
-    }
-#define PD_AR_LAUNCH(Wv)                                                                                                  \
-    do {                                                                                                                  \
-        if (variant & 1)                                                                                                  \
-            allreduce_p2p_kernel<Wv, true, 1><<<nblocks, 512, 0, s>>>(P, rank, off4, n4, scale, (unsigned*)epoch, err,   \
-                                                                       norm_slot, G);                                    \
-        else if (variant & 2)                                                                                             \
-            allreduce_p2p_kernel<Wv, false, 1><<<nblocks, 512, 0, s>>>(P, rank, off4, n4, scale, (unsigned*)epoch, err,  \
-                                                                        norm_slot, G);                                   \
-        else                                                                                                              \
-            allreduce_p2p_kernel<Wv, false, 2><<<nblocks, 512, 0, s>>>(P, rank, off4, n4, scale, (unsigned*)epoch, err,  \
-                                                                        norm_slot, G);                                   \
-    } while (0)
+    unsigned* ep = reinterpret_cast<unsigned*>(epoch) + (long)bucket * PD_AR_MAX_BLOCKS;
+#define PD_AR_LAUNCH(Wv) allreduce_p2p_kernel<Wv><<<nblocks, PD_AR_THREADS, 0, s>>>(P, rank, off4, n4, scale, ep, err, with_norm, G)
     switch (world) {
         case 2: PD_AR_LAUNCH(2); break;
         case 3: PD_AR_LAUNCH(3); break;
@@ -323,11 +307,10 @@ PD_API int pd_allreduce_p2p(const void* const* peers, int rank, int world, long 
     return pd_launch_status();
 }
 
-// out[0] = sum over the first n_slots buckets of the squared-norm partials pd_allreduce_p2p(norm_slot >= 0) left in
-// this rank's region (the squared global norm of the averaged gradient; same bits on every rank)
+// out[0] = sum over the first n_slots buckets of the squared-norm partials pd_allreduce_p2p(with_norm) left in this
+// rank's region (the squared global norm of the averaged gradient; same bits on every rank)
 PD_API int pd_ar_norm_total(const void* region, int n_slots, int world, int nblocks, float* out, void* stream) {
     if (n_slots < 1 || world < 2 || world > PD_AR_MAX_RANKS) return PD_BAD_ARG;
-    const float* parts = reinterpret_cast<const float*>(reinterpret_cast<const unsigned*>(region) + PD_AR_FLAG_WORDS);
-    ar_norm_total_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(parts, n_slots, world, nblocks, out);
+    ar_norm_total_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const unsigned*>(region), n_slots, world, nblocks, out);
     return pd_launch_status();
 }

@@ -97,6 +97,15 @@ class BucketedGradAllReduce:
         if impl == "p2p":
             self._setup_p2p(ar_blocks)
         self.comm = torch.cuda.Stream(priority=comm_priority) if self.cuda else None
+        # p2p: the exchanges of different buckets are independent (a flag slot each), so they are dealt onto several
+        # streams -- when many buckets become ready together (backward's end) their barrier latencies overlap and the tail
+        # is bound by NVLink bytes, not by ~25 us per launch.  n_streams x ar_blocks <= SM count keeps every in-flight
+        # exchange block resident on every rank (two ranks that scheduled different buckets first still both progress).
+        self.comms = [self.comm]
+        if impl == "p2p":
+            n_comm = int(os.environ.get("PD_AR_STREAMS", "4"))
+            assert n_comm * self.ar_blocks <= 148, "PD_AR_STREAMS x PD_AR_BLOCKS must not exceed the SM count"
+            self.comms += [torch.cuda.Stream(priority=comm_priority) for _ in range(n_comm - 1)]
         self._handles = []
         for bi, b in enumerate(self.buckets):
             for pi, p in enumerate(b["params"]):
@@ -129,7 +138,7 @@ class BucketedGradAllReduce:
             raise RuntimeError("impl='p2p' needs CUDA parameters and a process group of 2..8 ranks on one node")
         self._lib = lib
         self.rank = dist.get_rank(self.group)
-        self.ar_blocks = int(ar_blocks or os.environ.get("PD_AR_BLOCKS", "48"))
+        self.ar_blocks = int(ar_blocks or os.environ.get("PD_AR_BLOCKS", "32"))
         assert 1 <= self.ar_blocks <= lib.pd_ar_limit(1)
         self.max_src = lib.pd_ar_limit(2)
         dev = self.params[0].device
@@ -175,7 +184,7 @@ class BucketedGradAllReduce:
             b["off"] = off
             self._bind(b, data[off:off + b["n"]])
             off += b["n"]
-        self._epoch = torch.zeros(lib.pd_ar_limit(1), device=dev, dtype=torch.int32)
+        self._epoch = torch.zeros(len(self.buckets) * lib.pd_ar_limit(1), device=dev, dtype=torch.int32)
         self._err = torch.zeros(1, device=dev, dtype=torch.int32)
         self._sumsq = torch.zeros(1, device=dev, dtype=torch.float32)
         dist.barrier(group=self.group)          # every rank has mapped every region before the first kernel touches one
@@ -195,7 +204,7 @@ class BucketedGradAllReduce:
             n_src, src, soff, sn = 0, None, None, None
         from . import _lib
         _lib.call("pd_allreduce_p2p", self._peer_ptrs, self.rank, self.world, self.flag_bytes, b["off"], b["n"],
-                  1.0 / self.world, self._epoch.data_ptr(), self._err.data_ptr(), bi, self.ar_blocks, src, soff, sn, n_src,
+                  1.0 / self.world, self._epoch.data_ptr(), self._err.data_ptr(), bi, 1, self.ar_blocks, src, soff, sn, n_src,
                   torch.cuda.current_stream().cuda_stream)
 
     def _make_hook(self, bi, pi):
@@ -215,9 +224,10 @@ class BucketedGradAllReduce:
         if any(g is None for g in grads):
             raise RuntimeError("BucketedGradAllReduce: a parameter's hook fired without a gradient")
         if self.cuda:
+            comm = self.comms[b["index"] % len(self.comms)]
             for ev in b["events"]:
-                self.comm.wait_event(ev)
-            with torch.cuda.stream(self.comm):
+                comm.wait_event(ev)
+            with torch.cuda.stream(comm):
                 if self.impl == "p2p":
                     self._exchange_p2p(b["index"], b, grads)
                 else:
@@ -247,7 +257,8 @@ class BucketedGradAllReduce:
             if b["pending"] != 0:
                 raise RuntimeError("a parameter received no gradient; its bucket was never reduced")
         if self.cuda:
-            torch.cuda.current_stream().wait_stream(self.comm)
+            for comm in self.comms:
+                torch.cuda.current_stream().wait_stream(comm)
         for b in self.buckets:
             b["adopted"] = None
         self.check_grad_views()

@@ -28,6 +28,77 @@ def _free_port():
     return p
 
 
+def _worker_kernel(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from polydis_b200.ddp import BucketedGradAllReduce
+        # the exchange kernel alone: odd-sized parameters, sources that are only 4-byte aligned, several rounds on the
+        # same flags (epochs), exact expected values; norm partials vs torch
+        sizes = (5, 1024, 3, 77777, 1, 4096 * 33 + 2, 130, 2000003)
+        ps = [torch.nn.Parameter(torch.zeros(n, device=dev)) for n in sizes]
+        redk = BucketedGradAllReduce(ps, bucket_mb=0.3, impl="p2p")
+        assert len(redk.buckets) >= 3
+        for rnd in range(3):
+            redk.reset()
+            keep = []
+            for i, p_ in enumerate(ps):
+                base = torch.arange(p_.numel() + 1, device=dev, dtype=torch.float32) + (2 * rank + rnd + i)
+                keep.append(base)
+                p_.grad = base[1:] if i % 2 else base[1:].clone()      # odd ones: data_ptr % 16 == 4
+            torch.cuda.synchronize()            # (the hooks' events order this in training; here the gradients are set by hand)
+            for b in redk.buckets:
+                b["pending"] = 0
+                redk._launch(b)
+            redk.finish()
+            total = redk.clip_grad_norm_(1e30)
+            torch.cuda.synchronize()
+            assert not redk.peer_error()
+            ref_sq = 0.0
+            for i, p_ in enumerate(ps):
+                # mean over ranks of (k + 2 rank + rnd + i): every partial sum is an integer below 2^24 and world is a
+                # power of two, so the fp32 result is exact
+                want = (torch.arange(p_.numel() + 1, device=dev, dtype=torch.float64)[1:] + (world - 1) + (rnd + i)).float()
+                assert torch.equal(p_.grad, want), (rnd, i, float((p_.grad - want).abs().max()))
+                ref_sq += float(want.double().pow(2).sum())
+            assert abs(float(total) - ref_sq ** 0.5) <= 1e-5 * ref_sq ** 0.5, (float(total), ref_sq ** 0.5)
+        redk.remove()
+
+        q.put((rank, "ok"))
+        torch.cuda.synchronize()
+        dist.barrier()
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        q.put((rank, "error: " + repr(ex) + "\n" + traceback.format_exc()))
+    finally:
+        os._exit(0)
+
+
+def test_p2p_exchange_kernel_exact():
+    """csrc/allreduce_p2p.cu alone on all GPUs of the box (2, 4 or 8 ranks): exact averages, in-kernel gather from unaligned sources, epochs over several
+    rounds, several buckets in flight on different streams, norm partials."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    n = torch.cuda.device_count()
+    world = 8 if n >= 8 else 4 if n >= 4 else 2            # (powers of two: the expected averages are exact)
+    procs = [ctx.Process(target=_worker_kernel, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status in res:
+        assert status == "ok", status
+
+
 def _worker(rank, world, port, q, impl="nccl"):
     try:
         sys.path.insert(0, ROOT)
@@ -42,36 +113,6 @@ def _worker(rank, world, port, q, impl="nccl"):
         from polydis_b200.model import DisentangleVAE
         from polydis_b200.synth import synth_batch
         from polydis_b200.weights import make_state_dict
-
-        if impl == "p2p":
-            # the exchange kernel alone: odd-sized parameters, sources that are only 4-byte aligned, several rounds on the
-            # same flags (epochs), exact expected values; norm partials vs torch
-            sizes = (5, 1024, 3, 77777, 1, 4096 * 33 + 2, 130)
-            ps = [torch.nn.Parameter(torch.zeros(n, device=dev)) for n in sizes]
-            redk = BucketedGradAllReduce(ps, bucket_mb=0.3, impl="p2p")
-            assert len(redk.buckets) >= 3
-            for rnd in range(3):
-                redk.reset()
-                keep = []
-                for i, p_ in enumerate(ps):
-                    base = torch.arange(p_.numel() + 1, device=dev, dtype=torch.float32) * (rank + 1) + (rnd + i)
-                    keep.append(base)
-                    p_.grad = base[1:] if i % 2 else base[1:].clone()      # odd ones: data_ptr % 16 == 4
-                for b in redk.buckets:
-                    b["pending"] = 0
-                    redk._launch(b)
-                redk.finish()
-                total = redk.clip_grad_norm_(1e30)
-                torch.cuda.synchronize()
-                assert not redk.peer_error()
-                ref_sq = 0.0
-                for i, p_ in enumerate(ps):
-                    want = (torch.arange(p_.numel() + 1, device=dev, dtype=torch.float64)[1:] * (sum(range(1, world + 1)) / world)
-                            + (rnd + i)).float()
-                    assert torch.equal(p_.grad, want), (rnd, i, float((p_.grad - want).abs().max()))
-                    ref_sq += float(want.double().pow(2).sum())
-                assert abs(float(total) - ref_sq ** 0.5) <= 1e-5 * ref_sq ** 0.5, (float(total), ref_sq ** 0.5)
-            redk.remove()
 
         B = 4
         shards = [[torch.from_numpy(a) for a in synth_batch(B, 60 + r)] for r in range(world)]

@@ -7,6 +7,7 @@ Per bucket size and grid: 20 exchanges captured in one CUDA graph (as the traini
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("PD_AR_STREAMS", "1")
 import torch
 import torch.distributed as dist
 from polydis_b200.ddp import BucketedGradAllReduce
@@ -43,7 +44,7 @@ def time_graph(fn):
 
 
 rows = []
-for blocks in (32, 64, 128, 148):
+for blocks in (16, 32, 64):
     red = BucketedGradAllReduce(params, bucket_mb=0.001, impl="p2p", ar_blocks=blocks)   # one bucket per parameter
     for b in red.buckets:
         mb = b["n"] * 4 / (1 << 20)
@@ -58,7 +59,7 @@ for blocks in (32, 64, 128, 148):
                 def fn():       # exchange only: the bucket already in place
                     from polydis_b200 import _lib
                     _lib.call("pd_allreduce_p2p", red._peer_ptrs, red.rank, red.world, red.flag_bytes, b["off"], b["n"],
-                              1.0 / red.world, red._epoch.data_ptr(), red._err.data_ptr(), b["index"], red.ar_blocks,
+                              1.0 / red.world, red._epoch.data_ptr(), red._err.data_ptr(), b["index"], 1, red.ar_blocks,
                               None, None, None, 0, torch.cuda.current_stream().cuda_stream)
             us = time_graph(fn)
             rows.append((f"p2p blocks={blocks} gather={int(gather)}", mb, us))

@@ -5,7 +5,8 @@ CUPTI kernel timeline of rank 0 (where the exchange kernels sit relative to back
     python tools/ddp_trace.py "reducer=0" "bucket_mb=8"            # world 1: cost of the reducer's gather path alone
 
 Variant keys: reducer (0: plain p.grad, world 1 only), bucket_mb, ready (bucket order = observed gradient-ready order),
-prio (communication stream priority), impl ("nccl" | "p2p": the repo's peer-memory all-reduce kernel).
+prio (communication stream priority), impl ("nccl" | "p2p": the repo's peer-memory all-reduce kernel), streams / blocks
+(p2p: exchange streams, CTAs per exchange).
 """
 import json, os, sys, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -50,6 +51,10 @@ def build(spec):
         kw = {}
         if "impl" in kv:
             kw["impl"] = kv["impl"]
+        if "streams" in kv:
+            os.environ["PD_AR_STREAMS"] = kv["streams"]
+        if "blocks" in kv:
+            kw["ar_blocks"] = int(kv["blocks"])
         reducer = ddp.BucketedGradAllReduce(params, bucket_mb=float(kv.get("bucket_mb", "8")), ready_order=order,
                                             comm_priority=int(kv.get("prio", "0")), **kw)
     opt = torch.optim.Adam(params, lr=1e-3, fused=True, capturable=True)
