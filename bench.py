@@ -494,6 +494,8 @@ def run_b200(args):
     # note-level and only its live share is computed in loss mode (packed note level)
     gflop_exec = TRAIN_GFLOP_PER_SAMPLE * (1.0 - 0.6647 * (1.0 - live_frac))
     achieved = gflop_exec * B / (ms_step * 1e-3) / 1e3                   # TFLOP/s per GPU
+    if getattr(reducer, "impl", None) == "p2p" and reducer.peer_error():
+        raise RuntimeError("bench: a gradient-exchange kernel gave up waiting for a peer; the timed steps are invalid")
     out = {"metric": METRIC, "value": sps, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "tf32+bf16", "data": "synthetic",
@@ -506,7 +508,8 @@ def run_b200(args):
                       "note_level": "packed: rows sorted by token count, note slots whose target is PAD are not computed in "
                                     "loss mode (losses and gradients unchanged; tests/test_gpu_model.py)",
                       "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else "torch clip_grad_norm_ + Adam(fused)",
+                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else ("clip from the exchange kernels' norm partials + torch Adam(fused)" if getattr(reducer, "impl", None) == "p2p"
+                                                                                                     else "torch clip_grad_norm_ + Adam(fused)"),
                       **({"gradient_exchange": EXCHANGE_NOTE[reducer.impl], "bucket_mb": args.bucket_mb} if reducer is not None and world > 1 else {})},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4,

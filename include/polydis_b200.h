@@ -330,7 +330,7 @@ int pd_set_pdl(int on);
  * pd_allreduce_p2p: peers[p] = rank p's region as mapped here (own region for p == rank); off / n: element offset and
  * count of the bucket in the data part (multiples of 4); bucket: the flag slot / epoch row of this exchange (exchanges of
  * different buckets may overlap on different streams; those of one bucket are issued in the same order on every rank);
- * epoch: n_buckets x pd_ar_limit(1) zeroed uint32 of this rank; err: set to 1 if a peer did not answer within ~4 s (the
+ * epoch: n_buckets x pd_ar_limit(1) zeroed uint32 of this rank; err: set to 1 if a peer did not answer within ~20 s (the
  * kernel then gives up instead of hanging); with_norm: leave the squared-norm partials of the averaged bucket
  * (pd_ar_norm_total sums the first n_slots buckets' partials into out[0], same bits on every rank); nblocks <=
  * pd_ar_limit(1), identical on all ranks; src / src_off / src_n / n_src: the gather table (n_src = 0: the bucket is

@@ -75,12 +75,13 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-// wait until *flag >= e (wrap-safe); gives up after ~4 s and raises *err (a dead peer must not hang the GPU)
+// wait until *flag >= e (wrap-safe); gives up after ~20 s and raises *err (a dead peer must not hang the GPU forever;
+// ranks may legitimately be seconds apart in their first, eager steps)
 __device__ __forceinline__ void wait_flag(const unsigned* flag, unsigned e, int* err) {
     if ((int)(ld_acquire_sys(flag) - e) >= 0) return;
     const unsigned long long t0 = globaltimer_ns();
     while ((int)(ld_acquire_sys(flag) - e) < 0) {
-        if (globaltimer_ns() - t0 > 4000000000ull) {
+        if (globaltimer_ns() - t0 > 20000000000ull) {
             if (err) atomicExch(err, 1);
             return;
         }

@@ -128,12 +128,19 @@ class GraphedTrainStep:
                 self._step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self.check_exchange()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.losses = self._step()
         if snap is not None:
             self._restore(snap)
         return self
+
+    def check_exchange(self):
+        """Raise if a peer-memory gradient exchange gave up waiting for a peer (the step's gradients would be wrong).
+        Synchronises; call it at checkpoints, not every step."""
+        if self.reducer is not None and getattr(self.reducer, "impl", None) == "p2p" and self.reducer.peer_error():
+            raise RuntimeError("gradient exchange: a peer did not reach its exchange kernel within the time limit")
 
     def __call__(self, x, c, pr_mat):
         """Copy one batch into the static buffers (H2D if the sources are pinned host tensors), replay,
