@@ -508,8 +508,10 @@ def run_b200(args):
                       "note_level": "packed: rows sorted by token count, note slots whose target is PAD are not computed in "
                                     "loss mode (losses and gradients unchanged; tests/test_gpu_model.py)",
                       "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else ("clip from the exchange kernels' norm partials + torch Adam(fused)" if getattr(reducer, "impl", None) == "p2p"
-                                                                                                     else "torch clip_grad_norm_ + Adam(fused)"),
+                      "optimizer": "FusedClipAdam (clip 1.0, lr 1e-3, gamma 0.9999, floor 1e-5)" if fused_opt else ("global norm from the exchange kernels' partials, clip folded into torch Adam(fused) via grad_scale"
+                                                                  if getattr(reducer, "impl", None) == "p2p" else
+                                                                  "torch _foreach_norm, clip folded into torch Adam(fused) via grad_scale"
+                                                                  if graphed is not None else "torch clip_grad_norm_ + Adam(fused)"),
                       **({"gradient_exchange": EXCHANGE_NOTE[reducer.impl], "bucket_mb": args.bucket_mb} if reducer is not None and world > 1 else {})},
            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": 4,

@@ -301,6 +301,12 @@ int pd_texture_frontend_bwd_ix(const float* pr_mat, const signed char* amax, int
 int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
                          long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
                          void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H, void* stream);
+/* the same step with a chosen tile width: units = 32 (one wave of 128 CTAs for a 512-row recurrence) or 64 (64 CTAs: two
+ * independent recurrences run side by side on disjoint SMs) */
+int pd_gru_step_tma_bf16_units(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
+                               long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
+                               void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H, int units,
+                               void* stream);
 int pd_gru_gates_bwd_zb(const float* dh, long lddh, const float* dh2, long lddh2, const float* dh3, long lddh3,
                         const float* rzn, long ldrzn, const float* hn, long ldhn, const float* hprev, long ldhp, float* dgi,
                         long lddgi, float* dgh, long lddgh, float* dhprev, long lddhp, const int* lengths, int t, int B, int H,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "pd_texture_frontend_fwd_ix": [_P, _P, _P, _I, _I, _P, _P, _P],
     "pd_texture_frontend_bwd_ix": [_P, _P, _I, _I, _P, _P, _P, _P],
     "pd_gru_step_tma_bf16": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
+    "pd_gru_step_tma_bf16_units": [_P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P],
     "pd_gru_gates_bwd_zb": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P,
                             _L, _P],
     "pd_set_pdl": [_I],

@@ -180,8 +180,8 @@ gru_step_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
 }
 
-// ---- persistent variant with TMA epilogue I/O (EXPERIMENTAL: written at the end of round 1 without GPU time left;
-// compiled and exported, not routed to -- ops.FUSED_GRU_STEP_TMA stays False until it is validated on a B200) -------------
+// ---- persistent variant with TMA epilogue I/O (the fused step the training and decode paths run: ops.FUSED_GRU_STEP_TMA;
+// validated on B200 in round 2, tests/test_gpu_kernels.py::test_gru_step_tma* and the whole-model parity tests) ---------
 // Lessons applied: (1) the first fused kernel above lost to GEMM + gate kernel on its row-per-thread global I/O (seven
 // arrays read / written as 64-byte pieces per lane) and its 2-stage, one-tile-per-CTA main loop; (2) the TMA bulk-store
 // epilogue of the persistent GEMM took output-bound GEMMs to the HBM roofline.  Here: persistent CTAs, 4-stage
@@ -560,7 +560,7 @@ PD_API int pd_gru_step_tf32(const float* hprev, long ldhp, const float* w_hh, lo
     return pd_launch_status();
 }
 
-// EXPERIMENTAL (not validated on hardware yet; nothing routes to it): persistent fused GRU step with TMA epilogue I/O.
+// Persistent fused GRU step with TMA epilogue I/O (routed for recurrences of >= ops.FUSED_GRU_STEP_TMA_MIN_ROWS rows).
 // Same contract as pd_gru_step_tf32 without the length mask; hout must not alias hprev.  gi: (B,3H) rows of the step
 // (row stride ldgi), gi2 / rzn / hn optional.
 PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, long ldw, const float* b_hh, const float* gi,
@@ -638,11 +638,15 @@ PD_API int pd_gru_step_tma(const float* hprev, long ldhp, const float* w_hh, lon
 // copy of W_hh (3H x H) -- half the bytes and half the k-blocks of the latency-bound main loop -- while the accumulators,
 // the gate math, h_prev in the blend and every saved array stay fp32.  Besides hout the kernel writes hb_out, the bf16
 // copy of the new state that the next step multiplies.  32-unit tiles; H % 64 == 0.
-PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
-                                long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
-                                void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H,
-                                void* stream) {
+// units: hidden units per tile, 32 (a 512-row recurrence fills the machine with one wave of 128 CTAs: the fastest single
+// step) or 64 (64 CTAs per step: two independent recurrences -- the directions of a bi-GRU, the two encoders -- then run
+// side by side on disjoint SMs instead of queueing behind each other's full wave).
+PD_API int pd_gru_step_tma_bf16_units(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh,
+                                      const float* gi, long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp,
+                                      float* hout, long ldho, void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn,
+                                      long ldhn, int B, int H, int units, void* stream) {
     if (B <= 0) return 0;
+    if (units != 32 && units != 64) return PD_BAD_ARG;
     if (H % 64 != 0 || hb_prev == nullptr || hprev == nullptr || hout == hprev || hb_out == hb_prev || hb_out == nullptr)
         return PD_BAD_ARG;
     if (!al16(hprev, ldhp) || !al16(gi, ldgi) || (gi2 && !al16(gi2, ldgi2)) || !al16(hout, ldho) || (rzn && !al16(rzn, ldrzn)) ||
@@ -651,7 +655,7 @@ PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb,
         return PD_BAD_ARG;
     CUtensorMap ta, tb, tgi, tgi2, thp, tho, trzn, thn;
     int rc = make_map(&ta, hb_prev, 2, H, B, ldhbp, BM, false);
-    if (!rc) rc = make_map(&tb, wb, 2, H, 3L * H, ldwb, 32, false);
+    if (!rc) rc = make_map(&tb, wb, 2, H, 3L * H, ldwb, units, false);
     if (!rc) rc = make_map_io(&tgi, gi, 3L * H, B, ldgi);
     if (!rc) rc = make_map_io(&thp, hprev, H, B, ldhp);
     if (!rc) rc = make_map_io(&tho, hout, H, B, ldho);
@@ -661,9 +665,22 @@ PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb,
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
     StepIo g{b_hh, gi2 != nullptr, rzn != nullptr, hn != nullptr, B, H, H, 0, 0, nullptr, (uint16_t*)hb_out, ldhbo};
-    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / 32;
+    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / units;
     const long items = (long)tiles_m * tiles_u;
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+    if (units == 64) {
+        constexpr int ST = 3, NS = 1;
+        constexpr int smem = ST * (BM * 128 + 192 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+        static unsigned long long attr64 = 0;
+        if (pd_first_use_on_device(attr64)) {
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST, NS, true, false, false, 64, 2>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, false, false, 64, 2>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
+                ta, tb, tgi, tgi2, thp, tho, trzn, thn, tho, ta, tb, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
+        return pd_launch_status();
+    }
     constexpr int ST = 4, NS = 1;
     constexpr int smem = ST * (BM * 128 + 96 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
     static unsigned long long attr = 0;
@@ -675,6 +692,14 @@ PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb,
     { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST, NS, true, false, false, 32, 2>, dim3(grid), dim3(NUM_THREADS), (size_t)smem, (cudaStream_t)stream,
             ta, tb, tgi, tgi2, thp, tho, trzn, thn, tho, ta, tb, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
     return pd_launch_status();
+}
+
+PD_API int pd_gru_step_tma_bf16(const void* hb_prev, long ldhbp, const void* wb, long ldwb, const float* b_hh, const float* gi,
+                                long ldgi, const float* gi2, long ldgi2, const float* hprev, long ldhp, float* hout, long ldho,
+                                void* hb_out, long ldhbo, float* rzn, long ldrzn, float* hn, long ldhn, int B, int H,
+                                void* stream) {
+    return pd_gru_step_tma_bf16_units(hb_prev, ldhbp, wb, ldwb, b_hh, gi, ldgi, gi2, ldgi2, hprev, ldhp, hout, ldho, hb_out,
+                                      ldhbo, rzn, ldrzn, hn, ldhn, B, H, 32, stream);
 }
 
 // Training form with the x-projection folded in (SEG2, TF32 single pass): gi = W_x x is computed inside the kernel as a

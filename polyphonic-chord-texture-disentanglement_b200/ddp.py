@@ -263,20 +263,22 @@ class BucketedGradAllReduce:
             b["adopted"] = None
         self.check_grad_views()
 
-    def clip_grad_norm_(self, max_norm):
-        """Global-norm clip of the averaged gradients (call after ``finish()``): torch's ``clip_grad_norm_`` semantics
-        (coef = max_norm / (norm + 1e-6), capped at 1, always applied).  With ``impl="p2p"`` the squared norm comes from
-        the partials the exchange kernels left (no pass over the gradients); returns the norm as a device scalar."""
-        flats = [b["flat"] for b in self.buckets]
+    def grad_norm(self):
+        """Global L2 norm of the averaged gradients as a device scalar (call after ``finish()``).  With ``impl="p2p"`` it
+        comes from the partials the exchange kernels left: no pass over the gradients, same bits on every rank."""
         if self.impl == "p2p":
             from . import _lib
             _lib.call("pd_ar_norm_total", self._region, len(self.buckets), self.world, self.ar_blocks,
                       self._sumsq.data_ptr(), torch.cuda.current_stream().cuda_stream)
-            norm = self._sumsq.sqrt().squeeze(0)
-        else:
-            norm = torch.linalg.vector_norm(torch.stack(torch._foreach_norm(flats)))
+            return self._sumsq.sqrt().squeeze(0)
+        return torch.linalg.vector_norm(torch.stack(torch._foreach_norm([b["flat"] for b in self.buckets])))
+
+    def clip_grad_norm_(self, max_norm):
+        """Global-norm clip of the averaged gradients (call after ``finish()``): torch's ``clip_grad_norm_`` semantics
+        (coef = max_norm / (norm + 1e-6), capped at 1, always applied).  Returns the norm as a device scalar."""
+        norm = self.grad_norm()
         coef = torch.clamp(max_norm / (norm + 1e-6), max=1.0)
-        torch._foreach_mul_(flats, coef)
+        torch._foreach_mul_([b["flat"] for b in self.buckets], coef)
         return norm
 
     def peer_error(self):

@@ -302,6 +302,12 @@ FUSED_GRU_STEP_X = True
 # alone vs the fp32 reference: 1.0e-3 (tolerance 1e-2; measured on the CPU emulation, all-TF32: 7e-4).
 BF16_RECURRENT = True
 BF16_RECURRENT_MAX_ROWS = 4096
+# tile width of the bf16 fused step for SHORT recurrences (<= BF16_STEP_SHORT_T steps: the encoders' bi-GRUs and the chord
+# decoder, which run concurrently on forked streams): 64 = 64 CTAs per step, so two chains fit on the machine side by
+# side; 32 = a full wave per step (what the 32-step time GRU, which runs alone, always uses).  Default = the measured-
+# faster setting (tools/step_ab.py BF16_STEP_UNITS_SHORT=32 / 64).
+BF16_STEP_UNITS_SHORT = 64       # B200, batch 512: 7.86 -> 7.80 ms/step (GPU call 36)
+BF16_STEP_SHORT_T = 8
 
 
 def fold_x_ok(rows, H, x, w_x):
@@ -922,10 +928,13 @@ def _gru_steps_fwd(gi, gi2, h0, w_hh, b_hh, lengths, order, h_all, rzn, hn, fuse
             if use_bf16:
                 if not hb_valid:                          # first fused step: the incoming state has no bf16 copy yet
                     _call("pd_f32_to_bf16", _ptr(hprev), hprev.stride(0), B, H, _ptr(hb[hb_cur]), H, _stream())
-                _call("pd_gru_step_tma_bf16", _ptr(hb[hb_cur]), H, _ptr(wb), wb.stride(0), _ptr(b_hh), _ptr(gi[:, t]),
+                # short recurrences (the encoders' bi-GRUs, the chord decoder) run next to each other on forked streams:
+                # 64-unit tiles (64 CTAs per step) let two of them share the machine; the 32-step time GRU runs alone
+                units = 64 if (BF16_STEP_UNITS_SHORT == 64 and len(order) <= BF16_STEP_SHORT_T) else 32
+                _call("pd_gru_step_tma_bf16_units", _ptr(hb[hb_cur]), H, _ptr(wb), wb.stride(0), _ptr(b_hh), _ptr(gi[:, t]),
                       gi.stride(0), _ptr(gi2), 0 if gi2 is None else gi2.stride(0), _ptr(hprev), hprev.stride(0),
                       _ptr(h_all[:, t]), h_all.stride(0), _ptr(hb[hb_cur ^ 1]), H, _ptr(rzn[:, t]), rzn.stride(0),
-                      _ptr(hn[:, t]), hn.stride(0), B, H, _stream())
+                      _ptr(hn[:, t]), hn.stride(0), B, H, units, _stream())
                 hb_cur ^= 1
                 hb_valid = True
                 hprev = h_all[:, t]

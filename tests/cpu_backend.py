@@ -392,6 +392,12 @@ class CpuBackend:
                               B, H, st)
         _arr(hbo, (B, H), (ldhbo, 1), np.uint16)[...] = self._to_bf16_bits(_arr(ho, (B, H), (ldho, 1)))
 
+    def pd_gru_step_tma_bf16_units(self, hb, ldhb, wb, ldwb, b_hh, gi, ldgi, gi2, ldgi2, hp, ldhp, ho, ldho, hbo, ldhbo, rzn,
+                                   ldrzn, hn, ldhn, B, H, units, st):
+        assert units in (32, 64)                 # (a launch-shape choice: same arithmetic)
+        self.pd_gru_step_tma_bf16(hb, ldhb, wb, ldwb, b_hh, gi, ldgi, gi2, ldgi2, hp, ldhp, ho, ldho, hbo, ldhbo, rzn, ldrzn,
+                                  hn, ldhn, B, H, st)
+
     def pd_gru_gates_bwd_zb(self, dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,
                             dhp, lddhp, lengths, t, B, H, zero_out, ldzo, dgh_b, lddghb, st):
         self.pd_gru_gates_bwd_z(dh, lddh, dh2, lddh2, dh3, lddh3, rzn, ldrzn, hn, ldhn, hp, ldhp, dgi, lddgi, dgh, lddgh,

@@ -664,8 +664,9 @@ def test_gru_step_tma(B, H, bcast, save):
         assert torch.allclose(g, c, atol=4e-3, rtol=0), float((g - c).abs().max())
 
 
+@pytest.mark.parametrize("units", [0, 32, 64])
 @pytest.mark.parametrize("B,H,bcast", [(512, 1024, True), (512, 512, False), (300, 128, True), (2048, 1024, False)])
-def test_gru_step_tma_bf16_operands(B, H, bcast):
+def test_gru_step_tma_bf16_operands(B, H, bcast, units):
     """Fused step with bf16 copies of h_prev / W_hh as the tcgen05 operands (kind::f16, fp32 accumulate; the batch-sized
     recurrences in training): both sides multiply the SAME bf16 values, so the comparison is tight; the kernel also emits
     the bf16 copy of the new state."""
@@ -679,8 +680,9 @@ def test_gru_step_tma_bf16_operands(B, H, bcast):
         ho, hbo = torch.zeros(B, H), torch.zeros(B, H, dtype=torch.bfloat16)
         rzn, hn = torch.zeros(B, 3 * H), torch.zeros(B, H)
         return ([hb, H, wb, H, b, torch.randn(B, 3 * H), 3 * H, torch.randn(B, 3 * H) if bcast else None, 3 * H, hp, H, ho, H,
-                 hbo, H, rzn, 3 * H, hn, H, B, H, None], [ho, hbo, rzn, hn])
-    (gh, ch), (gb, cb), (gr, cr), (gn, cn) = _both("pd_gru_step_tma_bf16", mk)
+                 hbo, H, rzn, 3 * H, hn, H, B, H] + ([units] if units else []) + [None], [ho, hbo, rzn, hn])
+    # units: 0 = the default entry point (32-unit tiles); 32 / 64 = pd_gru_step_tma_bf16_units
+    (gh, ch), (gb, cb), (gr, cr), (gn, cn) = _both("pd_gru_step_tma_bf16_units" if units else "pd_gru_step_tma_bf16", mk)
     assert torch.allclose(gh, ch, atol=2e-5, rtol=0), float((gh - ch).abs().max())
     assert torch.allclose(gr, cr, atol=2e-5, rtol=0) and torch.allclose(gn, cn, atol=2e-5, rtol=0)
     assert float((gb.float() - cb.float()).abs().max()) <= 2 ** -7           # (one bf16 ulp where h' straddles a boundary)

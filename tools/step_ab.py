@@ -22,7 +22,9 @@ def run(spec):
     from polydis_b200 import _lib
     pdl = "PDL=1" in spec
     _lib.lib.pd_set_pdl(1 if pdl else 0)
-    spec = ",".join(kv for kv in spec.split(",") if not kv.startswith("PDL="))
+    from polydis_b200 import graphs
+    graphs.FOLD_CLIP_INTO_ADAM = "FOLD=0" not in spec          # FOLD=0: separate clip_grad_norm_ pass
+    spec = ",".join(kv for kv in spec.split(",") if not kv.startswith("PDL=") and not kv.startswith("FOLD="))
     saved = {}
     for kv in filter(None, spec.split(",")):
         k, v = kv.split("=")
