@@ -117,7 +117,7 @@ def test_bf16_recurrent_operands_meet_the_gradient_tolerance(golden_dir, monkeyp
     losses = m.loss(x, c, pr, 1., 1., 1., eps=eps)
     losses[0].backward()
     # time GRU 31 + encoders 4 x 7 + chord decoder 8 fused steps (first steps without an initial state stay unfused)
-    assert be.calls.count("pd_gru_step_tma_bf16") >= 60 and be.calls.count("pd_gru_gates_bwd_zb") >= 60
+    assert be.calls.count("pd_gru_step_tma_bf16_units") >= 60 and be.calls.count("pd_gru_gates_bwd_zb") >= 60
     assert be.calls.count("pd_gemm_bf16") == be.calls.count("pd_gru_gates_bwd_zb")
     np.testing.assert_allclose([float(v.detach()) for v in losses], g["losses"], rtol=3e-4, atol=1e-6)
     params = dict(m.named_parameters())
