@@ -50,6 +50,10 @@ int pd_tf32_split(const float* x, long ldx, long rows, int cols, float* hi, floa
 int pd_tf32_split3(const float* x, long ldx, long rows, int cols, float* out, long ldo, int order, void* stream);
 /* out[n] (+)= sum_m X[m*ldx+n]   (bias gradients) */
 int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int accumulate, void* stream);
+/* the same sum over the live rows only of an (R, T, N) buffer of a length-masked recurrence: row (r, t) is read iff
+ * t < lengths[r] (the dead rows hold zeros).  16-byte aligned X, ldx % 4 == 0, N % 4 == 0. */
+int pd_colsum_seq_f32(const float* X, long ldx, int R, int T, int N, const int* lengths, float* out, int accumulate,
+                      void* stream);
 int pd_transpose_f32(const float* in, int rows, int cols, float* out, void* stream);
 /* out[r*ldo+c] = sum_t X[r*ldr + t*ldt + c]: gradient of a projection broadcast over a GRU's steps (the hoisted
  * z / summary terms of ptvae.py:394-395,458-460) in one pass instead of a read-modify-write per step */

@@ -20,6 +20,7 @@ SIGNATURES = {
     "pd_tf32_split": [_P, _L, _L, _I, _P, _P, _L, _P],
     "pd_tf32_split3": [_P, _L, _L, _I, _P, _L, _I, _P],
     "pd_colsum_f32": [_P, _L, _I, _I, _P, _I, _P],
+    "pd_colsum_seq_f32": [_P, _L, _I, _I, _I, _P, _P, _I, _P],
     "pd_sum_steps_f32": [_P, _L, _L, _I, _P, _L, _L, _I, _P],
     "pd_gru_gates_fwd": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P],
     "pd_gru_gates_fwd_split3": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P],

@@ -143,8 +143,11 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ldx, int M, int 
 // Vector variant for 16-byte aligned inputs: a block sums one 128-column strip over its row range with 8 warps
 // striding the rows (lane = 4 columns, float4 loads, 4 rows in flight per thread), reduces the warps through
 // shared memory and issues one atomicAdd per column.
+// SEQ: the rows are the (sequence, step) pairs of an (R, T, N) buffer and row m is only read if its step m % T lies below
+// its sequence's length (the rest are the zeros a masked recurrence's backward left there: 3/4 of the summariser's rows).
+template <bool SEQ>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict__ X, long ldx, int M, int N, float* out,
-                                                         int rows_per_blk) {
+                                                         int rows_per_blk, const int* __restrict__ lengths, int T) {
     __shared__ float4 part[8][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.x * 128 + lane * 4;
@@ -154,14 +157,17 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict
     for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N) {
         int m = mb + warp;
+        auto live = [&](int row) { return !SEQ || (row % T) < __ldg(lengths + row / T); };
         for (; m + 24 < me; m += 32) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
+                if (!live(m + 8 * i)) continue;
                 const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)(m + 8 * i) * ldx + n));
                 s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
             }
         }
         for (; m < me; m += 8) {
+            if (!live(m)) continue;
             const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)m * ldx + n));
             s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
         }
@@ -250,7 +256,7 @@ PD_API int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int
         int rows = (M + want - 1) / want;
         rows = ((rows < 64 ? 64 : rows) + 7) / 8 * 8;
         dim3 gridv(nbx, (M + rows - 1) / rows);
-        colsum_vec_kernel<<<gridv, 256, 0, st>>>(X, ldx, M, N, out, rows);
+        colsum_vec_kernel<false><<<gridv, 256, 0, st>>>(X, ldx, M, N, out, rows, nullptr, 1);
         return pd_launch_status();
     }
     int want_y = (4 * PD_NUM_SMS + nbx - 1) / nbx;
@@ -258,6 +264,26 @@ PD_API int pd_colsum_f32(const float* X, long ldx, int M, int N, float* out, int
     if (rows_per < 32) rows_per = 32;
     dim3 grid(nbx, (M + rows_per - 1) / rows_per);
     colsum_kernel<<<grid, 128, 0, st>>>(X, ldx, M, N, out, rows_per);
+    return pd_launch_status();
+}
+
+// out[n] (+)= sum over the LIVE rows of X (R*T rows of N columns, row stride ldx): row m = (sequence m / T, step m % T) is
+// live iff m % T < lengths[m / T].  The bias gradients of a length-masked recurrence (the note-summary bi-GRU): the dead
+// rows hold zeros, so the result equals pd_colsum_f32's without reading them.  16-byte aligned X, ldx % 4 == 0, N % 4 == 0.
+PD_API int pd_colsum_seq_f32(const float* X, long ldx, int R, int T, int N, const int* lengths, float* out, int accumulate,
+                             void* stream) {
+    if (N <= 0) return 0;
+    if ((((uintptr_t)X) & 15) || (ldx & 3) || (N & 3) || T <= 0 || lengths == nullptr || (long)R * T > 2147483647L) return PD_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
+    const int M = R * T;
+    if (M <= 0) return pd_launch_status();
+    const int nbx = (N + 127) / 128;
+    int want = (6 * PD_NUM_SMS + nbx - 1) / nbx;
+    int rows = (M + want - 1) / want;
+    rows = ((rows < 64 ? 64 : rows) + 7) / 8 * 8;
+    dim3 gridv(nbx, (M + rows - 1) / rows);
+    colsum_vec_kernel<true><<<gridv, 256, 0, st>>>(X, ldx, M, N, out, rows, lengths, T);
     return pd_launch_status();
 }
 

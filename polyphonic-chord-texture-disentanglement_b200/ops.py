@@ -1128,9 +1128,14 @@ class _GruSeq(torch.autograd.Function):
         first = order[0]
         reverse = ctx.reverse
 
+        seq_lengths = lengths if (lengths is not None and ctx.resident and dgh.is_contiguous()) else None
+
         def wgrads():
             if has_gi2:
                 colsum(dgh_flat[:, 2 * H:], db[2 * H:])
+            elif seq_lengths is not None:
+                # length-masked recurrence (the note summariser): 3/4 of dgh's rows are the zeros of masked steps -- not read
+                _call("pd_colsum_seq_f32", _ptr(dgh), 3 * H, B, T, 3 * H, _ptr(seq_lengths), _ptr(db), 0, _stream())
             else:
                 colsum(dgh_flat, db)
             # dW_hh = sum_{b,t} dgh[b,t]^T h_prev[b,t] as ONE split-K GEMM over all (b,t) rows: h_prev of row r is

@@ -102,6 +102,13 @@ class CpuBackend:
         s = _arr(X, (M, N), (ldx, 1)).sum(0, dtype=np.float32) if M > 0 else 0.0
         o[...] = o + s if acc else s
 
+    def pd_colsum_seq_f32(self, X, ldx, R, T, N, lengths, out, acc, st):
+        o = _arr(out, (N,), (1,))
+        x = _arr(X, (R, T, N), (T * ldx, ldx, 1))
+        live = np.arange(T)[None, :] < _arr(lengths, (R,), (1,), np.int32)[:, None]
+        s = np.where(live[:, :, None], x, 0.0).sum((0, 1), dtype=np.float32)       # dead rows are never read (may hold NaN)
+        o[...] = o + s if acc else s
+
     def pd_sum_steps_f32(self, X, ldr, ldt, T, out, ldo, R, C, st):
         _arr(out, (R, C), (ldo, 1))[...] = _arr(X, (R, T, C), (ldr, ldt, 1)).sum(1, dtype=np.float32)
 

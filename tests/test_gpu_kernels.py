@@ -161,6 +161,25 @@ def test_gemm_tf32_rejects_unaligned_operands():
                   torch.cuda.current_stream().cuda_stream)
 
 
+def test_colsum_seq_skips_masked_steps():
+    """Length-aware column sum (bias gradients of the masked note-summary GRU): only (sequence, step) rows below the
+    sequence's length are read -- the others are poisoned with NaN here."""
+    _dev()
+    rng = np.random.RandomState(3)
+    R, T, N = 3000, 16, 384
+    lengths = torch.from_numpy(rng.randint(0, 18, R).astype(np.int32))          # incl. 0 and > T
+    x = torch.randn(R, T, N)
+    dead = torch.arange(T)[None, :] >= lengths[:, None]
+    x[dead] = float("nan")
+    for acc in (0, 1):
+        def mk():
+            out = torch.full((N,), 0.5)
+            return ([x, N, R, T, N, lengths, out, acc, None], [out])
+        (g, c), = _both("pd_colsum_seq_f32", mk)
+        assert bool(torch.isfinite(g).all())
+        assert torch.allclose(g, c, rtol=1e-4, atol=2e-3), float((g - c).abs().max())
+
+
 def test_colsum_and_transpose():
     _dev()
     (g, c), = _both("pd_colsum_f32",

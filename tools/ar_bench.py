@@ -3,7 +3,8 @@
     PD_AR_VARIANT=0 torchrun --nproc-per-node 2 tools/ar_bench.py
 
 Per bucket size and grid: 20 exchanges captured in one CUDA graph (as the training step issues them), time per exchange
-= max over ranks.  PD_AR_VARIANT: bit 0 strong sys-scope accesses, bit 1 half unroll (read once per process).
+= max over ranks, with and without the in-kernel gather.  (profiles/r02_ar_bench_2gpu.txt also holds the PD_AR_VARIANT runs
+of the first kernel version: sys-scope strong vs weak accesses, unroll.)
 """
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -50,12 +51,10 @@ for blocks in (16, 32, 64):
         mb = b["n"] * 4 / (1 << 20)
         src = [torch.randn(b["n"], device=dev)]
         for gather in (True, False):
-            def fn():
-                if gather:
+            if gather:
+                def fn():       # the exchange as the training step issues it: gather from the producer's buffer, then average
                     red._exchange_p2p(b["index"], b, src)
-                else:
-                    red._exchange_p2p(b["index"], b, [src[0][::2]])      # non-contiguous -> in-place path ... (copy first)
-            if not gather:
+            else:
                 def fn():       # exchange only: the bucket already in place
                     from polydis_b200 import _lib
                     _lib.call("pd_allreduce_p2p", red._peer_ptrs, red.rank, red.world, red.flag_bytes, b["off"], b["n"],
@@ -70,8 +69,8 @@ for mb in sizes_mb:
     us = time_graph(lambda: dist.all_reduce(buf, op=dist.ReduceOp.AVG))
     rows.append(("nccl all_reduce(AVG)", float(mb), us))
 if rank == 0:
-    print(f"PD_AR_VARIANT={os.environ.get('PD_AR_VARIANT', '0')} world={world}")
+    print(f"world={world}")
     for name, mb, us in rows:
-        print(f"  {name:34s} {mb:6.1f} MB  {us:8.1f} us   {2 * mb * (world - 1) / world * 1.048576 / us * 1e3 / 1e3:7.1f} GB/s per direction x2" if False else
-              f"  {name:34s} {mb:6.1f} MB  {us:8.1f} us   bus {mb * 1.048576 * (world - 1) / world / us * 1e3:7.1f} GB/s/dir")
+        # bus: bytes one rank RECEIVES as read responses (= what it also receives as peer stores) per second
+        print(f"  {name:34s} {mb:6.1f} MB  {us:8.1f} us   bus {mb * 1.048576 * (world - 1) / world / us * 1e3:7.1f} GB/s/dir")
 dist.destroy_process_group()
