@@ -340,6 +340,10 @@ BF16_STEP_UNITS_SHORT = 64       # B200, batch 512: 7.86 -> 7.80 ms/step (GPU ca
 BF16_STEP_SHORT_T = 8
 
 
+#: the plain-TF32 greedy pass (training with tfr < 1) runs its note-GRU slot as one fused launch (ptvae._greedy_fast)
+GREEDY_FUSED_TF32_STEP = True
+
+
 def fold_x_ok(rows, H, x, w_x):
     """Can a recurrence over ``rows`` sequences take its x-projection inside the fused step kernel?  x (rows,T,K2)
     contiguous inputs, w_x (3H,K2) the matching W_ih columns (may be a column slice of a wider matrix)."""

@@ -720,6 +720,11 @@ class PtvaeDecoder(nn.Module):
         fuse_x = fuse_n and ops.FUSED_DECODE_STEP_X
         w_tok_n3 = ops.weight_split3(w_tok_n) if fuse_x else None          # (1536, 384)
         e3 = torch.empty(B, 3 * E, **f32) if fuse_x else None
+        # plain-TF32 decode (the no-grad greedy pass of free-running / scheduled-sampling TRAINING, batch >= 256 rows): the
+        # note GRU's x-projection, recurrent GEMM and gate math as ONE tcgen05 launch per slot (the training kernel
+        # pd_gru_step_tmax without its saves) instead of GEMM + GEMM + gate kernel: 7 -> 5 launches per note slot
+        fuse_tf = (not x3) and ops.GREEDY_FUSED_TF32_STEP and ops.fold_x_ok(B, Hn, pred, w_tok_n)
+        h_nb = torch.empty(B, Hn, **f32) if fuse_tf else None
         for t in range(T):
             ops.gemm_nt(tok_time, w_tok_t, gi_t)
             if fuse_t:
@@ -749,6 +754,12 @@ class PtvaeDecoder(nn.Module):
                     ops.gru_step_split3(a_n, wn_hh3, bn_hh, gi_n, gi_s, h_n, n3b)
                     a_n = n3b
                     n3, n3b = n3b, n3
+                elif fuse_tf:
+                    xt = pred[:, n - 1]
+                    ops._call("pd_gru_step_tmax", ops._ptr(h_n), h_n.stride(0), ops._ptr(wn_hh), wn_hh.stride(0), ops._ptr(xt),
+                              pred.stride(0), ops._ptr(w_tok_n), w_tok_n.stride(0), E, ops._ptr(bn_hh), ops._ptr(gi_s),
+                              gi_s.stride(0), ops._ptr(h_nb), h_nb.stride(0), None, 0, None, 0, B, Hn, st())
+                    h_n, h_nb = h_nb, h_n
                 else:
                     ops.gemm_nt(pred[:, n - 1], w_tok_n, gi_n)
                     ops.gemm_nt(h_n, wn_hh, gh_n, bn_hh, a3=a_n)

@@ -361,6 +361,31 @@ def test_large_batch_decode_matches_oracle(prec, fused, monkeypatch):
     print(f"1024-segment {prec} decode (fused step {fused}) vs oracle: token match {match:.6f}")
 
 
+def test_greedy_pass_fused_tf32_step_matches_unfused(monkeypatch):
+    """The plain-TF32 greedy pass of free-running training (no-grad, batch >= 256): its fused note-GRU slot
+    (pd_gru_step_tmax: x-projection + recurrent GEMM + gates in one launch) feeds back the tokens of the three-kernel
+    route -- both multiply the same TF32 operands, only the accumulation order differs -- and a free-running training
+    step through it has the oracle's loss on the tokens it fed."""
+    dev = _dev()
+    from polydis_b200 import ops
+    B = 256
+    x, c, pr = (torch.from_numpy(a).to(dev) for a in synth_batch(B, 79))
+    m = _model(dev, 7, 2.0, 0.75)
+    m.train()
+    toks = []
+    for on in (True, False):
+        monkeypatch.setattr(ops, "GREEDY_FUSED_TF32_STEP", on)
+        torch.manual_seed(3); random.seed(3)
+        eps = (torch.zeros(B, 256, device=dev), torch.zeros(B, 256, device=dev))
+        loss = m('train', x, c, pr, tfr1=0., tfr2=0., tfr3=0., beta=0.1, weights=(1, 0.5), eps=eps)
+        assert bool(torch.isfinite(loss[0]))
+        toks.append((m.decoder._last_tokens.clone(), float(loss[0])))
+    match = float((toks[0][0] == toks[1][0]).float().mean())
+    print(f"free-running greedy pass, fused vs unfused TF32 slot: token match {match:.6f}, losses {toks[0][1]:.5f} {toks[1][1]:.5f}")
+    assert match >= 0.99, match
+    assert abs(toks[0][1] - toks[1][1]) <= 2e-2 * abs(toks[1][1])
+
+
 def test_graphed_decode_matches_eager_decode():
     """GraphedDecode (what bench.py replays) returns the tokens of the eager public API on the same inputs."""
     dev = _dev()
