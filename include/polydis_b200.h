@@ -179,6 +179,10 @@ int pd_note_embed_bwd(const int* tok, long R, const float* g, long ldg, float* d
  * lens[r] = first n with EOS (15 if none; lens must start at 0). */
 int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok, long ldtok,
                    int* lens, void* stream);
+/* the same pick followed by the embedding of the picked tokens (pd_note_embed_fwd: emb (R,128; row stride lde)) in one
+ * launch -- the tail of a greedy note slot (ptvae.py:408-416 + :333) */
+int pd_greedy_pick_embed(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok, long ldtok,
+                         int* lens, const float* WT, const float* bias, float* emb, long lde, void* stream);
 /* duration feedback token (ptvae.py:322-326): 5-wide, 1 at index == argmax bit */
 int pd_dur_token(const float* logit, long ldl, long R, float* tok, void* stream);
 /* fused duration decoder (ptvae.py:345-367): 5-step GRU(5->64) + Linear(64->2) with greedy bit feedback.

@@ -45,6 +45,7 @@ SIGNATURES = {
     "pd_note_embed_fwd": [_P, _L, _P, _P, _P, _L, _P],
     "pd_note_embed_bwd": [_P, _L, _P, _L, _P, _P, _P],
     "pd_greedy_pick": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P],
+    "pd_greedy_pick_embed": [_P, _L, _P, _L, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P],
     "pd_dur_token": [_P, _L, _L, _P, _P],
     "pd_dur_decode_fwd": [_P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
     "pd_dur_decode_bwd": [_P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _P],

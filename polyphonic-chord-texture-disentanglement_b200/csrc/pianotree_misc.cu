@@ -107,13 +107,8 @@ __global__ void __launch_bounds__(EMB) note_embed_bwd_kernel(const int* __restri
 // Greedy pick for one note slot n (1..15): argmax pitch (first maximum, like torch.max on CPU),
 // argmax of each duration bit, token row for the embedding gather, EOS length bookkeeping
 // (first n whose pitch is EOS; 15 if none).                           ptvae.py:408-416,:425
-__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ pitch, long ldp,
-                                                          const float* __restrict__ dur, long ldd, long R, int n,
-                                                          int* tok, long ldtok, int* lens) {
-    long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= R) return;
-    const int lane = threadIdx.x & 31;
-    const float* p = pitch + r * ldp;
+// one warp per row: returns (all lanes) the picked pitch; lane k < 5 returns its duration bit in `bit`
+__device__ __forceinline__ int greedy_pick_row(const float* __restrict__ p, const float* __restrict__ d, int lane, int& bit) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = lane; i < P_RANGE; i += 32) {
@@ -126,6 +121,19 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
         int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
+    bit = 0;
+    if (lane < 5) bit = (d[lane * 2 + 1] > d[lane * 2]) ? 1 : 0;
+    return bi;
+}
+
+__global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restrict__ pitch, long ldp,
+                                                          const float* __restrict__ dur, long ldd, long R, int n,
+                                                          int* tok, long ldtok, int* lens) {
+    long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    const int lane = threadIdx.x & 31;
+    int bit;
+    const int bi = greedy_pick_row(pitch + r * ldp, dur + r * ldd, lane, bit);
     if (lane == 0) {
         int* t = tok + r * ldtok;
         t[0] = bi;
@@ -136,10 +144,47 @@ __global__ void __launch_bounds__(256) greedy_pick_kernel(const float* __restric
             lens[r] = L;
         }
     }
-    if (lane < 5) {
-        const float* d = dur + r * ldd + lane * 2;
-        tok[r * ldtok + 1 + lane] = (d[1] > d[0]) ? 1 : 0;
+    if (lane < 5) tok[r * ldtok + 1 + lane] = bit;
+}
+
+// The same pick followed, in the same warp, by the embedding of the picked token (note_embed_fwd_kernel's arithmetic: bias
+// first, then the pitch row, then the duration rows in bit order): the two tail kernels of a greedy note slot as one launch.
+__global__ void __launch_bounds__(256) greedy_pick_embed_kernel(const float* __restrict__ pitch, long ldp,
+                                                                const float* __restrict__ dur, long ldd, long R, int n,
+                                                                int* tok, long ldtok, int* lens,
+                                                                const float* __restrict__ WT, const float* __restrict__ bias,
+                                                                float* emb, long lde) {
+    long r = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= R) return;
+    const int lane = threadIdx.x & 31;
+    int bit;
+    const int bi = greedy_pick_row(pitch + r * ldp, dur + r * ldd, lane, bit);
+    if (lane == 0) {
+        int* t = tok + r * ldtok;
+        t[0] = bi;
+        if (lens) {
+            int L = lens[r];
+            if (L == 0 && bi == P_EOS) L = n;
+            if (n == NOTE_SLOTS - 1 && L == 0) L = NOTE_SLOTS - 1;
+            lens[r] = L;
+        }
     }
+    if (lane < 5) tok[r * ldtok + 1 + lane] = bit;
+    const unsigned bits = __ballot_sync(0xffffffffu, bit != 0);
+    float4 acc = *reinterpret_cast<const float4*>(bias + lane * 4);
+    if (bi >= 0 && bi < P_RANGE) {
+        float4 w = *reinterpret_cast<const float4*>(WT + (long)bi * EMB + lane * 4);
+        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (bits & (1u << k)) {
+            float4 w = *reinterpret_cast<const float4*>(WT + (long)(P_RANGE + k) * EMB + lane * 4);
+            acc.x = fmaf(1.0f, w.x, acc.x); acc.y = fmaf(1.0f, w.y, acc.y);
+            acc.z = fmaf(1.0f, w.z, acc.z); acc.w = fmaf(1.0f, w.w, acc.w);
+        }
+    }
+    *reinterpret_cast<float4*>(emb + r * lde + lane * 4) = acc;
 }
 
 // Duration feedback token: 5-wide vector with a single 1 at index == argmax bit (ptvae.py:322-326).
@@ -417,6 +462,16 @@ PD_API int pd_greedy_pick(const float* pitch, long ldp, const float* dur, long l
     if (R <= 0) return 0;
     greedy_pick_kernel<<<pd_blocks(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(pitch, ldp, dur, ldd, R, n, tok,
                                                                                  ldtok, lens);
+    return pd_launch_status();
+}
+
+// pd_greedy_pick + pd_note_embed_fwd of the picked tokens in one launch: emb (R,128; row stride lde) = embedding of tok
+PD_API int pd_greedy_pick_embed(const float* pitch, long ldp, const float* dur, long ldd, long R, int n, int* tok,
+                                long ldtok, int* lens, const float* WT, const float* bias, float* emb, long lde, void* stream) {
+    if (R <= 0) return 0;
+    if ((lde & 3) || ((uintptr_t)emb & 15) || ((uintptr_t)WT & 15) || ((uintptr_t)bias & 15)) return PD_BAD_ARG;
+    greedy_pick_embed_kernel<<<pd_blocks(R * 32, 256), 256, 0, (cudaStream_t)stream>>>(pitch, ldp, dur, ldd, R, n, tok, ldtok,
+                                                                                       lens, WT, bias, emb, lde);
     return pd_launch_status();
 }
 

@@ -1676,6 +1676,17 @@ def greedy_pick(pitch, dur, n, tok_out, lens):
           tok_out.stride(0), _ptr(lens), _stream())
 
 
+def greedy_pick_embed(pitch, dur, n, tok_out, lens, emb_wt, emb_b, emb_out):
+    """``greedy_pick`` + the embedding of the picked tokens (``pd_note_embed_fwd``) in one launch: emb_out (R,128) view."""
+    p2, _ = _rows(pitch)
+    d2 = dur.reshape(dur.shape[0], 10)
+    if d2.stride(1) != 1:
+        d2 = d2.contiguous()
+    R = p2.shape[0]
+    _call("pd_greedy_pick_embed", _ptr(p2), p2.stride(0), _ptr(d2), d2.stride(0), R, n, _ptr(tok_out), tok_out.stride(0),
+          _ptr(lens), _ptr(emb_wt), _ptr(emb_b), _ptr(emb_out), emb_out.stride(0), _stream())
+
+
 def dur_token(logit):
     """(R,2) logits -> (R,5) feedback token with the 1 at index == argmax bit (ptvae.py:322-326)."""
     l2, _ = _rows(logit)
@@ -1760,8 +1771,16 @@ class _DurDecode(torch.autograd.Function):
                 db_hh.contiguous(), dsos, dw_out.contiguous(), db_out.contiguous(), None, None, None)
 
 
-def dur_mode():
+#: below this many notes per call the TF32 (one warp per 16 notes) duration decoder is latency bound -- a 512-note slot
+#: of the training-time greedy pass takes 21 us, 27 % of a free-running step -- and the fp32 FFMA kernel, which spreads a
+#: tile over six warps, is used instead (0: never)
+DUR_FFMA_MAX_NOTES = 0
+
+
+def dur_mode(n_notes=None):
     """Arithmetic flag of the duration-decoder kernels for the current precision scope (csrc/dur_decoder.cu)."""
+    if PRECISION == "tf32" and n_notes is not None and n_notes < DUR_FFMA_MAX_NOTES:
+        return 0
     return {"fp32": 0, "tf32": 1, "tf32x3": 3}[PRECISION]
 
 

@@ -770,10 +770,9 @@ class PtvaeDecoder(nn.Module):
                         ops._gates_fwd(gi_n, gi_s, gh_n, h_n, h_n, None, None, None, 0)
                 ops.gemm_nt(h_n, w_heads, heads[:, :NH], b_heads, a3=a_n)
                 ops._call("pd_dur_decode_fwd", ops._ptr(heads[:, self.pitch_range:]), heads.stride(0), B,
-                          *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, ops.dur_mode(), st())
-                ops.greedy_pick(heads[:, :self.pitch_range], dlog, n, tokens[t, n - 1], lens)
-                ops._call("pd_note_embed_fwd", ops._ptr(tokens[t, n - 1]), B, ops._ptr(emb_wt), ops._ptr(emb_b),
-                          ops._ptr(pred[:, n]), pred.stride(0), st())
+                          *[ops._ptr(p_) for p_ in dur_par], ops._ptr(dlog), None, ops.dur_mode(B), st())
+                # argmax pick + embedding of the picked token: one launch
+                ops.greedy_pick_embed(heads[:, :self.pitch_range], dlog, n, tokens[t, n - 1], lens, emb_wt, emb_b, pred[:, n])
             if lens_out is not None:
                 lens_out[t].copy_(lens)
             if t == T - 1:

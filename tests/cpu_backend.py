@@ -609,6 +609,11 @@ class CpuBackend:
             if n == 15:
                 L[L == 0] = 15
 
+    def pd_greedy_pick_embed(self, pitch, ldp, dur, ldd, R, n, tok, ldtok, lens, WT, bias, emb, lde, st):
+        self.pd_greedy_pick(pitch, ldp, dur, ldd, R, n, tok, ldtok, lens, st)
+        T = np.ascontiguousarray(_arr(tok, (R, 6), (ldtok, 1), np.int32))
+        self.pd_note_embed_fwd(T.ctypes.data, R, WT, bias, emb, lde, st)
+
     def pd_dur_token(self, logit, ldl, R, tok, st):
         Lg = _arr(logit, (R, 2), (ldl, 1))
         T = _arr(tok, (R, 5), (5, 1))

@@ -291,6 +291,17 @@ def test_greedy_pick_dur_token_chord():
     (g, c), = _both("pd_dur_token", lambda: (lambda t: ([torch.randn(R, 2), 2, R, t, None], [t]))(torch.zeros(R, 5)))
     assert torch.equal(g, c)
 
+    def mke():           # pick + embedding of the picked token in one launch == pd_greedy_pick then pd_note_embed_fwd
+        p = torch.randn(R, 132)
+        p[::7, 129] = 50.0
+        d = torch.randn(R, 10)
+        tok, lens = torch.zeros(R, 6, dtype=torch.int32), torch.zeros(R, dtype=torch.int32)
+        ev = torch.zeros(R, 16, 128)[:, 3]               # a slot of the (R,16,128) predicted-note buffer
+        return [p, 132, d, 10, R, 4, tok, 6, lens, torch.randn(135, 128), torch.randn(128), ev, 16 * 128, None], [tok, lens, ev]
+    (gt, ct), (gl, cl), (ge, ce) = _both("pd_greedy_pick_embed", mke)
+    assert torch.equal(gt, ct) and torch.equal(gl, cl)
+    assert torch.allclose(ge, ce, atol=1e-6, rtol=0), float((ge - ce).abs().max())
+
     def mkc():
         tok = torch.zeros(9, 36)
         return ([torch.randn(9, 12), 12, torch.randn(9, 24), 24, torch.randn(9, 12), 12, 9, torch.zeros(24), tok, 36,
