@@ -68,10 +68,17 @@ def observe_ready_order(params, run_backward):
 
 
 class BucketedGradAllReduce:
+    """Bucketed, backward-overlapped gradient averaging over the ranks of a process group (see the module docstring).
+    Per step: ``reset()`` .. forward .. backward .. ``finish()`` .. (``clip_grad_norm_`` | ``grad_norm``) .. optimizer step;
+    ``p.grad`` of every parameter is then a view of its bucket holding the averaged gradient."""
+
     def __init__(self, params, bucket_mb=8, group=None, ready_order=None, comm_priority=0, impl="nccl", ar_blocks=None):
         """``ready_order``: the parameters in the order their gradients become ready (``observe_ready_order``); default
         reverse registration order.  ``comm_priority``: CUDA priority of the communication stream (negative = higher).
-        ``impl``: "nccl" | "p2p" (the library's peer-memory kernel; falls back to "nccl" semantics only by raising)."""
+        ``impl``: "nccl" (gather + ``ncclAllReduce`` per bucket) | "p2p" (the library's peer-memory exchange kernel; raises
+        ``RuntimeError`` on every rank if CUDA IPC / peer access is unavailable -- the caller decides about a fall-back).
+        ``ar_blocks``: CTAs per exchange kernel (default ``PD_AR_BLOCKS`` or 32; ``PD_AR_STREAMS``, default 4, exchange
+        streams)."""
         self.group = group
         self.impl = impl
         assert impl in ("nccl", "p2p")
@@ -104,7 +111,8 @@ class BucketedGradAllReduce:
         self.comms = [self.comm]
         if impl == "p2p":
             n_comm = int(os.environ.get("PD_AR_STREAMS", "4"))
-            assert n_comm * self.ar_blocks <= 148, "PD_AR_STREAMS x PD_AR_BLOCKS must not exceed the SM count"
+            n_sm = torch.cuda.get_device_properties(self.params[0].device).multi_processor_count
+            assert n_comm * self.ar_blocks <= n_sm, "PD_AR_STREAMS x PD_AR_BLOCKS must not exceed the SM count"
             self.comms += [torch.cuda.Stream(priority=comm_priority) for _ in range(n_comm - 1)]
         self._handles = []
         for bi, b in enumerate(self.buckets):
