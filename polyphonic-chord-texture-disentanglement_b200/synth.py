@@ -54,6 +54,11 @@ def synth_batch(B, seed=0, max_notes=8, p_active=0.6, lo=36, hi=96):
     Per (segment, step): active with prob ``p_active``; k ~ U{1..max_notes} distinct pitches from
     [lo,hi); each duration ~ U{1..32-t}.  Per chord slot: root ~ U{0..11}, 12 chroma bits
     ~ Bernoulli(0.3), bass ~ U{0..11}.  Deterministic in (B, seed, ...).
+
+    This is the VECTORISED form of the recipe (one PCG64 stream, whole-batch draws: 65,536 segments in about a second);
+    ``synth_batch_recipe`` below is the recipe of BASELINE.md / SURVEY.md appendix A verbatim (a ``RandomState`` loop over
+    segments and steps): the same distribution, a different random stream.  The golden fixtures and every test / bench
+    input are drawn with this function.
     """
     rng = np.random.Generator(np.random.PCG64(seed))
     n_p = hi - lo
@@ -78,3 +83,27 @@ def synth_batch(B, seed=0, max_notes=8, p_active=0.6, lo=36, hi=96):
     c[:, :, 12:24] = chroma
     c[bi, si, 24 + bass] = 1.0
     return x, c, pr_mat
+
+
+def synth_batch_recipe(B, seed=0, max_notes=8):
+    """The synthetic-input recipe of BASELINE.md section 3 / SURVEY.md appendix A, statement for statement: one
+    ``np.random.RandomState(seed)``, a python loop over segments, steps and chord slots.  Same distribution as
+    ``synth_batch`` (tests/test_api_surface_cpu.py compares their statistics); use it to reproduce the survey's probe
+    numbers, not for large batches."""
+    rng = np.random.RandomState(seed)
+    pr_mat = np.zeros((B, 32, 128), dtype=np.float32)
+    c = np.zeros((B, 8, 36), dtype=np.float32)
+    for b in range(B):
+        for t in range(32):
+            if rng.rand() < 0.6:
+                k = rng.randint(1, max_notes + 1)
+                ps = rng.choice(np.arange(36, 96), size=k, replace=False)
+                pr_mat[b, t, ps] = rng.randint(1, min(32, 32 - t) + 1, size=k)
+        for s_ in range(8):
+            root = rng.randint(12)
+            chroma = rng.rand(12) < 0.3
+            bass = rng.randint(12)
+            c[b, s_, root] = 1.0                 # expand_chord(., shift 0): root one-hot | chroma bits | bass one-hot
+            c[b, s_, 12:24] = chroma
+            c[b, s_, 24 + bass] = 1.0
+    return pr_mat_to_grid(pr_mat), c, pr_mat

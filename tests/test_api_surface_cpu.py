@@ -185,3 +185,24 @@ def test_ptvae_encoder_matches_reference_golden(monkeypatch, golden_dir):
     for i, (name, _, _) in enumerate(PTVAE_ENCODER_SPEC):
         gn = float(params[name].grad.double().norm())
         assert abs(gn - g["enc_grad_norm"][i]) <= 1e-3 * g["enc_grad_norm"][i] + 1e-9, name
+
+
+def test_vectorised_synth_has_the_recipe_distribution():
+    """``synth_batch`` (vectorised, PCG64) draws from the distribution of the BASELINE / SURVEY recipe
+    (``synth_batch_recipe``: RandomState loop): active-step rate, notes per step, pitch range, duration law, chord stats."""
+    import numpy as np
+    from polydis_b200.synth import synth_batch, synth_batch_recipe
+    xa, ca, pa = synth_batch(256, 11)
+    xb, cb, pb = synth_batch_recipe(256, 11)
+    assert xa.shape == xb.shape and ca.shape == cb.shape and pa.shape == pb.shape and xb.dtype == np.int64
+    for pr in (pa, pb):
+        assert pr[:, :, :36].sum() == 0 and pr[:, :, 96:].sum() == 0
+        assert (pr.max(-1) <= (32 - np.arange(32))[None, :]).all()
+    na, nb = (pa != 0).sum(-1), (pb != 0).sum(-1)
+    assert abs((na > 0).mean() - (nb > 0).mean()) < 0.02 and abs((na > 0).mean() - 0.6) < 0.02
+    assert abs(na[na > 0].mean() - nb[nb > 0].mean()) < 0.12 and na.max() <= 8 and nb.max() <= 8
+    assert abs(pa[pa != 0].mean() - pb[pb != 0].mean()) < 0.25            # mean duration
+    assert abs(ca[:, :, 12:24].mean() - cb[:, :, 12:24].mean()) < 0.02
+    assert (ca[:, :, :12].sum(-1) == 1).all() and (cb[:, :, 24:].sum(-1) == 1).all()
+    # the grid builder is shared: token counts per step follow from the note counts (SOS + notes + EOS)
+    assert ((xb[..., 0] != 130).sum(-1) == nb + 2).all()
