@@ -193,6 +193,9 @@ int pd_dur_token(const float* logit, long ldl, long R, float* tok, void* stream)
 int pd_dur_decode_fwd(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih, const float* w_hh,
                       const float* b_hh, const float* sos, const float* w_out, const float* b_out, float* logits,
                       float* S, int tf32, void* stream);
+/* TF32 calls without saves (S == NULL) of at most n notes run the four-warps-per-tile inference kernel (default 2048;
+ * 0 = never): library-wide tuning switch */
+int pd_dur_quad_max_notes(int n);
 int pd_dur_decode_bwd(const float* S, const float* dlogits, long Q, const float* w_ih, const float* b_ih,
                       const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
                       const float* b_out, float* GX, float* dh0, long lddh0, int tf32, void* stream);

@@ -89,6 +89,7 @@ SIGNATURES = {
     "pd_gru_gates_bwd_zb": [_P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _P, _I, _I, _I, _P, _L, _P,
                             _L, _P],
     "pd_set_pdl": [_I],
+    "pd_dur_quad_max_notes": [_I],
     "pd_ar_flag_bytes": [_I],                      # (returns bytes, not a status)
     "pd_ar_limit": [_I],                           # (returns the limit, not a status)
     "pd_ipc_alloc": [_L, _P, _P],

@@ -488,6 +488,136 @@ __global__ void __launch_bounds__(FW_WARPS * 32, 1) dur_fwd_warp_kernel(const fl
     }
 }
 
+// ---- small-Q inference form (TF32, no saves): ONE 16-note tile per CTA, spread over four warps -------------------------
+// A greedy note slot of a few hundred rows (the no-grad greedy pass of free-running / scheduled-sampling training at batch
+// 512, step-wise decodes) is a latency chain: with one warp per tile the five GRU steps take ~12 us behind a ~5 us
+// shared-memory staging of W_hh (21 us per 512-note call, 27 % of a free-running training step).  Here warp w owns
+// hidden units [16w, 16w+16) of all three gates -- 6 of the 24 n-tiles -- so a step's matvec and gate math are a quarter as
+// long; its 96 B-fragment values of W_hh (L2-resident) live in REGISTERS for the five steps, so nothing is staged; the new
+// state goes to the other half of a double-buffered shared tile and the duration head's partial dot products meet
+// through shared memory, with one block barrier per step.
+constexpr int QW = 4;
+struct QuadShared {
+    float gi_t[3 * TS];
+    float bhn[H];
+    float wo[2 * H];
+    float hw[2][WM][HS];
+    float lpart[2][QW][WM][2];
+};
+
+__global__ void __launch_bounds__(QW * 32) dur_fwd_quad_kernel(const float* __restrict__ h0, long ldh0, long Q, DurParams p,
+                                                               float* __restrict__ logits) {
+    __shared__ __align__(16) QuadShared sh;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tig = lane & 3;
+    const long q0 = (long)blockIdx.x * WM;
+    const int rows = (int)min((long)WM, Q - q0);
+    uint32_t bf[6][8][2];                     // [gate * 2 + unit block][k-tile][k, k+4]
+#pragma unroll
+    for (int gt = 0; gt < 3; ++gt)
+#pragma unroll
+        for (int ub = 0; ub < 2; ++ub) {
+            const float* wr = p.w_hh + (long)(gt * H + (2 * warp + ub) * 8 + g) * H;
+#pragma unroll
+            for (int kt = 0; kt < 8; ++kt) {
+                bf[gt * 2 + ub][kt][0] = to_tf32(__ldg(wr + 8 * kt + tig));
+                bf[gt * 2 + ub][kt][1] = to_tf32(__ldg(wr + 8 * kt + tig + 4));
+            }
+        }
+    for (int j = threadIdx.x; j < G3; j += QW * 32) {              // x-projection per input token (as warp_setup)
+        const float bh = j < 2 * H ? p.b_hh[j] : 0.0f;
+        float b = p.b_ih[j], sos = b;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sos = fmaf(p.w_ih[j * 5 + c], p.sos[c], sos);
+        sh.gi_t[j] = sos + bh;
+        sh.gi_t[TS + j] = p.w_ih[j * 5 + 0] + b + bh;
+        sh.gi_t[2 * TS + j] = p.w_ih[j * 5 + 1] + b + bh;
+        if (j >= 2 * H) sh.bhn[j - 2 * H] = p.b_hh[j];
+    }
+    for (int i = threadIdx.x; i < 2 * H; i += QW * 32) sh.wo[i] = p.w_out[i];
+    const bool al16 = (((uintptr_t)h0 & 15) == 0) && ((ldh0 & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {                                  // state tile: 16 rows x 16 float4
+        const int idx = threadIdx.x + QW * 32 * i, r = idx >> 4, c4 = (idx & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+            const float* q = h0 + (q0 + r) * ldh0 + c4;
+            if (al16) {
+                v = __ldg(reinterpret_cast<const float4*>(q));
+            } else {
+                const float2 a = __ldg(reinterpret_cast<const float2*>(q)), b = __ldg(reinterpret_cast<const float2*>(q + 2));
+                v = make_float4(a.x, a.y, b.x, b.y);
+            }
+        }
+        *reinterpret_cast<float4*>(&sh.hw[0][r][c4]) = v;
+    }
+    __syncthreads();
+    const float bo0 = p.b_out[0], bo1 = p.b_out[1];
+    int tok[2] = {0, 0};
+    int cur = 0;
+    for (int k = 0; k < NSTEP; ++k) {
+        const float (*hc)[HS] = sh.hw[cur];
+        float (*hx)[HS] = sh.hw[cur ^ 1];
+        float acc[6][4];
+#pragma unroll
+        for (int nt = 0; nt < 6; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.0f;
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) {
+            const uint32_t a[4] = {to_tf32(hc[g][8 * kt + tig]), to_tf32(hc[g + 8][8 * kt + tig]),
+                                   to_tf32(hc[g][8 * kt + tig + 4]), to_tf32(hc[g + 8][8 * kt + tig + 4])};
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) mma_tf32(acc[nt], a, bf[nt][kt][0], bf[nt][kt][1]);
+        }
+        float l0[2] = {0.f, 0.f}, l1[2] = {0.f, 0.f};
+#pragma unroll
+        for (int ub = 0; ub < 2; ++ub) {
+            const int u = (2 * warp + ub) * 8 + 2 * tig;
+            const float2 bn = *reinterpret_cast<const float2*>(&sh.bhn[u]);
+            const float2 w0 = *reinterpret_cast<const float2*>(&sh.wo[u]);
+            const float2 w1 = *reinterpret_cast<const float2*>(&sh.wo[H + u]);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int row = g + 8 * half;
+                const float* tb = sh.gi_t + tok[half] * TS + u;
+                const float2 gr = *reinterpret_cast<const float2*>(tb);
+                const float2 gz = *reinterpret_cast<const float2*>(tb + H);
+                const float2 gn = *reinterpret_cast<const float2*>(tb + 2 * H);
+                const float2 hp = *reinterpret_cast<const float2*>(&hc[row][u]);
+                const float r0 = pd_sigmoid_fast(gr.x + acc[ub][2 * half]), r1 = pd_sigmoid_fast(gr.y + acc[ub][2 * half + 1]);
+                const float z0 = pd_sigmoid_fast(gz.x + acc[2 + ub][2 * half]), z1 = pd_sigmoid_fast(gz.y + acc[2 + ub][2 * half + 1]);
+                const float n0 = pd_tanh_fast(gn.x + r0 * (acc[4 + ub][2 * half] + bn.x));
+                const float n1 = pd_tanh_fast(gn.y + r1 * (acc[4 + ub][2 * half + 1] + bn.y));
+                const float2 hn = make_float2((1.0f - z0) * n0 + z0 * hp.x, (1.0f - z1) * n1 + z1 * hp.y);
+                *reinterpret_cast<float2*>(&hx[row][u]) = hn;
+                l0[half] = fmaf(hn.x, w0.x, fmaf(hn.y, w0.y, l0[half]));
+                l1[half] = fmaf(hn.x, w1.x, fmaf(hn.y, w1.y, l1[half]));
+            }
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            l0[half] += __shfl_xor_sync(0xffffffffu, l0[half], 1);
+            l1[half] += __shfl_xor_sync(0xffffffffu, l1[half], 1);
+            l0[half] += __shfl_xor_sync(0xffffffffu, l0[half], 2);
+            l1[half] += __shfl_xor_sync(0xffffffffu, l1[half], 2);
+            if (tig == 0) *reinterpret_cast<float2*>(&sh.lpart[k & 1][warp][g + 8 * half][0]) = make_float2(l0[half], l1[half]);
+        }
+        __syncthreads();                       // new state + the four partial heads are in shared memory
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int row = g + 8 * half;
+            float a0 = bo0, a1 = bo1;
+#pragma unroll
+            for (int w = 0; w < QW; ++w) {
+                const float2 v = *reinterpret_cast<const float2*>(&sh.lpart[k & 1][w][row][0]);
+                a0 += v.x; a1 += v.y;
+            }
+            tok[half] = a1 > a0 ? 2 : 1;           // every warp takes the same decision from the same numbers
+            if (warp == 0 && tig == 0 && row < rows)
+                *reinterpret_cast<float2*>(logits + ((q0 + row) * NSTEP + k) * 2) = make_float2(a0, a1);
+        }
+        cur ^= 1;
+    }
+}
+
 __global__ void __launch_bounds__(BW_WARPS * 32, 1) dur_bwd_warp_kernel(const float* __restrict__ S,
                                                                          const float* __restrict__ dlog, long Q, DurParams p,
                                                                          float* __restrict__ GX, float* __restrict__ dh0,
@@ -642,6 +772,13 @@ unsigned warp_grid(long Q) {
 // logits (Q,5,2) <- 5-step greedy-feedback duration GRU from h0 (Q,64; row stride ldh0).  S (Q,6,72) may be
 // NULL (inference).  tf32: 0 = fp32 FFMA kernels, 1 = TF32 tensor-core matvecs, 3 = error-compensated 3xTF32 matvecs with
 // expf / tanhf gates (fp32-class, forward only).  Nonzero: S must be 16-byte and h0 8-byte aligned, ldh0 even.
+// calls of at most this many notes without saves take dur_fwd_quad_kernel (pd_dur_quad_max_notes: tuning / A-B switch)
+static long g_dur_quad_max = 2048;
+PD_API int pd_dur_quad_max_notes(int n) {
+    g_dur_quad_max = n;
+    return 0;
+}
+
 static int dur_fwd_impl(const float* h0, long ldh0, long Q, const float* w_ih, const float* b_ih,
                         const float* w_hh, const float* b_hh, const float* sos, const float* w_out,
                         const float* b_out, float* logits, float* S, int tf32, PdRows live, void* stream) {
@@ -654,6 +791,11 @@ static int dur_fwd_impl(const float* h0, long ldh0, long Q, const float* w_ih, c
     if (tf32 == 3 && Q < 4096) tf32 = 0;
     if (tf32) {
         if (((uintptr_t)S & 15) || ((uintptr_t)h0 & 7) || (ldh0 & 1) || ((uintptr_t)logits & 7)) return PD_BAD_ARG;
+        if (tf32 == 1 && S == nullptr && live.cp == nullptr && Q <= g_dur_quad_max) {
+            // small inference call: one tile per CTA over four warps, W_hh fragments in registers (no staging)
+            dur_fwd_quad_kernel<<<(unsigned)((Q + WM - 1) / WM), QW * 32, 0, (cudaStream_t)stream>>>(h0, ldh0, Q, p, logits);
+            return pd_launch_status();
+        }
         static unsigned long long attr = 0;
         if (pd_first_use_on_device(attr)) {
             cudaError_t e = cudaFuncSetAttribute(dur_fwd_warp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);

@@ -429,6 +429,37 @@ def test_dur_decoder_fused(Q, tf32):
         assert torch.allclose(g, c, atol=(5e-3 if tf32 else 3e-5), rtol=1e-4), float((g - c).abs().max())   # bwd: 3 -> TF32
 
 
+@pytest.mark.parametrize("Q", [1, 33, 512, 2048])
+def test_dur_decoder_small_inference_kernel(Q):
+    """TF32 calls without saves of <= 2048 notes (a greedy note slot): the four-warps-per-tile kernel (W_hh fragments in
+    registers, state and head partials exchanged through shared memory) against the numpy restatement and against the
+    one-warp-per-tile kernel (pd_dur_quad_max_notes(0)); the duration head's input rows sit in a wider buffer at an even
+    column offset, as in the decoder."""
+    _dev()
+    from polydis_b200 import _lib
+    par = lambda: [torch.randn(192, 5) * 0.3, torch.randn(192) * 0.1, torch.randn(192, 64) * 0.2, torch.randn(192) * 0.1,
+                   torch.rand(5), torch.randn(2, 64) * 0.3, torch.randn(2) * 0.1]
+
+    def mk():
+        lg = torch.zeros(Q, 5, 2)
+        return [torch.randn(Q, 196)[:, 130:194], 196, Q] + par() + [lg, None, 1, None], [lg]
+    outs = []
+    for limit in (2048, 0):
+        assert _lib.lib.pd_dur_quad_max_notes(limit) == 0
+        try:
+            (gl, cl), = _both("pd_dur_decode_fwd", mk)
+        finally:
+            _lib.lib.pd_dur_quad_max_notes(2048)
+        outs.append(gl)
+        bits_g, bits_c = gl[:, :, 1] > gl[:, :, 0], cl[:, :, 1] > cl[:, :, 0]
+        same = (bits_g == bits_c).all(-1)
+        assert same.float().mean() > 0.97                      # a near-tied bit may flip by TF32 rounding
+        assert torch.allclose(gl[same], cl[same], atol=3e-3), float((gl - cl)[same].abs().max())
+    same = ((outs[0][:, :, 1] > outs[0][:, :, 0]) == (outs[1][:, :, 1] > outs[1][:, :, 0])).all(-1)
+    assert same.float().mean() > 0.99                          # same TF32 operands, different summation order
+    assert torch.allclose(outs[0][same], outs[1][same], atol=2e-5), float((outs[0] - outs[1])[same].abs().max())
+
+
 def test_prmat_grid_conversions():
     _dev()
     from polydis_b200.synth import synth_batch
