@@ -727,8 +727,29 @@ static int gru_step_tmax_impl(const float* hprev, long ldhp, const float* w_hh, 
     if (!rc && hn) rc = make_map_io(&thn, hn, H, B, ldhn);
     if (rc) return rc;
     StepIo g{b_hh, 1, rzn != nullptr, hn != nullptr, B, H, H, 0, K2, nrows, nullptr, 0};
-    const int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
-    const long items = (long)tiles_m * tiles_u;
+    int tiles_m = (B + BM - 1) / BM, tiles_u = H / UN;
+    long items = (long)tiles_m * tiles_u;
+    if (nrows == nullptr && 2 * items <= PD_NUM_SMS && H % 32 == 0) {
+        // a few hundred rows (a note slot of the greedy pass at batch 512: 32 tiles of 64 units on 148 SMs): 32-unit tiles
+        // double the CTAs and halve each CTA's weight stream and epilogue -- the step is a latency chain, not a throughput job
+        rc = make_map(&tb, w_hh, 4, H, 3L * H, ldw, 32, false);
+        if (!rc) rc = make_map(&tb2, w_x, 4, K2, 3L * H, ldwx, 32, false);
+        if (rc) return rc;
+        tiles_u = H / 32;
+        items = (long)tiles_m * tiles_u;
+        const int grid32 = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
+        constexpr int ST32 = 4, NS32 = 1;
+        constexpr int smem32 = ST32 * (BM * 128 + 96 * 128) + 4 * NS32 * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;
+        static unsigned long long attr32 = 0;
+        if (pd_first_use_on_device(attr32)) {
+            cudaError_t e = cudaFuncSetAttribute(gru_step_tma_kernel<ST32, NS32, true, false, true, 32>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, smem32);
+            if (e != cudaSuccess) return (int)e;
+        }
+        { cudaError_t le = pd_launch_pdl(gru_step_tma_kernel<ST32, NS32, true, false, true, 32>, dim3(grid32), dim3(NUM_THREADS), (size_t)smem32, (cudaStream_t)stream,
+                ta, tb, tgi2, tgi2, thp, tho, trzn, thn, tho, ta2, tb2, g, tiles_m, tiles_u); if (le != cudaSuccess) return (int)le; }
+        return pd_launch_status();
+    }
     const int grid = (int)(items < PD_NUM_SMS ? items : PD_NUM_SMS);
     constexpr int ST = 3, NS = 1;
     constexpr int smem = ST * (BM * 128 + BN3 * 128) + 4 * NS * N_IOB * IOB + 4 * N_OUTB * IOB + 1024 + 256;

@@ -796,10 +796,12 @@ def test_gru_step_tma3_split3_inference(B, H, bcast):
     assert torch.equal(hi.view(torch.int32) & 0x1FFF, torch.zeros(B, H, dtype=torch.int32))
 
 
-@pytest.mark.parametrize("B,H,K,save", [(300, 128, 128, True), (4100, 512, 128, True), (129, 64, 36, False)])
+@pytest.mark.parametrize("B,H,K,save", [(300, 128, 128, True), (4100, 512, 128, True), (129, 64, 36, False),
+                                        (512, 512, 128, False), (512, 512, 128, True), (1300, 512, 128, False)])
 def test_gru_step_tmax_folded_x_projection(B, H, K, save):
     """Training form of the fused step with the x-projection as a second K segment (pd_gru_step_tmax): x rows with a wide
-    stride (slot n of a (B,16,K) embedding buffer), w_x a column slice of a wider W_ih, saved gates for the backward."""
+    stride (slot n of a (B,16,K) embedding buffer), w_x a column slice of a wider W_ih, saved gates for the backward.
+    Row counts that leave half the SMs without a 64-unit tile (<= 74 tiles: the 512-row greedy slot) take 32-unit tiles."""
     _dev()
     torch.manual_seed(9)
     w, b = torch.randn(3 * H, H) / np.sqrt(H), torch.randn(3 * H) * 0.1
