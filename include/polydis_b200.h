@@ -145,6 +145,11 @@ int pd_greedy_decode_small(int B, const float* h_time0, const float* gi_z, const
 int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
                   float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R, int T,
                   int reverse, int passes, void* stream);
+/* the same forward with the rows VISITED in the order perm (R) gives (pd_pack_order's: longest first) -- a 16-row tile runs to
+ * its longest sequence; every array stays indexed by the original row */
+int pd_gru128_fwd_perm(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
+                       float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R, int T,
+                       int reverse, int passes, const int* perm, void* stream);
 int pd_gru128_bwd(const float* dout, long dr, long dt, const float* h_all, long hr, long ht, const float* rzn, long zr,
                   long zt, const float* hn, long nr, long nt, const int* lengths, const float* w_hh, float* dgi, long gr,
                   long gt, float* dgh, long qr, long qt, long R, int T, int reverse, void* stream);

@@ -33,6 +33,7 @@ SIGNATURES = {
     "pd_gru_step_tma3x": [_P, _L, _P, _L, _P, _L, _P, _L, _I, _P, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _P],
     "pd_gru_step_tma_variant": [_I],
     "pd_gru128_fwd": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P],
+    "pd_gru128_fwd_perm": [_P, _L, _L, _P, _P, _P, _P, _L, _L, _P, _L, _L, _P, _L, _L, _L, _I, _I, _I, _P, _P],
     "pd_gru128_bwd": [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _P, _P, _L, _L, _P, _L, _L, _L, _I, _I, _P],
     "pd_greedy_decode_small": [_I] + [_P] * 3 + [_L] + [_P] * 6 + [_L] + [_P] * 27 + [_P],
     "pd_grid_prepare": [_P, _L, _P, _P, _P, _P, _P],

@@ -56,6 +56,8 @@ struct FwdArgs {
     float* rzn; long zr, zt;              // optional saves for the backward pass
     float* hn; long nr, nt;
     long R; int T; int reverse;
+    const int* perm;                      // optional (R): tile i processes rows perm[16 i .. 16 i + 15] -- rows visited in
+                                          // sorted-length order (a tile runs to ITS longest sequence) without moving data
 };
 
 template <int RT, int PASSES>
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
     float (*w_s)[WS] = reinterpret_cast<float (*)[WS]>(smem);                       // [384][132]
     float (*h_s)[WS] = reinterpret_cast<float (*)[WS]>(smem + G3 * WS);             // [2][16][132] double buffer
     __shared__ int len_s[16];
+    __shared__ long row_s[16];                  // global row of every tile row
     __shared__ int tmax_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
     for (int i = tid; i < G3 * (H / 4); i += NTHR) {
@@ -88,7 +91,12 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long r0 = tile * RT;
         __syncthreads();
-        if (tid < 16) len_s[tid] = (tid < RT && r0 + tid < a.R) ? min(a.lengths[r0 + tid], a.T) : 0;
+        if (tid < 16) {
+            const bool ok = tid < RT && r0 + tid < a.R;
+            const long rr = ok ? (a.perm ? (long)a.perm[r0 + tid] : r0 + tid) : 0;
+            row_s[tid] = rr;
+            len_s[tid] = ok ? min(a.lengths[rr], a.T) : 0;
+        }
         for (int i = tid; i < 2 * 16 * WS; i += NTHR) (&h_s[0][0])[i] = 0.0f;
         __syncthreads();
         if (tid == 0) {
@@ -102,6 +110,7 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
         // rows of the m16 tile: g and g+8 (rows >= RT are padding)
         const int ra = g, rb = g + 8;
         const int la = len_s[ra], lb = len_s[rb];
+        const long rga = row_s[ra], rgb = row_s[rb];
         // x-projections of the NEXT step are fetched while this step's matvec runs (they do not depend on h)
         float2 xi[2][2][3], xn[2][2][3];
         auto fetch = [&](float2 (&xi)[2][2][3], int t) {
@@ -111,7 +120,7 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
                 for (int half = 0; half < 2; ++half) {
                     const int row = half ? rb : ra, len = half ? lb : la;
                     if (t < len) {                              // len == 0 for padding rows
-                        const float* gi = a.gi + (r0 + row) * a.ldr + (long)t * a.ldt + u0 + nt * 8 + 2 * tig;
+                        const float* gi = a.gi + (half ? rgb : rga) * a.ldr + (long)t * a.ldt + u0 + nt * 8 + 2 * tig;
 #pragma unroll
                         for (int gt = 0; gt < 3; ++gt) xi[nt][half][gt] = __ldg(reinterpret_cast<const float2*>(gi + gt * H));
                     }
@@ -154,8 +163,8 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
                         const int u = u0 + nt * 8 + 2 * tig;
                         float2 hp = *reinterpret_cast<const float2*>(&hc[row][u]);
                         float2 ho = hp;
-                        const long rr = r0 + row;
-                        if (row < RT && rr < a.R) {
+                        const long rr = half ? rgb : rga;
+                        if (row < RT && r0 + row < a.R) {
                             if (t < len) {
                                 const float2 ir = xi[nt][half][0], iz = xi[nt][half][1], in = xi[nt][half][2];
                                 const float g0 = acc[2][nt][half * 2], g1 = acc[2][nt][half * 2 + 1];
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_fwd_kernel(FwdArgs a) {
                 for (int i = tid; i < RT * (H / 4); i += NTHR) {
                     const int row = i / (H / 4), c4 = (i % (H / 4)) * 4;
                     if (r0 + row < a.R)
-                        *reinterpret_cast<float4*>(a.h_all + (r0 + row) * a.hr + (long)t * a.ht + c4) =
+                        *reinterpret_cast<float4*>(a.h_all + row_s[row] * a.hr + (long)t * a.ht + c4) =
                             *reinterpret_cast<const float4*>(&hc[row][c4]);
                 }
             }
@@ -360,14 +369,36 @@ __global__ void __launch_bounds__(NTHR, 1) gru128_bwd_kernel(BwdArgs a) {
 // h_all (R,T,128) <- variable-length GRU over gi (R,T,384) with per-row lengths, h0 = 0; rows past their length
 // carry their state (final state of row r is h_all[r, T-1], or h_all[r, 0] when reverse != 0).  rzn / hn optional
 // saves for pd_gru128_bwd.  passes: 1 = TF32, 3 = error-compensated TF32 (fp32-class).  Strides in floats.
+static int gru128_fwd_impl(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
+                           float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R,
+                           int T, int reverse, int passes, const int* perm, void* stream);
+
 PD_API int pd_gru128_fwd(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
                          float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R,
                          int T, int reverse, int passes, void* stream) {
+    return gru128_fwd_impl(gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse, passes,
+                           nullptr, stream);
+}
+
+// The same recurrence with the rows VISITED in the order perm (R) gives (e.g. pd_pack_order's: longest first): a tile of 16
+// rows runs to its longest sequence, so with unsorted lengths most of a tile's steps serve one or two rows.  Data stays where
+// it is: every array is still indexed by the original row.
+PD_API int pd_gru128_fwd_perm(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
+                              float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R,
+                              int T, int reverse, int passes, const int* perm, void* stream) {
+    if (perm == nullptr) return PD_BAD_ARG;
+    return gru128_fwd_impl(gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse, passes, perm,
+                           stream);
+}
+
+static int gru128_fwd_impl(const float* gi, long ldr, long ldt, const int* lengths, const float* w_hh, const float* b_hh,
+                           float* h_all, long hr, long ht, float* rzn, long zr, long zt, float* hn, long nr, long nt, long R,
+                           int T, int reverse, int passes, const int* perm, void* stream) {
     if (R <= 0 || T <= 0) return 0;
     if (((uintptr_t)w_hh & 15) || ((uintptr_t)gi & 7) || (ldr & 1) || (ldt & 1) || ((uintptr_t)h_all & 15) || (hr & 3) ||
         (ht & 3) || (rzn && (((uintptr_t)rzn & 7) || (zr & 1) || (zt & 1))) || (hn && (((uintptr_t)hn & 7) || (nr & 1) || (nt & 1))))
         return PD_BAD_ARG;
-    FwdArgs a{gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse};
+    FwdArgs a{gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse, perm};
     constexpr int smem = (G3 * WS + 2 * 16 * WS) * (int)sizeof(float);
     static unsigned long long attr = 0;
     if (pd_first_use_on_device(attr)) {

@@ -340,6 +340,9 @@ BF16_STEP_UNITS_SHORT = 64       # B200, batch 512: 7.86 -> 7.80 ms/step (GPU ca
 BF16_STEP_SHORT_T = 8
 
 
+#: greedy decoding: the summary bi-GRU of the predicted notes visits its rows in sorted-length order (pd_gru128_fwd_perm)
+GREEDY_SORT_SUMMARY_ROWS = True
+
 #: the plain-TF32 greedy pass (training with tfr < 1) runs its note-GRU slot as one fused launch (ptvae._greedy_fast)
 GREEDY_FUSED_TF32_STEP = True
 

@@ -704,6 +704,10 @@ class PtvaeDecoder(nn.Module):
         gh_e, h_e = [torch.empty(B, 3 * He, **f32) for _ in range(2)], torch.empty(B, He, **f32)
         h_sum = [torch.empty(B, NS, He, **f32) for _ in range(2)]
         st = ops._stream
+        sort_rows = ops.GREEDY_SORT_SUMMARY_ROWS and 64 <= B <= (1 << 17)
+        if sort_rows:
+            perm_s, inv_s = (torch.empty(B, device=dev, dtype=torch.int32) for _ in range(2))
+            table_s = torch.empty(64, device=dev, dtype=torch.int32)
         # 3xTF32 mode: a state that feeds several GEMMs is split into its [hi | hi | lo] operand once, by the gate
         # kernel that produces it (ops.gates_fwd_split3) or by ops.split3_act
         x3 = ops.split3_applies(h_time)
@@ -785,10 +789,17 @@ class PtvaeDecoder(nn.Module):
                 ops.gemm_nt(flat, w_ih, gi_e[d].view(B * NS, 3 * He), b_ih)
                 out = tok_time[:, d * He:(d + 1) * He]
                 if ops._resident128_ok(gi_e[d], None, None, lens, He):
-                    # whole variable-length recurrence in one weight-resident kernel
-                    ops._call("pd_gru128_fwd", ops._ptr(gi_e[d]), gi_e[d].stride(0), gi_e[d].stride(1), ops._ptr(lens),
-                              ops._ptr(w_hh), ops._ptr(b_hh), ops._ptr(h_sum[d]), h_sum[d].stride(0), h_sum[d].stride(1),
-                              None, 0, 0, None, 0, 0, B, NS, int(rev), 3 if ops.PRECISION == "tf32x3" else 1, st())
+                    # whole variable-length recurrence in one weight-resident kernel; with many rows they are VISITED in
+                    # sorted-length order (a 16-row tile runs to its longest sequence: unsorted, most steps serve a row or two)
+                    if sort_rows:
+                        ops._call("pd_gru128_fwd_perm", ops._ptr(gi_e[d]), gi_e[d].stride(0), gi_e[d].stride(1), ops._ptr(lens),
+                                  ops._ptr(w_hh), ops._ptr(b_hh), ops._ptr(h_sum[d]), h_sum[d].stride(0), h_sum[d].stride(1),
+                                  None, 0, 0, None, 0, 0, B, NS, int(rev), 3 if ops.PRECISION == "tf32x3" else 1,
+                                  ops._ptr(perm_s), st())
+                    else:
+                        ops._call("pd_gru128_fwd", ops._ptr(gi_e[d]), gi_e[d].stride(0), gi_e[d].stride(1), ops._ptr(lens),
+                                  ops._ptr(w_hh), ops._ptr(b_hh), ops._ptr(h_sum[d]), h_sum[d].stride(0), h_sum[d].stride(1),
+                                  None, 0, 0, None, 0, 0, B, NS, int(rev), 3 if ops.PRECISION == "tf32x3" else 1, st())
                     out.copy_(h_sum[d][:, 0 if rev else NS - 1])
                     return
                 first = True
@@ -799,6 +810,8 @@ class PtvaeDecoder(nn.Module):
                         ops.gemm_nt(out, w_hh, gh_e[d], b_hh)
                     ops._gates_fwd(gi_e[d][:, k], None, gh_e[d], None if first else out, out, None, None, lens, k)
                     first = False
+            if sort_rows:                        # visiting order of this step's rows: longest predicted sequence first
+                ops._call("pd_pack_order", ops._ptr(lens), B, ops._ptr(perm_s), ops._ptr(inv_s), ops._ptr(table_s), st())
             ops.fork_join([lambda: summarise(0, False), lambda: summarise(1, True)])   # the two directions overlap
         return tokens
 

@@ -171,6 +171,12 @@ class CpuBackend:
         self.pd_gru_gates_fwd(gi, ldgi, gi2, ldgi2, gh_ptr, 3 * H, hp, ldhp, ho, ldho, rzn, ldrzn, hn, ldhn, lengths, t,
                               B, H, st)
 
+    def pd_gru128_fwd_perm(self, gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse,
+                           passes, perm, st):
+        p = _arr(perm, (R,), (1,), np.int32)
+        assert sorted(p.tolist()) == list(range(R))          # (a visiting order: same arithmetic per row)
+        self.pd_gru128_fwd(gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse, passes, st)
+
     def pd_gru128_fwd(self, gi, ldr, ldt, lengths, w_hh, b_hh, h_all, hr, ht, rzn, zr, zt, hn, nr, nt, R, T, reverse,
                       passes, st):
         H = 128

@@ -675,6 +675,34 @@ def test_gru128_resident(R, T, reverse, passes):
         assert torch.allclose(g, c, atol=5e-3, rtol=1e-3), float((g - c).abs().max())
 
 
+@pytest.mark.parametrize("R,reverse,passes", [(1000, 0, 1), (333, 1, 3), (21, 0, 1)])
+def test_gru128_resident_visits_rows_in_a_given_order(R, reverse, passes):
+    """pd_gru128_fwd_perm: the rows are processed in the order of a permutation (greedy decoding sorts them by predicted
+    length: a 16-row tile runs to its longest sequence) -- every output row is bit-for-bit what pd_gru128_fwd writes."""
+    _dev()
+    from polydis_b200 import _lib
+    H, T = 128, 16
+    torch.manual_seed(6)
+    w, b = (torch.randn(3 * H, H) / np.sqrt(H)).cuda(), (torch.randn(3 * H) * 0.1).cuda()
+    lengths = torch.randint(0, T + 1, (R,), dtype=torch.int32).cuda()
+    gi = torch.randn(R, T, 3 * H).cuda()
+    perm, inv, table = (torch.zeros(n, dtype=torch.int32).cuda() for n in (R, R, 64))
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.call("pd_pack_order", lengths.data_ptr(), R, perm.data_ptr(), inv.data_ptr(), table.data_ptr(), st)
+    outs = []
+    for use_perm in (False, True):
+        h_all, rzn, hn = (torch.zeros(R, T, n).cuda() for n in (H, 3 * H, H))
+        args = [gi.data_ptr(), T * 3 * H, 3 * H, lengths.data_ptr(), w.data_ptr(), b.data_ptr(), h_all.data_ptr(), T * H, H,
+                rzn.data_ptr(), T * 3 * H, 3 * H, hn.data_ptr(), T * H, H, R, T, reverse, passes]
+        _lib.call("pd_gru128_fwd_perm" if use_perm else "pd_gru128_fwd", *(args + ([perm.data_ptr()] if use_perm else [])), st)
+        torch.cuda.synchronize()
+        outs.append((h_all, rzn, hn))
+    ls = lengths[perm.long()]
+    assert bool((ls[:-1] >= ls[1:]).all())
+    for a, c in zip(*outs):
+        assert torch.equal(a, c)
+
+
 @pytest.mark.parametrize("order", [0, 1])
 def test_tf32_split3(order):
     """[hi | hi | lo] / [hi | lo | hi] operand builder of the single-launch 3xTF32 GEMM (zero padded to K % 4 == 0)."""
