@@ -422,7 +422,7 @@ def run_b200(args):
     step_bytes = R * (9 * H_ + K2_) * 4 + 3 * H_ * (H_ + K2_) * 4
     step_gbs = step_bytes / (ms_fstep * 1e-3) / 1e9
     del x_, gi2_, h_, rzn_, hn_
-    # the kernel family with the largest share of the packed step (profiles/r02_v6_train_step_launches.txt): the
+    # the kernel family with the largest share of the packed step (profiles/r02_v7_train_step_launches.txt): the
     # dgh . W_hh GEMM of the batch-sized recurrences' backward steps (time GRU, both encoder bi-GRUs, chord decoder):
     # [B x 3H] . [3H x H], H = 1024, split over K with a red.add epilogue into an accumulator the gate kernel cleared.
     # 32 launches over distinct gate-gradient slices (as in the 32-step time GRU), W_hh stays L2-resident as in the step.
@@ -535,7 +535,7 @@ def run_b200(args):
                                   "batch-sized recurrence (time GRU / encoders / chord decoder), [B x 1024] . [1024 x 3072] on "
                                   "tcgen05 (kind::f16, fp32 accumulate) + gate math in the epilogue",
                         "ms_per_launch": ms_bstep, "algorithmic_flop_per_launch": dh_flop,
-                        "what": "the kernel family with the largest share of the packed step (profiles/r02_v6_train_step_launches.txt: "
+                        "what": "the kernel family with the largest share of the packed step (profiles/r02_v7_train_step_launches.txt: "
                                 "32 launches of this 32-unit form for the time GRU + 36 of the 64-unit form the short concurrent "
                                 "recurrences use, 11.9 % together), timed alone with CUDA events as a captured graph of 32 dependent launches "
                                 "over the slices of a (B,33,.) sequence (10 replays): 2 M N K / launch time vs the measured "
