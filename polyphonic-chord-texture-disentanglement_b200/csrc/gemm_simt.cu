@@ -143,8 +143,10 @@ __global__ void colsum_kernel(const float* __restrict__ X, long ldx, int M, int 
 // Vector variant for 16-byte aligned inputs: a block sums one 128-column strip over its row range with 8 warps
 // striding the rows (lane = 4 columns, float4 loads, 4 rows in flight per thread), reduces the warps through
 // shared memory and issues one atomicAdd per column.
-// SEQ: the rows are the (sequence, step) pairs of an (R, T, N) buffer and row m is only read if its step m % T lies below
-// its sequence's length (the rest are the zeros a masked recurrence's backward left there: 3/4 of the summariser's rows).
+// SEQ: the rows are the (sequence, step) pairs of an (R, T, N) buffer and only the steps below a sequence's length are
+// read (the rest are the zeros a masked recurrence's backward left there: 3/4 of the summariser's rows).  In SEQ mode M
+// counts SEQUENCES, rows_per_blk sequences per block, and a warp walks the live steps of every 8th sequence (no per-row
+// division; consecutive steps of a sequence are consecutive rows).
 template <bool SEQ>
 __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict__ X, long ldx, int M, int N, float* out,
                                                          int rows_per_blk, const int* __restrict__ lengths, int T) {
@@ -156,20 +158,36 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const float* __restrict
 #pragma unroll
     for (int i = 0; i < 4; ++i) s[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n < N) {
-        int m = mb + warp;
-        auto live = [&](int row) { return !SEQ || (row % T) < __ldg(lengths + row / T); };
-        for (; m + 24 < me; m += 32) {
+        if (SEQ) {
+            for (int q = mb + warp; q < me; q += 8) {
+                const int len = min(__ldg(lengths + q), T);
+                const float* row = X + (long)q * T * ldx + n;
+                int t = 0;
+                for (; t + 3 < len; t += 4) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (!live(m + 8 * i)) continue;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)(m + 8 * i) * ldx + n));
-                s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(row + (long)(t + i) * ldx));
+                        s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+                    }
+                }
+                for (; t < len; ++t) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(row + (long)t * ldx));
+                    s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+                }
             }
-        }
-        for (; m < me; m += 8) {
-            if (!live(m)) continue;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)m * ldx + n));
-            s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+        } else {
+            int m = mb + warp;
+            for (; m + 24 < me; m += 32) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)(m + 8 * i) * ldx + n));
+                    s[i].x += v.x; s[i].y += v.y; s[i].z += v.z; s[i].w += v.w;
+                }
+            }
+            for (; m < me; m += 8) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(X + (long)m * ldx + n));
+                s[0].x += v.x; s[0].y += v.y; s[0].z += v.z; s[0].w += v.w;
+            }
         }
     }
     part[warp][lane] = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
@@ -276,14 +294,13 @@ PD_API int pd_colsum_seq_f32(const float* X, long ldx, int R, int T, int N, cons
     if ((((uintptr_t)X) & 15) || (ldx & 3) || (N & 3) || T <= 0 || lengths == nullptr || (long)R * T > 2147483647L) return PD_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, st);
-    const int M = R * T;
-    if (M <= 0) return pd_launch_status();
+    if (R <= 0) return pd_launch_status();
     const int nbx = (N + 127) / 128;
-    int want = (6 * PD_NUM_SMS + nbx - 1) / nbx;
-    int rows = (M + want - 1) / want;
-    rows = ((rows < 64 ? 64 : rows) + 7) / 8 * 8;
-    dim3 gridv(nbx, (M + rows - 1) / rows);
-    colsum_vec_kernel<true><<<gridv, 256, 0, st>>>(X, ldx, M, N, out, rows, lengths, T);
+    int want = (6 * PD_NUM_SMS + nbx - 1) / nbx;                 // blocks per column strip
+    int seqs = (R + want - 1) / want;                           // sequences per block
+    seqs = ((seqs < 8 ? 8 : seqs) + 7) / 8 * 8;
+    dim3 gridv(nbx, (R + seqs - 1) / seqs);
+    colsum_vec_kernel<true><<<gridv, 256, 0, st>>>(X, ldx, R, N, out, seqs, lengths, T);
     return pd_launch_status();
 }
 
