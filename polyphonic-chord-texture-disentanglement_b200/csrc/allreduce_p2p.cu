@@ -21,6 +21,7 @@
 // port (900 GB/s per direction), latency-bound for the 8 MB buckets used here; grid and unroll are sized to keep
 // ~2 MB of peer loads in flight.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 #define PD_AR_MAX_RANKS 8
@@ -293,8 +294,17 @@ PD_API int pd_allreduce_p2p(const void* const* peers, int rank, int world, long 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const long off4 = off / 4, n4 = n / 4;
+    // threads per block: 512 by default; PD_AR_THREADS=256 (with twice the blocks) lets an exchange block share an SM with a
+    // CTA of the recurrent chain's tcgen05 kernels (192 threads x 255 registers leave 16 K registers) -- measured equal
+    // (2 GPUs, GPU call 56: 7.98 ms/step with 32 x 512 threads on 4 streams, 8.00 with 64 x 256 on 2, 8.01 with 48 x 256 on 3)
+    static int threads = 0;
+    if (threads == 0) {
+        const char* v = getenv("PD_AR_THREADS");
+        threads = v ? atoi(v) : PD_AR_THREADS;
+        if (threads != 128 && threads != 256 && threads != 512) threads = PD_AR_THREADS;
+    }
     unsigned* ep = reinterpret_cast<unsigned*>(epoch) + (long)bucket * PD_AR_MAX_BLOCKS;
-#define PD_AR_LAUNCH(Wv) allreduce_p2p_kernel<Wv><<<nblocks, PD_AR_THREADS, 0, s>>>(P, rank, off4, n4, scale, ep, err, with_norm, G)
+#define PD_AR_LAUNCH(Wv) allreduce_p2p_kernel<Wv><<<nblocks, threads, 0, s>>>(P, rank, off4, n4, scale, ep, err, with_norm, G)
     switch (world) {
         case 2: PD_AR_LAUNCH(2); break;
         case 3: PD_AR_LAUNCH(3); break;
